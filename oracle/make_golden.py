@@ -1,0 +1,324 @@
+"""Mints tests/golden/*.npz by running the UNMODIFIED reference functions on torch-CPU.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (needs /root/reference); the .npz files it
+writes are committed and are the only thing that travels to the GPU box.
+
+    python oracle/make_golden.py            # rewrites every fixture
+
+Each fixture stores the exact inputs next to the reference's outputs, so that tests never depend on
+RNG reproducibility across machines.  Reference call sites: train_dino.py:171-239 (vote_center,
+vote_rotation), dataset.py:118-135 (generate_target_pairs), eval.py:37-51 (get_topk_dir),
+eval.py:219-313 (per-branch instance body), train_shot.py:117-122 / train_dino.py:128-133 (heads).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle.ref_import import REFERENCE_ROOT, load_reference  # noqa: E402
+from cppf2_b200 import synth  # noqa: E402
+from cppf2_b200.heads_spec import init_state_dict  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def angle_tables(num_rots: int):
+    """The literal reference expression (train_dino.py:195-196) evaluated on torch-CPU."""
+    angles = torch.arange(num_rots).to(torch.float32) / num_rots * 2 * np.pi
+    return torch.cos(angles).numpy().copy(), torch.sin(angles).numpy().copy()
+
+
+def save(name: str, **arrays):
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"  wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def voxel_downsample(pc: np.ndarray, res: float, rng: np.random.Generator) -> np.ndarray:
+    """One random member per occupied voxel (what utils/util.py:39-46 does through Open3D)."""
+    key = np.floor((pc - pc.min(0)) / res).astype(np.int64)
+    _, inv = np.unique(key, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    order = np.lexsort((rng.random(pc.shape[0]), inv))
+    first = np.ones(order.shape[0], bool)
+    first[1:] = inv[order][1:] != inv[order][:-1]
+    return np.sort(order[first])
+
+
+def example_cloud(ref) -> np.ndarray:
+    """example_data/{depth,mask}.png -> camera-frame cloud, 2 mm voxels (notebook cell 11/13)."""
+    import cv2
+    depth = cv2.imread(os.path.join(REFERENCE_ROOT, "example_data", "depth.png"), -1)
+    mask = cv2.imread(os.path.join(REFERENCE_ROOT, "example_data", "mask.png"), -1)
+    if mask.ndim == 3:
+        mask = mask[..., 0]
+    K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]])
+    pc, _ = ref.backproject(depth / 10000.0, K, mask > 0)
+    pc[:, 0] = -pc[:, 0]
+    pc[:, 1] = -pc[:, 1]
+    pc = pc.astype(np.float32)
+    keep = voxel_downsample(pc, 0.002, np.random.default_rng(0))
+    return np.ascontiguousarray(pc[keep])
+
+
+def adversarial_cloud_and_pairs(seed=3, n=4000, t=20000):
+    """Half cylinder + crafted points/pairs hitting every branch of vote_center (SURVEY 8c golden list)."""
+    pc = synth.half_cylinder_cloud(n, seed=seed)
+    extra = np.array([
+        pc[10] + np.float32([0.01, 0, 0]),      # pair (10, n)   -> ab parallel to the x axis ('invalid' co)
+        pc[11] + np.float32([-0.02, 0, 0]),     # pair (n+1, 11) -> ab parallel to -x
+        pc[12],                                 # exact duplicate of point 12 -> |ab| = 0
+    ], np.float32)
+    pc = np.concatenate([pc, extra]).astype(np.float32)
+    idx = synth.sample_tuples(pc.shape[0], t, 5, seed=11)
+    idx[0, :2] = (10, n)
+    idx[1, :2] = (n + 1, 11)
+    idx[2, :2] = (12, n + 2)
+    idx[3, :2] = (77, 77)
+    center = 0.5 * (pc.min(0) + pc.max(0)).astype(np.float64)
+    tr = synth.noisy_center_targets(pc, idx, center, sigma=0.002, seed=5)
+    tr[4, 1] = 0.002          # odist == res (float32) -> rejected by the strict '>'
+    tr[5, 1] = 0.0019
+    tr[6, 1] = 0.5            # huge circle, every vote falls outside the grid
+    tr[7, 0] = -0.03
+    return pc, idx, tr, center
+
+
+def mint_vote_center(ref):
+    print("vote_center")
+    pc, idx, tr, _ = adversarial_cloud_and_pairs()
+    for name, cloud, T, R in (("vote_center_halfcyl", pc, idx.shape[0], 180),
+                              ("vote_center_halfcyl_r36", pc, 4000, 36)):
+        res = 0.002
+        grid, cand = ref.vote_center(torch.from_numpy(cloud), torch.from_numpy(tr[:T]), res,
+                                     torch.from_numpy(idx[:T, :2]), num_rots=R)
+        ct, st = angle_tables(R)
+        assert grid.max() < 2 ** 31
+        save(name, pc=cloud, idx=idx[:T, :2].astype(np.int32), tr=tr[:T], res=np.float64(res), num_rots=R,
+             cos_tab=ct, sin_tab=st, grid=grid.astype(np.int32), cand_world=cand)
+        print("    grid", grid.shape, "votes", int(grid.sum()), "peak", int(grid.max()))
+
+    # example_data cloud: grid about 118x51x133 -> keep the hash + coarse digests, not 0.8 M cells
+    cloud = example_cloud(ref)
+    T, R, res = 50000, 180, 0.002
+    eidx = synth.sample_tuples(cloud.shape[0], T, 5, seed=12)
+    center = np.median(cloud, 0).astype(np.float64) + np.array([0, 0, 0.03])
+    etr = synth.noisy_center_targets(cloud, eidx, center, sigma=0.002, seed=8)
+    grid, cand = ref.vote_center(torch.from_numpy(cloud), torch.from_numpy(etr), res,
+                                 torch.from_numpy(eidx[:, :2]), num_rots=R)
+    ct, st = angle_tables(R)
+    g64 = np.ascontiguousarray(grid.astype(np.int64))
+    save("vote_center_example", pc=cloud, idx=eidx[:, :2].astype(np.int32), tr=etr, res=np.float64(res), num_rots=R,
+         cos_tab=ct, sin_tab=st, grid_shape=np.array(grid.shape), grid_sha256=np.frombuffer(
+             hashlib.sha256(g64.tobytes()).digest(), np.uint8), grid_sum_x=g64.sum((1, 2)), grid_sum_y=g64.sum((0, 2)),
+         grid_sum_z=g64.sum((0, 1)), argmax=np.int64(g64.argmax()), peak=np.int64(g64.max()), cand_world=cand)
+    print("    example grid", grid.shape, "votes", int(grid.sum()), "peak", int(grid.max()), "N", cloud.shape[0])
+
+
+def mint_targets(ref):
+    print("generate_target_pairs")
+    rng = np.random.default_rng(21)
+    pairs = rng.uniform(-0.3, 0.3, (3000, 2, 3)).astype(np.float32)
+    pairs[0, 1] = pairs[0, 0]                     # zero-length pair
+    pairs[1, 1] = pairs[1, 0] + np.float32([0, 0.1, 0])   # exactly along 'up'
+    pairs[2, 1] = pairs[2, 0] - np.float32([0, 0.1, 0])
+    up, right, front = np.array([0, 1, 0]), np.array([1, 0, 0]), np.array([0, 0, 1])
+    # positional order of the call sites (eval.py:237-240): (up, front, right)
+    tr0, rot0 = ref.generate_target_pairs(pairs, up, front, right)
+    center = np.array([0.0123, -0.0456, 0.789])
+    tr1, rot1 = ref.generate_target_pairs(pairs, up, front, right, center)
+    save("targets", pairs=pairs, up=up, right=right, front=front, center=center, tr0=tr0, rot0=rot0, tr1=tr1, rot1=rot1)
+
+
+def mint_rotation(ref):
+    print("vote_rotation + get_topk_dir")
+    pc = synth.half_cylinder_cloud(2000, seed=4)
+    M, R = 400, 180
+    idx = synth.sample_tuples(pc.shape[0], M, 2, seed=13)
+    idx[0] = (5, 5)                                # masked out
+    axis = np.array([0.0, 1.0, 0.0])
+    theta = synth.noisy_axis_angles(pc, idx, axis, sigma_deg=2.0, seed=6)
+    theta[1] = np.float32(np.pi / 2)               # tan blow-up
+    theta[2] = 0.0                                 # tan == 0 -> sign -1
+    rng = np.random.default_rng(17)
+    wt = rng.uniform(0.01, 2.01, M)                # float64, like imp_pair_wt (eval.py:274-275)
+    up, mask = ref.vote_rotation(torch.from_numpy(pc), torch.from_numpy(theta), torch.from_numpy(idx), R)
+    sphere = np.array(ref.fibonacci_sphere(720), dtype=np.float32)
+    wt_rows = torch.from_numpy(wt)[mask, None].expand(-1, R).reshape(-1, 1)
+    dirs, cnts = ref.get_topk_dir(up.reshape(-1, 3), sphere, 100000, 1.0, wt_rows, topk=720)
+    # counts for every bin, recovered in bin order from the full top-k
+    order = np.array([int(np.argmin(np.abs(sphere - d).sum(-1))) for d in dirs])
+    counts = np.zeros(720, np.float32)
+    counts[order] = cnts
+    ct, st = angle_tables(R)
+    save("rotation", pc=pc, idx=idx.astype(np.int32), theta=theta, wt=wt, num_rots=R, cos_tab=ct, sin_tab=st,
+         sphere=sphere, mask=mask.numpy(), up_head=up[:16].numpy(), up_sum=up.double().sum((0, 1)).numpy(),
+         counts=counts, best=np.int64(order[0]), angle_tol=1.0)
+    print("    kept", int(mask.sum()), "best bin", order[0], "count", cnts[0])
+
+
+def _cfg(num_more=3):
+    return types.SimpleNamespace(num_more=num_more, up=[0, 1, 0], right=[1, 0, 0], front=[0, 0, 1], res=0.002)
+
+
+def _load(model, sd):
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return model.eval()
+
+
+def mint_heads(ref):
+    print("heads")
+    rng = np.random.default_rng(31)
+    N, T = 300, 96
+    pc = synth.half_cylinder_cloud(N, seed=9)
+    idx = synth.sample_tuples(N, T, 5, seed=14)
+    shot = np.abs(rng.standard_normal((N, 352))).astype(np.float32)
+    shot /= np.linalg.norm(shot, axis=-1, keepdims=True)
+    normal = rng.standard_normal((N, 3)).astype(np.float32)
+    normal /= np.linalg.norm(normal, axis=-1, keepdims=True)
+    desc = synth.unit_descriptors(N, 1024, seed=2)
+    with torch.no_grad():
+        m = _load(ref.BeyondCPPFSHOT(_cfg()), init_state_dict("shot", 1234))
+        cls_s, scale_s = m(torch.from_numpy(pc), torch.from_numpy(idx), torch.from_numpy(shot), torch.from_numpy(normal))
+        enc_in = m.prepare_tuple_inputs(torch.from_numpy(pc), torch.from_numpy(idx), m.shot_encoder(torch.from_numpy(shot)),
+                                        torch.from_numpy(normal))
+        m = _load(ref.BeyondCPPFDINO(_cfg()), init_state_dict("dino", 4321))
+        cls_d, scale_d = m(torch.from_numpy(pc), torch.from_numpy(desc), torch.from_numpy(idx))
+    save("heads", pc=pc, idx=idx.astype(np.int32), shot=shot.astype(np.float16), normal=normal, desc_seed=2,
+         seed_shot=1234, seed_dino=4321, cls_shot=cls_s.numpy(), scale_shot=scale_s.numpy(),
+         enc_in_shot_head=enc_in[:8].numpy(), cls_dino=cls_d.numpy(), scale_dino=scale_d.numpy())
+
+
+def reference_instance_body(ref, pc, point_idxs_all, pred_cls, pred_scales, bins, cfg, num_rots=180,
+                            backproj_ratio=0.1, imp_wt_margin=0.01, angle_tol=1.0):
+    """eval.py:225-313 for ONE branch with opt=False, calling the reference's own functions.
+
+    `pred_cls`/`pred_scales` are the head outputs (torch f32) and `bins` the injected multinomial draws
+    [T,6] (eval.py:229 is the reference's only device RNG).  Returns every intermediate the parity
+    tests look at.
+    """
+    sphere_pts = np.array(ref.fibonacci_sphere(int(4 * np.pi / (angle_tol / 180 * np.pi))), dtype=np.float32)
+    input_pairs = pc[point_idxs_all[:, :2]]
+    num_bins = pred_cls.shape[-1]
+    pred_pairs = torch.from_numpy(bins).float().reshape(-1, 2, 3)
+    pred_pairs = (pred_pairs / (num_bins - 1) - 0.5)
+    scale = torch.from_numpy(np.linalg.norm(input_pairs[:, 1] - input_pairs[:, 0], axis=-1)).float() \
+        / torch.clamp_min(torch.norm(pred_pairs[:, 1] - pred_pairs[:, 0], dim=-1), 1e-7)
+    pred_pairs_scaled = pred_pairs * scale[:, None, None]
+    targets_tr, targets_rot = ref.generate_target_pairs(pred_pairs_scaled.numpy(), np.array(cfg.up), np.array(cfg.front),
+                                                        np.array(cfg.right))
+    grid_obj, pred_trans = ref.vote_center(torch.from_numpy(pc).float(), torch.from_numpy(targets_tr).float(), cfg.res,
+                                           torch.from_numpy(point_idxs_all[:, :2]).long(), num_rots=num_rots, vis=None)
+    T_est = pred_trans
+    targets_tr_back, _ = ref.generate_target_pairs(input_pairs, np.array(cfg.up), np.array(cfg.front), np.array(cfg.right), T_est)
+    back_errs = np.linalg.norm(targets_tr - targets_tr_back, axis=-1)
+    thr = np.percentile(back_errs, backproj_ratio * 100)
+    pairs_mask = back_errs < thr
+    flat = torch.from_numpy(point_idxs_all[pairs_mask, :2].reshape(-1)).long()
+    imp_wt = torch.zeros(pc.shape[0], dtype=torch.int64).scatter_add_(0, flat, torch.ones_like(flat)).numpy()
+    filt = point_idxs_all[pairs_mask]
+    targets_rot_f = targets_rot[pairs_mask]
+    pred_scales_f = pred_scales[torch.from_numpy(pairs_mask)]
+    imp_wt = imp_wt / imp_wt.max()
+    imp_pair_wt = torch.from_numpy(imp_wt[filt[:, :2]]).sum(-1) + imp_wt_margin
+    out_dirs, out_counts = [], []
+    for col in (0, 2):
+        cand, valid = ref.vote_rotation(torch.from_numpy(pc).float(), torch.from_numpy(targets_rot_f[..., col]).float(),
+                                        torch.from_numpy(filt[:, :2]).long(), num_rots)
+        dirs, cnts = ref.get_topk_dir(cand.reshape(-1, 3), sphere_pts, 100000, angle_tol,
+                                      imp_pair_wt[valid, None].expand(-1, num_rots).reshape(-1, 1), topk=720)
+        order = np.array([int(np.argmin(np.abs(sphere_pts - d).sum(-1))) for d in dirs])
+        counts = np.zeros(720, np.float32)
+        counts[order] = cnts
+        out_dirs.append(dirs[0].copy())
+        out_counts.append(counts)
+    preds_up, preds_right = out_dirs[0].astype(np.float32), out_dirs[1].astype(np.float32)
+    preds_right -= np.dot(preds_up, preds_right) * preds_up
+    preds_right /= (np.linalg.norm(preds_right) + 1e-9)
+    up_loc = np.where(cfg.up)[0][0]
+    right_loc = np.where(cfg.right)[0][0]
+    R_est = np.eye(3)
+    R_est[:3, up_loc] = preds_up
+    R_est[:3, right_loc] = preds_right
+    pred_scale = torch.median(pred_scales_f, 0)[0].numpy()
+    pred_scale_norm = np.linalg.norm(pred_scale)
+    other_loc = list(set([0, 1, 2]) - set([up_loc, right_loc]))[0]
+    R_est[:3, other_loc] = np.cross(R_est[:3, (other_loc + 1) % 3], R_est[:3, (other_loc + 2) % 3])
+    pc_canon = (pc - T_est) @ R_est / pred_scale_norm
+    loss = np.abs(pc_canon[filt[:, :2]] - pred_pairs[torch.from_numpy(pairs_mask)].numpy())
+    loss_all = np.clip(loss, 0, 0.1).mean()
+    loss_y = np.clip(loss[..., 1], 0, 0.1).mean()
+    return dict(targets_tr=targets_tr, targets_rot=targets_rot, pair_scale=scale.numpy(), grid=grid_obj, T_est=T_est,
+                back_errs=back_errs, thr=np.float64(thr), pairs_mask=pairs_mask, imp_pair_wt=imp_pair_wt.numpy(),
+                counts_up=out_counts[0], counts_right=out_counts[1], R_est=R_est, pred_scale=pred_scale,
+                loss_all=np.float64(loss_all), loss_y=np.float64(loss_y))
+
+
+def mint_instance(ref):
+    print("instance (eval.py:225-313, one branch, opt=False, draws injected)")
+    rng = np.random.default_rng(41)
+    pc = synth.half_cylinder_cloud(3000, seed=15)
+    N, T = pc.shape[0], 20000
+    idx = synth.sample_tuples(N, T, 5, seed=16)
+    cfg = _cfg()
+    # injected multinomial draws: the true canonical coordinates of the pair (object centre (0,0,0.8),
+    # identity rotation, diagonal 0.14 m) quantised to the 32 bins, +-1 bin of noise, 5 % outliers
+    canon = (pc[idx[:, :2]].astype(np.float64) - np.array([0.0, 0.0, 0.8])) / 0.14
+    bins = np.rint((canon + 0.5) * 31).astype(np.int64) + rng.integers(-1, 2, canon.shape)
+    outl = rng.uniform(0, 1, T) < 0.05
+    bins[outl] = rng.integers(0, 32, (int(outl.sum()), 2, 3))
+    bins = np.clip(bins, 0, 31).reshape(T, 6)
+    pred_scales = (np.array([0.57, 0.71, 0.41]) + 0.02 * rng.standard_normal((T, 3))).astype(np.float16).astype(np.float32)
+    pred_cls = torch.zeros(T, 6, 32)   # only its trailing dimension (num_bins) is read by the body
+    out = reference_instance_body(ref, pc, idx, pred_cls, torch.from_numpy(pred_scales), bins, cfg)
+    grid = out.pop("grid")
+    out["pairs_mask"] = np.packbits(out["pairs_mask"])
+    for k in ("targets_tr", "targets_rot", "pair_scale", "back_errs"):
+        out[k + "_head"] = out.pop(k)[:512]
+    save("instance", pc=pc, idx=idx.astype(np.int16), bins=bins.astype(np.uint8), pred_scales=pred_scales.astype(np.float16),
+         grid=grid.astype(np.int32), num_tuples=T, **out)
+    print("    T_est", out["T_est"], "kept", int(np.unpackbits(out["pairs_mask"])[:T].sum()), "scale", out["pred_scale"])
+    print("    R_est", out["R_est"].round(3).tolist())
+
+
+def mint_percentile():
+    print("np.percentile semantics (eval.py:257)")
+    rng = np.random.default_rng(51)
+    cases = {}
+    for name, n in (("a", 20001), ("b", 11), ("c", 1000), ("d", 7), ("e", 20000)):
+        e = rng.uniform(0, 0.05, n).astype(np.float32)
+        if name == "c":
+            e = np.round(e, 3)          # heavy ties around the order statistic
+        thr = np.percentile(e, 10.0)
+        cases["errs_" + name] = e
+        cases["thr_" + name] = np.float64(thr)
+        cases["kept_" + name] = np.int64((e < thr).sum())
+        cases["thr_dtype_" + name] = np.array(str(np.asarray(thr).dtype))
+    save("percentile", **cases)
+
+
+def main():
+    torch.set_grad_enabled(False)
+    ref = load_reference()
+    mint_vote_center(ref)
+    mint_targets(ref)
+    mint_rotation(ref)
+    mint_heads(ref)
+    mint_instance(ref)
+    mint_percentile()
+    meta = dict(torch=torch.__version__, numpy=np.__version__, cpu=str(torch.backends.cpu.get_cpu_capability()))
+    save("meta", **{k: np.array(v) for k, v in meta.items()})
+
+
+if __name__ == "__main__":
+    main()
