@@ -1,0 +1,123 @@
+"""ctypes binding of libcppf_b200.so (the C ABI declared in include/cppf_b200.h).
+
+There is no fallback: if the shared library is missing or a call returns an error code, a Python
+exception is raised.  PyTorch is only used by the callers for device memory and streams; nothing
+torch-typed crosses this boundary (plain pointers and sizes).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcppf_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+CPPF_STATUS_GRID_OVERFLOW = 1
+CPPF_STATUS_GRID_GUARD = 2
+CPPF_STATUS_EMPTY = 4
+
+
+class CppfError(RuntimeError):
+    pass
+
+
+class GridGeom(C.Structure):
+    _fields_ = [("lo", C.c_float * 3), ("hi", C.c_float * 3), ("res", C.c_float), ("flags", C.c_uint32),
+                ("grid_res", C.c_int64 * 3), ("cells", C.c_int64)]
+
+
+class Center(C.Structure):
+    _fields_ = [("world", C.c_double * 3), ("cell", C.c_int64 * 3), ("linear", C.c_int64), ("votes", C.c_uint32),
+                ("pad", C.c_uint32)]
+
+
+class BackvoteSummary(C.Structure):
+    _fields_ = [("threshold", C.c_float), ("s_lo", C.c_float), ("s_hi", C.c_float), ("imp_max", C.c_int32),
+                ("kept", C.c_int64)]
+
+
+class Pose(C.Structure):
+    _fields_ = [("R", C.c_double * 9), ("t", C.c_double * 3), ("scale", C.c_float * 3), ("scale_norm", C.c_float),
+                ("loss", C.c_double), ("bin_up", C.c_int32), ("bin_right", C.c_int32), ("count_up", C.c_float),
+                ("count_right", C.c_float), ("kept", C.c_int64), ("status", C.c_uint32), ("pad", C.c_uint32)]
+
+
+P, I, I64, F, D, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); mirrors include/cppf_b200.h one to one
+SIGNATURES = {
+    "cppf_error_string": (C.c_char_p, [I]),
+    "cppf_version": (I, []),
+    "cppf_device_info": (I, [_IP, C.POINTER(I64), _IP, _IP]),
+    "cppf_cloud_bounds": (I, [P, I64, F, P, P]),
+    "cppf_vote_center": (I, [P, I64, P, I, I64, P, I64, P, P, I, P, P, I64, I, P, P]),
+    "cppf_grid_argmax": (I, [P, P, D, P, P]),
+    "cppf_grid_to_i64": (I, [P, P, P, P]),
+    "cppf_sample_bins": (I, [P, I64, I, P, U64, P, P]),
+    "cppf_decode_targets": (I, [P, P, I, I64, P, I64, I, _DP, P, P, P, P, P]),
+    "cppf_generate_targets": (I, [P, I64, _DP, P, P, P, P]),
+    "cppf_backvote_workspace_bytes": (I64, [I64, I64]),
+    "cppf_backvote_filter": (I, [P, I64, P, I, I64, P, I64, _DP, P, I64, F, P, P, P, P, P, P, I64, P]),
+    "cppf_backvote_errors": (I, [P, P, I, I64, P, I64, P, P, P]),
+    "cppf_backvote_select": (I, [P, I64, I64, F, P, P, I64, P]),
+    "cppf_backvote_mask": (I, [P, P, I, I64, I64, I64, P, P, P, P, I, P]),
+    "cppf_backvote_imp_max": (I, [P, I64, P, P]),
+    "cppf_vote_rotation": (I, [P, P, I, I64, P, I64, P, P, I, P, P, P]),
+    "cppf_sphere_hist": (I, [P, I64, P, P, I, F, I, P, P]),
+    "cppf_sphere_band": (I, [I, F]),
+    "cppf_rotation_hist": (I, [P, P, I, I64, P, I64, _IP, I, P, P, I64, P, P, D, P, P, I, P, I, F, I, P, P]),
+    "cppf_pose_workspace_bytes": (I64, [I64]),
+    "cppf_pose_finalize": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, I64, P]),
+    "cppf_shot_workspace_bytes": (I64, [I64]),
+    "cppf_shot_compute": (I, [P, I64, F, F, P, P, P, I64, P]),
+    "cppf_estimate_normal": (I, [P, I64, F, P, P, I64, P]),
+    "cppf_shot_compute_color": (I, [P, P, I64, F, F, P, P]),
+    "cppf_heads_create": (I, [I, I, C.POINTER(C.c_float), I64, C.POINTER(P)]),
+    "cppf_heads_destroy": (I, [P]),
+    "cppf_heads_workspace_bytes": (I64, [P, I64, I64, I]),
+    "cppf_heads_forward": (I, [P, I, P, I64, P, I, I64, I64, P, P, P, P, P, I64, P]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compiles every CUDA source for sm_100a into libcppf_b200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j8"] + ([] if verbose else ["-s"])
+    subprocess.run(cmd, check=True)
+    if not os.path.exists(LIB_PATH):
+        raise CppfError(f"build finished but {LIB_PATH} is missing")
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Loads the library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CppfError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback for the cppf2_b200 hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = load().cppf_error_string(code).decode()
+        raise CppfError(f"{what or 'libcppf_b200'} failed: {msg} (code {code})")
+
+
+def axes_array(up, right, front):
+    """9 doubles: (up, right, front) in the positional order of dataset.py:118."""
+    vals = [float(v) for ax in (up, right, front) for v in ax]
+    return (C.c_double * 9)(*vals)

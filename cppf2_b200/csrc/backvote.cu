@@ -1,0 +1,263 @@
+// Back-vote filter on B200 -- replaces eval.py:251-275.
+//
+//   errs[t]   = || targets_tr[t] - targets(real pair t, voted centre) ||_2          (float32, numpy order)
+//   threshold = np.percentile(errs, ratio*100)  (numpy 'linear': float32 lerp of two order statistics)
+//   keep[t]   = errs[t] < threshold;  imp[p] = #occurrences of p among kept pair endpoints
+//
+// The order statistics are exact: a 4 x 8-bit most-significant-digit radix selection over the
+// order-preserving uint32 image of the float32 errors.  Each pass is one grid-wide histogram
+// (shared-memory privatised, one global atomic per non-empty bin per CTA); the last CTA to finish a
+// pass (ticket counter) scans the 256 bins and narrows the prefix, so the whole selection is four
+// stream-ordered launches with no host involvement.  It is split into errors / select / mask entry
+// points so that a tuple-sharded run can all-gather the errors (4*T bytes) between them.
+#include "common.cuh"
+
+namespace cppf {
+
+struct Axes {
+    double v[9];
+};
+
+struct SelectState {          // lives at the head of the workspace, zeroed by the host wrapper
+    uint32_t hist[4][256];
+    uint32_t prefix;          // key bits decided so far
+    uint32_t min_gt;          // smallest key strictly greater than the selected one
+    unsigned long long k;     // rank still to resolve inside the current prefix
+    unsigned long long below; // #keys < prefix (final)
+    unsigned long long equal; // #keys == prefix (final)
+    uint32_t tickets[8];
+};
+
+__device__ __forceinline__ void back_targets(const float a[3], const float b[3], const double ctr[3], float tr[2]) {
+    // generate_target_pairs(input_pairs, ..., center=T_est) -- dataset.py:118-128, translation part only
+    const float pd0 = __fsub_rn(a[0], b[0]), pd1 = __fsub_rn(a[1], b[1]), pd2 = __fsub_rn(a[2], b[2]);
+    const float nrm = __fadd_rn(norm3_numpy(pd0, pd1, pd2), 1e-7f);
+    const double u0 = static_cast<double>(__fdiv_rn(pd0, nrm)), u1 = static_cast<double>(__fdiv_rn(pd1, nrm)),
+                 u2 = static_cast<double>(__fdiv_rn(pd2, nrm));
+    const double am0 = __dsub_rn(static_cast<double>(a[0]), ctr[0]), am1 = __dsub_rn(static_cast<double>(a[1]), ctr[1]),
+                 am2 = __dsub_rn(static_cast<double>(a[2]), ctr[2]);
+    const double proj = __dadd_rn(__dadd_rn(__dmul_rn(am0, u0), __dmul_rn(am1, u1)), __dmul_rn(am2, u2));
+    const double oc0 = __dsub_rn(am0, __dmul_rn(proj, u0)), oc1 = __dsub_rn(am1, __dmul_rn(proj, u1)),
+                 oc2 = __dsub_rn(am2, __dmul_rn(proj, u2));
+    const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(oc0, oc0), __dmul_rn(oc1, oc1)), __dmul_rn(oc2, oc2)));
+    tr[0] = static_cast<float>(proj);
+    tr[1] = static_cast<float>(dist);
+}
+
+__global__ void __launch_bounds__(256) backvote_errors_kernel(const float *__restrict__ pc, IdxView idx,
+                                                              const float *__restrict__ targets_tr, int64_t T,
+                                                              const cppf_center *__restrict__ center,
+                                                              float *__restrict__ errs) {
+    const double ctr[3] = {center->world[0], center->world[1], center->world[2]};
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < T; t += stride) {
+        const int64_t ia = idx.at(t, 0), ib = idx.at(t, 1);
+        const float a[3] = {pc[3 * ia], pc[3 * ia + 1], pc[3 * ia + 2]};
+        const float b[3] = {pc[3 * ib], pc[3 * ib + 1], pc[3 * ib + 2]};
+        float back[2];
+        back_targets(a, b, ctr, back);
+        const float2 tr = reinterpret_cast<const float2 *>(targets_tr)[t];
+        const float d0 = __fsub_rn(tr.x, back[0]), d1 = __fsub_rn(tr.y, back[1]);
+        errs[t] = __fsqrt_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));  // np.linalg.norm(axis=-1), eval.py:256
+    }
+}
+
+// One radix pass: histogram digit `pass` (most significant first) of the keys that match the prefix
+// found so far; the last CTA narrows the prefix.  pass == 4 instead finds min_gt and the threshold.
+__global__ void __launch_bounds__(256) select_pass_kernel(const float *__restrict__ errs, int64_t T, int pass,
+                                                          SelectState *__restrict__ st, int64_t rank_lo, float gamma,
+                                                          cppf_backvote_summary *__restrict__ summary) {
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_min;
+    __shared__ bool s_last;
+    s_hist[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) s_min = 0xffffffffu;
+    __syncthreads();
+    const uint32_t prefix = st->prefix;
+    const int shift = 24 - 8 * pass;
+    const uint32_t decided = pass == 0 ? 0u : (pass >= 4 ? 0xffffffffu : ~((1u << (shift + 8)) - 1u));
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    uint32_t local_min = 0xffffffffu;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < T; t += stride) {
+        const uint32_t key = float_to_key(errs[t]);
+        if (pass < 4) {
+            if ((key & decided) == (prefix & decided)) atomicAdd(&s_hist[(key >> shift) & 0xffu], 1u);
+        } else if (key > prefix) {
+            local_min = key < local_min ? key : local_min;
+        }
+    }
+    if (pass < 4) {
+        __syncthreads();
+        const uint32_t c = s_hist[threadIdx.x];
+        if (c) atomicAdd(&st->hist[pass][threadIdx.x], c);
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            uint32_t other = __shfl_xor_sync(0xffffffffu, local_min, o);
+            local_min = other < local_min ? other : local_min;
+        }
+        if (lane_id() == 0) atomicMin(&s_min, local_min);
+        __syncthreads();
+        if (threadIdx.x == 0) atomicMin(&st->min_gt, s_min);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->tickets[pass], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    if (pass < 4) {
+        unsigned long long k = pass == 0 ? static_cast<unsigned long long>(rank_lo) : st->k;
+        unsigned long long below = pass == 0 ? 0ull : st->below;
+        volatile uint32_t *h = st->hist[pass];
+        int d = 0;
+        unsigned long long cum = 0;
+        for (; d < 256; ++d) {
+            const unsigned long long c = h[d];
+            if (cum + c > k) break;
+            cum += c;
+        }
+        if (d == 256) d = 255;  // rank beyond the data (T == 0); keeps the state well defined
+        st->prefix = prefix | (static_cast<uint32_t>(d) << shift);
+        st->k = k - cum;
+        st->below = below + cum;
+        st->equal = h[d];
+    } else {
+        // both order statistics are known: s[rank_lo] = prefix; s[rank_lo+1] is the same value when the
+        // run of equal keys extends past rank_lo, else the smallest larger key (numpy clips at T-1)
+        const float s_lo = key_to_float(prefix);
+        float s_hi = s_lo;
+        const unsigned long long next_rank = static_cast<unsigned long long>(rank_lo) + 1ull;
+        if (next_rank >= st->below + st->equal && next_rank < static_cast<unsigned long long>(T))
+            s_hi = key_to_float(*reinterpret_cast<volatile uint32_t *>(&st->min_gt));
+        // numpy _lerp in float32: a + (b-a)*t, replaced by b - (b-a)*(1-t) when t >= 0.5
+        const float diff = __fsub_rn(s_hi, s_lo);
+        float thr = __fadd_rn(s_lo, __fmul_rn(diff, gamma));
+        if (gamma >= 0.5f) thr = __fsub_rn(s_hi, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+        summary->threshold = thr;
+        summary->s_lo = s_lo;
+        summary->s_hi = s_hi;
+    }
+}
+
+__global__ void __launch_bounds__(256) backvote_mask_kernel(const float *__restrict__ errs, IdxView idx, int64_t T,
+                                                            const cppf_backvote_summary *__restrict__ summary_in,
+                                                            uint8_t *__restrict__ keep, int32_t *__restrict__ kept_list,
+                                                            int32_t *__restrict__ imp,
+                                                            unsigned long long *__restrict__ kept_counter) {
+    const float thr = summary_in->threshold;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    // whole warps iterate together so that the ballot below is always full-width
+    for (int64_t base = t0 - lane_id(); base < T; base += stride) {
+        const int64_t t = base + lane_id();
+        const bool k = t < T && errs[t] < thr;  // strict '<' (eval.py:257)
+        if (t < T && keep) keep[t] = k ? 1 : 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, k);
+        if (m == 0u) continue;
+        unsigned long long slot = 0;
+        if (lane_id() == 0) slot = atomicAdd(kept_counter, static_cast<unsigned long long>(__popc(m)));
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (k) {
+            if (kept_list) kept_list[slot + __popc(m & ((1u << lane_id()) - 1u))] = static_cast<int32_t>(t);
+            if (imp) {
+                atomicAdd(&imp[idx.at(t, 0)], 1);  // scatter_add of the flattened endpoints (eval.py:260-266)
+                atomicAdd(&imp[idx.at(t, 1)], 1);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) imp_max_kernel(const int32_t *__restrict__ imp, int64_t n,
+                                                       cppf_backvote_summary *__restrict__ summary) {
+    __shared__ int s_max[32];
+    int m = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = max(m, imp[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane_id() == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = s_max[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) summary->imp_max = m;
+    }
+}
+
+}  // namespace cppf
+
+using namespace cppf;
+
+CPPF_API int64_t cppf_backvote_workspace_bytes(int64_t T, int64_t n) {
+    (void)T;
+    (void)n;
+    return static_cast<int64_t>((sizeof(SelectState) + 255) / 256 * 256);
+}
+
+CPPF_API int cppf_backvote_errors(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride,
+                                  const float *targets_tr, int64_t T, const cppf_center *center, float *errs,
+                                  void *stream) {
+    if (!pc || !idx || !targets_tr || !center || !errs || T < 0 || idx_stride < 2) return CPPF_ERR_INVALID_ARGUMENT;
+    if (T == 0) return CPPF_OK;
+    IdxView iv{idx, idx_stride, idx_is_i64};
+    backvote_errors_kernel<<<grid_for(T, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(pc, iv, targets_tr, T,
+                                                                                                center, errs);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_backvote_select(const float *errs, int64_t T, int64_t rank_lo, float gamma,
+                                  cppf_backvote_summary *summary, void *ws, int64_t ws_bytes, void *stream) {
+    if (!errs || !summary || !ws || T <= 0 || rank_lo < 0 || rank_lo >= T) return CPPF_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < cppf_backvote_workspace_bytes(T, 0)) return CPPF_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SelectState *st = static_cast<SelectState *>(ws);
+    CPPF_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(SelectState), s));
+    CPPF_CUDA_TRY(cudaMemsetAsync(&st->min_gt, 0xff, sizeof(uint32_t), s));
+    const int blocks = grid_for(T, 256, 4);
+    for (int pass = 0; pass <= 4; ++pass) {
+        select_pass_kernel<<<blocks, 256, 0, s>>>(errs, T, pass, st, rank_lo, gamma, summary);
+        CPPF_LAUNCH_CHECK();
+    }
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_backvote_mask(const float *errs, const void *idx, int idx_is_i64, int64_t idx_stride, int64_t T,
+                                int64_t n, cppf_backvote_summary *summary, uint8_t *keep, int32_t *kept_list,
+                                int32_t *imp, int zero_outputs, void *stream) {
+    if (!errs || !idx || !summary || T < 0 || idx_stride < 2) return CPPF_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (zero_outputs) {
+        if (imp) CPPF_CUDA_TRY(cudaMemsetAsync(imp, 0, sizeof(int32_t) * static_cast<size_t>(n), s));
+        CPPF_CUDA_TRY(cudaMemsetAsync(&summary->kept, 0, sizeof(int64_t), s));
+    }
+    if (T == 0) return CPPF_OK;
+    IdxView iv{idx, idx_stride, idx_is_i64};
+    backvote_mask_kernel<<<grid_for(T, 256, 8), 256, 0, s>>>(errs, iv, T, summary, keep, kept_list, imp,
+                                                            reinterpret_cast<unsigned long long *>(&summary->kept));
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_backvote_imp_max(const int32_t *imp, int64_t n, cppf_backvote_summary *summary, void *stream) {
+    if (!imp || !summary || n <= 0) return CPPF_ERR_INVALID_ARGUMENT;
+    imp_max_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(imp, n, summary);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_backvote_filter(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride,
+                                  const float *targets_tr, int64_t T, const double *axes_host,
+                                  const cppf_center *center, int64_t rank_lo, float gamma, float *errs, uint8_t *keep,
+                                  int32_t *kept_list, int32_t *imp, cppf_backvote_summary *summary, void *ws,
+                                  int64_t ws_bytes, void *stream) {
+    (void)axes_host;  // the translation targets do not depend on the axes
+    int rc = cppf_backvote_errors(pc, idx, idx_is_i64, idx_stride, targets_tr, T, center, errs, stream);
+    if (rc) return rc;
+    rc = cppf_backvote_select(errs, T, rank_lo, gamma, summary, ws, ws_bytes, stream);
+    if (rc) return rc;
+    rc = cppf_backvote_mask(errs, idx, idx_is_i64, idx_stride, T, n, summary, keep, kept_list, imp, 1, stream);
+    if (rc) return rc;
+    return cppf_backvote_imp_max(imp, n, summary, stream);
+}

@@ -1,0 +1,131 @@
+// Shared device/host helpers of libcppf_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cppf_b200.h"
+
+#define CPPF_API extern "C" __attribute__((visibility("default")))
+
+#define CPPF_CUDA_TRY(expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            fprintf(stderr, "[cppf_b200] %s failed at %s:%d: %s\n", #expr, __FILE__, __LINE__,           \
+                    cudaGetErrorString(_e));                                                             \
+            return CPPF_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+#define CPPF_LAUNCH_CHECK() CPPF_CUDA_TRY(cudaGetLastError())
+
+namespace cppf {
+
+struct DeviceInfo {
+    int sm_count;
+    int64_t l2_bytes;
+    int cc_major, cc_minor;
+    int max_smem_optin;
+};
+
+// Cached per process; B200: 148 SMs, ~126 MB L2, 227 KB opt-in shared memory.
+const DeviceInfo &device_info();
+
+// Row of the tuple-index matrix, int64 (reference dtype) or int32, arbitrary row stride.
+struct IdxView {
+    const void *ptr;
+    int64_t stride;
+    int is_i64;
+    __device__ __forceinline__ int64_t at(int64_t row, int col) const {
+        return is_i64 ? static_cast<const int64_t *>(ptr)[row * stride + col]
+                      : static_cast<int64_t>(static_cast<const int32_t *>(ptr)[row * stride + col]);
+    }
+};
+
+// ---- float32 recipes that must match torch-CPU bit for bit ----------------
+// Every operation is an explicit round-to-nearest intrinsic so that neither -fmad nor the optimiser
+// can contract or reassociate them.
+
+__device__ __forceinline__ float norm3_torch(float x, float y, float z) {
+    // torch.norm(dim=-1) over 3 contiguous floats on CPU: sqrt(fma(z,z,fma(y,y,x*x)))
+    return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+}
+
+__device__ __forceinline__ float norm3_numpy(float x, float y, float z) {
+    // np.linalg.norm(axis=-1) on float32: sqrt((x*x + y*y) + z*z)
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+// torch.cross(x, ab) on CPU: fma(x1, ab2, -(x2*ab1)) and cyclic
+__device__ __forceinline__ void cross_torch(const float x[3], const float ab[3], float y[3]) {
+    y[0] = __fmaf_rn(x[1], ab[2], -__fmul_rn(x[2], ab[1]));
+    y[1] = __fmaf_rn(x[2], ab[0], -__fmul_rn(x[0], ab[2]));
+    y[2] = __fmaf_rn(x[0], ab[1], -__fmul_rn(x[1], ab[0]));
+}
+
+// Unit pair direction `ab` and the in-plane unit vector `x` (train_dino.py:178-191 / :219-229).
+// Returns false when |a-b| <= 1e-7 (masked pair).
+__device__ __forceinline__ bool pair_frame(const float a[3], const float b[3], bool clamp_co, float ab[3], float x[3]) {
+    ab[0] = __fsub_rn(a[0], b[0]);
+    ab[1] = __fsub_rn(a[1], b[1]);
+    ab[2] = __fsub_rn(a[2], b[2]);
+    float n = norm3_torch(ab[0], ab[1], ab[2]);
+    if (!(n > 1e-7f)) return false;
+    float d = n < 1e-7f ? 1e-7f : n;
+    ab[0] = __fdiv_rn(ab[0], d);
+    ab[1] = __fdiv_rn(ab[1], d);
+    ab[2] = __fdiv_rn(ab[2], d);
+    float co[3] = {0.0f, -ab[2], ab[1]};
+    float cn = norm3_torch(co[0], co[1], co[2]);
+    if (cn < 1e-7f) {  // ab parallel to the x axis
+        co[0] = -ab[1];
+        co[1] = ab[0];
+        co[2] = 0.0f;
+        cn = norm3_torch(co[0], co[1], co[2]);
+    }
+    if (clamp_co && cn < 1e-7f) cn = 1e-7f;
+    x[0] = __fdiv_rn(co[0], cn);
+    x[1] = __fdiv_rn(co[1], cn);
+    x[2] = __fdiv_rn(co[2], cn);
+    return true;
+}
+
+// Order-preserving float32 <-> uint32 key (for radix selection and atomic min/max on floats).
+__device__ __host__ __forceinline__ uint32_t float_to_key(float f) {
+    uint32_t u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint(f);
+#else
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+inline int div_up(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+// Grid size for a grid-stride kernel: whole multiples of the SM count, capped by the work available.
+inline int grid_for(int64_t work_items, int threads_per_block, int blocks_per_sm) {
+    const DeviceInfo &d = device_info();
+    int64_t need = (work_items + threads_per_block - 1) / threads_per_block;
+    int64_t cap = static_cast<int64_t>(d.sm_count) * blocks_per_sm;
+    if (need < 1) need = 1;
+    return static_cast<int>(need < cap ? need : cap);
+}
+
+}  // namespace cppf

@@ -1,0 +1,186 @@
+// Decode + vote-target generation on B200 -- replaces eval.py:225-235 (softmax, multinomial draw,
+// per-pair metric scale) and generate_target_pairs (dataset.py:118-135).
+//
+// dtype flow follows the reference when it is fed float32 pairs: the pair difference and its unit
+// vector are float32 (numpy norm order, +1e-7 as a weak scalar), everything that meets the float64
+// centre or the integer axes is float64, results are rounded to float32 at the end.  Every operation is
+// an explicit _rn intrinsic, so targets_tr is bit-exact against numpy; targets_rot differs by at most
+// 1 ulp of float32 (device acos vs libm acos, both < 1 ulp in float64).
+#include "common.cuh"
+
+namespace cppf {
+
+struct Axes {
+    double v[9];  // rows: positional (up, right, front) of dataset.py:118
+};
+
+__device__ __forceinline__ void targets_of_pair(const float a[3], const float b[3], const double center[3],
+                                                const Axes &ax, float tr[2], float rot[3], bool want_rot) {
+    const float pd0 = __fsub_rn(a[0], b[0]), pd1 = __fsub_rn(a[1], b[1]), pd2 = __fsub_rn(a[2], b[2]);
+    const float nrm = __fadd_rn(norm3_numpy(pd0, pd1, pd2), 1e-7f);
+    const double u0 = static_cast<double>(__fdiv_rn(pd0, nrm)), u1 = static_cast<double>(__fdiv_rn(pd1, nrm)),
+                 u2 = static_cast<double>(__fdiv_rn(pd2, nrm));
+    const double am0 = __dsub_rn(static_cast<double>(a[0]), center[0]), am1 = __dsub_rn(static_cast<double>(a[1]), center[1]),
+                 am2 = __dsub_rn(static_cast<double>(a[2]), center[2]);
+    const double proj = __dadd_rn(__dadd_rn(__dmul_rn(am0, u0), __dmul_rn(am1, u1)), __dmul_rn(am2, u2));
+    const double oc0 = __dsub_rn(am0, __dmul_rn(proj, u0)), oc1 = __dsub_rn(am1, __dmul_rn(proj, u1)),
+                 oc2 = __dsub_rn(am2, __dmul_rn(proj, u2));
+    const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(oc0, oc0), __dmul_rn(oc1, oc1)), __dmul_rn(oc2, oc2)));
+    tr[0] = static_cast<float>(proj);
+    tr[1] = static_cast<float>(dist);
+    if (want_rot) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double d = __dadd_rn(__dadd_rn(__dmul_rn(u0, ax.v[3 * k]), __dmul_rn(u1, ax.v[3 * k + 1])),
+                                       __dmul_rn(u2, ax.v[3 * k + 2]));
+            rot[k] = static_cast<float>(acos(d));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) generate_targets_kernel(const float *__restrict__ pairs, int64_t T, Axes ax,
+                                                               const double *__restrict__ center,
+                                                               float *__restrict__ targets_tr,
+                                                               float *__restrict__ targets_rot) {
+    const double ctr[3] = {center ? center[0] : 0.0, center ? center[1] : 0.0, center ? center[2] : 0.0};
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < T; t += stride) {
+        const float2 *p = reinterpret_cast<const float2 *>(pairs + 6 * t);  // 24 B per tuple, 8 B aligned
+        const float2 p0 = p[0], p1 = p[1], p2 = p[2];
+        const float a[3] = {p0.x, p0.y, p1.x}, b[3] = {p1.y, p2.x, p2.y};
+        float tr[2], rot[3];
+        targets_of_pair(a, b, ctr, ax, tr, rot, targets_rot != nullptr);
+        if (targets_tr) reinterpret_cast<float2 *>(targets_tr)[t] = make_float2(tr[0], tr[1]);
+        if (targets_rot) {
+            targets_rot[3 * t] = rot[0];
+            targets_rot[3 * t + 1] = rot[1];
+            targets_rot[3 * t + 2] = rot[2];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) decode_targets_kernel(const float *__restrict__ pc, IdxView idx,
+                                                             const uint8_t *__restrict__ bins, int64_t T, int num_bins,
+                                                             Axes ax, float *__restrict__ targets_tr,
+                                                             float *__restrict__ targets_rot,
+                                                             float *__restrict__ pair_scale,
+                                                             float *__restrict__ scaled_out) {
+    const float denom = static_cast<float>(num_bins - 1);
+    const double zero[3] = {0.0, 0.0, 0.0};
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < T; t += stride) {
+        float p[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)  // bin/(num_bins-1) - 0.5  (eval.py:230)
+            p[k] = __fsub_rn(__fdiv_rn(static_cast<float>(bins[6 * t + k]), denom), 0.5f);
+        const int64_t ia = idx.at(t, 0), ib = idx.at(t, 1);
+        const float a[3] = {pc[3 * ia], pc[3 * ia + 1], pc[3 * ia + 2]};
+        const float b[3] = {pc[3 * ib], pc[3 * ib + 1], pc[3 * ib + 2]};
+        // eval.py:233: numpy norm of (input_pairs[:,1]-input_pairs[:,0]) / clamp_min(torch norm of pred pair)
+        const float real = norm3_numpy(__fsub_rn(b[0], a[0]), __fsub_rn(b[1], a[1]), __fsub_rn(b[2], a[2]));
+        const float pn = norm3_torch(__fsub_rn(p[3], p[0]), __fsub_rn(p[4], p[1]), __fsub_rn(p[5], p[2]));
+        const float s = __fdiv_rn(real, pn < 1e-7f ? 1e-7f : pn);
+        float q[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q[k] = __fmul_rn(p[k], s);
+        if (pair_scale) pair_scale[t] = s;
+        if (scaled_out) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) scaled_out[6 * t + k] = q[k];
+        }
+        float tr[2], rot[3];
+        targets_of_pair(q, q + 3, zero, ax, tr, rot, targets_rot != nullptr);
+        if (targets_tr) reinterpret_cast<float2 *>(targets_tr)[t] = make_float2(tr[0], tr[1]);
+        if (targets_rot) {
+            targets_rot[3 * t] = rot[0];
+            targets_rot[3 * t + 1] = rot[1];
+            targets_rot[3 * t + 2] = rot[2];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// softmax + one multinomial draw per row: one warp per row of `num_bins` (<= 32) logits, lane = bin,
+// coalesced 128 B row reads, softmax and inclusive CDF by shuffles, draw = #(cdf <= u*total).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float uniform_from_counter(uint64_t seed, uint64_t ctr) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (ctr + 1);  // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);  // [0,1)
+}
+
+__global__ void __launch_bounds__(256) sample_bins_kernel(const float *__restrict__ logits, int64_t rows, int num_bins,
+                                                          const float *__restrict__ u01, uint64_t seed,
+                                                          uint8_t *__restrict__ bins) {
+    const int lane = lane_id();
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = warp; row < rows; row += n_warps) {
+        const float v = lane < num_bins ? logits[row * num_bins + lane] : -INFINITY;
+        float m = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float e = lane < num_bins ? expf(v - m) : 0.0f;
+        float cdf = e;  // inclusive scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, cdf, o);
+            if (lane >= o) cdf += up;
+        }
+        const float total = __shfl_sync(0xffffffffu, cdf, 31);
+        const float u = u01 ? u01[row] : uniform_from_counter(seed, static_cast<uint64_t>(row));
+        const uint32_t below = __ballot_sync(0xffffffffu, lane < num_bins && cdf <= u * total);
+        if (lane == 0) {
+            int b = __popc(below);
+            bins[row] = static_cast<uint8_t>(b < num_bins ? b : num_bins - 1);
+        }
+    }
+}
+
+}  // namespace cppf
+
+using namespace cppf;
+
+static Axes axes_from_host(const double *axes_host) {
+    Axes ax;
+    for (int i = 0; i < 9; ++i) ax.v[i] = axes_host[i];
+    return ax;
+}
+
+CPPF_API int cppf_sample_bins(const float *logits, int64_t T, int num_bins, const float *u01, uint64_t seed,
+                              uint8_t *bins, void *stream) {
+    if (!logits || !bins || T < 0 || num_bins < 2 || num_bins > 32) return CPPF_ERR_INVALID_ARGUMENT;
+    if (T == 0) return CPPF_OK;
+    const int64_t rows = T * 6;
+    int blocks = grid_for(rows * 32, 256, 8);
+    sample_bins_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, rows, num_bins, u01, seed, bins);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_decode_targets(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride,
+                                 const uint8_t *bins, int64_t T, int num_bins, const double *axes_host,
+                                 float *targets_tr, float *targets_rot, float *pair_scale, float *pred_pairs_scaled,
+                                 void *stream) {
+    if (!pc || !idx || !bins || !axes_host || T < 0 || num_bins < 2 || idx_stride < 2) return CPPF_ERR_INVALID_ARGUMENT;
+    if (T == 0) return CPPF_OK;
+    IdxView iv{idx, idx_stride, idx_is_i64};
+    int blocks = grid_for(T, 256, 8);
+    decode_targets_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        pc, iv, bins, T, num_bins, axes_from_host(axes_host), targets_tr, targets_rot, pair_scale, pred_pairs_scaled);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_generate_targets(const float *pairs, int64_t T, const double *axes_host, const double *center,
+                                   float *targets_tr, float *targets_rot, void *stream) {
+    if (!pairs || !axes_host || T < 0) return CPPF_ERR_INVALID_ARGUMENT;
+    if (T == 0) return CPPF_OK;
+    int blocks = grid_for(T, 256, 8);
+    generate_targets_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(pairs, T, axes_from_host(axes_host),
+                                                                                  center, targets_tr, targets_rot);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}

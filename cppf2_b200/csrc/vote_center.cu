@@ -1,0 +1,326 @@
+// Centre Hough voting on B200 -- replaces vote_center (reference train_dino.py:171-215).
+//
+// Layout in HBM: cloud f32 [N,3] (replicated per GPU, ~50 KB), tuple indices int64/int32 [T,stride],
+// vote targets f32 [T,2], grid uint32 [gx*gy*gz] (0.2-4 MB: always L2 resident on a 126 MB L2).
+//
+// Kernel shape: one warp owns CHUNK tuples at a time.  Lanes < CHUNK build the pair frame of one
+// tuple each (c, x*odist, y -- ~100 flops incl. 2 sqrt and 6 IEEE divisions), then the warp walks
+// the CHUNK tuples and its 32 lanes take the R=180 rotations of one tuple 32 at a time, so the
+// cos/sin table reads are conflict-free shared-memory loads and every lane issues one fire-and-forget
+// RED.ADD.U32 to L2 per vote.  The geometry (lo, grid_res) is read from the device-resident
+// cppf_grid_geom, so no host round trip separates bounds -> vote -> arg-max.
+//
+// Arithmetic: every float op is an explicit _rn intrinsic following SURVEY.md Appendix B (torch-CPU
+// semantics: FMA chain in norm, FMA in cross, true division by float32(res), trunc(x+0.5)).  The
+// integer grid is bit-exact against the oracle and the reference golden vectors.
+#include "common.cuh"
+
+namespace cppf {
+
+// ---------------------------------------------------------------------------------------------------
+// bounds: single CTA, coalesced sweep, shared-memory tree reduction.  N <= 50 000 by eval.py:195.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) cloud_bounds_kernel(const float *__restrict__ pc, int64_t n, float res,
+                                                            cppf_grid_geom *__restrict__ geom) {
+    __shared__ float s_lo[3][32], s_hi[3][32];
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    // flat float index i = 3*p + k: consecutive threads read consecutive floats; k = i % 3
+    for (int64_t i = threadIdx.x; i < 3 * n; i += 3 * 1024) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            int64_t j = i + static_cast<int64_t>(u) * 1024;
+            if (j < 3 * n) {
+                float v = pc[j];
+                int k = static_cast<int>(j % 3);
+                // k is thread-dependent; keep the three accumulators in registers with selects
+                lo[0] = (k == 0 && v < lo[0]) ? v : lo[0];
+                lo[1] = (k == 1 && v < lo[1]) ? v : lo[1];
+                lo[2] = (k == 2 && v < lo[2]) ? v : lo[2];
+                hi[0] = (k == 0 && v > hi[0]) ? v : hi[0];
+                hi[1] = (k == 1 && v > hi[1]) ? v : hi[1];
+                hi[2] = (k == 2 && v > hi[2]) ? v : hi[2];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if (lane_id() == 0) {
+            s_lo[k][threadIdx.x >> 5] = lo[k];
+            s_hi[k][threadIdx.x >> 5] = hi[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float l = s_lo[k][threadIdx.x], h = s_hi[k][threadIdx.x];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+                h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+            }
+            lo[k] = l;
+            hi[k] = h;
+        }
+        if (threadIdx.x == 0) {
+            uint32_t flags = (n <= 0) ? CPPF_STATUS_EMPTY : 0u;
+            float ext_max = 0.0f;
+            int64_t cells = 1;
+            for (int k = 0; k < 3; ++k) {
+                geom->lo[k] = lo[k];
+                geom->hi[k] = hi[k];
+                float ext = __fsub_rn(hi[k], lo[k]);
+                ext_max = fmaxf(ext_max, ext);
+                int64_t g = (n > 0) ? static_cast<int64_t>(__fdiv_rn(ext, res)) + 1 : 1;  // trunc toward zero
+                geom->grid_res[k] = g;
+                cells *= g;
+            }
+            if (__fdiv_rn(ext_max, res) > 1000.0f) flags |= CPPF_STATUS_GRID_GUARD;  // eval.py:200
+            geom->res = res;
+            geom->cells = cells;
+            geom->flags = flags;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// zero the live part of the grid (size known only on the device)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ grid, int64_t capacity,
+                                                        const cppf_grid_geom *__restrict__ geom,
+                                                        uint32_t *__restrict__ status) {
+    int64_t cells = geom->cells;
+    if (cells > capacity) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && status) atomicOr(status, CPPF_STATUS_GRID_OVERFLOW);
+        cells = capacity;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && status && geom->flags) atomicOr(status, geom->flags);
+    int64_t vec = cells >> 2;
+    uint4 *g4 = reinterpret_cast<uint4 *>(grid);
+    int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int64_t i = tid; i < vec; i += stride) g4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = (vec << 2) + tid; i < cells; i += stride) grid[i] = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the vote kernel
+// ---------------------------------------------------------------------------------------------------
+constexpr int kVoteThreads = 256;
+constexpr int kMaxRotsSmem = 1024;
+
+template <int CHUNK>
+__global__ void __launch_bounds__(kVoteThreads) vote_center_kernel(
+    const float *__restrict__ pc, IdxView idx, const float *__restrict__ preds_tr, int64_t T,
+    const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R,
+    const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ grid, int64_t capacity) {
+    __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        s_cos[r] = cos_tab[r];
+        s_sin[r] = sin_tab[r];
+    }
+    __syncthreads();
+
+    if (geom->cells > capacity) return;  // flagged by grid_zero_kernel
+    const float res = geom->res;
+    const float lo0 = geom->lo[0], lo1 = geom->lo[1], lo2 = geom->lo[2];
+    const int g0 = static_cast<int>(geom->grid_res[0]), g1 = static_cast<int>(geom->grid_res[1]),
+              g2 = static_cast<int>(geom->grid_res[2]);
+
+    const int lane = lane_id();
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+
+    for (int64_t base = warp * CHUNK; base < T; base += n_warps * CHUNK) {
+        // ---- per-tuple frame, one tuple per lane (train_dino.py:176-192) -------------------------
+        float c[3] = {0.f, 0.f, 0.f}, x[3] = {0.f, 0.f, 0.f}, y[3] = {0.f, 0.f, 0.f};
+        bool ok = false;
+        const int64_t t = base + lane;
+        if (lane < CHUNK && t < T) {
+            const float2 tr = reinterpret_cast<const float2 *>(preds_tr)[t];  // (proj_len, odist)
+            const int64_t ia = idx.at(t, 0), ib = idx.at(t, 1);
+            float a[3] = {pc[3 * ia], pc[3 * ia + 1], pc[3 * ia + 2]};
+            float b[3] = {pc[3 * ib], pc[3 * ib + 1], pc[3 * ib + 2]};
+            float ab[3];
+            ok = (tr.y > res) && pair_frame(a, b, false, ab, x);  // :182
+            if (ok) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    c[k] = __fsub_rn(a[k], __fmul_rn(ab[k], tr.x));  // :186
+                    x[k] = __fmul_rn(x[k], tr.y);                    // :191
+                }
+                cross_torch(x, ab, y);  // :192
+            }
+        }
+        const uint32_t ok_mask = __ballot_sync(0xffffffffu, ok);
+
+        // ---- votes: lanes sweep the rotations of one tuple at a time -----------------------------
+#pragma unroll 1
+        for (int j = 0; j < CHUNK; ++j) {
+            if (!((ok_mask >> j) & 1u)) continue;  // warp-uniform
+            const float c0 = __shfl_sync(0xffffffffu, c[0], j), c1 = __shfl_sync(0xffffffffu, c[1], j),
+                        c2 = __shfl_sync(0xffffffffu, c[2], j);
+            const float x0 = __shfl_sync(0xffffffffu, x[0], j), x1 = __shfl_sync(0xffffffffu, x[1], j),
+                        x2 = __shfl_sync(0xffffffffu, x[2], j);
+            const float y0 = __shfl_sync(0xffffffffu, y[0], j), y1 = __shfl_sync(0xffffffffu, y[1], j),
+                        y2 = __shfl_sync(0xffffffffu, y[2], j);
+#pragma unroll 2
+            for (int r = lane; r < R; r += 32) {
+                const float cr = s_cos[r], sr = s_sin[r];
+                // offset = cos*x + sin*y (mul, mul, add); g = ((c + offset) - lo) / res; cell = trunc(g + 0.5)
+                const float o0 = __fadd_rn(__fmul_rn(cr, x0), __fmul_rn(sr, y0));
+                const float o1 = __fadd_rn(__fmul_rn(cr, x1), __fmul_rn(sr, y1));
+                const float o2 = __fadd_rn(__fmul_rn(cr, x2), __fmul_rn(sr, y2));
+                const float q0 = __fdiv_rn(__fsub_rn(__fadd_rn(c0, o0), lo0), res);
+                const float q1 = __fdiv_rn(__fsub_rn(__fadd_rn(c1, o1), lo1), res);
+                const float q2 = __fdiv_rn(__fsub_rn(__fadd_rn(c2, o2), lo2), res);
+                const int i0 = __float2int_rz(__fadd_rn(q0, 0.5f));
+                const int i1 = __float2int_rz(__fadd_rn(q1, 0.5f));
+                const int i2 = __float2int_rz(__fadd_rn(q2, 0.5f));
+                // strictly inside (cell 0 never receives votes, :200)
+                if (i0 > 0 && i1 > 0 && i2 > 0 && i0 < g0 && i1 < g1 && i2 < g2) {
+                    const int64_t lin = (static_cast<int64_t>(i0) * g1 + i1) * g2 + i2;
+                    atomicAdd(grid + lin, 1u);  // result unused -> RED.E.ADD
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// arg-max: first maximum in C order.  key = count<<32 | ~index so that atomicMax picks the largest
+// count and, among equals, the smallest index.  The last block to finish converts to world space.
+// ---------------------------------------------------------------------------------------------------
+struct CenterScratch {  // lives in the tail of cppf_center (pad fields), zeroed by cudaMemsetAsync
+    unsigned long long key;
+    unsigned int ticket;
+};
+
+__global__ void __launch_bounds__(256) grid_argmax_kernel(const uint32_t *__restrict__ grid,
+                                                          const cppf_grid_geom *__restrict__ geom, double res,
+                                                          cppf_center *__restrict__ out,
+                                                          unsigned long long *__restrict__ key,
+                                                          unsigned int *__restrict__ ticket) {
+    const int64_t cells = geom->cells;
+    unsigned long long best = 0ull;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < cells; i += stride) {
+        unsigned long long k = (static_cast<unsigned long long>(grid[i]) << 32) |
+                               static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(i));
+        best = k > best ? k : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    __shared__ unsigned long long s_best[8];
+    __shared__ bool s_last;
+    if (lane_id() == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) best = s_best[w] > best ? s_best[w] : best;
+        atomicMax(key, best);
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(key);
+        int64_t lin = static_cast<int64_t>(0xffffffffu - static_cast<uint32_t>(k & 0xffffffffull));
+        if (cells <= 0) lin = 0;
+        const int64_t g1 = geom->grid_res[1], g2 = geom->grid_res[2];
+        int64_t cell[3] = {lin / (g1 * g2), (lin / g2) % g1, lin % g2};
+        for (int a = 0; a < 3; ++a) {
+            out->cell[a] = cell[a];
+            // corners[0].numpy() (f32) + cand (int64) * res (python float) -> float64 (train_dino.py:213)
+            out->world[a] = __dadd_rn(static_cast<double>(geom->lo[a]), __dmul_rn(static_cast<double>(cell[a]), res));
+        }
+        out->linear = lin;
+        out->votes = static_cast<uint32_t>(k >> 32);
+    }
+}
+
+__global__ void __launch_bounds__(256) grid_widen_kernel(const uint32_t *__restrict__ grid,
+                                                         const cppf_grid_geom *__restrict__ geom,
+                                                         int64_t *__restrict__ out) {
+    const int64_t cells = geom->cells;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < cells; i += stride)
+        out[i] = static_cast<int64_t>(grid[i]);
+}
+
+}  // namespace cppf
+
+using namespace cppf;
+
+CPPF_API int cppf_cloud_bounds(const float *pc, int64_t n, float res, cppf_grid_geom *geom, void *stream) {
+    if (!pc || !geom || n < 0 || !(res > 0.0f)) return CPPF_ERR_INVALID_ARGUMENT;
+    cloud_bounds_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(pc, n, res, geom);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_vote_center(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride,
+                              const float *preds_tr, int64_t T, const float *cos_tab, const float *sin_tab, int R,
+                              const cppf_grid_geom *geom, uint32_t *grid, int64_t grid_capacity, int accumulate,
+                              uint32_t *status, void *stream) {
+    if (!pc || !idx || !preds_tr || !cos_tab || !sin_tab || !geom || !grid) return CPPF_ERR_INVALID_ARGUMENT;
+    if (n <= 0 || T < 0 || R <= 0 || R > kMaxRotsSmem || idx_stride < 2 || grid_capacity <= 0)
+        return CPPF_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const DeviceInfo &dev = device_info();
+    if (!accumulate) {
+        int zb = grid_for(grid_capacity / 4 + 1, 256, 8);
+        grid_zero_kernel<<<zb, 256, 0, s>>>(grid, grid_capacity, geom, status);
+        CPPF_LAUNCH_CHECK();
+    }
+    if (T == 0) return CPPF_OK;
+    IdxView iv{idx, idx_stride, idx_is_i64};
+    // Tuples per warp pass: small chunks when T is small so that every SM still gets >= ~32 warps.
+    const int64_t warps_full = static_cast<int64_t>(dev.sm_count) * 8 * (kVoteThreads / 32);
+    const int warps_per_block = kVoteThreads / 32;
+    if (T >= warps_full * 32) {
+        int blocks = dev.sm_count * 8;
+        vote_center_kernel<32><<<blocks, kVoteThreads, 0, s>>>(pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid,
+                                                               grid_capacity);
+    } else {
+        int64_t warps = (T + 7) / 8;
+        int64_t blocks = (warps + warps_per_block - 1) / warps_per_block;
+        int64_t cap = static_cast<int64_t>(dev.sm_count) * 8;
+        if (blocks > cap) blocks = cap;
+        vote_center_kernel<8><<<static_cast<int>(blocks), kVoteThreads, 0, s>>>(pc, iv, preds_tr, T, cos_tab, sin_tab, R,
+                                                                               geom, grid, grid_capacity);
+    }
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_grid_argmax(const uint32_t *grid, const cppf_grid_geom *geom, double res, cppf_center *center,
+                              void *stream) {
+    if (!grid || !geom || !center) return CPPF_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CPPF_CUDA_TRY(cudaMemsetAsync(center, 0, sizeof(cppf_center), s));
+    // scratch words live in the struct's tail (`votes` is written last by the finalising thread; `pad`
+    // doubles as the ticket, `linear` as the packed key until then)
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(&center->linear);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(&center->pad);
+    int blocks = device_info().sm_count * 4;
+    grid_argmax_kernel<<<blocks, 256, 0, s>>>(grid, geom, res, center, key, ticket);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_grid_to_i64(const uint32_t *grid, const cppf_grid_geom *geom, int64_t *grid_i64, void *stream) {
+    if (!grid || !geom || !grid_i64) return CPPF_ERR_INVALID_ARGUMENT;
+    int blocks = device_info().sm_count * 4;
+    grid_widen_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(grid, geom, grid_i64);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}

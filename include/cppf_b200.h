@@ -1,0 +1,229 @@
+/*
+ * cppf_b200.h -- C ABI of libcppf_b200.so, the B200-native (sm_100a) pose-voting hot path of CPPF++.
+ *
+ * Every entry point replaces one operator of the reference (cited per function as file:line relative
+ * to the reference root).  Conventions, identical for all calls:
+ *   - plain C types only; pointers are DEVICE pointers unless the parameter name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered, allocates nothing and
+ *     never synchronises the host (workspaces are passed in; `cppf_*_workspace_bytes` size them);
+ *   - the return value is 0 (CPPF_OK) or a CPPF_ERR_* code; cppf_error_string() names it.  Launch
+ *     errors are reported by the call that made the launch; data-dependent conditions that only the
+ *     device can see (grid larger than the caller's buffer) are written to the `status` word the
+ *     caller passes and are sticky across calls;
+ *   - thread-safe as long as two host threads do not share one workspace; no global mutable state.
+ *   - indices are int64 (the reference's dtype) or int32, selected by `idx_is_i64`, with a row stride
+ *     in elements so that `point_idxs_all[:, :2]` views (stride 5) can be passed without a copy.
+ */
+#ifndef CPPF_B200_H
+#define CPPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPPF_OK 0
+#define CPPF_ERR_INVALID_ARGUMENT 1
+#define CPPF_ERR_CUDA 2            /* a CUDA runtime call or kernel launch failed (sticky error logged) */
+#define CPPF_ERR_WORKSPACE 3       /* workspace too small for the requested sizes */
+#define CPPF_ERR_UNSUPPORTED 4     /* e.g. compute_color (SHOT1344): no caller in the reference */
+#define CPPF_ERR_NO_DEVICE 5
+
+/* bits of the device-side status word */
+#define CPPF_STATUS_GRID_OVERFLOW 1u   /* gx*gy*gz exceeds the grid buffer handed to cppf_vote_center */
+#define CPPF_STATUS_GRID_GUARD 2u      /* extent/res > 1000 on some axis: the reference skips the instance (eval.py:200) */
+#define CPPF_STATUS_EMPTY 4u           /* no tuple survived a stage (empty cloud, no kept pair) */
+
+#define CPPF_SHOT_DIM 352
+#define CPPF_NUM_BINS 32
+
+/* Geometry of the centre-vote grid, produced on the device by cppf_cloud_bounds and consumed by the
+ * vote kernels without a host round trip (train_dino.py:172-173). */
+typedef struct cppf_grid_geom {
+    float lo[3];            /* pc.min(0) */
+    float hi[3];            /* pc.max(0) */
+    float res;              /* float32(res) */
+    uint32_t flags;         /* CPPF_STATUS_* raised while building the geometry */
+    int64_t grid_res[3];    /* trunc((hi-lo)/res) + 1 */
+    int64_t cells;          /* gx*gy*gz */
+} cppf_grid_geom;
+
+/* Result of the centre vote: first maximum in C order and its world position (train_dino.py:212-213). */
+typedef struct cppf_center {
+    double world[3];        /* float64(lo) + cell*res */
+    int64_t cell[3];
+    int64_t linear;         /* flat C-order index of the arg-max cell */
+    uint32_t votes;         /* count in that cell */
+    uint32_t pad;
+} cppf_center;
+
+/* Per-instance pose record written by cppf_pose_finalize (eval.py:284-313, :358-363). */
+typedef struct cppf_pose {
+    double R[9];            /* row-major R_est */
+    double t[3];            /* T_est */
+    float scale[3];         /* lower median of the kept per-tuple scale predictions */
+    float scale_norm;       /* ||scale||  (RT[:3,:3] = R*scale_norm, scales = scale/scale_norm) */
+    double loss;            /* mean clip(|canon - pred|, 0, 0.1) over kept pairs */
+    int32_t bin_up, bin_right;
+    float count_up, count_right;
+    int64_t kept;           /* pairs surviving the back-vote filter */
+    uint32_t status;        /* CPPF_STATUS_* */
+    uint32_t pad;
+} cppf_pose;
+
+const char *cppf_error_string(int code);
+int cppf_version(void);
+/* Number of SMs / bytes of L2 of the current device, as the launch heuristics see them. */
+int cppf_device_info(int *sm_count, int64_t *l2_bytes, int *cc_major, int *cc_minor);
+
+/* ---- centre voting ------------------------------------------------------------------------------
+ * replaces vote_center, train_dino.py:171-215 (integer Hough grid, bit-exact vs torch-CPU).          */
+
+/* corners / grid_res of `pc [n,3]` -> *geom (device).  train_dino.py:172-173; guard eval.py:200. */
+int cppf_cloud_bounds(const float *pc, int64_t n, float res, cppf_grid_geom *geom, void *stream);
+
+/* Zeroes geom->cells counters of `grid` and accumulates the T*R votes.  cos_tab/sin_tab [R] are the
+ * caller's torch-CPU evaluation of cos/sin(arange(R)/R*2*pi) (train_dino.py:195-196; inputs because
+ * Sleef, libm and CUDA differ in the last ulp).  grid is uint32 [grid_capacity]; `status` (uint32,
+ * device) receives CPPF_STATUS_GRID_OVERFLOW when geom->cells > grid_capacity.
+ * `accumulate` != 0 skips the zeroing (tuple shards voting into one grid). */
+int cppf_vote_center(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride,
+                     const float *preds_tr, int64_t T, const float *cos_tab, const float *sin_tab, int R,
+                     const cppf_grid_geom *geom, uint32_t *grid, int64_t grid_capacity, int accumulate,
+                     uint32_t *status, void *stream);
+
+/* First-maximum arg-max of the grid and its world position -> *center (device).  train_dino.py:212-213. */
+int cppf_grid_argmax(const uint32_t *grid, const cppf_grid_geom *geom, double res, cppf_center *center, void *stream);
+
+/* uint32 -> int64 widening of the grid (the reference returns an int64 numpy grid, train_dino.py:204-206). */
+int cppf_grid_to_i64(const uint32_t *grid, const cppf_grid_geom *geom, int64_t *grid_i64, void *stream);
+
+/* ---- decode + vote targets ----------------------------------------------------------------------
+ * replaces eval.py:225-235 (softmax, multinomial, pair scale) and generate_target_pairs,
+ * dataset.py:118-135 (float64 where the reference is float64).                                        */
+
+/* logits [T,6,num_bins] f32 -> bins uint8 [T,6].  One draw per (tuple, coordinate) by inverse CDF of
+ * softmax(logits): with u01 [T,6] given the draw is the first bin whose cumulative probability exceeds
+ * u; with u01 == NULL uniforms come from a counter-based generator keyed by (seed, tuple, coordinate). */
+int cppf_sample_bins(const float *logits, int64_t T, int num_bins, const float *u01, uint64_t seed,
+                     uint8_t *bins, void *stream);
+
+/* bins -> pred_pairs (bin/(num_bins-1)-0.5), per-pair metric scale, scaled pairs, and the vote
+ * targets of the scaled pairs w.r.t. the origin.  axes_host = {up, right, front} in the POSITIONAL
+ * order of dataset.py:118 (the eval.py call sites pass cfg.up, cfg.front, cfg.right).
+ * Outputs (any may be NULL): targets_tr f32 [T,2], targets_rot f32 [T,3], pair_scale f32 [T],
+ * pred_pairs_scaled f32 [T,2,3]. */
+int cppf_decode_targets(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const uint8_t *bins,
+                        int64_t T, int num_bins, const double *axes_host, float *targets_tr, float *targets_rot,
+                        float *pair_scale, float *pred_pairs_scaled, void *stream);
+
+/* generate_target_pairs on explicit float32 pairs [T,2,3] with a float64 centre (device pointer, 3
+ * doubles, or NULL for the origin).  dataset.py:118-135. */
+int cppf_generate_targets(const float *pairs, int64_t T, const double *axes_host, const double *center,
+                          float *targets_tr, float *targets_rot, void *stream);
+
+/* ---- back-vote filter ---------------------------------------------------------------------------
+ * replaces eval.py:251-275.  ws sized by cppf_backvote_workspace_bytes(T, n).                         */
+int64_t cppf_backvote_workspace_bytes(int64_t T, int64_t n);
+
+/* errs[t] = || targets_tr[t] - targets(real pair t, centre) ||  (float32, numpy order), then the exact
+ * order statistics `rank_lo` and `rank_lo+1`, threshold = lerp (numpy 'linear' percentile, float32),
+ * keep[t] = errs[t] < threshold, imp[p] = occurrences of point p among kept pair endpoints.
+ * rank_lo / gamma come from the host (functions of T and backproj_ratio only).
+ * Outputs: errs f32 [T], keep uint8 [T], kept_list int32 [T] (+ count in summary), imp int32 [n],
+ * summary: {threshold f32, s_lo f32, s_hi f32, imp_max i32, kept i64} as cppf_backvote_summary. */
+typedef struct cppf_backvote_summary {
+    float threshold, s_lo, s_hi;
+    int32_t imp_max;
+    int64_t kept;
+} cppf_backvote_summary;
+
+int cppf_backvote_filter(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride,
+                         const float *targets_tr, int64_t T, const double *axes_host, const cppf_center *center,
+                         int64_t rank_lo, float gamma, float *errs, uint8_t *keep, int32_t *kept_list, int32_t *imp,
+                         cppf_backvote_summary *summary, void *ws, int64_t ws_bytes, void *stream);
+
+/* The three stages of cppf_backvote_filter, separately callable so that a tuple-sharded run can
+ * all-gather `errs` before the selection and all-reduce `imp` before the maximum. */
+int cppf_backvote_errors(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *targets_tr,
+                         int64_t T, const cppf_center *center, float *errs, void *stream);
+int cppf_backvote_select(const float *errs, int64_t T, int64_t rank_lo, float gamma, cppf_backvote_summary *summary,
+                         void *ws, int64_t ws_bytes, void *stream);
+int cppf_backvote_mask(const float *errs, const void *idx, int idx_is_i64, int64_t idx_stride, int64_t T, int64_t n,
+                       cppf_backvote_summary *summary, uint8_t *keep, int32_t *kept_list, int32_t *imp,
+                       int zero_outputs, void *stream);
+int cppf_backvote_imp_max(const int32_t *imp, int64_t n, cppf_backvote_summary *summary, void *stream);
+
+/* ---- rotation voting ----------------------------------------------------------------------------
+ * replaces vote_rotation (train_dino.py:218-239) + get_topk_dir (eval.py:37-51) + fibonacci_sphere
+ * (utils/util.py:191-207).                                                                            */
+
+/* Materialising form, for the drop-in shim: up f32 [M,R,3] (rows of masked pairs zeroed), mask u8 [M]. */
+int cppf_vote_rotation(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *preds_rot,
+                       int64_t M, const float *cos_tab, const float *sin_tab, int R, float *up, uint8_t *mask,
+                       void *stream);
+
+/* counts[s] += sum over rows of [dot(pred_row, sphere_s) > cos_thr] / wt_row  (float64 bins).
+ * pred f32 [rows,3]; wt f64 [rows] or NULL; band = half-width (in sphere indices) of the latitude band
+ * searched around each row (cppf_sphere_band computes a safe value; band >= S means brute force). */
+int cppf_sphere_hist(const float *pred, int64_t rows, const double *wt, const float *sphere, int S, float cos_thr,
+                     int band, double *counts, void *stream);
+int cppf_sphere_band(int S, float cos_thr);
+
+/* Fused form used by the pipeline: for every kept tuple in kept_list (or all M when NULL) form the R
+ * candidate directions for n_theta angle columns of `theta` [M, theta_stride] and vote them into
+ * counts f64 [n_theta, S]; pair weight = imp[i]/imp_max + imp[j]/imp_max + margin when imp != NULL. */
+int cppf_rotation_hist(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *theta,
+                       int64_t theta_stride, const int *theta_cols_host, int n_theta, const int32_t *kept_list,
+                       const int64_t *kept_count, int64_t M, const int32_t *imp, const cppf_backvote_summary *summary,
+                       double margin, const float *cos_tab, const float *sin_tab, int R, const float *sphere, int S,
+                       float cos_thr, int band, double *counts, void *stream);
+
+/* ---- pose assembly ------------------------------------------------------------------------------
+ * replaces eval.py:284-313 (top-1 directions, Gram-Schmidt, scale median) and :358-363 (branch loss). */
+int64_t cppf_pose_workspace_bytes(int64_t T);
+int cppf_pose_finalize(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const uint8_t *bins,
+                       int num_bins, const float *pred_scales, const int32_t *kept_list,
+                       const cppf_backvote_summary *summary, const double *counts /* [2,S] */, const float *sphere,
+                       int S, const cppf_center *center, int up_loc, int right_loc, int loss_y_only,
+                       const float *scale_override /* 3 floats or NULL: eval.py:308 reuses the DINO scale */,
+                       cppf_pose *pose, void *ws, int64_t ws_bytes, void *stream);
+
+/* ---- SHOT descriptor ----------------------------------------------------------------------------
+ * replaces shot.compute / shot.estimate_normal, src_shot/shot.cpp:12-42, :45-100 (PCL NormalEstimation +
+ * SHOTEstimation<SHOT352>, radius search, viewpoint at the origin, NaN rows for invalid points).       */
+int64_t cppf_shot_workspace_bytes(int64_t n);
+/* pc [n,3] f32 -> normals [n,3] f32 and (when desc != NULL) desc [n,352] f32. */
+int cppf_shot_compute(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals,
+                      void *ws, int64_t ws_bytes, void *stream);
+int cppf_estimate_normal(const float *pc, int64_t n, float normal_r, float *normals, void *ws, int64_t ws_bytes,
+                         void *stream);
+/* SHOT1344 (shot.cpp:102-161) has no caller in the reference: always CPPF_ERR_UNSUPPORTED. */
+int cppf_shot_compute_color(const float *pc, const float *rgb, int64_t n, float normal_r, float shot_r, float *desc,
+                            void *stream);
+
+/* ---- learned heads ------------------------------------------------------------------------------
+ * replaces BeyondCPPF.forward, train_shot.py:117-122 and train_dino.py:128-133 (ResLayer stacks,
+ * train_shot.py:19-43), including prepare_tuple_inputs (train_shot.py:75-83, train_dino.py:91-97).
+ * Weights are packed once by cppf_heads_pack (host arrays in state_dict order) into a device blob.     */
+typedef struct cppf_heads cppf_heads;   /* opaque, device-resident packed weights */
+
+/* branch: 0 = SHOT, 1 = DINO.  weights_host: concatenated float32 [out,in] weight then [out] bias of
+ * every nn.Linear in the order of cppf2_b200.heads_spec.linear_shapes(); n_floats is checked. */
+int cppf_heads_create(int branch, int num_more, const float *weights_host, int64_t n_floats, cppf_heads **out);
+int cppf_heads_destroy(cppf_heads *h);
+int64_t cppf_heads_workspace_bytes(const cppf_heads *h, int64_t T, int64_t n, int precision);
+
+/* precision: 0 = fp32 CUDA-core reference path, 1 = bf16 tensor-core (tcgen05) path.
+ * SHOT branch: feat = shot descriptors [n,352] f32, normal [n,3] f32.
+ * DINO branch: feat = descriptors [n,1024] f32, normal = NULL.
+ * Outputs: logits f32 [T,6,32], scale f32 [T,3]. */
+int cppf_heads_forward(const cppf_heads *h, int precision, const float *pc, int64_t n, const void *idx, int idx_is_i64,
+                       int64_t idx_stride, int64_t T, const float *feat, const float *normal, float *logits,
+                       float *scale, void *ws, int64_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPPF_B200_H */
