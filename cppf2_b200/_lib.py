@@ -54,7 +54,9 @@ SIGNATURES = {
     "cppf_version": (I, []),
     "cppf_device_info": (I, [_IP, C.POINTER(I64), _IP, _IP]),
     "cppf_cloud_bounds": (I, [P, I64, F, P, P]),
-    "cppf_vote_center": (I, [P, I64, P, I, I64, P, I64, P, P, I, P, P, I64, I, P, P]),
+    "cppf_vote_center": (I, [P, I64, P, I, I64, P, I64, P, P, I, P, P, I64, I64, I, P, P]),
+    "cppf_vote_center_ex": (I, [P, I64, P, I, I64, P, I64, P, P, I, P, P, I64, I, P, I, I, I64, P]),
+    "cppf_vote_center_smem_cells": (I64, []),
     "cppf_grid_argmax": (I, [P, P, D, P, P]),
     "cppf_grid_to_i64": (I, [P, P, P, P]),
     "cppf_sample_bins": (I, [P, I64, I, P, U64, P, P]),

@@ -17,6 +17,17 @@
 
 namespace cppf {
 
+constexpr int kMaxReplicas = 32;
+
+// Number of grid copies the vote is spread over (MODE 0): as many as fit the caller's buffer, at most
+// `replicas_max`.  Computed on the device from the device-resident geometry, identically by the zero,
+// vote and fold kernels.
+__device__ __forceinline__ int replica_count(int64_t cells, int64_t capacity, int replicas_max) {
+    if (cells <= 0 || replicas_max <= 1) return 1;
+    const int64_t fit = capacity / cells;
+    return static_cast<int>(fit < 1 ? 1 : (fit > replicas_max ? replicas_max : fit));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // bounds: single CTA, coalesced sweep, shared-memory tree reduction.  N <= 50 000 by eval.py:195.
 // ---------------------------------------------------------------------------------------------------
@@ -93,8 +104,9 @@ __global__ void __launch_bounds__(1024) cloud_bounds_kernel(const float *__restr
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ grid, int64_t capacity,
                                                         const cppf_grid_geom *__restrict__ geom,
-                                                        uint32_t *__restrict__ status) {
+                                                        uint32_t *__restrict__ status, int replicas_max) {
     int64_t cells = geom->cells;
+    if (cells <= capacity) cells *= replica_count(cells, capacity, replicas_max);
     if (cells > capacity) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && status) atomicOr(status, CPPF_STATUS_GRID_OVERFLOW);
         cells = capacity;
@@ -114,19 +126,33 @@ __global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ g
 constexpr int kVoteThreads = 256;
 constexpr int kMaxRotsSmem = 1024;
 
-template <int CHUNK>
-__global__ void __launch_bounds__(kVoteThreads) vote_center_kernel(
+// MODE 0: RED straight to the L2-resident grid; `replicas` copies of the grid (copy = block % replicas)
+//         spread the hot cache lines of the vote peak over several L2 slices.
+// MODE 1: the whole grid lives in this CTA's shared memory (cells*4 B <= ~220 KB), flushed at the end.
+template <int CHUNK, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) vote_center_kernel(
     const float *__restrict__ pc, IdxView idx, const float *__restrict__ preds_tr, int64_t T,
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R,
-    const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ grid, int64_t capacity) {
+    const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ grid, int64_t capacity, int replicas_max,
+    int64_t smem_cells, uint32_t *__restrict__ status) {
     __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
+    extern __shared__ __align__(16) uint32_t s_grid[];
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         s_cos[r] = cos_tab[r];
         s_sin[r] = sin_tab[r];
     }
+    const int64_t cells = geom->cells;
+    if (MODE == 1) {
+        if (cells > smem_cells) {  // the caller's bound on the grid size was wrong: flag, never corrupt
+            if (blockIdx.x == 0 && threadIdx.x == 0 && status) atomicOr(status, CPPF_STATUS_GRID_OVERFLOW);
+            return;
+        }
+        for (int64_t i = threadIdx.x; i < cells; i += blockDim.x) s_grid[i] = 0u;
+    }
     __syncthreads();
 
-    if (geom->cells > capacity) return;  // flagged by grid_zero_kernel
+    if (cells > capacity) return;  // flagged by grid_zero_kernel
+    if (MODE == 0) grid += (blockIdx.x % replica_count(cells, capacity, replicas_max)) * cells;
     const float res = geom->res;
     const float lo0 = geom->lo[0], lo1 = geom->lo[1], lo2 = geom->lo[2];
     const int g0 = static_cast<int>(geom->grid_res[0]), g1 = static_cast<int>(geom->grid_res[1]),
@@ -185,10 +211,37 @@ __global__ void __launch_bounds__(kVoteThreads) vote_center_kernel(
                 // strictly inside (cell 0 never receives votes, :200)
                 if (i0 > 0 && i1 > 0 && i2 > 0 && i0 < g0 && i1 < g1 && i2 < g2) {
                     const int64_t lin = (static_cast<int64_t>(i0) * g1 + i1) * g2 + i2;
-                    atomicAdd(grid + lin, 1u);  // result unused -> RED.E.ADD
+                    if (MODE == 1) atomicAdd(s_grid + lin, 1u);   // ATOMS
+                    else atomicAdd(grid + lin, 1u);               // result unused -> RED.E.ADD
                 }
             }
         }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        // staggered flush: CTA b starts at its own offset so that the CTAs do not sweep the lines in lock step
+        const int64_t start = (cells / gridDim.x) * blockIdx.x;
+        for (int64_t i = threadIdx.x; i < cells; i += blockDim.x) {
+            int64_t j = i + start;
+            j = j >= cells ? j - cells : j;
+            const uint32_t v = s_grid[j];
+            if (v) atomicAdd(grid + j, v);
+        }
+    }
+}
+
+// sums replicas 1..K-1 into replica 0
+__global__ void __launch_bounds__(256) grid_fold_kernel(uint32_t *__restrict__ grid, const cppf_grid_geom *__restrict__ geom,
+                                                        int64_t capacity, int replicas_max) {
+    const int64_t cells = geom->cells;
+    if (cells > capacity) return;
+    const int replicas = replica_count(cells, capacity, replicas_max);
+    if (replicas <= 1) return;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < cells; i += stride) {
+        uint32_t acc = grid[i];
+        for (int k = 1; k < replicas; ++k) acc += grid[k * cells + i];
+        grid[i] = acc;
     }
 }
 
@@ -267,39 +320,85 @@ CPPF_API int cppf_cloud_bounds(const float *pc, int64_t n, float res, cppf_grid_
     return CPPF_OK;
 }
 
-CPPF_API int cppf_vote_center(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride,
-                              const float *preds_tr, int64_t T, const float *cos_tab, const float *sin_tab, int R,
-                              const cppf_grid_geom *geom, uint32_t *grid, int64_t grid_capacity, int accumulate,
-                              uint32_t *status, void *stream) {
-    if (!pc || !idx || !preds_tr || !cos_tab || !sin_tab || !geom || !grid) return CPPF_ERR_INVALID_ARGUMENT;
-    if (n <= 0 || T < 0 || R <= 0 || R > kMaxRotsSmem || idx_stride < 2 || grid_capacity <= 0)
+// mode: 0 = RED to L2 with up to `replicas_max` grid copies, 1 = grid privatised in shared memory
+// (smem_cells = caller's upper bound of geom->cells).  Exported for the tuning tool as well.
+CPPF_API int cppf_vote_center_ex(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride,
+                                 const float *preds_tr, int64_t T, const float *cos_tab, const float *sin_tab, int R,
+                                 const cppf_grid_geom *geom, uint32_t *grid, int64_t grid_capacity, int accumulate,
+                                 uint32_t *status, int mode, int replicas_max, int64_t smem_cells, void *stream) {
+    if (!pc || !cos_tab || !sin_tab || !geom || !grid) return CPPF_ERR_INVALID_ARGUMENT;
+    if (T > 0 && (!preds_tr || !idx)) return CPPF_ERR_INVALID_ARGUMENT;
+    if (n <= 0 || T < 0 || R <= 0 || R > kMaxRotsSmem || idx_stride < 2 || grid_capacity <= 0 || replicas_max < 0)
         return CPPF_ERR_INVALID_ARGUMENT;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const DeviceInfo &dev = device_info();
+    if (replicas_max > kMaxReplicas) replicas_max = kMaxReplicas;
+    if (accumulate || mode == 1 || replicas_max < 1) replicas_max = 1;  // partial grids must add into one copy
     if (!accumulate) {
         int zb = grid_for(grid_capacity / 4 + 1, 256, 8);
-        grid_zero_kernel<<<zb, 256, 0, s>>>(grid, grid_capacity, geom, status);
+        grid_zero_kernel<<<zb, 256, 0, s>>>(grid, grid_capacity, geom, status, replicas_max);
         CPPF_LAUNCH_CHECK();
     }
     if (T == 0) return CPPF_OK;
     IdxView iv{idx, idx_stride, idx_is_i64};
-    // Tuples per warp pass: small chunks when T is small so that every SM still gets >= ~32 warps.
-    const int64_t warps_full = static_cast<int64_t>(dev.sm_count) * 8 * (kVoteThreads / 32);
     const int warps_per_block = kVoteThreads / 32;
+    if (mode == 1) {
+        const size_t smem = static_cast<size_t>(smem_cells) * sizeof(uint32_t);
+        const int smem_max = dev.max_smem_optin - 2 * kMaxRotsSmem * static_cast<int>(sizeof(float)) - 1024;
+        if (smem_cells <= 0 || smem > static_cast<size_t>(smem_max)) return CPPF_ERR_UNSUPPORTED;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CPPF_CUDA_TRY(cudaFuncSetAttribute(vote_center_kernel<8, 1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               smem_max));
+            attr_set = true;
+        }
+        int64_t warps = (T + 7) / 8;
+        int64_t blocks = (warps + 31) / 32;
+        const int64_t per_sm = smem > 100 * 1024 ? 1 : 2;
+        if (blocks > dev.sm_count * per_sm) blocks = dev.sm_count * per_sm;
+        vote_center_kernel<8, 1, 1024><<<static_cast<int>(blocks), 1024, smem, s>>>(
+            pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, 1, smem_cells, status);
+        CPPF_LAUNCH_CHECK();
+        return CPPF_OK;
+    }
+    // Tuples per warp pass: small chunks when T is small so that every SM still gets >= ~32 warps.
+    const int64_t warps_full = static_cast<int64_t>(dev.sm_count) * 8 * warps_per_block;
     if (T >= warps_full * 32) {
         int blocks = dev.sm_count * 8;
-        vote_center_kernel<32><<<blocks, kVoteThreads, 0, s>>>(pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid,
-                                                               grid_capacity);
+        vote_center_kernel<32, 0, kVoteThreads><<<blocks, kVoteThreads, 0, s>>>(pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom,
+                                                                                grid, grid_capacity, replicas_max, 0, status);
     } else {
         int64_t warps = (T + 7) / 8;
         int64_t blocks = (warps + warps_per_block - 1) / warps_per_block;
         int64_t cap = static_cast<int64_t>(dev.sm_count) * 8;
         if (blocks > cap) blocks = cap;
-        vote_center_kernel<8><<<static_cast<int>(blocks), kVoteThreads, 0, s>>>(pc, iv, preds_tr, T, cos_tab, sin_tab, R,
-                                                                               geom, grid, grid_capacity);
+        vote_center_kernel<8, 0, kVoteThreads><<<static_cast<int>(blocks), kVoteThreads, 0, s>>>(
+            pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, replicas_max, 0, status);
     }
     CPPF_LAUNCH_CHECK();
+    if (replicas_max > 1) {
+        grid_fold_kernel<<<dev.sm_count * 4, 256, 0, s>>>(grid, geom, grid_capacity, replicas_max);
+        CPPF_LAUNCH_CHECK();
+    }
     return CPPF_OK;
+}
+
+// Shared-memory budget of the privatised mode, in cells.
+CPPF_API int64_t cppf_vote_center_smem_cells(void) {
+    const DeviceInfo &dev = device_info();
+    return (dev.max_smem_optin - 2 * kMaxRotsSmem * static_cast<int64_t>(sizeof(float)) - 1024) / 4;
+}
+
+CPPF_API int cppf_vote_center(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride,
+                              const float *preds_tr, int64_t T, const float *cos_tab, const float *sin_tab, int R,
+                              const cppf_grid_geom *geom, uint32_t *grid, int64_t grid_capacity, int64_t cells_hint,
+                              int accumulate, uint32_t *status, void *stream) {
+    // cells_hint > 0: the caller knows gx*gy*gz (it built the cloud on the host).  Grids that fit one SM's
+    // shared memory are privatised there; everything else votes with RED into up to 32 L2-resident copies
+    // of the grid (as many as grid_capacity holds), which spreads the hot lines of the vote peak.
+    const bool smem_ok = cells_hint > 0 && cells_hint <= cppf_vote_center_smem_cells() && T >= 16384;
+    return cppf_vote_center_ex(pc, n, idx, idx_is_i64, idx_stride, preds_tr, T, cos_tab, sin_tab, R, geom, grid,
+                               grid_capacity, accumulate, status, smem_ok ? 1 : 0, kMaxReplicas, cells_hint, stream);
 }
 
 CPPF_API int cppf_grid_argmax(const uint32_t *grid, const cppf_grid_geom *geom, double res, cppf_center *center,

@@ -167,8 +167,8 @@ class PoseVoter:
         check(lib.cppf_cloud_bounds(pc.data_ptr(), N, float(cfg.res), self.geom.data_ptr(), s), "cppf_cloud_bounds")
         self.status.zero_()
         check(lib.cppf_vote_center(pc.data_ptr(), N, ip, i64, istr, self.targets_tr.data_ptr(), T, ct.data_ptr(),
-                                   st.data_ptr(), R, self.geom.data_ptr(), self.grid.data_ptr(), self.grid.numel(), 0,
-                                   self.status.data_ptr(), s), "cppf_vote_center")
+                                   st.data_ptr(), R, self.geom.data_ptr(), self.grid.data_ptr(), self.grid.numel(),
+                                   int(cells_hint or 0), 0, self.status.data_ptr(), s), "cppf_vote_center")
         check(lib.cppf_grid_argmax(self.grid.data_ptr(), self.geom.data_ptr(), float(cfg.res), self.center.data_ptr(), s),
               "cppf_grid_argmax")
         launches += 1 + 1 + 1 + 2 + 2

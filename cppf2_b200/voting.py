@@ -149,11 +149,13 @@ def vote_center(pc, preds_tr, res, point_idxs, num_rots=36, vis=None):
     geom = read_struct(geom_t, GridGeom)  # the reference synchronises here as well (grid_res.long() -> zeros)
     shape = tuple(int(g) for g in geom.grid_res)
     cells = int(geom.cells)
-    grid = torch.empty(max(cells, 1), dtype=torch.int32, device=dev)
+    # room for up to 32 copies of the grid (<= 64 MB): the kernel spreads the vote peak over them
+    copies = max(1, min(32, (1 << 24) // max(cells, 1)))
+    grid = torch.empty(max(cells, 1) * copies, dtype=torch.int32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     ip, i64, istr = idx_args(idx)
     check(lib.cppf_vote_center(pc.data_ptr(), pc.shape[0], ip, i64, istr, tr.data_ptr(), T, ct.data_ptr(), st.data_ptr(),
-                               int(num_rots), geom_t.data_ptr(), grid.data_ptr(), grid.numel(), 0, status.data_ptr(), s),
+                               int(num_rots), geom_t.data_ptr(), grid.data_ptr(), grid.numel(), cells, 0, status.data_ptr(), s),
           "cppf_vote_center")
     center_t = struct_tensor(Center, dev)
     check(lib.cppf_grid_argmax(grid.data_ptr(), geom_t.data_ptr(), float(res), center_t.data_ptr(), s), "cppf_grid_argmax")

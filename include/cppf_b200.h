@@ -83,15 +83,24 @@ int cppf_device_info(int *sm_count, int64_t *l2_bytes, int *cc_major, int *cc_mi
 /* corners / grid_res of `pc [n,3]` -> *geom (device).  train_dino.py:172-173; guard eval.py:200. */
 int cppf_cloud_bounds(const float *pc, int64_t n, float res, cppf_grid_geom *geom, void *stream);
 
-/* Zeroes geom->cells counters of `grid` and accumulates the T*R votes.  cos_tab/sin_tab [R] are the
- * caller's torch-CPU evaluation of cos/sin(arange(R)/R*2*pi) (train_dino.py:195-196; inputs because
- * Sleef, libm and CUDA differ in the last ulp).  grid is uint32 [grid_capacity]; `status` (uint32,
- * device) receives CPPF_STATUS_GRID_OVERFLOW when geom->cells > grid_capacity.
- * `accumulate` != 0 skips the zeroing (tuple shards voting into one grid). */
+/* Zeroes the grid and accumulates the T*R votes.  cos_tab/sin_tab [R] are the caller's torch-CPU
+ * evaluation of cos/sin(arange(R)/R*2*pi) (train_dino.py:195-196; inputs because Sleef, libm and CUDA
+ * differ in the last ulp).  grid is uint32 [grid_capacity]; the result occupies its first geom->cells
+ * words, the rest is scratch: when capacity allows, up to 32 copies of the grid take the votes (spreading
+ * the hot cache lines of the vote peak over L2 slices) and are folded into the first.  cells_hint > 0
+ * (gx*gy*gz, when the caller knows it) lets grids that fit one SM's shared memory be privatised there.
+ * `status` (uint32, device) receives CPPF_STATUS_GRID_OVERFLOW when geom->cells > grid_capacity (or >
+ * cells_hint).  `accumulate` != 0 skips the zeroing and adds into the existing grid (chunked voting). */
 int cppf_vote_center(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride,
                      const float *preds_tr, int64_t T, const float *cos_tab, const float *sin_tab, int R,
-                     const cppf_grid_geom *geom, uint32_t *grid, int64_t grid_capacity, int accumulate,
-                     uint32_t *status, void *stream);
+                     const cppf_grid_geom *geom, uint32_t *grid, int64_t grid_capacity, int64_t cells_hint,
+                     int accumulate, uint32_t *status, void *stream);
+/* Same with the strategy explicit (mode 0: L2 copies, replicas_max of them; mode 1: shared memory). */
+int cppf_vote_center_ex(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride,
+                        const float *preds_tr, int64_t T, const float *cos_tab, const float *sin_tab, int R,
+                        const cppf_grid_geom *geom, uint32_t *grid, int64_t grid_capacity, int accumulate,
+                        uint32_t *status, int mode, int replicas_max, int64_t smem_cells, void *stream);
+int64_t cppf_vote_center_smem_cells(void);
 
 /* First-maximum arg-max of the grid and its world position -> *center (device).  train_dino.py:212-213. */
 int cppf_grid_argmax(const uint32_t *grid, const cppf_grid_geom *geom, double res, cppf_center *center, void *stream);

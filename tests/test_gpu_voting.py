@@ -100,7 +100,7 @@ def test_vote_center_linearity_at_full_size(V, oracle):
         sub_idx, sub_tr = idx[lo:hi], tr[lo:hi]
         ip, i64, istr = idx_args(sub_idx)
         _lib.check(lib.cppf_vote_center(pc.data_ptr(), n, ip, i64, istr, sub_tr.data_ptr(), hi - lo, ct.data_ptr(),
-                                        st.data_ptr(), R, geom.data_ptr(), grid.data_ptr(), cap, accumulate,
+                                        st.data_ptr(), R, geom.data_ptr(), grid.data_ptr(), cap, 0, accumulate,
                                         status.data_ptr(), s))
 
     full = torch.empty(cap, dtype=torch.int32, device=pc.device)
@@ -119,6 +119,34 @@ def test_vote_center_linearity_at_full_size(V, oracle):
     assert np.array_equal(pre[:g.cells].cpu().numpy().astype(np.int64).reshape(ref.shape), ref)
 
 
+@pytest.mark.parametrize("T", [5000, 200000])
+def test_vote_strategies_agree(oracle, T):
+    """L2 copies (1, 4, 32) and the shared-memory privatised grid produce the same integer grid."""
+    from cppf2_b200 import _lib
+    from cppf2_b200.voting import angle_tables, idx_args, struct_tensor, stream_ptr
+    lib = _lib.load()
+    n, R = 3000, 180
+    pc_h = synth.half_cylinder_cloud(n, seed=21)
+    idx_h = synth.sample_tuples(n, T, 2, seed=22)
+    tr_h = synth.noisy_center_targets(pc_h, idx_h, np.array([0.0, 0.0, 0.78]), seed=23)
+    pc, idx, tr = torch.from_numpy(pc_h).cuda(), torch.from_numpy(idx_h).cuda(), torch.from_numpy(tr_h).cuda()
+    ct, st = angle_tables(R)
+    geom = struct_tensor(_lib.GridGeom, pc.device)
+    s = stream_ptr()
+    _lib.check(lib.cppf_cloud_bounds(pc.data_ptr(), n, 0.002, geom.data_ptr(), s))
+    cells = int(_lib.GridGeom.from_buffer_copy(geom.cpu().numpy().tobytes()).cells)
+    ip, i64, istr = idx_args(idx)
+    ref, _ = oracle.vote_center(pc_h, tr_h, 0.002, idx_h, R)
+    for mode, reps in ((0, 1), (0, 4), (0, 32), (1, 1)):
+        grid = torch.full((cells * 32,), 3, dtype=torch.int32, device="cuda")
+        status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.check(lib.cppf_vote_center_ex(pc.data_ptr(), n, ip, i64, istr, tr.data_ptr(), T, ct.data_ptr(), st.data_ptr(), R,
+                                           geom.data_ptr(), grid.data_ptr(), grid.numel(), 0, status.data_ptr(), mode, reps,
+                                           cells, s))
+        assert int(status.item()) == 0
+        assert np.array_equal(grid[:cells].cpu().numpy().astype(np.int64).reshape(ref.shape), ref), (mode, reps)
+
+
 def test_grid_overflow_is_flagged_not_silent(V):
     from cppf2_b200 import _lib
     from cppf2_b200.voting import angle_tables, idx_args, struct_tensor, stream_ptr
@@ -134,7 +162,14 @@ def test_grid_overflow_is_flagged_not_silent(V):
     _lib.check(lib.cppf_cloud_bounds(pc.data_ptr(), 512, 0.002, geom.data_ptr(), s))
     ip, i64, istr = idx_args(idx)
     _lib.check(lib.cppf_vote_center(pc.data_ptr(), 512, ip, i64, istr, tr.data_ptr(), 64, ct.data_ptr(), st.data_ptr(), 180,
-                                    geom.data_ptr(), grid.data_ptr(), 128, 0, status.data_ptr(), s))
+                                    geom.data_ptr(), grid.data_ptr(), 128, 0, 0, status.data_ptr(), s))
+    assert int(grid.sum().item()) == 0      # the live prefix is zeroed, nothing was voted out of bounds
+    # a wrong shared-memory bound is flagged the same way
+    status.zero_()
+    big = torch.zeros(1 << 20, dtype=torch.int32, device="cuda")
+    _lib.check(lib.cppf_vote_center_ex(pc.data_ptr(), 512, ip, i64, istr, tr.data_ptr(), 64, ct.data_ptr(), st.data_ptr(), 180,
+                                       geom.data_ptr(), big.data_ptr(), big.numel(), 0, status.data_ptr(), 1, 1, 1000, s))
+    assert int(status.item()) & _lib.CPPF_STATUS_GRID_OVERFLOW and int(big.sum().item()) == 0
     assert int(status.item()) & _lib.CPPF_STATUS_GRID_OVERFLOW
 
 

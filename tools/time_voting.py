@@ -37,26 +37,35 @@ def main():
     out = []
     for n, extent_name in ((4096, "halfcyl"),):
         pc_h = synth.half_cylinder_cloud(n, seed=3)
-        for T in (50000, 1 << 18, 1 << 20, 1 << 22):
+        for T in (50000, 1 << 20):
             idx_h = synth.sample_tuples(n, T, 2, seed=11)
             tr_h = synth.noisy_center_targets(pc_h, idx_h, np.array([0, 0, 0.78]), seed=5)
             pc, idx, tr = torch.from_numpy(pc_h).to(dev), torch.from_numpy(idx_h).to(dev), torch.from_numpy(tr_h).to(dev)
             ct, st = angle_tables(180)
             geom = struct_tensor(_lib.GridGeom, dev)
             status = torch.zeros(1, dtype=torch.int32, device=dev)
-            grid = torch.empty(1 << 22, dtype=torch.int32, device=dev)
+            grid = torch.empty(1 << 23, dtype=torch.int32, device=dev)
             s = stream_ptr()
             _lib.check(lib.cppf_cloud_bounds(pc.data_ptr(), n, 0.002, geom.data_ptr(), s))
             ip, i64, istr = idx_args(idx)
 
-            def vote():
-                _lib.check(lib.cppf_vote_center(pc.data_ptr(), n, ip, i64, istr, tr.data_ptr(), T, ct.data_ptr(), st.data_ptr(),
-                                                180, geom.data_ptr(), grid.data_ptr(), grid.numel(), 0, status.data_ptr(), s))
-            med, mn = time_fn(vote, flush=flush)
-            votes = int(grid[:40 * 50 * 20 * 4].sum().item())
-            out.append(dict(kernel="vote_center", cloud=extent_name, T=T, ms_med=med, ms_min=mn, tuples_per_s=T / med * 1e3,
-                            votes_landed=votes, alg_GBps=(T * 24 + n * 12) / med / 1e6))
-            print(json.dumps(out[-1]), flush=True)
+            import ctypes as C
+            ex = lib.cppf_vote_center_ex
+            ref = None
+            for reps in (1, 2, 4, 8, 16, 32, 64, 0):
+                def vote():
+                    _lib.check(ex(pc.data_ptr(), n, ip, i64, istr, tr.data_ptr(), T, ct.data_ptr(), st.data_ptr(), 180,
+                                  geom.data_ptr(), grid.data_ptr(), grid.numel(), 0, status.data_ptr(), int(reps == 0),
+                                  max(reps, 1), 40 * 50 * 20, s))
+                med, mn = time_fn(vote, flush=flush)
+                g = grid[:40 * 50 * 20].clone()
+                if ref is None:
+                    ref = g
+                same = bool(torch.equal(g, ref))
+                out.append(dict(kernel="vote_center", variant=("smem" if reps == 0 else f"reps{reps}"), T=T, ms_med=round(med, 4),
+                                ms_min=round(mn, 4), Mtuples_per_s=round(T / med / 1e3, 1), same_grid=same,
+                                status=int(status.item())))
+                print(json.dumps(out[-1]), flush=True)
     # whole chain at the reference's default size
     n, T = 4096, 50000
     pc_h = synth.half_cylinder_cloud(n, seed=3)
