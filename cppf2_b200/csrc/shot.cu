@@ -1,0 +1,657 @@
+// SHOT-352 descriptors and normals on B200 -- replaces shot.compute / shot.estimate_normal
+// (reference src_shot/shot.cpp:12-42, :45-100: PCL NormalEstimation + SHOTEstimation<SHOT352> with the
+// default SHOT local reference frame, radius search, viewpoint at the origin).
+//
+// Search structure: instead of three kd-trees (normals, LRF, SHOT) one uniform grid with cell edge >=
+// radius is built on the device: bounds -> cell histogram -> exclusive scan -> scatter into a cell-sorted
+// float4 copy (x, y, z, original index).  A radius query then reads the 27 surrounding cells, which are 9
+// contiguous runs of the sorted array (the 3 z-neighbours of a cell are adjacent), with coalesced 16-byte
+// loads; queries are processed in sorted order, one warp per key-point, so consecutive warps hit the same
+// runs in L1.  Membership uses FLANN's float arithmetic exactly (((dx*dx)+dy*dy)+dz*dz < float(r*r)),
+// so the neighbour SETS are identical to the CPU restatement; only accumulation order differs.
+//
+// Per key-point (one warp):  normals: 9 float sums + count, warp-shuffle reduction, pcl::eigen33 closed
+// form in float, flip towards the origin.  LRF: weighted scatter matrix in double, cyclic Jacobi, sign
+// votes.  Histogram: every neighbour's quadrilinear contributions go to a per-warp 352-float histogram in
+// shared memory (float atomics), then L2-normalised and written as one coalesced 1408-byte row.
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace cppf {
+
+constexpr int kShotWarps = 8;                    // key-points in flight per CTA
+constexpr int kShotMaxCells = 1 << 21;           // cell table capacity (coarsened beyond that)
+
+struct ShotGrid {        // device-resident search grid header
+    float lo[3];
+    float inv;           // 1 / cell edge
+    int dim[3];
+    int cells;
+};
+
+__device__ __forceinline__ int shot_coord(float v, float lo, float inv, int dim) {
+    int c = static_cast<int>((v - lo) * inv);
+    return min(max(c, 0), dim - 1);
+}
+
+__global__ void shot_grid_setup_kernel(const cppf_grid_geom *__restrict__ bounds, float radius, ShotGrid *__restrict__ g) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float inv = 1.0f / radius;
+    int dim[3];
+    long long cells;
+    for (;;) {
+        cells = 1;
+        for (int k = 0; k < 3; ++k) {
+            float ext = bounds->hi[k] - bounds->lo[k];
+            dim[k] = max(1, static_cast<int>(ext * inv) + 1);
+            cells *= dim[k];
+        }
+        if (cells <= kShotMaxCells) break;
+        inv *= 0.5f;  // coarser cells keep the 27-cell stencil valid (edge stays >= radius)
+    }
+    for (int k = 0; k < 3; ++k) {
+        g->lo[k] = bounds->lo[k];
+        g->dim[k] = dim[k];
+    }
+    g->inv = inv;
+    g->cells = static_cast<int>(cells);
+}
+
+__global__ void __launch_bounds__(256) shot_cell_count_kernel(const float *__restrict__ pc, int n,
+                                                              const ShotGrid *__restrict__ g, int *__restrict__ cell_of,
+                                                              int *__restrict__ cell_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = pc[3 * i], y = pc[3 * i + 1], z = pc[3 * i + 2];
+    int cell = -1;
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+        cell = (shot_coord(x, g->lo[0], g->inv, g->dim[0]) * g->dim[1] + shot_coord(y, g->lo[1], g->inv, g->dim[1])) * g->dim[2] +
+               shot_coord(z, g->lo[2], g->inv, g->dim[2]);
+        atomicAdd(&cell_count[cell], 1);
+    }
+    cell_of[i] = cell;
+}
+
+// exclusive scan of cell_count[0..cells) into cell_start[0..cells], single CTA
+__global__ void __launch_bounds__(1024) shot_cell_scan_kernel(const ShotGrid *__restrict__ g, const int *__restrict__ cell_count,
+                                                              int *__restrict__ cell_start, int *__restrict__ cell_fill) {
+    __shared__ int s_part[1024];
+    const int cells = g->cells;
+    const int per = (cells + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(b + per, cells);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += cell_count[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the partials
+        int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = threadIdx.x ? s_part[threadIdx.x - 1] : 0;
+    for (int i = b; i < e; ++i) {
+        cell_start[i] = run;
+        cell_fill[i] = run;
+        run += cell_count[i];
+    }
+    if (threadIdx.x == 1023) cell_start[cells] = s_part[1023];
+}
+
+__global__ void __launch_bounds__(256) shot_scatter_kernel(const float *__restrict__ pc, int n, const int *__restrict__ cell_of,
+                                                           int *__restrict__ cell_fill, float4 *__restrict__ sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cell = cell_of[i];
+    if (cell < 0) return;
+    const int pos = atomicAdd(&cell_fill[cell], 1);
+    sorted[pos] = make_float4(pc[3 * i], pc[3 * i + 1], pc[3 * i + 2], __int_as_float(i));
+}
+
+// Points with non-finite coordinates never enter the grid: their outputs are NaN (PCL: isFinite checks).
+__global__ void __launch_bounds__(256) shot_nan_fill_kernel(const int *__restrict__ cell_of, int n, float *__restrict__ normals,
+                                                            float *__restrict__ desc) {
+    const int i = blockIdx.x;
+    if (i >= n || cell_of[i] >= 0) return;
+    const float nanv = CUDART_NAN_F;
+    if (threadIdx.x < 3) normals[3 * i + threadIdx.x] = nanv;
+    if (desc)
+        for (int j = threadIdx.x; j < CPPF_SHOT_DIM; j += blockDim.x) desc[static_cast<size_t>(i) * CPPF_SHOT_DIM + j] = nanv;
+}
+
+// Visits the candidates of the 27-cell stencil around p, lane-strided; f(j, q) is called for every
+// candidate slot j of the sorted array with its float4 (the caller applies the radius test).
+template <typename F>
+__device__ __forceinline__ void for_each_candidate(const ShotGrid &g, const int *__restrict__ cell_start,
+                                                   const float4 *__restrict__ sorted, const float p[3], int lane, F &&f) {
+    const int cx = shot_coord(p[0], g.lo[0], g.inv, g.dim[0]);
+    const int cy = shot_coord(p[1], g.lo[1], g.inv, g.dim[1]);
+    const int cz = shot_coord(p[2], g.lo[2], g.inv, g.dim[2]);
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+    for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+            const int row = (x * g.dim[1] + y) * g.dim[2];
+            const int b = cell_start[row + z0], e = cell_start[row + z1 + 1];  // z-neighbours are contiguous
+            for (int j = b + lane; j < e; j += 32) f(j, sorted[j]);
+        }
+}
+
+// FLANN L2_Simple in float: ((dx*dx) + dy*dy) + dz*dz
+__device__ __forceinline__ float flann_dist2(const float p[3], const float4 &q) {
+    const float dx = __fsub_rn(p[0], q.x), dy = __fsub_rn(p[1], q.y), dz = __fsub_rn(p[2], q.z);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ---- pcl::computeRoots2 / computeRoots / eigen33 (float; common/impl/eigen.hpp) ------------------------
+__device__ __forceinline__ void compute_roots2(float b, float c, float roots[3]) {
+    roots[0] = 0.0f;
+    float d = static_cast<float>(static_cast<double>(b * b) - 4.0 * static_cast<double>(c));
+    if (d < 0.0f) d = 0.0f;
+    const float sd = sqrtf(d);
+    roots[2] = 0.5f * (b + sd);
+    roots[1] = 0.5f * (b - sd);
+}
+
+__device__ void compute_roots(const float m[9], float roots[3]) {
+    const float c0 = m[0] * m[4] * m[8] + 2.0f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] - m[8] * m[1] * m[1];
+    const float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+    const float c2 = m[0] + m[4] + m[8];
+    if (fabsf(c0) < 1.1920929e-07f) {
+        compute_roots2(c2, c1, roots);
+        return;
+    }
+    const float s_inv3 = static_cast<float>(1.0 / 3.0);
+    const float s_sqrt3 = sqrtf(3.0f);
+    const float c2_over_3 = c2 * s_inv3;
+    float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+    if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+    const float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+    float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+    if (q > 0.0f) q = 0.0f;
+    const float rho = sqrtf(-a_over_3);
+    const float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+    float sin_theta, cos_theta;
+    sincosf(theta, &sin_theta, &cos_theta);
+    roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+    roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+    roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+    float t;
+    if (roots[0] >= roots[1]) { t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+    if (roots[1] >= roots[2]) {
+        t = roots[1]; roots[1] = roots[2]; roots[2] = t;
+        if (roots[0] >= roots[1]) { t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+    }
+    if (roots[0] <= 0.0f) compute_roots2(c2, c1, roots);
+}
+
+__device__ __forceinline__ void cross3f(const float a[3], const float b[3], float out[3]) {
+    out[0] = a[1] * b[2] - a[2] * b[1];
+    out[1] = a[2] * b[0] - a[0] * b[2];
+    out[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__device__ void eigen33_smallest(const float mat[9], float evec[3]) {
+    float scale = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(mat[i]));
+    if (scale <= 1.17549435e-38f) scale = 1.0f;
+    float s[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s[i] = mat[i] / scale;
+    float roots[3];
+    compute_roots(s, roots);
+    s[0] -= roots[0];
+    s[4] -= roots[0];
+    s[8] -= roots[0];
+    float v1[3], v2[3], v3[3];
+    cross3f(s + 0, s + 3, v1);
+    cross3f(s + 0, s + 6, v2);
+    cross3f(s + 3, s + 6, v3);
+    const float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+    const float l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+    const float l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+    const float *v;
+    float l;
+    if (l1 >= l2 && l1 >= l3) { v = v1; l = l1; }
+    else if (l2 >= l1 && l2 >= l3) { v = v2; l = l2; }
+    else { v = v3; l = l3; }
+    const float len = sqrtf(l);
+    evec[0] = v[0] / len;
+    evec[1] = v[1] / len;
+    evec[2] = v[2] / len;
+}
+
+// ---- normals: NormalEstimation::computePointNormal + flipNormalTowardsViewpoint(origin) ----------------
+__global__ void __launch_bounds__(kShotWarps * 32) shot_normals_kernel(const ShotGrid *__restrict__ gp,
+                                                                      const int *__restrict__ cell_start,
+                                                                      const float4 *__restrict__ sorted, int n_sorted_max,
+                                                                      float radius_sq, float *__restrict__ normals,
+                                                                      float4 *__restrict__ normals_sorted) {
+    const ShotGrid g = *gp;
+    const int n_sorted = cell_start[g.cells];
+    const int lane = lane_id();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    (void)n_sorted_max;
+    for (int s = warp; s < n_sorted; s += n_warps) {
+        const float4 pq = sorted[s];
+        const float p[3] = {pq.x, pq.y, pq.z};
+        float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int cnt = 0;
+        for_each_candidate(g, cell_start, sorted, p, lane, [&](int, const float4 &q) {
+            if (flann_dist2(p, q) < radius_sq) {
+                acc[0] += q.x * q.x;
+                acc[1] += q.x * q.y;
+                acc[2] += q.x * q.z;
+                acc[3] += q.y * q.y;
+                acc[4] += q.y * q.z;
+                acc[5] += q.z * q.z;
+                acc[6] += q.x;
+                acc[7] += q.y;
+                acc[8] += q.z;
+                ++cnt;
+            }
+        });
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] = warp_sum(acc[i]);
+        cnt = warp_sum(cnt);
+        float nrm[3] = {CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F};
+        if (cnt >= 3) {
+            const float c = static_cast<float>(cnt);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) acc[i] /= c;
+            float cov[9];
+            cov[0] = acc[0] - acc[6] * acc[6];
+            cov[1] = acc[1] - acc[6] * acc[7];
+            cov[2] = acc[2] - acc[6] * acc[8];
+            cov[4] = acc[3] - acc[7] * acc[7];
+            cov[5] = acc[4] - acc[7] * acc[8];
+            cov[8] = acc[5] - acc[8] * acc[8];
+            cov[3] = cov[1];
+            cov[6] = cov[2];
+            cov[7] = cov[5];
+            eigen33_smallest(cov, nrm);
+            const float cos_theta = (-p[0]) * nrm[0] + (-p[1]) * nrm[1] + (-p[2]) * nrm[2];
+            if (cos_theta < 0.0f) {
+                nrm[0] = -nrm[0];
+                nrm[1] = -nrm[1];
+                nrm[2] = -nrm[2];
+            }
+        }
+        if (lane == 0) {
+            const int orig = __float_as_int(pq.w);
+            normals[3 * orig] = nrm[0];
+            normals[3 * orig + 1] = nrm[1];
+            normals[3 * orig + 2] = nrm[2];
+            if (normals_sorted) normals_sorted[s] = make_float4(nrm[0], nrm[1], nrm[2], 0.0f);
+        }
+    }
+}
+
+// ---- cyclic Jacobi, symmetric 3x3, double (stands in for Eigen::SelfAdjointEigenSolver<Matrix3d>) ------
+__device__ void jacobi_eigen3(const double Ain[6] /* xx xy xz yy yz zz */, double w[3], double V[9]) {
+    double A[9] = {Ain[0], Ain[1], Ain[2], Ain[1], Ain[3], Ain[4], Ain[2], Ain[4], Ain[5]};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        const double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+        const double diag = A[0] * A[0] + A[4] * A[4] + A[8] * A[8];
+        if (off <= 1e-34 * diag || off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 3; ++q) {
+                const double apq = A[3 * p + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[3 * q + q] - A[3 * p + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = A[3 * k + p], akq = A[3 * k + q];
+                    A[3 * k + p] = c * akp - s * akq;
+                    A[3 * k + q] = s * akp + c * akq;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = A[3 * p + k], aqk = A[3 * q + k];
+                    A[3 * p + k] = c * apk - s * aqk;
+                    A[3 * q + k] = s * apk + c * aqk;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[3 * k + p], vkq = V[3 * k + q];
+                    V[3 * k + p] = c * vkp - s * vkq;
+                    V[3 * k + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    // ascending eigenvalues (3-element sorting network on columns)
+    double d[3] = {A[0], A[4], A[8]};
+    int o0 = 0, o1 = 1, o2 = 2, t;
+    if (d[o0] > d[o1]) { t = o0; o0 = o1; o1 = t; }
+    if (d[o1] > d[o2]) { t = o1; o1 = o2; o2 = t; }
+    if (d[o0] > d[o1]) { t = o0; o0 = o1; o1 = t; }
+    double Vs[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        Vs[3 * k + 0] = V[3 * k + o0];
+        Vs[3 * k + 1] = V[3 * k + o1];
+        Vs[3 * k + 2] = V[3 * k + o2];
+    }
+    w[0] = d[o0];
+    w[1] = d[o1];
+    w[2] = d[o2];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) V[i] = Vs[i];
+}
+
+// ---- LRF + SHOT352 histogram ----------------------------------------------------------------------------
+// REAL = double reproduces PCL's double interpolation weights; REAL = float evaluates acos/atan2 and the
+// weights in float (SHOT's quadrilinear interpolation is continuous across every bin boundary, so the
+// descriptor moves by ~1e-7).
+template <typename REAL>
+__global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
+    const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
+    const float4 *__restrict__ normals_sorted, float radius_f, double radius, float *__restrict__ desc,
+    float *__restrict__ rf_out) {
+    __shared__ float s_hist[kShotWarps][CPPF_SHOT_DIM];
+    const ShotGrid g = *gp;
+    const int n_sorted = cell_start[g.cells];
+    const float radius_sq = static_cast<float>(radius * radius);
+    const int lane = lane_id();
+    const int wib = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    float *hist = s_hist[wib];
+    (void)radius_f;
+    const REAL r12 = static_cast<REAL>(radius / 2), r14 = static_cast<REAL>(radius / 4), r34 = static_cast<REAL>((radius * 3) / 4);
+    const REAL RAD_45 = static_cast<REAL>(0.78539816339744830961566084581988);
+    const REAL RAD_90 = static_cast<REAL>(1.5707963267948966192313216916398);
+    const REAL RAD_135 = static_cast<REAL>(2.3561944901923449288469825374596);
+    const REAL RAD_7_8 = static_cast<REAL>(2.7488935718910690836548129603691);
+
+    for (int s = warp; s < n_sorted; s += n_warps) {
+        const float4 pq = sorted[s];
+        const float p[3] = {pq.x, pq.y, pq.z};
+        const int orig = __float_as_int(pq.w);
+        float *out = desc + static_cast<size_t>(orig) * CPPF_SHOT_DIM;
+
+        // pass A: weighted scatter matrix in double (shot_lrf.hpp::getLocalRF)
+        double cov[6] = {0, 0, 0, 0, 0, 0}, wsum = 0.0;
+        int valid = 0, total = 0;
+        for_each_candidate(g, cell_start, sorted, p, lane, [&](int, const float4 &q) {
+            const float d2 = flann_dist2(p, q);
+            if (d2 < radius_sq) {
+                ++total;
+                if (!(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
+                    const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
+                                 vz = static_cast<double>(__fsub_rn(q.z, p[2]));
+                    const double w = radius - sqrt(static_cast<double>(d2));
+                    cov[0] += w * (vx * vx);
+                    cov[1] += w * (vx * vy);
+                    cov[2] += w * (vx * vz);
+                    cov[3] += w * (vy * vy);
+                    cov[4] += w * (vy * vz);
+                    cov[5] += w * (vz * vz);
+                    wsum += w;
+                    ++valid;
+                }
+            }
+        });
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cov[i] = warp_sum(cov[i]);
+        wsum = warp_sum(wsum);
+        valid = warp_sum(valid);
+        total = warp_sum(total);
+
+        bool ok = valid >= 5 && total >= 5;
+        float fx[3], fy[3], fz[3];
+        if (ok) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cov[i] /= wsum;
+            double w[3], V[9];
+            jacobi_eigen3(cov, w, V);
+            ok = isfinite(w[0]) && isfinite(w[1]) && isfinite(w[2]);
+            double v1[3] = {V[2], V[5], V[8]};  // largest eigenvalue  -> x
+            double v3[3] = {V[0], V[3], V[6]};  // smallest eigenvalue -> z
+            // pass B: sign disambiguation votes
+            int plus_t = 0, plus_n = 0;
+            for_each_candidate(g, cell_start, sorted, p, lane, [&](int, const float4 &q) {
+                if (flann_dist2(p, q) < radius_sq && !(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
+                    const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
+                                 vz = static_cast<double>(__fsub_rn(q.z, p[2]));
+                    if (vx * v1[0] + vy * v1[1] + vz * v1[2] >= 0.0) ++plus_t;
+                    if (vx * v3[0] + vy * v3[1] + vz * v3[2] >= 0.0) ++plus_n;
+                }
+            });
+            plus_t = 2 * warp_sum(plus_t) - valid;
+            plus_n = 2 * warp_sum(plus_n) - valid;
+            // exact ties fall back to PCL's search-order dependent rule (5 neighbours around the median
+            // of the kd-tree order); without that order the axis is left as the solver produced it.
+            if (plus_t < 0) { v1[0] = -v1[0]; v1[1] = -v1[1]; v1[2] = -v1[2]; }
+            if (plus_n < 0) { v3[0] = -v3[0]; v3[1] = -v3[1]; v3[2] = -v3[2]; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                fx[k] = static_cast<float>(v1[k]);
+                fz[k] = static_cast<float>(v3[k]);
+            }
+            cross3f(fz, fx, fy);
+        }
+        if (rf_out && lane < 9) {
+            const float v = !ok ? CUDART_NAN_F : (lane < 3 ? fx[lane] : (lane < 6 ? fy[lane - 3] : fz[lane - 6]));
+            rf_out[static_cast<size_t>(orig) * 9 + lane] = v;
+        }
+        if (!ok) {  // invalid LRF or fewer than 5 neighbours: NaN row (shot.hpp::computeFeature / computePointSHOT)
+            for (int j = lane; j < CPPF_SHOT_DIM; j += 32) out[j] = CUDART_NAN_F;
+            continue;
+        }
+
+        // pass C: histogram (shot.hpp::createBinDistanceShape + interpolateSingleChannel)
+        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) hist[j] = 0.0f;
+        __syncwarp();
+        for_each_candidate(g, cell_start, sorted, p, lane, [&](int j, const float4 &q) {
+            const float d2 = flann_dist2(p, q);
+            if (!(d2 < radius_sq)) return;
+            const float4 nq = normals_sorted[j];
+            if (!(isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z))) return;
+            REAL cosine = static_cast<REAL>(nq.x * fz[0] + nq.y * fz[1] + nq.z * fz[2]);
+            cosine = cosine > REAL(1) ? REAL(1) : (cosine < REAL(-1) ? REAL(-1) : cosine);
+            REAL bin = ((REAL(1) + cosine) * REAL(10)) / REAL(2);
+            const float dl[3] = {__fsub_rn(q.x, p[0]), __fsub_rn(q.y, p[1]), __fsub_rn(q.z, p[2])};
+            const REAL distance = static_cast<REAL>(sqrt(static_cast<double>(d2)));
+            if (fabs(static_cast<double>(distance)) < 1e-15) return;
+            REAL xr = static_cast<REAL>(dl[0] * fx[0] + dl[1] * fx[1] + dl[2] * fx[2]);
+            REAL yr = static_cast<REAL>(dl[0] * fy[0] + dl[1] * fy[1] + dl[2] * fy[2]);
+            REAL zr = static_cast<REAL>(dl[0] * fz[0] + dl[1] * fz[1] + dl[2] * fz[2]);
+            if (fabs(static_cast<double>(yr)) < 1e-30) yr = 0;
+            if (fabs(static_cast<double>(xr)) < 1e-30) xr = 0;
+            if (fabs(static_cast<double>(zr)) < 1e-30) zr = 0;
+            const int bit4 = ((yr > 0) || ((yr == 0) && (xr < 0))) ? 1 : 0;
+            const int bit3 = ((xr > 0) || ((xr == 0) && (yr > 0))) ? (1 - bit4) : bit4;
+            int di = ((bit4 << 3) + (bit3 << 2)) << 1;
+            const REAL ax = xr < 0 ? -xr : xr, ay = yr < 0 ? -yr : yr;
+            if ((xr * yr > 0) || (xr == 0))
+                di += (ax >= ay) ? 0 : 4;
+            else
+                di += (ax > ay) ? 4 : 0;
+            di += zr > 0 ? 1 : 0;
+            di += (distance > r12) ? 2 : 0;
+            const int step = static_cast<int>(floor(static_cast<double>(bin) + 0.5));
+            const int vol = di * 11;
+            bin -= static_cast<REAL>(step);
+            REAL wgt = REAL(1) - (bin < 0 ? -bin : bin);
+            if (bin > 0)
+                atomicAdd(&hist[vol + ((step + 1) % 10)], static_cast<float>(bin));
+            else
+                atomicAdd(&hist[vol + ((step - 1 + 10) % 10)], -static_cast<float>(bin));
+            if (distance > r12) {
+                const REAL rd = (distance - r34) / r12;
+                if (distance > r34)
+                    wgt += REAL(1) - rd;
+                else {
+                    wgt += REAL(1) + rd;
+                    atomicAdd(&hist[(di - 2) * 11 + step], -static_cast<float>(rd));
+                }
+            } else {
+                const REAL rd = (distance - r14) / r12;
+                if (distance < r14)
+                    wgt += REAL(1) + rd;
+                else {
+                    wgt += REAL(1) - rd;
+                    atomicAdd(&hist[(di + 2) * 11 + step], static_cast<float>(rd));
+                }
+            }
+            REAL ic = zr / distance;
+            ic = ic < REAL(-1) ? REAL(-1) : (ic > REAL(1) ? REAL(1) : ic);
+            const REAL incl = acos(ic);
+            if (incl > RAD_90 || (fabs(static_cast<double>(incl - RAD_90)) < 1e-30 && zr <= 0)) {
+                const REAL id = (incl - RAD_135) / RAD_90;
+                if (incl > RAD_135)
+                    wgt += REAL(1) - id;
+                else {
+                    wgt += REAL(1) + id;
+                    atomicAdd(&hist[(di + 1) * 11 + step], -static_cast<float>(id));
+                }
+            } else {
+                const REAL id = (incl - RAD_45) / RAD_90;
+                if (incl < RAD_45)
+                    wgt += REAL(1) + id;
+                else {
+                    wgt += REAL(1) - id;
+                    atomicAdd(&hist[(di - 1) * 11 + step], static_cast<float>(id));
+                }
+            }
+            if (yr != 0 || xr != 0) {
+                const REAL az = atan2(yr, xr);
+                const int sel = di >> 2;
+                REAL ad = (az - (-RAD_7_8 + RAD_45 * static_cast<REAL>(sel))) / RAD_45;
+                ad = ad < REAL(-0.5) ? REAL(-0.5) : (ad > REAL(0.5) ? REAL(0.5) : ad);
+                if (ad > 0) {
+                    wgt += REAL(1) - ad;
+                    atomicAdd(&hist[((di + 4) % 32) * 11 + step], static_cast<float>(ad));
+                } else {
+                    wgt += REAL(1) + ad;
+                    atomicAdd(&hist[((di - 4 + 32) % 32) * 11 + step], -static_cast<float>(ad));
+                }
+            }
+            atomicAdd(&hist[vol + step], static_cast<float>(wgt));
+        });
+        __syncwarp();
+        // normalizeHistogram: float squares accumulated in double, divide by float(norm)
+        double acc = 0.0;
+        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) acc += static_cast<double>(hist[j] * hist[j]);
+        acc = warp_sum(acc);
+        const float nrm = static_cast<float>(sqrt(acc));
+        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) out[j] = hist[j] / nrm;
+        __syncwarp();
+    }
+}
+
+struct ShotWorkspace {
+    cppf_grid_geom *bounds;
+    ShotGrid *grid;
+    int *cell_of, *cell_count, *cell_start, *cell_fill;
+    float4 *sorted, *normals_sorted;
+};
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+static size_t shot_carve(void *ws, int64_t n, ShotWorkspace *out) {
+    unsigned char *base = static_cast<unsigned char *>(ws);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void *p = base ? base + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    ShotWorkspace w;
+    w.bounds = static_cast<cppf_grid_geom *>(take(sizeof(cppf_grid_geom)));
+    w.grid = static_cast<ShotGrid *>(take(sizeof(ShotGrid)));
+    w.cell_count = static_cast<int *>(take(sizeof(int) * (kShotMaxCells + 1)));
+    w.cell_start = static_cast<int *>(take(sizeof(int) * (kShotMaxCells + 1)));
+    w.cell_fill = static_cast<int *>(take(sizeof(int) * (kShotMaxCells + 1)));
+    w.cell_of = static_cast<int *>(take(sizeof(int) * static_cast<size_t>(n)));
+    w.sorted = static_cast<float4 *>(take(sizeof(float4) * static_cast<size_t>(n)));
+    w.normals_sorted = static_cast<float4 *>(take(sizeof(float4) * static_cast<size_t>(n)));
+    if (out) *out = w;
+    return off;
+}
+
+static int shot_build_grid(const float *pc, int64_t n, float radius, const ShotWorkspace &w, cudaStream_t s) {
+    int rc = cppf_cloud_bounds(pc, n, radius, w.bounds, s);
+    if (rc) return rc;
+    shot_grid_setup_kernel<<<1, 32, 0, s>>>(w.bounds, radius, w.grid);
+    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (kShotMaxCells + 1), s));
+    const int nb = div_up(n, 256);
+    shot_cell_count_kernel<<<nb, 256, 0, s>>>(pc, static_cast<int>(n), w.grid, w.cell_of, w.cell_count);
+    CPPF_LAUNCH_CHECK();
+    shot_cell_scan_kernel<<<1, 1024, 0, s>>>(w.grid, w.cell_count, w.cell_start, w.cell_fill);
+    CPPF_LAUNCH_CHECK();
+    shot_scatter_kernel<<<nb, 256, 0, s>>>(pc, static_cast<int>(n), w.cell_of, w.cell_fill, w.sorted);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+}  // namespace cppf
+
+using namespace cppf;
+
+CPPF_API int64_t cppf_shot_workspace_bytes(int64_t n) { return static_cast<int64_t>(shot_carve(nullptr, n < 1 ? 1 : n, nullptr)); }
+
+static int shot_run(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals, float *rf_out,
+                    int fast_math, void *ws, int64_t ws_bytes, void *stream) {
+    if (!pc || !normals || !ws || n < 0 || !(normal_r > 0.0f) || (desc && !(shot_r > 0.0f))) return CPPF_ERR_INVALID_ARGUMENT;
+    if (n > (1ll << 30)) return CPPF_ERR_UNSUPPORTED;
+    if (n == 0) return CPPF_OK;
+    if (ws_bytes < cppf_shot_workspace_bytes(n)) return CPPF_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ShotWorkspace w;
+    shot_carve(ws, n, &w);
+    // one grid serves both searches: its cell edge is the larger of the two radii
+    const float cell_r = desc ? fmaxf(normal_r, shot_r) : normal_r;
+    int rc = shot_build_grid(pc, n, cell_r, w, s);
+    if (rc) return rc;
+    shot_nan_fill_kernel<<<static_cast<int>(n), 64, 0, s>>>(w.cell_of, static_cast<int>(n), normals, desc);
+    CPPF_LAUNCH_CHECK();
+    const int blocks = grid_for(n * 32, kShotWarps * 32, 8);
+    const float nr2 = static_cast<float>(static_cast<double>(normal_r) * static_cast<double>(normal_r));
+    shot_normals_kernel<<<blocks, kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted, static_cast<int>(n), nr2, normals,
+                                                          w.normals_sorted);
+    CPPF_LAUNCH_CHECK();
+    if (!desc) return CPPF_OK;
+    const int dblocks = grid_for(n * 32, kShotWarps * 32, 4);
+    if (fast_math)
+        shot_descriptor_kernel<float><<<dblocks, kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted, w.normals_sorted,
+                                                                         shot_r, static_cast<double>(shot_r), desc, rf_out);
+    else
+        shot_descriptor_kernel<double><<<dblocks, kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted, w.normals_sorted,
+                                                                          shot_r, static_cast<double>(shot_r), desc, rf_out);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_shot_compute(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals,
+                               void *ws, int64_t ws_bytes, void *stream) {
+    if (!desc) return CPPF_ERR_INVALID_ARGUMENT;
+    return shot_run(pc, n, normal_r, shot_r, desc, normals, nullptr, 0, ws, ws_bytes, stream);
+}
+
+// Same with the interpolation weights in float (fast_math != 0) and the local reference frames exposed
+// (rf_out [n,9], rows x,y,z; may be NULL).
+CPPF_API int cppf_shot_compute_ex(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals,
+                                  float *rf_out, int fast_math, void *ws, int64_t ws_bytes, void *stream) {
+    if (!desc) return CPPF_ERR_INVALID_ARGUMENT;
+    return shot_run(pc, n, normal_r, shot_r, desc, normals, rf_out, fast_math, ws, ws_bytes, stream);
+}
+
+CPPF_API int cppf_estimate_normal(const float *pc, int64_t n, float normal_r, float *normals, void *ws, int64_t ws_bytes,
+                                  void *stream) {
+    return shot_run(pc, n, normal_r, 0.0f, nullptr, normals, nullptr, 0, ws, ws_bytes, stream);
+}
+
+CPPF_API int cppf_shot_compute_color(const float *, const float *, int64_t, float, float, float *, void *) {
+    return CPPF_ERR_UNSUPPORTED;  // SHOT1344 (shot.cpp:102-161) has no caller anywhere in the reference
+}

@@ -81,5 +81,19 @@ def main():
     print(json.dumps(dict(kernel="pose_chain", T=T, ms_med=med, ms_min=mn, launches=voter.launches, result=str(voter.result().t))))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def time_shot():
+    from cppf2_b200 import shot
+    for n in (10000, 50000, 200000):
+        pc = torch.from_numpy(synth.torus_cloud(n, 0.002)[0]).cuda()
+        for fast in (False, True):
+            med, mn = time_fn(lambda: shot.compute_device(pc, 0.02, 0.02, fast_math=fast), iters=5, warmup=2)
+            print(json.dumps(dict(kernel="shot", n=n, fast=fast, ms_med=round(med, 3), pts_per_s=round(n / med * 1e3),
+                                  alg_GBps=round(n * 1432 / med / 1e6, 1))), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "shot":
+    time_shot()
