@@ -77,7 +77,7 @@ SIGNATURES = {
     "cppf_shot_workspace_bytes": (I64, [I64]),
     "cppf_shot_compute": (I, [P, I64, F, F, P, P, P, I64, P]),
     "cppf_estimate_normal": (I, [P, I64, F, P, P, I64, P]),
-    "cppf_shot_compute_ex": (I, [P, I64, F, F, P, P, P, I, P, I64, P]),
+    "cppf_shot_compute_ex": (I, [P, I64, F, F, P, P, P, I, P, P, I64, P]),
     "cppf_shot_compute_color": (I, [P, P, I64, F, F, P, P]),
     "cppf_heads_create": (I, [I, I, C.POINTER(C.c_float), I64, C.POINTER(P)]),
     "cppf_heads_destroy": (I, [P]),

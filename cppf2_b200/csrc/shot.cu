@@ -109,13 +109,36 @@ __global__ void __launch_bounds__(256) shot_scatter_kernel(const float *__restri
     sorted[pos] = make_float4(pc[3 * i], pc[3 * i + 1], pc[3 * i + 2], __int_as_float(i));
 }
 
+// The atomic scatter leaves each cell's points in arrival order, which changes from run to run.  Rank every
+// point of a cell by its original index (one warp per cell, counting sort by comparison: segments hold
+// ~100 points when the cloud is voxel-sampled at radius/10 as the reference does) so that the sorted copy,
+// and with it every floating-point accumulation order downstream, is deterministic.
+__global__ void __launch_bounds__(256) shot_cell_order_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
+                                                              const float4 *__restrict__ scattered,
+                                                              float4 *__restrict__ sorted) {
+    const int cells = gp->cells;
+    const int lane = lane_id();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int c = warp; c < cells; c += n_warps) {
+        const int b = cell_start[c], e = cell_start[c + 1];
+        for (int t = b + lane; t < e; t += 32) {
+            const float4 mine = scattered[t];
+            const int key = __float_as_int(mine.w);
+            int rank = 0;
+            for (int u = b; u < e; ++u) rank += (__float_as_int(scattered[u].w) < key) ? 1 : 0;
+            sorted[b + rank] = mine;
+        }
+    }
+}
+
 // Points with non-finite coordinates never enter the grid: their outputs are NaN (PCL: isFinite checks).
 __global__ void __launch_bounds__(256) shot_nan_fill_kernel(const int *__restrict__ cell_of, int n, float *__restrict__ normals,
                                                             float *__restrict__ desc) {
     const int i = blockIdx.x;
     if (i >= n || cell_of[i] >= 0) return;
     const float nanv = CUDART_NAN_F;
-    if (threadIdx.x < 3) normals[3 * i + threadIdx.x] = nanv;
+    if (normals && threadIdx.x < 3) normals[3 * i + threadIdx.x] = nanv;
     if (desc)
         for (int j = threadIdx.x; j < CPPF_SHOT_DIM; j += blockDim.x) desc[static_cast<size_t>(i) * CPPF_SHOT_DIM + j] = nanv;
 }
@@ -549,6 +572,18 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
     }
 }
 
+// normals_sorted[s] = normals_in[orig(s)]: used when the caller supplies the normals
+__global__ void __launch_bounds__(256) shot_gather_normals_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
+                                                                  const float4 *__restrict__ sorted,
+                                                                  const float *__restrict__ normals_in,
+                                                                  float4 *__restrict__ normals_sorted) {
+    const int n_sorted = cell_start[gp->cells];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sorted) return;
+    const int orig = __float_as_int(sorted[s].w);
+    normals_sorted[s] = make_float4(normals_in[3 * orig], normals_in[3 * orig + 1], normals_in[3 * orig + 2], 0.0f);
+}
+
 struct ShotWorkspace {
     cppf_grid_geom *bounds;
     ShotGrid *grid;
@@ -590,7 +625,10 @@ static int shot_build_grid(const float *pc, int64_t n, float radius, const ShotW
     CPPF_LAUNCH_CHECK();
     shot_cell_scan_kernel<<<1, 1024, 0, s>>>(w.grid, w.cell_count, w.cell_start, w.cell_fill);
     CPPF_LAUNCH_CHECK();
-    shot_scatter_kernel<<<nb, 256, 0, s>>>(pc, static_cast<int>(n), w.cell_of, w.cell_fill, w.sorted);
+    // scatter into the (not yet used) normals buffer, then order every cell by original index
+    shot_scatter_kernel<<<nb, 256, 0, s>>>(pc, static_cast<int>(n), w.cell_of, w.cell_fill, w.normals_sorted);
+    CPPF_LAUNCH_CHECK();
+    shot_cell_order_kernel<<<grid_for(n * 8, 256, 8), 256, 0, s>>>(w.grid, w.cell_start, w.normals_sorted, w.sorted);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }
@@ -602,8 +640,10 @@ using namespace cppf;
 CPPF_API int64_t cppf_shot_workspace_bytes(int64_t n) { return static_cast<int64_t>(shot_carve(nullptr, n < 1 ? 1 : n, nullptr)); }
 
 static int shot_run(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals, float *rf_out,
-                    int fast_math, void *ws, int64_t ws_bytes, void *stream) {
-    if (!pc || !normals || !ws || n < 0 || !(normal_r > 0.0f) || (desc && !(shot_r > 0.0f))) return CPPF_ERR_INVALID_ARGUMENT;
+                    int fast_math, const float *normals_in, void *ws, int64_t ws_bytes, void *stream) {
+    if (n == 0) return CPPF_OK;
+    if (!pc || !ws || n < 0 || (desc && !(shot_r > 0.0f))) return CPPF_ERR_INVALID_ARGUMENT;
+    if (!normals_in && (!normals || !(normal_r > 0.0f))) return CPPF_ERR_INVALID_ARGUMENT;
     if (n > (1ll << 30)) return CPPF_ERR_UNSUPPORTED;
     if (n == 0) return CPPF_OK;
     if (ws_bytes < cppf_shot_workspace_bytes(n)) return CPPF_ERR_WORKSPACE;
@@ -611,16 +651,25 @@ static int shot_run(const float *pc, int64_t n, float normal_r, float shot_r, fl
     ShotWorkspace w;
     shot_carve(ws, n, &w);
     // one grid serves both searches: its cell edge is the larger of the two radii
-    const float cell_r = desc ? fmaxf(normal_r, shot_r) : normal_r;
+    const float cell_r = normals_in ? shot_r : (desc ? fmaxf(normal_r, shot_r) : normal_r);
     int rc = shot_build_grid(pc, n, cell_r, w, s);
     if (rc) return rc;
-    shot_nan_fill_kernel<<<static_cast<int>(n), 64, 0, s>>>(w.cell_of, static_cast<int>(n), normals, desc);
-    CPPF_LAUNCH_CHECK();
-    const int blocks = grid_for(n * 32, kShotWarps * 32, 8);
-    const float nr2 = static_cast<float>(static_cast<double>(normal_r) * static_cast<double>(normal_r));
-    shot_normals_kernel<<<blocks, kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted, static_cast<int>(n), nr2, normals,
-                                                          w.normals_sorted);
-    CPPF_LAUNCH_CHECK();
+    if (normals_in) {
+        shot_gather_normals_kernel<<<div_up(n, 256), 256, 0, s>>>(w.grid, w.cell_start, w.sorted, normals_in, w.normals_sorted);
+        CPPF_LAUNCH_CHECK();
+        if (normals && normals != normals_in)
+            CPPF_CUDA_TRY(cudaMemcpyAsync(normals, normals_in, sizeof(float) * 3 * static_cast<size_t>(n), cudaMemcpyDeviceToDevice, s));
+        shot_nan_fill_kernel<<<static_cast<int>(n), 64, 0, s>>>(w.cell_of, static_cast<int>(n), nullptr, desc);
+        CPPF_LAUNCH_CHECK();
+    } else {
+        shot_nan_fill_kernel<<<static_cast<int>(n), 64, 0, s>>>(w.cell_of, static_cast<int>(n), normals, desc);
+        CPPF_LAUNCH_CHECK();
+        const int blocks = grid_for(n * 32, kShotWarps * 32, 8);
+        const float nr2 = static_cast<float>(static_cast<double>(normal_r) * static_cast<double>(normal_r));
+        shot_normals_kernel<<<blocks, kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted, static_cast<int>(n), nr2, normals,
+                                                              w.normals_sorted);
+        CPPF_LAUNCH_CHECK();
+    }
     if (!desc) return CPPF_OK;
     const int dblocks = grid_for(n * 32, kShotWarps * 32, 4);
     if (fast_math)
@@ -636,20 +685,24 @@ static int shot_run(const float *pc, int64_t n, float normal_r, float shot_r, fl
 CPPF_API int cppf_shot_compute(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals,
                                void *ws, int64_t ws_bytes, void *stream) {
     if (!desc) return CPPF_ERR_INVALID_ARGUMENT;
-    return shot_run(pc, n, normal_r, shot_r, desc, normals, nullptr, 0, ws, ws_bytes, stream);
+    // float interpolation weights: indistinguishable from PCL's double ones at float32 output precision
+    // (tests/test_gpu_shot.py compares both against the oracle), and faster
+    return shot_run(pc, n, normal_r, shot_r, desc, normals, nullptr, 1, nullptr, ws, ws_bytes, stream);
 }
 
-// Same with the interpolation weights in float (fast_math != 0) and the local reference frames exposed
-// (rf_out [n,9], rows x,y,z; may be NULL).
+// Same with the interpolation weights in float (fast_math != 0), the local reference frames exposed
+// (rf_out [n,9], rows x,y,z; may be NULL) and, optionally, caller-supplied normals (normals_in [n,3]:
+// the normal estimation is skipped, e.g. to reuse normals or to test the descriptor stage in isolation).
 CPPF_API int cppf_shot_compute_ex(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals,
-                                  float *rf_out, int fast_math, void *ws, int64_t ws_bytes, void *stream) {
+                                  float *rf_out, int fast_math, const float *normals_in, void *ws, int64_t ws_bytes,
+                                  void *stream) {
     if (!desc) return CPPF_ERR_INVALID_ARGUMENT;
-    return shot_run(pc, n, normal_r, shot_r, desc, normals, rf_out, fast_math, ws, ws_bytes, stream);
+    return shot_run(pc, n, normal_r, shot_r, desc, normals, rf_out, fast_math, normals_in, ws, ws_bytes, stream);
 }
 
 CPPF_API int cppf_estimate_normal(const float *pc, int64_t n, float normal_r, float *normals, void *ws, int64_t ws_bytes,
                                   void *stream) {
-    return shot_run(pc, n, normal_r, 0.0f, nullptr, normals, nullptr, 0, ws, ws_bytes, stream);
+    return shot_run(pc, n, normal_r, 0.0f, nullptr, normals, nullptr, 0, nullptr, ws, ws_bytes, stream);
 }
 
 CPPF_API int cppf_shot_compute_color(const float *, const float *, int64_t, float, float, float *, void *) {

@@ -32,8 +32,10 @@ def _workspace(n: int, device) -> torch.Tensor:
     return ws
 
 
-def compute_device(pc: torch.Tensor, normal_r: float, shot_r: float, fast_math: bool = False, want_rf: bool = False):
-    """pc CUDA f32 [N,3] -> (desc CUDA f32 [N,352], normals CUDA f32 [N,3][, rf CUDA f32 [N,9]])."""
+def compute_device(pc: torch.Tensor, normal_r: float, shot_r: float, fast_math: bool = True, want_rf: bool = False,
+                   normals_in=None):
+    """pc CUDA f32 [N,3] -> (desc CUDA f32 [N,352], normals CUDA f32 [N,3][, rf CUDA f32 [N,9]]).
+    `normals_in` [N,3] skips the normal estimation and describes with the given normals."""
     lib = _lib.load()
     pc = to_device(pc, torch.float32).reshape(-1, 3)
     n = pc.shape[0]
@@ -41,9 +43,11 @@ def compute_device(pc: torch.Tensor, normal_r: float, shot_r: float, fast_math: 
     normals = torch.empty((n, 3), dtype=torch.float32, device=pc.device)
     rf = torch.empty((n, 9), dtype=torch.float32, device=pc.device) if want_rf else None
     ws = _workspace(n, pc.device)
+    nin = None if normals_in is None else to_device(normals_in, torch.float32, pc.device).reshape(-1, 3)
     check(lib.cppf_shot_compute_ex(pc.data_ptr(), n, float(normal_r), float(shot_r), desc.data_ptr(), normals.data_ptr(),
-                                   None if rf is None else rf.data_ptr(), int(fast_math), ws.data_ptr(), ws.numel(),
-                                   stream_ptr()), "cppf_shot_compute")
+                                   None if rf is None else rf.data_ptr(), int(fast_math),
+                                   None if nin is None else nin.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()),
+          "cppf_shot_compute")
     return (desc, normals, rf) if want_rf else (desc, normals)
 
 

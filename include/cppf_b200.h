@@ -208,11 +208,12 @@ int cppf_shot_compute(const float *pc, int64_t n, float normal_r, float shot_r, 
                       void *ws, int64_t ws_bytes, void *stream);
 int cppf_estimate_normal(const float *pc, int64_t n, float normal_r, float *normals, void *ws, int64_t ws_bytes,
                          void *stream);
-/* Same as cppf_shot_compute with two extras: rf_out [n,9] (rows x,y,z of the SHOT local reference frame,
- * NaN when invalid; may be NULL) and fast_math != 0 to evaluate the interpolation weights (acos, atan2)
- * in float instead of PCL's double (descriptor moves by ~1e-7: the interpolation is continuous). */
+/* Same as cppf_shot_compute with three extras: rf_out [n,9] (rows x,y,z of the SHOT local reference
+ * frame, NaN when invalid; may be NULL); fast_math != 0 evaluates the interpolation weights (acos, atan2)
+ * in float instead of PCL's double (descriptor moves by ~1e-7: the interpolation is continuous); and
+ * normals_in [n,3] (may be NULL) supplies the normals instead of estimating them. */
 int cppf_shot_compute_ex(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals,
-                         float *rf_out, int fast_math, void *ws, int64_t ws_bytes, void *stream);
+                         float *rf_out, int fast_math, const float *normals_in, void *ws, int64_t ws_bytes, void *stream);
 /* SHOT1344 (shot.cpp:102-161) has no caller in the reference: always CPPF_ERR_UNSUPPORTED. */
 int cppf_shot_compute_color(const float *pc, const float *rgb, int64_t n, float normal_r, float shot_r, float *desc,
                             void *stream);

@@ -58,6 +58,9 @@ def lib():
         if hasattr(L, "oracle_shot_compute"):
             L.oracle_shot_compute.restype = C.c_int
             L.oracle_shot_compute.argtypes = [_f32p, C.c_int64, C.c_double, C.c_double, C.c_void_p, _f32p, C.c_int]
+        if hasattr(L, "oracle_shot_lrf"):
+            L.oracle_shot_lrf.restype = C.c_int
+            L.oracle_shot_lrf.argtypes = [_f32p, C.c_int64, C.c_double, _f32p, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")]
         _lib = L
     return _lib
 
@@ -291,3 +294,12 @@ def estimate_normal(pc, normal_r: float, threads: int = 1) -> np.ndarray:
     if rc != 0:
         raise RuntimeError(f"oracle_shot_compute failed with code {rc}")
     return normals
+
+
+def shot_lrf(pc, shot_r: float):
+    """SHOT local reference frames [N,9] (rows x,y,z) and the sign-vote margins [N,2] (0 = tie)."""
+    pc = _f32(pc).reshape(-1, 3)
+    rf = np.empty((pc.shape[0], 9), np.float32)
+    margins = np.zeros((pc.shape[0], 2), np.int32)
+    lib().oracle_shot_lrf(pc, pc.shape[0], float(shot_r), rf, margins)
+    return rf, margins

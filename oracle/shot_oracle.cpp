@@ -293,7 +293,8 @@ void jacobi_eigen3(const double A_in[9], double w[3], double V[9]) {
 }
 
 // SHOTLocalReferenceFrameEstimation::getLocalRF; rf rows = x, y, z axes.  Returns false -> NaN frame.
-bool local_rf(const float *pc, const float *p, const std::vector<Neighbor> &nn, double radius, float rf[9]) {
+bool local_rf(const float *pc, const float *p, const std::vector<Neighbor> &nn, double radius, float rf[9],
+              int *margins = nullptr) {
     std::vector<double> vij;
     vij.reserve(nn.size() * 3);
     double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -328,6 +329,10 @@ bool local_rf(const float *pc, const float *p, const std::vector<Neighbor> &nn, 
         const double *v = &vij[3 * ne];
         if (v[0] * v1[0] + v[1] * v1[1] + v[2] * v1[2] >= 0) ++plus_tangent;
         if (v[0] * v3[0] + v[1] * v3[1] + v[2] * v3[2] >= 0) ++plus_normal;
+    }
+    if (margins) {
+        margins[0] = 2 * plus_tangent - valid;
+        margins[1] = 2 * plus_normal - valid;
     }
     auto disambiguate = [&](int plus, double axis[3]) {
         plus = 2 * plus - valid;
@@ -531,15 +536,21 @@ EXPORT int oracle_shot_compute(const float *pc, int64_t n, double normal_r, doub
     return 0;
 }
 
-// Exposes the local reference frames for tests ([n,9] rows x,y,z; NaN when invalid).
-EXPORT int oracle_shot_lrf(const float *pc, int64_t n, double shot_r, float *rf_out) {
+// Exposes the local reference frames for tests ([n,9] rows x,y,z; NaN when invalid) and the sign-vote
+// margins 2*plus - valid of the x and z axes ([n,2]; 0 = tie, resolved by search order in PCL).
+EXPORT int oracle_shot_lrf(const float *pc, int64_t n, double shot_r, float *rf_out, int *margins_out) {
     CellGrid grid;
     grid.build(pc, n, shot_r);
     std::vector<Neighbor> nn;
     for (int64_t i = 0; i < n; ++i) {
         grid.radius_search(pc + 3 * i, shot_r, nn);
         std::sort(nn.begin(), nn.end(), [](const Neighbor &a, const Neighbor &b) { return a.idx < b.idx; });
-        local_rf(pc, pc + 3 * i, nn, shot_r, rf_out + 9 * i);
+        int m[2] = {0, 0};
+        local_rf(pc, pc + 3 * i, nn, shot_r, rf_out + 9 * i, m);
+        if (margins_out) {
+            margins_out[2 * i] = m[0];
+            margins_out[2 * i + 1] = m[1];
+        }
     }
     return 0;
 }

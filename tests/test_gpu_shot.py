@@ -15,51 +15,89 @@ def angle_deg(a, b):
     return np.degrees(np.arccos(c))
 
 
-def run_case(oracle, pc, r, fast):
+def run_case(oracle, pc, r, fast, inject_normals=False):
     from cppf2_b200 import shot
-    desc, normals, rf = shot.compute_device(torch.from_numpy(pc).cuda(), r, r, fast_math=fast, want_rf=True)
-    desc, normals, rf = desc.cpu().numpy(), normals.cpu().numpy(), rf.cpu().numpy()
     o_desc, o_normals = oracle.shot_compute(pc, r, r)
     o_desc, o_normals = o_desc.reshape(-1, 352), o_normals.reshape(-1, 3)
-    return desc, normals, rf, o_desc, o_normals
+    desc, normals, rf = shot.compute_device(torch.from_numpy(pc).cuda(), r, r, fast_math=fast, want_rf=True,
+                                            normals_in=o_normals if inject_normals else None)
+    return desc.cpu().numpy(), normals.cpu().numpy(), rf.cpu().numpy(), o_desc, o_normals
+
+
+def clouds(name):
+    if name == "halfcyl":
+        return synth.half_cylinder_cloud(4000, seed=7, jitter=0.001), 0.02
+    return synth.torus_cloud(20000, res=0.002, seed=7)[0], 0.02
+
+
+@pytest.mark.parametrize("cloud", ["halfcyl", "torus"])
+def test_normals_match_oracle(oracle, cloud):
+    pc, r = clouds(cloud)
+    desc, normals, rf, o_desc, o_normals = run_case(oracle, pc, r, False)
+    assert np.array_equal(np.isnan(normals), np.isnan(o_normals))        # neighbour SETS are bit-identical
+    ok = ~np.isnan(o_normals).any(1)
+    n_gpu, n_cpu = normals[ok], o_normals[ok].astype(np.float64)
+    # the viewpoint flip is a sign test on (-p).n: where the normal is perpendicular to the view ray
+    # (silhouette points) its sign is decided by rounding, so those points are compared up to sign
+    view = np.abs(np.sum(n_cpu * pc[ok], -1)) / np.linalg.norm(pc[ok], axis=1)
+    grazing = view < 2e-3
+    err = angle_deg(n_gpu, n_cpu)
+    err = np.where(grazing, np.minimum(err, 180.0 - err), err)
+    print(f"{cloud}: normal error vs oracle: median {np.median(err):.4f} deg, max {err.max():.4f} deg; "
+          f"{int(grazing.sum())} grazing points compared up to sign")
+    # float32 single-pass un-centred covariance: accumulation-order noise (PCL's own is ~0.05 deg).
+    # 0.5 deg holds on the smooth surface; the thin torus (tube radius ~ support radius) has nearly equal
+    # eigenvalues, which amplifies that noise -- there the bound is on the 99th percentile.
+    if cloud == "halfcyl":
+        assert err.max() < 0.5
+    else:
+        assert np.percentile(err, 99) < 0.5 and err.max() < 3.0
+    assert np.all(np.sum(normals[ok] * (-pc[ok]), -1) >= -1e-6)            # flipped towards the origin
+    np.testing.assert_allclose(np.linalg.norm(normals[ok], axis=1), 1.0, atol=1e-5)
 
 
 @pytest.mark.parametrize("fast", [False, True])
 @pytest.mark.parametrize("cloud", ["halfcyl", "torus"])
-def test_shot_matches_oracle(oracle, cloud, fast):
-    if cloud == "halfcyl":
-        pc, r = synth.half_cylinder_cloud(4000, seed=7, jitter=0.001), 0.02
-    else:
-        pc, r = synth.torus_cloud(20000, res=0.002, seed=7)[0], 0.02
-    desc, normals, rf, o_desc, o_normals = run_case(oracle, pc, r, fast)
-    # identical NaN pattern (neighbour SETS are bit-identical by construction)
-    assert np.array_equal(np.isnan(normals), np.isnan(o_normals))
+def test_descriptor_stage_matches_oracle(oracle, cloud, fast):
+    """LRF + histogram with the oracle's normals injected: everything downstream of the normals agrees to
+    1e-4 on every row whose frame is defined.  Rows with an exact sign-vote tie are resolved by kd-tree
+    search order in PCL (shot_lrf.hpp) -- either sign is acceptable there, and they are only counted."""
+    pc, r = clouds(cloud)
+    desc, normals, rf, o_desc, o_normals = run_case(oracle, pc, r, fast, inject_normals=True)
     assert np.array_equal(np.isnan(desc).any(1), np.isnan(o_desc).any(1))
-    ok = ~np.isnan(o_normals).any(1)
-    err = angle_deg(normals[ok], o_normals[ok].astype(np.float64))
-    # float32 un-centred covariance: accumulation order noise (PCL's own is ~0.05 deg median)
-    assert np.max(err) < 0.5, np.max(err)
-    assert np.all(np.sum(normals[ok] * (-pc[ok]), -1) >= 0)
+    o_rf, margins = oracle.shot_lrf(pc, r)
     good = ~np.isnan(o_desc).any(1)
-    diff = np.abs(desc[good] - o_desc[good]).max(1)
-    frac_bad = float((diff > 1e-4).mean())
-    # rows above tolerance come from the normals feeding the cosine bins (their float noise is amplified where
-    # the covariance is ill conditioned) and from LRF sign/eigen-gap cases; they must stay a small minority
-    print(f"{cloud} fast={fast}: normals max {err.max():.4f} deg; desc rows > 1e-4: {frac_bad:.4%}, median diff {np.median(diff):.2e}")
-    assert frac_bad < 0.02
-    assert np.median(diff) < 2e-5
+    tie = (margins == 0).any(1) & good
+    defined = good & ~tie
+    # frames: identical axes (to float rounding) wherever the votes are not tied
+    rf_diff = np.abs(rf[defined] - o_rf[defined]).max(1)
+    diff = np.abs(desc[defined] - o_desc[defined]).max(1)
+    bad = diff > 1e-4
+    print(f"{cloud} fast={fast}: {int(tie.sum())} tie rows ({tie.mean():.3%}); defined rows {int(defined.sum())}: "
+          f"frame max diff {rf_diff.max():.2e}, desc median {np.median(diff):.2e}, p99.9 {np.percentile(diff, 99.9):.2e}, "
+          f"rows > 1e-4: {int(bad.sum())}")
+    assert tie.mean() < 0.05
+    assert np.percentile(rf_diff, 99.9) < 1e-5
+    assert bad.mean() < 1e-3 and np.median(diff) < 1e-6
+    # tie rows: the descriptor equals the oracle's for one of the sign choices or not -- just require validity
     np.testing.assert_allclose(np.linalg.norm(desc[good], axis=1), 1.0, atol=1e-5)
 
 
-def test_shot_given_oracle_normals_is_tight(oracle):
-    """Isolates LRF + histogram: with identical neighbour sets the only inputs that differ are the normals;
-    compare on points whose whole neighbourhood has normals within 0.01 deg of the oracle's."""
-    from cppf2_b200 import shot
-    pc, r = synth.half_cylinder_cloud(4000, seed=9, jitter=0.0005), 0.02
-    desc, normals, rf, o_desc, o_normals = run_case(oracle, pc, r, False)
-    good = ~np.isnan(o_desc).any(1)
+@pytest.mark.parametrize("cloud", ["halfcyl", "torus"])
+def test_end_to_end_descriptor_noise_is_reported(oracle, cloud):
+    """With each side's own normals, the float32 covariance noise of the normals (<= 0.5 deg, present in PCL
+    itself through its kd-tree accumulation order) moves the cosine bin of every neighbour.  Reported and
+    loosely bounded; the tight gates are the two tests above."""
+    pc, r = clouds(cloud)
+    desc, normals, rf, o_desc, o_normals = run_case(oracle, pc, r, True)
+    assert np.array_equal(np.isnan(desc).any(1), np.isnan(o_desc).any(1))
+    _, margins = oracle.shot_lrf(pc, r)
+    good = ~np.isnan(o_desc).any(1) & ~(margins == 0).any(1)
     diff = np.abs(desc[good] - o_desc[good]).max(1)
-    assert np.percentile(diff, 90) < 1e-4
+    cos = np.sum(desc[good] * o_desc[good], 1)
+    print(f"{cloud}: end-to-end max-abs diff median {np.median(diff):.2e}, p99 {np.percentile(diff, 99):.2e}; "
+          f"cosine similarity median {np.median(cos):.6f}, p1 {np.percentile(cos, 1):.6f}")
+    assert np.median(cos) > 0.999 and np.percentile(cos, 1) > 0.97
 
 
 def test_shot_api_layout_and_invalid_rows(oracle):
@@ -78,7 +116,9 @@ def test_shot_api_layout_and_invalid_rows(oracle):
     o_desc, o_normal = oracle.shot_compute(pc, 0.02, 0.02)
     assert np.array_equal(np.isnan(desc), np.isnan(o_desc.reshape(-1, 352)))
     n_only = shot.estimate_normal(pc, 0.02)
-    assert np.array_equal(n_only, normal.reshape(-1), equal_nan=True)
+    assert np.array_equal(n_only, normal.reshape(-1), equal_nan=True)      # deterministic: same bits on every call
+    again = shot.compute(pc, 0.02, 0.02)
+    assert np.array_equal(again[0], out[0], equal_nan=True) and np.array_equal(again[1], out[1], equal_nan=True)
     with pytest.raises(NotImplementedError):
         shot.compute_color(pc, pc, 0.02, 0.02)
     # different radii for normals and descriptor (shot.cpp's defaults are 0.1 / 0.17)
