@@ -1,0 +1,83 @@
+"""CUDA heads (through the C ABI) against the reference golden outputs and the torch float32 reference.
+float32 path: rtol 1e-4 / atol 2e-5 on logits and scale.  bf16 tensor-core path: against the bf16-emulated
+float32-accumulate reference, atol 1e-3 x logit range."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cppf2_b200 import synth  # noqa: E402
+from cppf2_b200.heads_spec import init_state_dict  # noqa: E402
+from tests.torch_heads_ref import Ref  # noqa: E402
+
+
+def make_inputs(n, t, seed):
+    rng = np.random.default_rng(seed)
+    pc = synth.half_cylinder_cloud(n, seed=seed)
+    idx = synth.sample_tuples(n, t, 5, seed=seed + 1)
+    shot = np.abs(rng.standard_normal((n, 352))).astype(np.float32)
+    shot /= np.linalg.norm(shot, axis=-1, keepdims=True)
+    shot[::17] = 0.0                                   # NaN rows scrubbed to zero by the caller (eval.py:215)
+    normal = rng.standard_normal((n, 3)).astype(np.float32)
+    normal /= np.linalg.norm(normal, axis=-1, keepdims=True)
+    desc = synth.unit_descriptors(n, 1024, seed=seed + 2)
+    return pc, idx, shot, normal, desc
+
+
+def test_fp32_heads_match_reference_golden(golden):
+    from cppf2_b200.heads import BeyondCPPFDINO, BeyondCPPFSHOT
+    g = golden("heads")
+    idx = g["idx"].astype(np.int64)
+    m = BeyondCPPFSHOT(dict(num_more=3)).cuda().eval()
+    m.load_state_dict(init_state_dict("shot", int(g["seed_shot"])))
+    cls, scale = m(torch.from_numpy(g["pc"]).cuda(), torch.from_numpy(idx).cuda(),
+                   torch.from_numpy(g["shot"].astype(np.float32)).cuda(), torch.from_numpy(g["normal"]).cuda())
+    assert cls.shape == (96, 6, 32) and scale.shape == (96, 3) and cls.is_cuda
+    np.testing.assert_allclose(cls.cpu().numpy(), g["cls_shot"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(scale.cpu().numpy(), g["scale_shot"], rtol=1e-4, atol=2e-5)
+    d = BeyondCPPFDINO(dict(num_more=3)).cuda().eval()
+    d.load_state_dict(init_state_dict("dino", int(g["seed_dino"])))
+    desc = synth.unit_descriptors(g["pc"].shape[0], 1024, seed=int(g["desc_seed"]))
+    cls, scale = d(g["pc"], desc, idx)                 # host inputs are accepted as well
+    np.testing.assert_allclose(cls.cpu().numpy(), g["cls_dino"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(scale.cpu().numpy(), g["scale_dino"], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("n,t", [(1000, 5000), (37, 1), (4096, 50000)])
+def test_fp32_heads_match_torch(n, t):
+    from cppf2_b200.heads import BeyondCPPFDINO, BeyondCPPFSHOT
+    pc, idx, shot, normal, desc = make_inputs(n, t, seed=n)
+    for branch, cls_ in (("shot", BeyondCPPFSHOT), ("dino", BeyondCPPFDINO)):
+        sd = init_state_dict(branch, 99)
+        m = cls_(dict(num_more=3)).cuda()
+        m.load_state_dict(sd)
+        ref = Ref(branch, sd, device="cuda")
+        tpc, tidx = torch.from_numpy(pc).cuda(), torch.from_numpy(idx).cuda()
+        with torch.no_grad():
+            if branch == "shot":
+                got = m(tpc, tidx, torch.from_numpy(shot).cuda(), torch.from_numpy(normal).cuda())
+                want = ref.forward_shot(tpc, tidx, torch.from_numpy(shot).cuda(), torch.from_numpy(normal).cuda())
+            else:
+                got = m(tpc, torch.from_numpy(desc).cuda(), tidx)
+                want = ref.forward_dino(tpc, torch.from_numpy(desc).cuda(), tidx)
+        for a, b in zip(got, want):
+            np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-4, atol=5e-5)
+
+
+def test_checkpoint_surface(tmp_path):
+    from cppf2_b200.heads import BeyondCPPFSHOT
+    sd = {k: torch.from_numpy(v) for k, v in init_state_dict("shot", 5).items()}
+    path = tmp_path / "ckpts" / "shot" / "bottle-num_more-3" / "lightning_logs" / "version_0" / "checkpoints" / "last.ckpt"
+    path.parent.mkdir(parents=True)
+    torch.save({"state_dict": sd, "epoch": 100}, path)
+    m = BeyondCPPFSHOT.load_from_checkpoint(path, cfg=dict(num_more=3)).cuda().eval()
+    assert m.checkpoint == str(path)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k])
+    missing = BeyondCPPFSHOT.load_from_checkpoint(tmp_path / "nope" / "a" / "b" / "last.ckpt", cfg=dict(num_more=3))
+    assert missing.checkpoint is None
+    with pytest.raises(ValueError):
+        bad = dict(sd)
+        bad["tuple_encoder.0.fc1.weight"] = torch.zeros(3, 3)
+        m.load_state_dict(bad)
