@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Contract benchmark of the CPPF++ pose-voting hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): one synthetic REAL275-shaped 640x480 depth frame with 6 instances,
+SHOT + DINO ensemble (random-init heads, seeded unit-norm stand-ins for the DINOv2 descriptors), T = 50 000
+tuples x 180 rotations per (instance, branch).  A step is one pass of the hot path over that frame: SHOT-352
++ normals, tuple sampling, both heads, multinomial decode, centre vote, back-vote filter, rotation votes,
+pose + ensemble selection -- 12 (instance, branch) votes = 600 000 tuples.  Depth back-projection and voxel
+down-sampling are "next" rows of the scope table and run once, untimed.
+
+metric / value : tuples voted per second, inputs resident in HBM when the timed region starts.
+e2e            : same metric through the public call (PoseEstimator.estimate) with HOST buffers: per step the
+                 clouds, descriptors and freshly sampled tuple indices are copied from pinned host memory and
+                 the pose records are read back.
+N > 1          : one process per GPU (torchrun), frames sharded across ranks, no data-path collective (weak
+                 scaling); time is the max over ranks.
+--impl reference: the CPU oracle (oracle/, the port of the reference's path: PCL-semantics SHOT in C++, torch-CPU
+                 float32 heads, C voting) on the host cores, one instance per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_PAIRS, NUM_ROTS, N_INSTANCES = 50000, 180, 6
+METRIC, UNIT = "tuples_voted_per_sec", "tuples/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def build_frame(frame_id: int):
+    """Synthetic frame -> per-instance clouds exactly as eval.py:185-201 prepares them (host, untimed)."""
+    from cppf2_b200 import synth
+    from cppf2_b200.config import default_category_cfg
+    from cppf2_b200.estimator import backproject_host, voxel_downsample_host
+    frame = synth.synth_real275_frame(frame_id, N_INSTANCES)
+    rng = np.random.default_rng(5000 + frame_id)
+    instances = []
+    for i, cat in enumerate(frame["cats"]):
+        cfg = default_category_cfg(cat)
+        pc, _ = backproject_host(frame["depth"] / 1000.0, synth.REAL275_K, frame["masks"][i])
+        if pc.shape[0] < 50:
+            continue
+        pc = pc[voxel_downsample_host(pc, cfg["res"], rng)]
+        if pc.shape[0] > 50000:                                              # eval.py:195-198
+            pc = pc[rng.integers(0, pc.shape[0], 50000)]
+        if ((pc.max(0) - pc.min(0)).max() / cfg["res"]) > 1000:              # eval.py:200
+            continue
+        desc = synth.unit_descriptors(pc.shape[0], 1024, seed=9000 + 10 * frame_id + i)
+        instances.append(dict(pc=np.ascontiguousarray(pc, dtype=np.float32), category=cat, desc=desc, cfg=cfg))
+    return instances
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                    reasons=reasons, samples=len(self.rows))
+
+
+def cpu_state_dicts(cats):
+    from cppf2_b200.heads_spec import init_state_dict
+    return {cat: {"dino": init_state_dict("dino", 1234 + 17 * ci), "shot": init_state_dict("shot", 1234 + 17 * ci + 1)}
+            for ci, cat in enumerate(cats)}
+
+
+def run_cpu_instance(inst, sds, rng, timings=None):
+    from oracle.pipeline_cpu import instance_pose_cpu
+    idx = rng.integers(0, inst["pc"].shape[0], (NUM_PAIRS, 5)).astype(np.int64)
+    return instance_pose_cpu(inst["pc"], idx, inst["cfg"], sds[inst["category"]], desc=inst["desc"], timings=timings,
+                             sym_y_only=inst["category"] in ("can", "bottle", "bowl"))
+
+
+def reference_arm(args):
+    """The reference's CPU implementation of the path (oracle port), all host threads, one instance per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import cpu as oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    oracle.set_num_threads(os.cpu_count() or 1)
+    instances = build_frame(0)
+    sds = cpu_state_dicts(sorted({i["category"] for i in instances}))
+    rng = np.random.default_rng(0)
+    per = 2 * NUM_PAIRS
+    for w in range(args.warmup):
+        run_cpu_instance(instances[w % len(instances)], sds, rng)
+    timings = {}
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        run_cpu_instance(instances[k % len(instances)], sds, rng, timings)
+    dt = time.perf_counter() - t0
+    value = per * args.steps / dt
+    sample = (f"1 instance x 2 branches x {NUM_PAIRS} tuples per step (of the {N_INSTANCES}-instance frame); stage seconds "
+              + ", ".join(f"{k} {v:.2f}" for k, v in timings.items()))
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": workload_config(),
+                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+def workload_config():
+    return {"workload": "synthetic REAL275-shaped 640x480 depth frame, 6 instances, SHOT+DINO ensemble (random-init heads, "
+                        "seeded unit-norm DINO descriptors), 50000 tuples x 180 rotations per (instance, branch)",
+            "tuples_per_step": 2 * NUM_PAIRS * N_INSTANCES, "num_pairs": NUM_PAIRS, "num_rots": NUM_ROTS, "sphere_bins": 720,
+            "l2": "256 MB buffer written between timed steps (L2 flush)", "parallelism": "frames sharded across ranks, no collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("CPPF_PRECISION", "-1")), help="heads: 0 fp32, 1 bf16 tcgen05, -1 best available")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the cppf2_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from cppf2_b200 import _lib
+    from cppf2_b200.estimator import Instance, PoseEstimator, build_models
+    from cppf2_b200.heads_spec import macs_per_tuple
+    _lib.load()
+    peaks = load_peaks()
+
+    raw = build_frame(rank)            # frame sharding: rank r owns frame r
+    cats = sorted({i["category"] for i in raw})
+    models, cfgs = build_models(cats, precision=0)
+    precision = args.precision
+    if precision < 0:                  # bf16 tcgen05 heads when the library carries them, else the float32 path
+        probe = models[cats[0]]["shot"]
+        probe._ensure(dev)
+        precision = 1 if _lib.load().cppf_heads_has_tc(probe._handle) else 0
+    for cat in models:
+        for m in models[cat].values():
+            m.precision = precision
+    est = PoseEstimator(models, cfgs, num_pairs=NUM_PAIRS, num_rots=NUM_ROTS, seed=rank)
+    n_inst = len(raw)
+    tuples_per_step = 2 * NUM_PAIRS * n_inst
+
+    # ---- device-resident inputs for the kernel-side number --------------------------------------------------
+    rng = np.random.default_rng(100 + rank)
+    dev_instances = []
+    for inst in raw:
+        idx = torch.from_numpy(rng.integers(0, inst["pc"].shape[0], (NUM_PAIRS, 5), dtype=np.int32)).to(dev)
+        di = Instance(pc=torch.from_numpy(inst["pc"]).to(dev), category=inst["category"], desc=torch.from_numpy(inst["desc"]).to(dev),
+                      point_idxs=idx)
+        di.cells_hint = est.voter.grid_cells_on_host(inst["pc"], inst["cfg"]["res"])
+        dev_instances.append(di)
+    pose_buf = torch.zeros((n_inst * 2, est.pose_bytes), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        est.enqueue(dev_instances, pose_buf)
+    torch.cuda.synchronize()
+    launches = est.launches
+
+    # per-stage CUDA events on the launching stream (for the roofline of the dominant kernel)
+    stage_events = {}
+
+    def hook(stage, begin):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        stage_events.setdefault(stage, []).append(ev)
+    est.timing_hook = hook
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    step_events = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        est.enqueue(dev_instances, pose_buf)
+        b.record()
+        step_events.append((a, b))
+    barrier()
+    clocks = sampler.summary()
+    est.timing_hook = None
+    step_ms = [a.elapsed_time(b) for a, b in step_events]
+    total_ms = float(sum(step_ms))
+    stage_ms = {}
+    for stage, evs in stage_events.items():
+        stage_ms[stage] = sum(evs[i].elapsed_time(evs[i + 1]) for i in range(0, len(evs) - 1, 2)) / args.steps
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        cnt = torch.tensor([tuples_per_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        tuples_all = float(cnt.item())
+    else:
+        tuples_all = float(tuples_per_step)
+    ms_per_step = total_ms / args.steps
+    value = tuples_all / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public call with host buffers -------------------------------------------------
+    host_instances = []
+    h2d = 0
+    for inst in raw:
+        pc_p, desc_p = torch.from_numpy(inst["pc"]).pin_memory(), torch.from_numpy(inst["desc"]).pin_memory()
+        host_instances.append((pc_p, desc_p, inst))
+        h2d += pc_p.numel() * 4 + desc_p.numel() * 4 + NUM_PAIRS * 5 * 4
+    idx_pinned = [torch.empty((NUM_PAIRS, 5), dtype=torch.int32).pin_memory() for _ in raw]
+    erng = np.random.default_rng(200 + rank)
+
+    def e2e_step():
+        insts = []
+        for k, (pc_p, desc_p, inst) in enumerate(host_instances):
+            idx_pinned[k].numpy()[...] = erng.integers(0, pc_p.shape[0], (NUM_PAIRS, 5), dtype=np.int32)   # eval.py:207
+            it = Instance(pc=pc_p, category=inst["category"], desc=desc_p, point_idxs=idx_pinned[k].to(dev, non_blocking=True))
+            it.cells_hint = dev_instances[k].cells_hint
+            insts.append(it)
+        return est.estimate(insts)
+
+    for _ in range(2):
+        poses = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        poses = e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = tuples_all / (e2e_ms / args.steps * 1e-3)
+    d2h = n_inst * 2 * est.pose_bytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------
+    n_pts = sum(i["pc"].shape[0] for i in raw)
+    shares = {k: v / ms_per_step for k, v in stage_ms.items()}
+    heads_ms = stage_ms.get("heads_shot", 0.0) + stage_ms.get("heads_dino", 0.0)
+    vote_ms = stage_ms.get("vote_shot", 0.0) + stage_ms.get("vote_dino", 0.0)
+    shot_ms = stage_ms.get("shot", 0.0)
+    flops = 2.0 * (macs_per_tuple("shot") + macs_per_tuple("dino")) * NUM_PAIRS * n_inst + 2.0 * (258048 + 262144) * n_pts
+    vote_bytes = 2 * n_inst * (NUM_PAIRS * 24) + 2 * n_pts * 12
+    shot_bytes = n_pts * 1432
+    kernels = {
+        "heads": {"ms": heads_ms, "share": heads_ms / ms_per_step, "achieved_tflops": flops / (heads_ms * 1e-3) / 1e12 if heads_ms else None},
+        "vote_chain": {"ms": vote_ms, "share": vote_ms / ms_per_step, "alg_GBps": vote_bytes / (vote_ms * 1e-3) / 1e9 if vote_ms else None},
+        "shot": {"ms": shot_ms, "share": shot_ms / ms_per_step, "alg_GBps": shot_bytes / (shot_ms * 1e-3) / 1e9 if shot_ms else None},
+    }
+    if heads_ms >= max(vote_ms, shot_ms):
+        peak = peaks["bf16_sustained"]
+        ach = kernels["heads"]["achieved_tflops"]
+        roofline = {"kernel": "heads (ResLayer chains, %s)" % ("bf16 tcgen05" if precision == 1 else "fp32 CUDA cores"), "bound": "tensor",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained"}
+    elif vote_ms >= shot_ms:
+        ach = kernels["vote_chain"]["alg_GBps"]
+        roofline = {"kernel": "vote chain (decode, centre vote, back-vote, rotation, pose)", "bound": "hbm", "achieved": ach,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+    else:
+        ach = kernels["shot"]["alg_GBps"]
+        roofline = {"kernel": "SHOT-352 (grid build, normals, LRF + histogram)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, one full frame ----------------------------------
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        from oracle import cpu as oracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        oracle.set_num_threads(os.cpu_count() or 1)
+        sds = cpu_state_dicts(cats)
+        crng = np.random.default_rng(0)
+        timings = {}
+        t0 = time.perf_counter()
+        n_done = 0
+        for inst in raw:
+            run_cpu_instance(inst, sds, crng, timings)
+            n_done += 1
+            if time.perf_counter() - t0 > 30.0:
+                break
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": 2 * NUM_PAIRS * n_done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"{n_done} of {n_inst} instances of the same frame, both branches, {dt:.1f} s; stage seconds "
+                                  + ", ".join(f"{k} {v:.2f}" for k, v in timings.items())}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if precision == 1 else "f32", "data": "synthetic", "config": workload_config(),
+            "frames_per_sec": world * 1e3 / ms_per_step, "instances": n_inst, "points": n_pts,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps, "frames_per_sec": world * 1e3 / (e2e_ms / args.steps)},
+            "gpu_launches": launches * args.steps,
+            "pose_check": {"finite": bool(all(p is not None and np.isfinite(p.RT).all() for p in poses)),
+                           "branches": [p.branch for p in poses if p is not None]}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,7 @@ SIGNATURES = {
     "cppf_shot_compute_color": (I, [P, P, I64, F, F, P, P]),
     "cppf_heads_create": (I, [I, I, C.POINTER(C.c_float), I64, C.POINTER(P)]),
     "cppf_heads_destroy": (I, [P]),
+    "cppf_heads_has_tc": (I, [P]),
     "cppf_heads_workspace_bytes": (I64, [P, I64, I64, I]),
     "cppf_heads_forward": (I, [P, I, P, I64, P, I, I64, I64, P, P, P, P, P, I64, P]),
 }

@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_f32_kernel(F32Chain chain
         if (a.prologue == kRowsFromGlobal) {
             for (int i = t; i < kTM * in_pad; i += kChainThreads) {
                 const int r = i / in_pad, c = i % in_pad;
-                buf[0][r * kW0 + c] = (r < valid && c < in_dim) ? a.x[(row_base + r) * a.x_dim + c] : 0.0f;
+                float v = (r < valid && c < in_dim) ? a.x[(row_base + r) * a.x_dim + c] : 0.0f;
+                buf[0][r * kW0 + c] = (v == v) ? v : 0.0f;   // NaN rows of invalid SHOT points count as zeros (eval.py:215)
             }
         } else {
             const int P = a.arity * (a.arity - 1) / 2;
@@ -251,7 +252,8 @@ __global__ void __launch_bounds__(kChainThreads) linear_f32_kernel(F32Linear lin
             __syncthreads();
             for (int i = t; i < kTM * 256; i += kChainThreads) {
                 const int r = i >> 8, k = i & 255;
-                s_x[i] = r < valid ? x[(row_base + r) * K + c * 256 + k] : 0.0f;
+                const float v = r < valid ? x[(row_base + r) * K + c * 256 + k] : 0.0f;
+                s_x[i] = (v == v) ? v : 0.0f;
             }
             __syncthreads();
             const float *wt = lin.wt + static_cast<int64_t>(c) * 256 * lin.dout;
@@ -431,6 +433,8 @@ CPPF_API int cppf_heads_destroy(cppf_heads *h) {
     delete h;
     return CPPF_OK;
 }
+
+CPPF_API int cppf_heads_has_tc(const cppf_heads *h) { return (h && h->tc) ? 1 : 0; }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 

@@ -114,7 +114,13 @@ __device__ __forceinline__ void encode_tuple_geometry(const float *__restrict__ 
     if (!with_normals) return;
     for (int i = 0; i < arity; ++i)
         for (int j = i + 1; j < arity; ++j) {
-            const float *a = normal + 3 * pt[i], *b = normal + 3 * pt[j];
+            float a[3], b[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {   // NaN normals of points with < 3 neighbours count as zeros (eval.py:216)
+                const float av = normal[3 * pt[i] + k], bv = normal[3 * pt[j] + k];
+                a[k] = (av == av) ? av : 0.0f;
+                b[k] = (bv == bv) ? bv : 0.0f;
+            }
             // torch.sum(n_i * n_j, -1) over 3 elements: ((x + y) + z); the second operand negates n_i first
             const float d = __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
             const float e = __fadd_rn(__fadd_rn(__fmul_rn(-a[0], b[0]), __fmul_rn(-a[1], b[1])), __fmul_rn(-a[2], b[2]));

@@ -13,6 +13,7 @@ CPPF_API int cppf_shot_compute_color(const float *, const float *, int64_t, floa
 #ifndef CPPF_HAVE_HEADS
 CPPF_API int cppf_heads_create(int, int, const float *, int64_t, cppf_heads **) { return CPPF_ERR_UNSUPPORTED; }
 CPPF_API int cppf_heads_destroy(cppf_heads *) { return CPPF_ERR_UNSUPPORTED; }
+CPPF_API int cppf_heads_has_tc(const cppf_heads *) { return 0; }
 CPPF_API int64_t cppf_heads_workspace_bytes(const cppf_heads *, int64_t, int64_t, int) { return 0; }
 CPPF_API int cppf_heads_forward(const cppf_heads *, int, const float *, int64_t, const void *, int, int64_t, int64_t, const float *,
                                 const float *, float *, float *, void *, int64_t, void *) { return CPPF_ERR_UNSUPPORTED; }

@@ -684,6 +684,7 @@ static int shot_run(const float *pc, int64_t n, float normal_r, float shot_r, fl
 
 CPPF_API int cppf_shot_compute(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals,
                                void *ws, int64_t ws_bytes, void *stream) {
+    if (n == 0) return CPPF_OK;
     if (!desc) return CPPF_ERR_INVALID_ARGUMENT;
     // float interpolation weights: indistinguishable from PCL's double ones at float32 output precision
     // (tests/test_gpu_shot.py compares both against the oracle), and faster
@@ -696,6 +697,7 @@ CPPF_API int cppf_shot_compute(const float *pc, int64_t n, float normal_r, float
 CPPF_API int cppf_shot_compute_ex(const float *pc, int64_t n, float normal_r, float shot_r, float *desc, float *normals,
                                   float *rf_out, int fast_math, const float *normals_in, void *ws, int64_t ws_bytes,
                                   void *stream) {
+    if (n == 0) return CPPF_OK;
     if (!desc) return CPPF_ERR_INVALID_ARGUMENT;
     return shot_run(pc, n, normal_r, shot_r, desc, normals, rf_out, fast_math, normals_in, ws, ws_bytes, stream);
 }

@@ -120,14 +120,16 @@ class PoseVoter:
 
     # -- the chain -----------------------------------------------------------------------------------
     def vote(self, pc, point_idxs_all, cfg: VoteConfig, pred_scales=None, *, bins=None, logits=None, u01=None,
-             seed: int = 0, scale_override=None, cells_hint: Optional[int] = None):
+             seed: int = 0, scale_override=None, cells_hint: Optional[int] = None, pose_out: Optional[torch.Tensor] = None):
         """Enqueues the whole chain on the current stream; returns self (read with .result()).
 
         Exactly one of `bins` (uint8 [T,6] injected multinomial draws) or `logits` (f32 [T,6,num_bins])
         must be given.  With logits, `u01` (f32 [T,6]) injects the uniforms, else a counter-based
         generator keyed by `seed` is used.  `pred_scales` f32 [T,3] is the scale head output;
         `scale_override` (3 floats, device or host) reproduces the reference's reuse of the DINO-branch
-        scale in the SHOT branch (eval.py:308-310).
+        scale in the SHOT branch (eval.py:308-310).  `pose_out` (uint8 CUDA tensor of sizeof(cppf_pose)
+        bytes) receives the pose record instead of the voter's own slot, so that many votes can be queued
+        before anything is read back.
         """
         lib = self.lib
         if isinstance(pc, np.ndarray) and cells_hint is None:
@@ -205,7 +207,8 @@ class PoseVoter:
                                      None if ps is None else ps.data_ptr(), self.kept_list.data_ptr(),
                                      self.summary.data_ptr(), self.counts.data_ptr(), sphere.data_ptr(), S,
                                      self.center.data_ptr(), up_loc, right_loc, int(cfg.loss_y_only),
-                                     None if so is None else so.data_ptr(), self.pose.data_ptr(), self.ws_pose.data_ptr(),
+                                     None if so is None else so.data_ptr(),
+                                     (self.pose if pose_out is None else pose_out).data_ptr(), self.ws_pose.data_ptr(),
                                      self.ws_pose.numel(), s), "cppf_pose_finalize")
         launches += 4
         self.launches = launches
@@ -213,8 +216,22 @@ class PoseVoter:
         self._T = T
         return self
 
+    @staticmethod
+    def scale_ptr_of(pose_tensor: torch.Tensor) -> torch.Tensor:
+        """View of the 3 scale floats inside a device pose record (to chain as `scale_override`)."""
+        off = Pose.scale.offset
+        return pose_tensor[off:off + 12].view(torch.float32)
+
+    @staticmethod
+    def parse(pose_bytes, extra_status: int = 0) -> "PoseResult":
+        p = Pose.from_buffer_copy(bytes(pose_bytes))
+        return PoseResult(R=np.array(list(p.R)).reshape(3, 3), t=np.array(list(p.t)), scale=np.array(list(p.scale), np.float32),
+                          scale_norm=float(p.scale_norm), loss=float(p.loss), kept=int(p.kept), bin_up=int(p.bin_up),
+                          bin_right=int(p.bin_right), count_up=float(p.count_up), count_right=float(p.count_right),
+                          status=int(p.status) | int(extra_status))
+
     def result(self) -> PoseResult:
-        """Synchronises the current stream and reads the pose record (200 bytes D2H)."""
+        """Synchronises the current stream and reads the pose record (152 bytes D2H)."""
         p = read_struct(self.pose, Pose)
         status = int(self.status.item()) | int(p.status)
         return PoseResult(R=np.array(list(p.R)).reshape(3, 3), t=np.array(list(p.t)), scale=np.array(list(p.scale), np.float32),

@@ -228,6 +228,8 @@ typedef struct cppf_heads cppf_heads;   /* opaque, device-resident packed weight
  * every nn.Linear in the order of cppf2_b200.heads_spec.linear_shapes(); n_floats is checked. */
 int cppf_heads_create(int branch, int num_more, const float *weights_host, int64_t n_floats, cppf_heads **out);
 int cppf_heads_destroy(cppf_heads *h);
+/* 1 when the bf16 tensor-core weights were packed (precision 1 available), else 0. */
+int cppf_heads_has_tc(const cppf_heads *h);
 int64_t cppf_heads_workspace_bytes(const cppf_heads *h, int64_t T, int64_t n, int precision);
 
 /* precision: 0 = fp32 CUDA-core reference path, 1 = bf16 tensor-core (tcgen05) path.

@@ -233,7 +233,7 @@ def lower_median(x: np.ndarray) -> np.ndarray:
 
 
 def instance_body(pc, point_idxs_all, bins, pred_scales, cfg_up, cfg_right, cfg_front, res, num_rots=180,
-                  backproj_ratio=0.1, imp_wt_margin=0.01, angle_tol=1.0, num_bins=32, sym_y_only=False):
+                  backproj_ratio=0.1, imp_wt_margin=0.01, angle_tol=1.0, num_bins=32, sym_y_only=False, scale_override=None):
     """One branch of the per-instance body, eval.py:225-313 and :358-363 with opt=False, draws injected.
 
     Returns a dict with every intermediate the CUDA pipeline is compared on.
@@ -257,7 +257,10 @@ def instance_body(pc, point_idxs_all, bins, pred_scales, cfg_up, cfg_right, cfg_
     b_up = int(np.argmax(counts_up.astype(np.float32)))
     b_right = int(np.argmax(counts_right.astype(np.float32)))
     R_est = assemble_rotation(sphere[b_up], sphere[b_right], cfg_up, cfg_right)
-    pred_scale = lower_median(np.asarray(pred_scales, dtype=np.float32)[mask])
+    if scale_override is not None:      # eval.py:308-310: the SHOT branch keeps the DINO branch's scale
+        pred_scale = np.asarray(scale_override, dtype=np.float32)
+    else:
+        pred_scale = lower_median(np.asarray(pred_scales, dtype=np.float32)[mask])
     scale_norm = np.linalg.norm(pred_scale)
     pc_canon = (pc - T_est) @ R_est / scale_norm
     loss = np.abs(pc_canon[idx[mask, :2]] - pred[mask])

@@ -1,5 +1,5 @@
-"""Plain PyTorch float32 restatement of the two BeyondCPPF heads (train_shot.py:19-122,
-train_dino.py:20-133), test-only.  Pinned against tests/golden/heads.npz (minted from the reference
+"""TEST INFRASTRUCTURE ONLY.  Plain PyTorch float32 restatement of the two BeyondCPPF heads
+(train_shot.py:19-122, train_dino.py:20-133); also the heads leg of the CPU baseline in bench.py.  Pinned against tests/golden/heads.npz (minted from the reference
 modules themselves); used as the CPU/GPU float32 reference for the CUDA heads at sizes the golden
 fixture does not cover, and -- with emulate_bf16=True -- as the bf16-rounded, fp32-accumulate
 reference of the tensor-core path."""

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 from cppf2_b200 import synth  # noqa: E402
 from cppf2_b200.heads_spec import init_state_dict  # noqa: E402
-from tests.torch_heads_ref import Ref  # noqa: E402
+from oracle.heads_torch import Ref  # noqa: E402
 
 
 def make_inputs(n, t, seed):

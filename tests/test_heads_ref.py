@@ -1,11 +1,11 @@
-"""The torch float32 restatement of the heads (tests/torch_heads_ref.py) against the golden outputs of
+"""The torch float32 restatement of the heads (oracle/heads_torch.py) against the golden outputs of
 the reference's own BeyondCPPF modules (tests/golden/heads.npz)."""
 import numpy as np
 import torch
 
 from cppf2_b200 import synth
 from cppf2_b200.heads_spec import init_state_dict, linear_shapes, macs_per_tuple
-from tests.torch_heads_ref import Ref
+from oracle.heads_torch import Ref
 
 
 def test_spec_counts_match_survey():
