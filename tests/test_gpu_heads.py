@@ -81,3 +81,40 @@ def test_checkpoint_surface(tmp_path):
         bad = dict(sd)
         bad["tuple_encoder.0.fc1.weight"] = torch.zeros(3, 3)
         m.load_state_dict(bad)
+
+
+def _tc_available(model):
+    from cppf2_b200 import _lib
+    model._ensure(torch.device("cuda", torch.cuda.current_device()))
+    return bool(_lib.load().cppf_heads_has_tc(model._handle))
+
+
+@pytest.mark.parametrize("n,t", [(700, 128), (1000, 5000), (4096, 50000), (333, 77)])
+def test_bf16_tensor_core_shot_head(n, t):
+    """tcgen05 path vs the bf16-emulated reference (operands rounded to bf16, float32 accumulate): the only
+    differences are accumulation order inside the tensor core and bf16 roundings that land on a tie."""
+    from cppf2_b200.heads import BeyondCPPFSHOT
+    pc, idx, shot, normal, desc = make_inputs(n, t, seed=n + 1)
+    sd = init_state_dict("shot", 321)
+    m = BeyondCPPFSHOT(dict(num_more=3), precision=1).cuda()
+    m.load_state_dict(sd)
+    if not _tc_available(m):
+        pytest.skip("library built without the tcgen05 heads")
+    tpc, tidx = torch.from_numpy(pc).cuda(), torch.from_numpy(idx).cuda()
+    tshot, tnormal = torch.from_numpy(shot).cuda(), torch.from_numpy(normal).cuda()
+    cls, scale = m(tpc, tidx, tshot, tnormal)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want_cls, want_scale = Ref("shot", sd, emulate_bf16=True, device="cuda").forward_shot(tpc, tidx, tshot, tnormal)
+        f32_cls, f32_scale = Ref("shot", sd, device="cuda").forward_shot(tpc, tidx, tshot, tnormal)
+    rng_cls = float(want_cls.max() - want_cls.min())
+    rng_scale = float(want_scale.max() - want_scale.min()) + 1e-3
+    err_cls = float((cls - want_cls).abs().max())
+    err_scale = float((scale - want_scale).abs().max())
+    print(f"T={t}: logits range {rng_cls:.3f}, max |tc - bf16 ref| {err_cls:.2e}, |tc - fp32 ref| {float((cls - f32_cls).abs().max()):.2e}; "
+          f"scale max err {err_scale:.2e}")
+    assert err_cls <= 2e-3 * rng_cls + 1e-4 and err_scale <= 2e-3 * rng_scale + 1e-4
+    # against float32: reported above, loosely bounded (about 1 % of the logit range with random-init weights)
+    assert float((cls - f32_cls).abs().max()) < 0.05 * rng_cls
+    agree = (cls.argmax(-1) == f32_cls.argmax(-1)).float().mean().item()
+    assert agree > 0.97
