@@ -186,14 +186,16 @@ def main():
     raw = build_frame(rank)            # frame sharding: rank r owns frame r
     cats = sorted({i["category"] for i in raw})
     models, cfgs = build_models(cats, precision=0)
-    precision = args.precision
-    if precision < 0:                  # bf16 tcgen05 heads when the library carries them, else the float32 path
-        probe = models[cats[0]]["shot"]
-        probe._ensure(dev)
-        precision = 1 if _lib.load().cppf_heads_has_tc(probe._handle) else 0
+    # heads precision per model: bf16 tcgen05 where the library carries the packed tensor-core weights for that
+    # branch, else the float32 path (--precision 0 forces float32 everywhere)
+    used = set()
     for cat in models:
         for m in models[cat].values():
-            m.precision = precision
+            m._ensure(dev)
+            has_tc = bool(_lib.load().cppf_heads_has_tc(m._handle))
+            m.precision = 1 if (has_tc and args.precision != 0) else 0
+            used.add((m.branch, m.precision))
+    precision = 1 if all(p == 1 for _, p in used) else (0 if all(p == 0 for _, p in used) else 2)
     est = PoseEstimator(models, cfgs, num_pairs=NUM_PAIRS, num_rots=NUM_ROTS, seed=rank)
     n_inst = len(raw)
     tuples_per_step = 2 * NUM_PAIRS * n_inst
@@ -317,7 +319,7 @@ def main():
     if heads_ms >= max(vote_ms, shot_ms):
         peak = peaks["bf16_sustained"]
         ach = kernels["heads"]["achieved_tflops"]
-        roofline = {"kernel": "heads (ResLayer chains, %s)" % ("bf16 tcgen05" if precision == 1 else "fp32 CUDA cores"), "bound": "tensor",
+        roofline = {"kernel": "heads (ResLayer chains, %s)" % {0: "fp32 CUDA cores", 1: "bf16 tcgen05", 2: "SHOT bf16 tcgen05 + DINO fp32 CUDA cores"}[precision], "bound": "tensor",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained"}
     elif vote_ms >= shot_ms:
         ach = kernels["vote_chain"]["alg_GBps"]
@@ -351,7 +353,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if precision == 1 else "f32", "data": "synthetic", "config": workload_config(),
+            "dtype": {0: "f32", 1: "bf16", 2: "bf16 (SHOT head, tcgen05) + f32 (DINO head)"}[precision], "data": "synthetic", "config": workload_config(),
             "frames_per_sec": world * 1e3 / ms_per_step, "instances": n_inst, "points": n_pts,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -62,6 +62,7 @@ struct Phase {
     int action;           // what warps 0-7 do before the phase's MMAs
     int wait_done;        // the action first waits for the previous phase's MMAs
     int has_mma;
+    int acc_prev;         // keep accumulating into the previous phase's D (K-chunked plain Linear)
     int n;                // UMMA N of this phase's accumulators (multiple of 16)
     int n_parts;
     Part part[2];
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__
                     ++act_seq;
                     tc_fence_after();
                     const uint32_t idesc = instr_desc(ph.n);
-                    uint32_t accumulate = 0;
+                    uint32_t accumulate = ph.acc_prev ? 1u : 0u;
                     for (int q = 0; q < ph.n_parts; ++q) {
                         const uint32_t a_base = smem_u32(ph.part[q].a_buf == 0 ? bufX : bufH);
                         int k_done = 0;
@@ -450,6 +451,15 @@ struct Builder {
                     bf16_bits(W[static_cast<size_t>(n) * k_real + src]);
         }
     }
+    // same for an explicit list of source columns of W [n_real][ld]
+    void push_weight_cols(const float *W, int n_real, int ld, int n_pad, int k_pad, const std::vector<int> &cols) {
+        const size_t off = stream.size();
+        stream.resize(off + static_cast<size_t>(n_pad) * k_pad, 0);
+        for (size_t k = 0; k < cols.size(); ++k)
+            for (int n = 0; n < n_real; ++n)
+                stream[off + (k >> 3) * static_cast<size_t>(n_pad) * 8 + static_cast<size_t>(n) * 8 + (k & 7)] =
+                    bf16_bits(W[static_cast<size_t>(n) * ld + cols[k]]);
+    }
     int64_t push_bias(const float *a, const float *b, int n_real, int n_pad) {
         const int64_t off = static_cast<int64_t>(bias.size());
         for (int i = 0; i < n_pad; ++i) bias.push_back(i < n_real ? a[i] + (b ? b[i] : 0.0f) : 0.0f);
@@ -549,28 +559,61 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         cur->out_ld = 64;
         cur->cols = 64;
         st->point_cols = 64;
-    } else {               // desc_transform: plain Linear 1024 -> 256 over four 256-column chunks
+    } else {               // desc_transform (train_dino.py:80,95), hoisted per point: Linear 1024 -> 256 as four K-chunks
+        const LinearDesc &L = m.desc_transform;
         for (int c = 0; c < 4; ++c) {
-            Phase &ph = pb.add(kActLoadRows, c > 0);
+            Phase &ph = pb.add(kActLoadRows, c > 0);     // X is refilled only after the previous chunk's MMAs retired
             ph.dst_buf = 0;
             ph.chunk = c;
             ph.cols = 256;
             ph.has_mma = 1;
+            ph.acc_prev = c > 0;
             ph.n = 256;
             ph.n_parts = 1;
             ph.part[0] = Part{0, 256, Builder::slabs(256)};
+            std::vector<int> cols(256);
+            for (int k = 0; k < 256; ++k) cols[k] = c * 256 + k;
+            pb.push_weight_cols(w + L.w, 256, L.din, 256, 256, cols);
+            ph.bias_off = pb.push_bias(w + L.b, nullptr, 256, 256);
         }
-        // one accumulator across the chunks would need D to survive between phases; instead pack the four chunk
-        // weights as four GEMMs whose partial sums are added by the chunked epilogue below
-        // (kept simple: each chunk's MMAs accumulate because `accumulate` is reset per phase only)
-        delete st;
-        return CPPF_ERR_UNSUPPORTED;
+        Phase &fin = pb.add(kActFinal, 1);
+        fin.out_sel = 2;
+        fin.out_ld = 256;
+        fin.cols = 256;
+        st->point_cols = 256;
     }
     // ---- per-tuple program -------------------------------------------------------------------------------
     Builder tb;
     tb.w = w;
-    Phase *cur = &tb.add(kActEncodeShot, 0);
-    cur = tb.stack(m.tuple_encoder, cur, Builder::pad16(m.tuple_encoder.in_dim()), nullptr);
+    Phase *cur;
+    if (m.branch == 0) {
+        cur = &tb.add(kActEncodeShot, 0);
+        cur = tb.stack(m.tuple_encoder, cur, Builder::pad16(m.tuple_encoder.in_dim()), nullptr);
+    } else {
+        // desc_pair_transform over the 5 gathered (already transformed) descriptors (train_dino.py:95-96), then
+        // the tile is [pair 256 | coords 30 | pad 2]: tuple_encoder.0's input columns are permuted to match
+        const LinearDesc &L = m.desc_pair_transform;
+        for (int c = 0; c < m.arity; ++c) {
+            Phase &ph = tb.add(kActGather, c > 0);
+            ph.dst_buf = 0;
+            ph.chunk = c;
+            ph.has_mma = 1;
+            ph.acc_prev = c > 0;
+            ph.n = 256;
+            ph.n_parts = 1;
+            ph.part[0] = Part{0, 256, Builder::slabs(256)};
+            std::vector<int> cols(256);
+            for (int k = 0; k < 256; ++k) cols[k] = c * 256 + k;
+            tb.push_weight_cols(w + L.w, 256, L.din, 256, 256, cols);
+            ph.bias_off = tb.push_bias(w + L.b, nullptr, 256, 256);
+        }
+        cur = &tb.add(kActPairOut, 1);
+        const int geo = 3 * m.n_pairs;
+        std::vector<int> perm;
+        for (int k = 0; k < 256; ++k) perm.push_back(geo + k);
+        for (int k = 0; k < geo; ++k) perm.push_back(k);
+        cur = tb.stack(m.tuple_encoder, cur, Builder::pad16(256 + geo), &perm);
+    }
     cur->store_feat = 1;                         // feat = tuple_encoder output, needed by both heads
     cur = tb.stack(m.logit_encoder, cur, 256, nullptr);
     cur->action = kActFinal;                     // logits [T,192] float32

