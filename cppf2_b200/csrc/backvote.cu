@@ -81,7 +81,15 @@ __global__ void __launch_bounds__(256) select_pass_kernel(const float *__restric
     for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < T; t += stride) {
         const uint32_t key = float_to_key(errs[t]);
         if (pass < 4) {
-            if ((key & decided) == (prefix & decided)) atomicAdd(&s_hist[(key >> shift) & 0xffu], 1u);
+            // back-vote errors share their leading digits (same exponent), so a plain shared-memory atomic per key
+            // serialises on a handful of bins: lanes with equal digits elect one leader that adds the group's size
+            const bool in_prefix = (key & decided) == (prefix & decided);
+            const uint32_t active = __ballot_sync(__activemask(), in_prefix);
+            if (in_prefix) {
+                const uint32_t digit = (key >> shift) & 0xffu;
+                const uint32_t peers = __match_any_sync(active, digit);
+                if (lane_id() == __ffs(peers) - 1) atomicAdd(&s_hist[digit], static_cast<uint32_t>(__popc(peers)));
+            }
         } else if (key > prefix) {
             local_min = key < local_min ? key : local_min;
         }
@@ -104,25 +112,36 @@ __global__ void __launch_bounds__(256) select_pass_kernel(const float *__restric
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&st->tickets[pass], 1u) == gridDim.x - 1);
     __syncthreads();
-    if (!s_last || threadIdx.x != 0) return;
+    if (!s_last) return;
     __threadfence();
     if (pass < 4) {
-        unsigned long long k = pass == 0 ? static_cast<unsigned long long>(rank_lo) : st->k;
-        unsigned long long below = pass == 0 ? 0ull : st->below;
-        volatile uint32_t *h = st->hist[pass];
-        int d = 0;
-        unsigned long long cum = 0;
-        for (; d < 256; ++d) {
-            const unsigned long long c = h[d];
-            if (cum + c > k) break;
-            cum += c;
+        // the last CTA scans the 256 bins together: inclusive prefix sum, then the first bin whose cumulative
+        // count exceeds the remaining rank is the digit (a one-thread scan costs ~200 dependent L2 reads)
+        __shared__ unsigned long long s_cum[256];
+        __shared__ int s_digit;
+        const unsigned long long k = pass == 0 ? static_cast<unsigned long long>(rank_lo) : st->k;
+        const unsigned long long below = pass == 0 ? 0ull : st->below;
+        const unsigned long long mine = *reinterpret_cast<volatile uint32_t *>(&st->hist[pass][threadIdx.x]);
+        s_cum[threadIdx.x] = mine;
+        if (threadIdx.x == 0) s_digit = 256;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const unsigned long long add = threadIdx.x >= o ? s_cum[threadIdx.x - o] : 0ull;
+            __syncthreads();
+            s_cum[threadIdx.x] += add;
+            __syncthreads();
         }
+        if (s_cum[threadIdx.x] > k) atomicMin(&s_digit, static_cast<int>(threadIdx.x));
+        __syncthreads();
+        if (threadIdx.x != 0) return;
+        int d = s_digit;
         if (d == 256) d = 255;  // rank beyond the data (T == 0); keeps the state well defined
+        const unsigned long long cum = d > 0 ? s_cum[d - 1] : 0ull;
         st->prefix = prefix | (static_cast<uint32_t>(d) << shift);
         st->k = k - cum;
         st->below = below + cum;
-        st->equal = h[d];
-    } else {
+        st->equal = s_cum[d] - cum;
+    } else if (threadIdx.x == 0) {
         // both order statistics are known: s[rank_lo] = prefix; s[rank_lo+1] is the same value when the
         // run of equal keys extends past rank_lo, else the smallest larger key (numpy clips at T-1)
         const float s_lo = key_to_float(prefix);

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
     const int32_t *__restrict__ kept_list, const int64_t *__restrict__ kept_count, int64_t M,
     const int32_t *__restrict__ imp, const cppf_backvote_summary *__restrict__ summary, double margin,
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R, const float *__restrict__ sphere, int S,
-    float cos_thr, int band, double *__restrict__ counts) {
+    float cos_thr, int band, double *__restrict__ counts, int part, int n_parts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_bins = reinterpret_cast<double *>(smem_raw);                   // [n_theta][S]
     float *s_sphere = reinterpret_cast<float *>(s_bins + cols.n * S);        // [S][3]
@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
     const int lane = lane_id();
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    for (int64_t it = warp; it < n_items; it += n_warps) {
+    // tuple-sharded runs give every rank the kept items congruent to `part` modulo `n_parts`
+    for (int64_t it = warp * n_parts + part; it < n_items; it += n_warps * n_parts) {
         const int64_t m = kept_list ? static_cast<int64_t>(kept_list[it]) : it;
         const int64_t ia = idx.at(m, 0), ib = idx.at(m, 1);
         const float a[3] = {pc[3 * ia], pc[3 * ia + 1], pc[3 * ia + 2]};
@@ -203,14 +204,15 @@ CPPF_API int cppf_sphere_hist(const float *pred, int64_t rows, const double *wt,
     return CPPF_OK;
 }
 
-CPPF_API int cppf_rotation_hist(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *theta,
-                                int64_t theta_stride, const int *theta_cols_host, int n_theta, const int32_t *kept_list,
-                                const int64_t *kept_count, int64_t M, const int32_t *imp,
-                                const cppf_backvote_summary *summary, double margin, const float *cos_tab,
-                                const float *sin_tab, int R, const float *sphere, int S, float cos_thr, int band,
-                                double *counts, void *stream) {
+CPPF_API int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *theta,
+                                     int64_t theta_stride, const int *theta_cols_host, int n_theta, const int32_t *kept_list,
+                                     const int64_t *kept_count, int64_t M, const int32_t *imp,
+                                     const cppf_backvote_summary *summary, double margin, const float *cos_tab,
+                                     const float *sin_tab, int R, const float *sphere, int S, float cos_thr, int band,
+                                     double *counts, int part, int n_parts, void *stream) {
     if (!pc || !idx || !theta || !theta_cols_host || !cos_tab || !sin_tab || !sphere || !counts)
         return CPPF_ERR_INVALID_ARGUMENT;
+    if (n_parts < 1 || part < 0 || part >= n_parts) return CPPF_ERR_INVALID_ARGUMENT;
     if (n_theta < 1 || n_theta > kMaxTheta || M < 0 || R <= 0 || S < 1 || idx_stride < 2) return CPPF_ERR_INVALID_ARGUMENT;
     if (imp && !summary) return CPPF_ERR_INVALID_ARGUMENT;
     if (M == 0) return CPPF_OK;
@@ -224,10 +226,21 @@ CPPF_API int cppf_rotation_hist(const float *pc, const void *idx, int idx_is_i64
         CPPF_CUDA_TRY(cudaFuncSetAttribute(rotation_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     IdxView iv{idx, idx_stride, idx_is_i64};
     // one warp per kept tuple; the kept count is only known on the device, so size for M/8 (ratio 0.1) at least
-    const int64_t guess = kept_list ? (M / 8 + 1) : M;
+    const int64_t guess = (kept_list ? (M / 8 + 1) : M) / n_parts + 1;
     rotation_hist_kernel<<<grid_for(guess * 32, 256, 4), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         pc, iv, theta, theta_stride, cols, kept_list, kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere, S,
-        cos_thr, band, counts);
+        cos_thr, band, counts, part, n_parts);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
+}
+
+CPPF_API int cppf_rotation_hist(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *theta,
+                                int64_t theta_stride, const int *theta_cols_host, int n_theta, const int32_t *kept_list,
+                                const int64_t *kept_count, int64_t M, const int32_t *imp,
+                                const cppf_backvote_summary *summary, double margin, const float *cos_tab,
+                                const float *sin_tab, int R, const float *sphere, int S, float cos_thr, int band,
+                                double *counts, void *stream) {
+    return cppf_rotation_hist_part(pc, idx, idx_is_i64, idx_stride, theta, theta_stride, theta_cols_host, n_theta, kept_list,
+                                   kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere, S, cos_thr, band, counts,
+                                   0, 1, stream);
 }

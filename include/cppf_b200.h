@@ -188,6 +188,14 @@ int cppf_rotation_hist(const float *pc, const void *idx, int idx_is_i64, int64_t
                        const int64_t *kept_count, int64_t M, const int32_t *imp, const cppf_backvote_summary *summary,
                        double margin, const float *cos_tab, const float *sin_tab, int R, const float *sphere, int S,
                        float cos_thr, int band, double *counts, void *stream);
+/* Same over the kept items congruent to `part` modulo `n_parts`: in a tuple-sharded run every
+ * rank votes its share of the global kept list and the [n_theta,S] bins are summed by one all-reduce. */
+int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *theta,
+                            int64_t theta_stride, const int *theta_cols_host, int n_theta, const int32_t *kept_list,
+                            const int64_t *kept_count, int64_t M, const int32_t *imp,
+                            const cppf_backvote_summary *summary, double margin, const float *cos_tab,
+                            const float *sin_tab, int R, const float *sphere, int S, float cos_thr, int band,
+                            double *counts, int part, int n_parts, void *stream);
 
 /* ---- pose assembly ------------------------------------------------------------------------------
  * replaces eval.py:284-313 (top-1 directions, Gram-Schmidt, scale median) and :358-363 (branch loss). */
