@@ -1,19 +1,23 @@
-// bf16 tensor-core path of the BeyondCPPF heads: tcgen05.mma with TMEM accumulators (sm_100a).
+// bf16 tensor-core path of the BeyondCPPF heads: tcgen05.mma with TMEM accumulators (sm_100a), version 2.
 //
-// One CTA carries a tile of 128 rows (tuples or points) through a whole *program* -- tuple encoding,
-// tuple_encoder, logit_encoder and scale_encoder (train_shot.py:117-122, train_dino.py:128-133) -- with
-//   * activations resident in shared memory as bf16, written by the epilogue directly in the UMMA
-//     K-major no-swizzle layout (8x16-byte core matrices; plane kc = 8 columns x 128 rows = 2 KB), so
-//     the output of one layer is the A operand of the next without any reshuffle;
-//   * accumulators in TMEM (128 lanes x N<=256 fp32 columns), read back with tcgen05.ld 32x32b;
-//   * weights pre-packed on the host as the exact shared-memory image of the B operand and streamed
-//     from L2 in 64-column slabs with cp.async.bulk (the TMA engine) through a 2-stage mbarrier ring.
-// Warp roles: warps 0-7 prologue/epilogue (thread <-> TMEM lane/row), warp 8 weight producer, warp 9 MMA
-// issuer (one elected thread).  A ResLayer y = fc2(relu(fc1 x)) + (fc0 x | x) is two phases:
-//   phase 1: D = X W1^T                      epilogue: H = relu(D + b1)                 (bf16 -> smem)
-//   phase 2: D = H W2^T (+ X W0^T)           epilogue: X = D + b2 (+ b0) (+ X)          (bf16 -> smem, in place)
-// so HBM sees only the program's inputs (points, normals, per-point features, tuple indices) and its
-// outputs (logits, scales).
+// One CTA carries TWO independent 128-row tiles ("slots") through a *program* -- tuple encoding, tuple_encoder,
+// logit_encoder and scale_encoder (train_shot.py:117-122, train_dino.py:128-133) -- so that the tensor pipe
+// works on one slot while the epilogue warps of the other turn its accumulators into the next layer's operand:
+//   * layer inputs X stay in shared memory as bf16 in the UMMA K-major no-swizzle layout (8x16-byte core
+//     matrices; plane kc = 8 columns x 128 rows = 2 KB), written by the epilogue in place;
+//   * accumulators D live in TMEM (128 lanes x <=256 fp32 columns per slot) and are read with tcgen05.ld;
+//   * the hidden activation H = relu(fc1 x + b1) never touches shared memory: the epilogue packs it to bf16 and
+//     writes it back to TMEM (tcgen05.st), where it is the A operand of the second GEMM (tcgen05.mma with A in
+//     TMEM), so a ResLayer y = fc2(H) + (fc0 x | x) costs one shared-memory activation buffer per slot;
+//   * every accumulator is at most 128 columns wide (256-wide layers are computed as two N-chunks), which is
+//     what lets two slots share the 512 TMEM columns; inputs wider than 256 columns (the 360/352/286-wide
+//     first layers) are fed as two K-chunks through the same X buffer;
+//   * weights are pre-packed on the host as the exact shared-memory image of the B operand and streamed from L2
+//     in 16 KB slabs with cp.async.bulk (the TMA engine) through a 5-stage mbarrier ring.
+// Warp roles: warps 0-7 epilogue of slot 0, warps 8-15 epilogue of slot 1 (thread <-> TMEM lane/row, two
+// threads per row splitting the columns), warp 16 weight producer, warp 17 MMA issuer (one elected thread).
+// The issue order is static (phase-major, slot-minor), so producer and issuer agree without communication.
+// HBM sees only the program's inputs (points, normals, per-point features, tuple indices) and its outputs.
 #include "heads_common.cuh"
 
 #include <cuda_bf16.h>
@@ -25,68 +29,74 @@ namespace tc {
 
 constexpr int kRows = 128;                 // rows per tile == TMEM lanes == UMMA M
 constexpr int kPlane = kRows * 16;         // bytes of one 8-column plane of an activation buffer
-constexpr int kXCols = 368;                // widest stack input (SHOT tuple encoding 360 -> 368)
-constexpr int kHCols = 256;
-constexpr int kSlabCols = 64;              // K columns per weight slab
-constexpr int kRing = 2;
-constexpr int kSlabBytesMax = 256 * kSlabCols * 2;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (kEpiWarps + 2) * 32;
-constexpr int kTmemCols = 256;
-constexpr int kMaxPhases = 40;
+constexpr int kXCols = 256;
+constexpr int kXBytes = (kXCols / 8) * kPlane;        // 65536
+constexpr int kSlots = 2;
+constexpr int kStages = 5;
+constexpr int kSlabBytes = 16384;          // N<=128: 64 K-columns, N=256: 32 K-columns
+constexpr int kSlotWarps = 8;
+constexpr int kEpiWarps = kSlots * kSlotWarps;
+constexpr int kThreads = (kEpiWarps + 2) * 32;        // 576
+constexpr int kTmemCols = 512;
+constexpr int kSlotTmem = 256;             // TMEM columns per slot: D at +0 (and +128), H at +128
+constexpr int kHTmem = 128;
+constexpr int kMaxPhases = 48;
 
 constexpr int kSmemX = 0;
-constexpr int kSmemH = kSmemX + (kXCols / 8) * kPlane;            //  94208
-constexpr int kSmemRing = kSmemH + (kHCols / 8) * kPlane;         // 159744
-constexpr int kSmemBar = kSmemRing + kRing * kSlabBytesMax;       // 225280
-constexpr int kSmemTotal = kSmemBar + 128;
+constexpr int kSmemRing = kSmemX + kSlots * kXBytes;              // 131072
+constexpr int kSmemBar = kSmemRing + kStages * kSlabBytes;        // 212992
+constexpr int kSmemTotal = kSmemBar + 256;
 
 // ---- program description (built on the host, read by every role) ---------------------------------------
 enum Action : int {
-    kActLoadRows = 0,     // rows of a float32 global matrix -> bf16 buffer (optionally a 256-column chunk)
-    kActEncodeShot = 1,   // SHOT tuple encoding: [coords 30 | normals 10 | feats 5x64 | pad] -> X
-    kActGather = 2,       // gathered per-point bf16 rows (chunk c of the tuple) -> buffer
-    kActHidden = 3,       // H = relu(D + b)
-    kActOut = 4,          // X = D + b (+ X)
-    kActFinal = 5,        // global float32 / bf16 output = D + b
-    kActPairOut = 6,      // X[0:256] = D + b, then DINO coords -> X[256:288]
+    kActLoadRows = 0,     // float32 rows of a global matrix (columns src_col .. +cols) -> X[0 : width)
+    kActEncodeShotA = 1,  // SHOT tuple encoding, chunk A: gathered features of tuple slots 0..3 -> X[0:256)
+    kActEncodeShotB = 2,  // chunk B: [features of slot 4 (64) | coords 30 | normals 10 | pad 8] -> X[0:112)
+    kActGather = 3,       // gathered 256-wide per-point bf16 rows of tuple slot `src_col` -> X[0:256)
+    kActCoordsB = 4,      // DINO chunk B: [coords 30 | pad 2] -> X[0:32)
+    kActHiddenT = 5,      // H[h_col : +n) = relu(D + b)      (bf16 -> TMEM)
+    kActHiddenS = 6,      // X[dst_col : +n) = relu(D + b)    (bf16 -> shared memory; first layers)
+    kActOut = 7,          // X[dst_col : +n) = D + b (+ X[res_col : +n))   (optionally spilled to the feature scratch)
+    kActFinal = 8,        // global output = D + b
 };
 
-struct Part {             // one A operand x one weight matrix, accumulated into the phase's D
-    int a_buf;            // 0 = X, 1 = H
+struct Part {             // one A operand x one weight matrix, accumulated into D[d_col : d_col + n)
+    int a_tmem;           // 0: A = X in shared memory, 1: A = H in TMEM
+    int a_col;            // first column of the operand (bf16 elements)
     int k_cols;           // multiple of 16
-    int n_slabs;
+    int d_col;            // accumulator column offset inside the slot
+    int n;                // UMMA N (16, 64, 128 or 256)
+    int init;             // 1: the first MMA overwrites D, 0: accumulates onto it
+    int64_t w_off;        // bytes, into the program's slab stream
 };
 
 struct Phase {
-    int action;           // what warps 0-7 do before the phase's MMAs
-    int wait_done;        // the action first waits for the previous phase's MMAs
-    int has_mma;
-    int acc_prev;         // keep accumulating into the previous phase's D (K-chunked plain Linear)
-    int n;                // UMMA N of this phase's accumulators (multiple of 16)
-    int n_parts;
+    int action;           // what the slot's epilogue warps do before the phase's MMAs
+    int wait_done;        // the action first waits for the slot's previous MMAs
+    int n_parts;          // 0: no MMA follows the action
     Part part[2];
     // action parameters
-    int dst_buf;          // kActLoadRows / kActGather destination
-    int chunk;            // kActLoadRows: column offset / 256; kActGather: tuple slot
-    int cols;             // kActLoadRows: valid columns to read; epilogues: real output columns
-    int residual;         // kActOut: add the previous X
-    int store_feat;       // kActOut: also spill X (bf16) to the feature scratch
-    int reload_feat;      // kActFinal: afterwards reload X from the feature scratch
-    int out_sel;          // kActFinal: 0 = out0 (float32), 1 = out1 (float32), 2 = point features (bf16)
-    int out_ld;           // leading dimension of that output
-    int64_t bias_off;     // floats, into the bias blob
+    int src_col;          // LoadRows: first source column; Gather: tuple slot
+    int cols;             // LoadRows: valid source columns; Final: valid output columns of this chunk
+    int width;            // LoadRows: columns written (zero padded), multiple of 32
+    int d_col, n;         // accumulator chunk the epilogue reads
+    int dst_col;          // X / H / global column the chunk is written to
+    int residual, res_col;
+    int store_feat, reload_feat;
+    int out_sel;          // Final: 0 = out0 (float32), 1 = out1 (float32), 2 = point features (bf16)
+    int out_ld;
+    int64_t bias_off;     // floats, into the bias blob (start of this chunk)
 };
 
 struct Program {
     int n_phases;
-    int gather_cols;      // per-point feature width gathered per tuple slot (64 SHOT, 256 DINO)
+    int gather_cols;
     Phase phase[kMaxPhases];
 };
 
 struct Args {
     int64_t rows;                       // tuples or points
-    const float *x;                     // kActLoadRows source [rows][x_ld]
+    const float *x;                     // LoadRows source [rows][x_ld]
     int x_ld;
     const float *pc, *normal;           // tuple encoders
     const __nv_bfloat16 *point_feat;    // [n][gather_cols] bf16 (per-point program output)
@@ -140,12 +150,31 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 __device__ __forceinline__ uint32_t instr_desc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(kRows >> 4) << 24);
 }
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand in TMEM: element (row m, k) at lane m, 32-bit column a_tmem + k/2 (tools/probes/probe_ts_mma.cu)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+        "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
     uint32_t r[8];
@@ -155,16 +184,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                 "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t r[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
 __device__ __forceinline__ uint4 pack8(const float v[8]) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t *>(&a);
-    o.y = *reinterpret_cast<uint32_t *>(&b);
-    o.z = *reinterpret_cast<uint32_t *>(&c);
-    o.w = *reinterpret_cast<uint32_t *>(&d);
-    return o;
+    return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
 }
 __device__ __forceinline__ void unpack8(const uint4 &p, float v[8]) {
     const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&p);
@@ -175,35 +212,107 @@ __device__ __forceinline__ void unpack8(const uint4 &p, float v[8]) {
         v[2 * i + 1] = f.y;
     }
 }
-// element (row, col) of an activation buffer: plane col/8, 16 bytes per row
+// 16-byte chunk (row, 8-column group col8) of an activation buffer
 __device__ __forceinline__ unsigned char *act_chunk(unsigned char *buf, int row, int col8) { return buf + col8 * kPlane + row * 16; }
-
 __device__ __forceinline__ void put_elem(unsigned char *buf, int row, int col, float v) {
     reinterpret_cast<__nv_bfloat16 *>(act_chunk(buf, row, col >> 3))[col & 7] = __float2bfloat16_rn(v);
+}
+
+// Static tile assignment: round r gives slot s of CTA b the tile (r*kSlots + s)*gridDim.x + b, so that a
+// partial last round leaves whole second slots idle instead of half of the CTAs.
+__device__ __forceinline__ int64_t tile_of(int round, int slot) {
+    return (static_cast<int64_t>(round) * kSlots + slot) * gridDim.x + blockIdx.x;
+}
+
+// One batch of NB accumulator columns of this thread's row: v = D + bias, then the action's sink.
+template <int NB>
+__device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, unsigned char *X, uint32_t t_slot_lane, int row,
+                                               int64_t grow, bool live, int c /* column inside the chunk */) {
+    float v[NB];
+    const float *bias = a.bias + ph.bias_off + c;
+    float4 b4[NB / 4];
+#pragma unroll
+    for (int j = 0; j < NB / 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4 *>(bias) + j);
+    if (NB == 32) tmem_ld32(t_slot_lane + static_cast<uint32_t>(ph.d_col + c), v);
+    else tmem_ld8(t_slot_lane + static_cast<uint32_t>(ph.d_col + c), v);
+#pragma unroll
+    for (int j = 0; j < NB / 4; ++j) {
+        v[4 * j] += b4[j].x;
+        v[4 * j + 1] += b4[j].y;
+        v[4 * j + 2] += b4[j].z;
+        v[4 * j + 3] += b4[j].w;
+    }
+    if (ph.action == kActHiddenT) {
+        uint32_t p[NB / 2];
+#pragma unroll
+        for (int j = 0; j < NB / 2; ++j) p[j] = pack2(fmaxf(v[2 * j], 0.0f), fmaxf(v[2 * j + 1], 0.0f));
+        const uint32_t h_addr = t_slot_lane + kHTmem + static_cast<uint32_t>((ph.dst_col + c) >> 1);
+        if (NB == 32) tmem_st16(h_addr, p);
+        else tmem_st4(h_addr, p);
+    } else if (ph.action == kActHiddenS) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) v[j] = fmaxf(v[j], 0.0f);
+#pragma unroll
+        for (int j = 0; j < NB / 8; ++j) *reinterpret_cast<uint4 *>(act_chunk(X, row, (ph.dst_col + c) / 8 + j)) = pack8(v + 8 * j);
+    } else if (ph.action == kActOut) {
+        if (ph.residual) {
+#pragma unroll
+            for (int j = 0; j < NB / 8; ++j) {
+                float x[8];
+                unpack8(*reinterpret_cast<const uint4 *>(act_chunk(X, row, (ph.res_col + c) / 8 + j)), x);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[8 * j + k] += x[k];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NB / 8; ++j) {
+            const uint4 packed = pack8(v + 8 * j);
+            *reinterpret_cast<uint4 *>(act_chunk(X, row, (ph.dst_col + c) / 8 + j)) = packed;
+            if (ph.store_feat && live) __stcg(reinterpret_cast<uint4 *>(a.feat_scratch + grow * 256 + ph.dst_col + c + 8 * j), packed);
+        }
+    } else if (live) {   // kActFinal
+        if (ph.out_sel == 2) {
+#pragma unroll
+            for (int j = 0; j < NB / 8; ++j)
+                if (c + 8 * j < ph.cols)
+                    *reinterpret_cast<uint4 *>(a.out_bf16 + grow * ph.out_ld + ph.dst_col + c + 8 * j) = pack8(v + 8 * j);
+        } else {
+            float *out = (ph.out_sel == 0 ? a.out0 : a.out1) + grow * ph.out_ld + ph.dst_col + c;
+            if ((ph.out_ld & 3) == 0 && c + NB <= ph.cols) {
+#pragma unroll
+                for (int j = 0; j < NB / 4; ++j) reinterpret_cast<float4 *>(out)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    if (c + j < ph.cols) out[j] = v[j];
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__restrict__ prog_g, Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ Program prog;
     __shared__ uint32_t s_tmem_base;
-    unsigned char *bufX = smem + kSmemX, *bufH = smem + kSmemH;
     const uint32_t ring0 = smem_u32(smem + kSmemRing);
     const uint32_t bar0 = smem_u32(smem + kSmemBar);
-    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * kRing, bar_act = bar0 + 16 * kRing, bar_done = bar_act + 8;
+    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * kStages, bar_act = bar0 + 16 * kStages, bar_done = bar_act + 8 * kSlots;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     for (int i = tid; i < static_cast<int>(sizeof(Program) / 4); i += kThreads)
         reinterpret_cast<uint32_t *>(&prog)[i] = reinterpret_cast<const uint32_t *>(prog_g)[i];
     if (tid == 0) {
-        for (int s = 0; s < kRing; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_act, kEpiWarps * 32);
-        mbar_init(bar_done, 1);
+        for (int s = 0; s < kSlots; ++s) {
+            mbar_init(bar_act + 8 * s, kSlotWarps);
+            mbar_init(bar_done + 8 * s, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {  // TMEM: 256 columns x 128 lanes of fp32 accumulators
+    if (warp == 0) {  // the whole TMEM: two slots x 256 columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -212,208 +321,201 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
     const int64_t n_tiles = (a.rows + kRows - 1) / kRows;
+    const int n_rounds = static_cast<int>((n_tiles + static_cast<int64_t>(kSlots) * gridDim.x - 1) / (static_cast<int64_t>(kSlots) * gridDim.x));
 
     if (warp == kEpiWarps) {
         // =============================== weight producer ===============================================
         if (lane == 0) {
-            uint32_t slab_seq = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const unsigned char *src = a.weights;
+            uint32_t seq = 0;
+            for (int round = 0; round < n_rounds; ++round)
                 for (int p = 0; p < prog.n_phases; ++p) {
                     const Phase &ph = prog.phase[p];
-                    if (!ph.has_mma) continue;
-                    for (int q = 0; q < ph.n_parts; ++q) {
-                        int k_left = ph.part[q].k_cols;
-                        for (int s = 0; s < ph.part[q].n_slabs; ++s, ++slab_seq) {
-                            const int cols = k_left < kSlabCols ? k_left : kSlabCols;
-                            const uint32_t bytes = static_cast<uint32_t>(ph.n) * 2u * cols;
-                            const uint32_t stage = slab_seq % kRing, round = slab_seq / kRing;
-                            mbar_wait(bar_empty + 8 * stage, (round & 1u) ^ 1u);
-                            mbar_expect_tx(bar_full + 8 * stage, bytes);
-                            bulk_load(ring0 + stage * kSlabBytesMax, src, bytes, bar_full + 8 * stage);
-                            src += bytes;
-                            k_left -= cols;
+                    if (ph.n_parts == 0) continue;
+                    for (int s = 0; s < kSlots; ++s) {
+                        if (tile_of(round, s) >= n_tiles) continue;
+                        for (int q = 0; q < ph.n_parts; ++q) {
+                            const Part &pt = ph.part[q];
+                            const int slab_k = pt.n <= 128 ? 64 : 32;
+                            const unsigned char *src = a.weights + pt.w_off;
+                            for (int k_left = pt.k_cols; k_left > 0; k_left -= slab_k, ++seq) {
+                                const int cols = k_left < slab_k ? k_left : slab_k;
+                                const uint32_t bytes = static_cast<uint32_t>(pt.n) * 2u * cols;
+                                const uint32_t stage = seq % kStages, turn = seq / kStages;
+                                mbar_wait(bar_empty + 8 * stage, (turn & 1u) ^ 1u);
+                                mbar_expect_tx(bar_full + 8 * stage, bytes);
+                                bulk_load(ring0 + stage * kSlabBytes, src, bytes, bar_full + 8 * stage);
+                                src += bytes;
+                            }
                         }
                     }
                 }
-            }
         }
     } else if (warp == kEpiWarps + 1) {
         // =============================== MMA issuer =====================================================
         if (lane == 0) {
-            uint32_t slab_seq = 0, act_seq = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            uint32_t seq = 0, act_seq[kSlots] = {0, 0};
+            for (int round = 0; round < n_rounds; ++round)
                 for (int p = 0; p < prog.n_phases; ++p) {
                     const Phase &ph = prog.phase[p];
-                    if (!ph.has_mma) continue;
-                    mbar_wait(bar_act, act_seq & 1u);   // the phase's A operand is in shared memory, D is free
-                    ++act_seq;
-                    tc_fence_after();
-                    const uint32_t idesc = instr_desc(ph.n);
-                    uint32_t accumulate = ph.acc_prev ? 1u : 0u;
-                    for (int q = 0; q < ph.n_parts; ++q) {
-                        const uint32_t a_base = smem_u32(ph.part[q].a_buf == 0 ? bufX : bufH);
-                        int k_done = 0;
-                        for (int s = 0; s < ph.part[q].n_slabs; ++s, ++slab_seq) {
-                            const int cols = ph.part[q].k_cols - k_done < kSlabCols ? ph.part[q].k_cols - k_done : kSlabCols;
-                            const uint32_t stage = slab_seq % kRing, round = slab_seq / kRing;
-                            mbar_wait(bar_full + 8 * stage, round & 1u);
-                            tc_fence_after();
-                            const uint32_t b_base = ring0 + stage * kSlabBytesMax;
-                            const uint32_t b_plane = static_cast<uint32_t>(ph.n) * 16u;
-                            for (int k = 0; k < cols; k += 16) {
-                                const uint64_t ad = smem_desc(a_base + ((k_done + k) >> 3) * kPlane, kPlane, 128);
-                                const uint64_t bd = smem_desc(b_base + (k >> 3) * b_plane, b_plane, 128);
-                                umma(tmem, ad, bd, idesc, accumulate);
-                                accumulate = 1;
+                    if (ph.n_parts == 0) continue;
+                    for (int s = 0; s < kSlots; ++s) {
+                        if (tile_of(round, s) >= n_tiles) continue;
+                        mbar_wait(bar_act + 8 * s, act_seq[s] & 1u);   // the slot's A operand is ready, its D is free
+                        ++act_seq[s];
+                        tc_fence_after();
+                        const uint32_t t_slot = tmem + static_cast<uint32_t>(s * kSlotTmem);
+                        const uint32_t x_base = smem_u32(smem + kSmemX + s * kXBytes);
+                        for (int q = 0; q < ph.n_parts; ++q) {
+                            const Part &pt = ph.part[q];
+                            const int slab_k = pt.n <= 128 ? 64 : 32;
+                            const uint32_t idesc = instr_desc(pt.n);
+                            const uint32_t b_plane = static_cast<uint32_t>(pt.n) * 16u;
+                            const uint32_t d_addr = t_slot + static_cast<uint32_t>(pt.d_col);
+                            uint32_t accumulate = pt.init ? 0u : 1u;
+                            for (int k_done = 0; k_done < pt.k_cols; k_done += slab_k, ++seq) {
+                                const int cols = pt.k_cols - k_done < slab_k ? pt.k_cols - k_done : slab_k;
+                                const uint32_t stage = seq % kStages, turn = seq / kStages;
+                                mbar_wait(bar_full + 8 * stage, turn & 1u);
+                                tc_fence_after();
+                                const uint32_t b_base = ring0 + stage * kSlabBytes;
+                                for (int k = 0; k < cols; k += 16) {
+                                    const uint64_t bd = smem_desc(b_base + (k >> 3) * b_plane, b_plane, 128);
+                                    const int ak = pt.a_col + k_done + k;
+                                    if (pt.a_tmem) umma_ts(d_addr, t_slot + kHTmem + static_cast<uint32_t>(ak >> 1), bd, idesc, accumulate);
+                                    else umma_ss(d_addr, smem_desc(x_base + (ak >> 3) * kPlane, kPlane, 128), bd, idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                                umma_commit(bar_empty + 8 * stage);   // slab consumed once these MMAs retire
                             }
-                            umma_commit(bar_empty + 8 * stage);   // slab consumed once these MMAs retire
-                            k_done += cols;
                         }
+                        umma_commit(bar_done + 8 * s);
                     }
-                    umma_commit(bar_done);
                 }
-            }
         }
     } else {
-        // =============================== prologue / epilogue warps ======================================
-        const int row = (warp & 3) * 32 + lane;        // TMEM lane == tile row
-        const int half = warp >> 2;                    // column half handled by this warpgroup
-        const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        // =============================== prologue / epilogue warps of one slot ===========================
+        const int slot = warp / kSlotWarps, sw = warp % kSlotWarps, stid = tid - slot * kSlotWarps * 32;
+        const int row = (sw & 3) * 32 + lane;          // TMEM lane == tile row  (warp % 4 selects the lane quadrant)
+        const int half = sw >> 2;                      // which half of the chunk's columns this thread handles
+        unsigned char *X = smem + kSmemX + slot * kXBytes;
+        const uint32_t t_slot_lane = tmem + static_cast<uint32_t>(slot * kSlotTmem) + (static_cast<uint32_t>((sw & 3) * 32) << 16);
+        // (8 rows x 4 chunks) per warp pass for the row movers: conflict-free 16-byte shared stores, whole 32 B sectors
+        const int mv_r = lane & 7, mv_c = lane >> 3;
         uint32_t done_seq = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int round = 0; round < n_rounds; ++round) {
+            const int64_t tile = tile_of(round, slot);
+            if (tile >= n_tiles) break;
             const int64_t row_base = tile * kRows;
             const int64_t grow = row_base + row;
             const bool live = grow < a.rows;
             for (int p = 0; p < prog.n_phases; ++p) {
                 const Phase &ph = prog.phase[p];
                 if (ph.wait_done) {
-                    mbar_wait(bar_done, done_seq & 1u);
+                    mbar_wait(bar_done + 8 * slot, done_seq & 1u);
                     ++done_seq;
                     tc_fence_after();
                 }
-                const Phase *prev = p > 0 ? &prog.phase[p - 1] : nullptr;
-                const float *bias = prev ? a.bias + prev->bias_off : nullptr;
-                const int n_prev = prev ? prev->n : 0;
                 switch (ph.action) {
                     case kActLoadRows: {
-                        unsigned char *dst = ph.dst_buf == 0 ? bufX : bufH;
-                        const int width = ph.part[0].k_cols;      // columns the MMA will read (multiple of 16)
-                        // thread <-> (row, 8-column chunk): 128 rows x width/8 chunks over 256 threads
-                        for (int i = tid; i < kRows * (width >> 3); i += kEpiWarps * 32) {
-                            const int r = i & (kRows - 1), c8 = i >> 7;
+                        const int cb_n = ph.width >> 5;                  // blocks of 4 chunks
+                        for (int it = sw; it < 16 * cb_n; it += kSlotWarps) {
+                            const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
                             float v[8];
+                            const int64_t gr = row_base + r;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int col = c8 * 8 + j;
-                                float x = 0.0f;
-                                if (row_base + r < a.rows && col < ph.cols) x = a.x[(row_base + r) * a.x_ld + ph.chunk * 256 + col];
-                                v[j] = (x == x) ? x : 0.0f;   // NaN rows of invalid SHOT points count as zeros (eval.py:215)
+                            for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+                            if (gr < a.rows && c8 * 8 < ph.cols) {      // cols is a multiple of 8
+                                const float4 *src = reinterpret_cast<const float4 *>(a.x + gr * a.x_ld + ph.src_col + c8 * 8);
+                                const float4 lo = __ldg(src), hi = __ldg(src + 1);
+                                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+                                v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = (v[j] == v[j]) ? v[j] : 0.0f;   // NaN rows of invalid SHOT points count as zeros (eval.py:215)
                             }
-                            *reinterpret_cast<uint4 *>(act_chunk(dst, r, c8)) = pack8(v);
+                            *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = pack8(v);
                         }
                         break;
                     }
-                    case kActEncodeShot: {
-                        const int P = a.arity * (a.arity - 1) / 2;
-                        if (tid < kRows) {
-                            int64_t pt[8];
-                            for (int k = 0; k < a.arity; ++k) pt[k] = live ? a.idx.at(grow, k) : 0;
-                            if (live)
-                                encode_tuple_geometry(a.pc, a.normal, pt, a.arity, true, [&](int col, float v) { put_elem(bufX, row, col, v); });
-                            else
-                                for (int c = 0; c < 4 * P; ++c) put_elem(bufX, row, c, 0.0f);
-                            for (int c = 4 * P + a.arity * 64; c < ph.part[0].k_cols; ++c) put_elem(bufX, row, c, 0.0f);
-                        }
-                        // gathered per-point features: slot s occupies columns 4P + 64 s .. + 63 (8 chunks of 8)
-                        for (int i = tid; i < kRows * a.arity * 8; i += kEpiWarps * 32) {
-                            const int r = i & (kRows - 1), c = i >> 7, slot = c >> 3, sub = c & 7;
-                            uint4 v = make_uint4(0, 0, 0, 0);
-                            if (row_base + r < a.rows)
-                                v = *reinterpret_cast<const uint4 *>(a.point_feat + a.idx.at(row_base + r, slot) * 64 + sub * 8);
-                            // 4P = 40 columns of geometry: the features start at column 40 = chunk 5
-                            *reinterpret_cast<uint4 *>(act_chunk(bufX, r, (4 * P) / 8 + c)) = v;
-                        }
-                        break;
-                    }
+                    case kActEncodeShotA:
                     case kActGather: {
-                        unsigned char *dst = ph.dst_buf == 0 ? bufX : bufH;
-                        for (int i = tid; i < kRows * 32; i += kEpiWarps * 32) {
-                            const int r = i & (kRows - 1), c8 = i >> 7;
+                        // 32 chunks of 8 bf16 per row: SHOT = features of tuple slots 0..3 (64 wide each), DINO = one 256-wide row
+                        for (int it = sw; it < 16 * 8; it += kSlotWarps) {
+                            const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
                             uint4 v = make_uint4(0, 0, 0, 0);
-                            if (row_base + r < a.rows)
-                                v = *reinterpret_cast<const uint4 *>(a.point_feat + a.idx.at(row_base + r, ph.chunk) * 256 + c8 * 8);
-                            *reinterpret_cast<uint4 *>(act_chunk(dst, r, c8)) = v;
+                            if (row_base + r < a.rows) {
+                                const __nv_bfloat16 *src = ph.action == kActGather
+                                                               ? a.point_feat + a.idx.at(row_base + r, ph.src_col) * 256 + c8 * 8
+                                                               : a.point_feat + a.idx.at(row_base + r, c8 >> 3) * 64 + (c8 & 7) * 8;
+                                v = __ldg(reinterpret_cast<const uint4 *>(src));
+                            }
+                            *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = v;
                         }
                         break;
                     }
-                    case kActHidden:
-                    case kActOut:
-                    case kActPairOut:
-                    case kActFinal: {
-                        // this warpgroup's half of the previous phase's accumulator columns, 8 at a time
-                        const int c_begin = half * (n_prev / 2), c_end = c_begin + n_prev / 2;
-                        for (int c = c_begin; c < c_end; c += 8) {
-                            float v[8];
-                            tmem_ld8(t_lane + static_cast<uint32_t>(c), v);
-                            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c + 4));
-                            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                            if (ph.action == kActHidden) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-                                *reinterpret_cast<uint4 *>(act_chunk(bufH, row, c >> 3)) = pack8(v);
-                            } else if (ph.action == kActOut || ph.action == kActPairOut) {
-                                uint4 *slot = reinterpret_cast<uint4 *>(act_chunk(bufX, row, c >> 3));
-                                if (ph.residual) {
-                                    float x[8];
-                                    unpack8(*slot, x);
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) v[j] += x[j];
-                                }
-                                const uint4 packed = pack8(v);
-                                *slot = packed;
-                                if (ph.store_feat && live) __stcg(reinterpret_cast<uint4 *>(a.feat_scratch + grow * 256 + c), packed);
-                            } else if (live) {
-                                if (ph.out_sel == 2) {
-                                    if (c < ph.cols) *reinterpret_cast<uint4 *>(a.out_bf16 + grow * ph.out_ld + c) = pack8(v);
-                                } else {
-                                    float *out = (ph.out_sel == 0 ? a.out0 : a.out1) + grow * ph.out_ld;
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j)
-                                        if (c + j < ph.cols) out[c + j] = v[j];
-                                }
+                    case kActEncodeShotB: {
+                        for (int it = sw; it < 16 * 2; it += kSlotWarps) {   // features of tuple slot 4 -> columns 0..63
+                            const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
+                            uint4 v = make_uint4(0, 0, 0, 0);
+                            if (row_base + r < a.rows) v = __ldg(reinterpret_cast<const uint4 *>(a.point_feat + a.idx.at(row_base + r, 4) * 64 + c8 * 8));
+                            *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = v;
+                        }
+                        if (stid < kRows) {   // geometry of row `stid`: coords -> columns 64..93, normals -> 94..103, zeros -> 104..111
+                            const int64_t g = row_base + stid;
+                            if (g < a.rows) {
+                                int64_t pt[8];
+                                for (int k = 0; k < a.arity; ++k) pt[k] = a.idx.at(g, k);
+                                encode_tuple_geometry(a.pc, a.normal, pt, a.arity, true, [&](int col, float v) { put_elem(X, stid, 64 + col, v); });
+                            } else {
+                                for (int c = 64; c < 104; ++c) put_elem(X, stid, c, 0.0f);
+                            }
+                            *reinterpret_cast<uint4 *>(act_chunk(X, stid, 13)) = make_uint4(0, 0, 0, 0);
+                        }
+                        break;
+                    }
+                    case kActCoordsB: {
+                        if (stid < kRows) {   // coords -> columns 0..29, zeros -> 30..31
+                            const int64_t g = row_base + stid;
+                            *reinterpret_cast<uint4 *>(act_chunk(X, stid, 3)) = make_uint4(0, 0, 0, 0);
+                            if (g < a.rows) {
+                                int64_t pt[8];
+                                for (int k = 0; k < a.arity; ++k) pt[k] = a.idx.at(g, k);
+                                encode_tuple_geometry(a.pc, a.normal, pt, a.arity, false, [&](int col, float v) { put_elem(X, stid, col, v); });
+                            } else {
+                                for (int c = 0; c < 30; ++c) put_elem(X, stid, c, 0.0f);
                             }
                         }
-                        if (ph.action == kActPairOut && tid < kRows) {   // DINO coords after the 256 pair columns
-                            int64_t pt[8];
-                            for (int k = 0; k < a.arity; ++k) pt[k] = live ? a.idx.at(grow, k) : 0;
-                            const int P = a.arity * (a.arity - 1) / 2;
-                            if (live)
-                                encode_tuple_geometry(a.pc, a.normal, pt, a.arity, false, [&](int col, float v) { put_elem(bufX, row, 256 + col, v); });
-                            else
-                                for (int c = 0; c < 3 * P; ++c) put_elem(bufX, row, 256 + c, 0.0f);
-                            for (int c = 256 + 3 * P; c < ph.part[0].k_cols; ++c) put_elem(bufX, row, c, 0.0f);
+                        break;
+                    }
+                    case kActHiddenT:
+                    case kActHiddenS:
+                    case kActOut:
+                    case kActFinal: {
+                        const int per = ph.n >> 1;               // columns of the chunk per thread: 8, 32, 64 or 128
+                        const int c0 = half * per;
+                        if (per >= 32) {
+                            for (int c = c0; c < c0 + per; c += 32) epilogue_batch<32>(ph, a, X, t_slot_lane, row, grow, live, c);
+                        } else {
+                            epilogue_batch<8>(ph, a, X, t_slot_lane, row, grow, live, c0);
                         }
+                        if (ph.action == kActHiddenT) tmem_st_wait();
                         if (ph.action == kActFinal && ph.reload_feat) {
-                            // all epilogue threads must be done reading D / writing outputs before X is refilled: the
-                            // refill only touches X, which no in-flight MMA reads (the phase waited for them)
-                            for (int i = tid; i < kRows * 32; i += kEpiWarps * 32) {
-                                const int r = i & (kRows - 1), c8 = i >> 7;
+                            // X <- the spilled tuple feature (written by this slot's own threads in an earlier phase)
+                            for (int it = sw; it < 16 * 8; it += kSlotWarps) {
+                                const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
                                 uint4 v = make_uint4(0, 0, 0, 0);
                                 if (row_base + r < a.rows) v = __ldcg(reinterpret_cast<const uint4 *>(a.feat_scratch + (row_base + r) * 256 + c8 * 8));
-                                *reinterpret_cast<uint4 *>(act_chunk(bufX, r, c8)) = v;
+                                *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = v;
                             }
                         }
                         break;
                     }
                     default: break;
                 }
-                if (ph.has_mma) {
+                if (ph.n_parts) {
                     fence_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
                     tc_fence_before();
-                    mbar_arrive(bar_act);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_act + 8 * slot);
                 }
             }
         }
@@ -439,34 +541,33 @@ struct Builder {
         const uint32_t lsb = (u >> 16) & 1u;
         return static_cast<uint16_t>((u + 0x7fffu + lsb) >> 16);            // round to nearest even
     }
+    static int pad16(int v) { return (v + 15) & ~15; }
+    // accumulator chunk widths the epilogue supports
+    static int chunk_pad(int v) { return v <= 16 ? 16 : (v <= 64 ? 64 : 128); }
 
-    // appends the UMMA image of W [n_real][k_real] (row-major, source column = perm ? perm[k] : k) padded to n_pad x k_pad
-    void push_weight(const float *W, int n_real, int k_real, int n_pad, int k_pad, const std::vector<int> *perm = nullptr) {
+    // Appends the UMMA image of rows [n0, n0+n_real) x the listed source columns of W [.][ld], padded to n_pad x k_pad;
+    // returns its byte offset in the stream.  cols[k] < 0 is a zero column.
+    int64_t push_weight(const float *W, int ld, int n0, int n_real, int n_pad, const std::vector<int> &cols, int k_pad) {
         const size_t off = stream.size();
         stream.resize(off + static_cast<size_t>(n_pad) * k_pad, 0);
-        for (int k = 0; k < k_real; ++k) {
-            const int src = perm ? (*perm)[k] : k;
-            for (int n = 0; n < n_real; ++n)
-                stream[off + static_cast<size_t>(k >> 3) * n_pad * 8 + static_cast<size_t>(n) * 8 + (k & 7)] =
-                    bf16_bits(W[static_cast<size_t>(n) * k_real + src]);
-        }
-    }
-    // same for an explicit list of source columns of W [n_real][ld]
-    void push_weight_cols(const float *W, int n_real, int ld, int n_pad, int k_pad, const std::vector<int> &cols) {
-        const size_t off = stream.size();
-        stream.resize(off + static_cast<size_t>(n_pad) * k_pad, 0);
-        for (size_t k = 0; k < cols.size(); ++k)
+        for (size_t k = 0; k < cols.size(); ++k) {
+            if (cols[k] < 0) continue;
             for (int n = 0; n < n_real; ++n)
                 stream[off + (k >> 3) * static_cast<size_t>(n_pad) * 8 + static_cast<size_t>(n) * 8 + (k & 7)] =
-                    bf16_bits(W[static_cast<size_t>(n) * ld + cols[k]]);
+                    bf16_bits(W[static_cast<size_t>(n0 + n) * ld + cols[k]]);
+        }
+        return static_cast<int64_t>(off) * 2;
     }
-    int64_t push_bias(const float *a, const float *b, int n_real, int n_pad) {
+    int64_t push_bias(const float *a, const float *b, int n0, int n_real, int n_pad) {
         const int64_t off = static_cast<int64_t>(bias.size());
-        for (int i = 0; i < n_pad; ++i) bias.push_back(i < n_real ? a[i] + (b ? b[i] : 0.0f) : 0.0f);
+        for (int i = 0; i < n_pad; ++i) bias.push_back(i < n_real ? a[n0 + i] + (b ? b[n0 + i] : 0.0f) : 0.0f);
         return off;
     }
-    static int pad16(int v) { return (v + 15) & ~15; }
-    static int slabs(int k) { return (k + kSlabCols - 1) / kSlabCols; }
+    static std::vector<int> iota(int n, int start = 0) {
+        std::vector<int> v(n);
+        for (int i = 0; i < n; ++i) v[i] = start + i;
+        return v;
+    }
 
     Phase &add(int action, int wait_done) {
         Phase &ph = prog.phase[prog.n_phases++];
@@ -475,44 +576,86 @@ struct Builder {
         ph.wait_done = wait_done;
         return ph;
     }
-
-    // Appends the two MMA phases of a ResLayer to the phase whose action produced X (`first`), returns the
-    // phase that must carry the layer's output epilogue.
-    void res_layer(const ResLayerDesc &L, Phase *first, int k_in_pad, const std::vector<int> *perm) {
-        const int n_pad = pad16(L.dout);
-        // phase A (already created by the caller): D = X W1^T
-        first->has_mma = 1;
-        first->n = n_pad;
-        first->n_parts = 1;
-        first->part[0] = Part{0, k_in_pad, slabs(k_in_pad)};
-        push_weight(w + L.w1, L.dout, L.din, n_pad, k_in_pad, perm);
-        first->bias_off = push_bias(w + L.b1, nullptr, L.dout, n_pad);
-        // phase B: H = relu(D + b1); D = H W2^T (+ X W0^T)
-        Phase &hb = add(kActHidden, 1);
-        hb.has_mma = 1;
-        hb.n = n_pad;
-        hb.n_parts = L.has_fc0 ? 2 : 1;
-        hb.part[0] = Part{1, n_pad, slabs(n_pad)};
-        push_weight(w + L.w2, L.dout, L.dout, n_pad, n_pad);
-        if (L.has_fc0) {
-            hb.part[1] = Part{0, k_in_pad, slabs(k_in_pad)};
-            push_weight(w + L.w0, L.dout, L.din, n_pad, k_in_pad, perm);
-        }
-        hb.bias_off = push_bias(w + L.b2, L.has_fc0 ? w + L.b0 : nullptr, L.dout, n_pad);
+    static void add_part(Phase &ph, int a_tmem, int a_col, int k_cols, int d_col, int n, int init, int64_t w_off) {
+        ph.part[ph.n_parts++] = Part{a_tmem, a_col, k_cols, d_col, n, init, w_off};
     }
 
-    // Runs a stack whose input X is produced by `*cur`'s action; on return `*cur` is the phase whose action
-    // must write the stack's output (its fields action/residual/... are set by the caller).
-    Phase *stack(const StackDesc &s, Phase *cur, int k_in_pad, const std::vector<int> *perm0) {
-        for (int l = 0; l < s.n_layers; ++l) {
-            const ResLayerDesc &L = s.layer[l];
-            res_layer(L, cur, l == 0 ? k_in_pad : pad16(L.din), l == 0 ? perm0 : nullptr);
-            Phase &out = add(kActOut, 1);
+    // ResLayer whose input (din <= 256 columns) sits in X at in_col; `cur` is the phase whose action produced it.
+    // Output chunks go to X at out_col.  Returns the phase(s) that carry the output epilogue: the LAST one is
+    // returned, earlier output chunks (256- and 192-wide layers) are complete Out phases unless `final_out`.
+    struct OutSpec {
+        int action = kActOut;       // kActOut or kActFinal
+        int out_col = 0;
+        int store_feat = 0;
+        int out_sel = 0, out_ld = 0;
+    };
+    Phase *res_layer(const ResLayerDesc &L, Phase *cur, int in_col, const OutSpec &os) {
+        const int k_in = pad16(L.din);
+        const std::vector<int> in_cols = iota(L.din);
+        // hidden / output chunks of at most 128 columns
+        std::vector<std::pair<int, int>> chunks;   // (first column, real width)
+        for (int c = 0; c < L.dout; c += 128) chunks.push_back({c, L.dout - c < 128 ? L.dout - c : 128});
+        int h_width = 0;
+        for (auto &ch : chunks) {
+            const int n_pad = chunk_pad(ch.second);
+            add_part(*cur, 0, in_col, k_in, 0, n_pad, 1, push_weight(w + L.w1, L.din, ch.first, ch.second, n_pad, in_cols, k_in));
+            Phase &hid = add(kActHiddenT, 1);
+            hid.d_col = 0;
+            hid.n = n_pad;
+            hid.dst_col = ch.first;
+            hid.bias_off = push_bias(w + L.b1, nullptr, ch.first, ch.second, n_pad);
+            cur = &hid;
+            h_width = ch.first + n_pad;
+        }
+        const std::vector<int> h_cols = iota(L.dout);   // hidden column j of H <-> fc2 input j (pad columns are zero in both)
+        for (size_t i = 0; i < chunks.size(); ++i) {
+            const auto &ch = chunks[i];
+            const int n_pad = chunk_pad(ch.second);
+            std::vector<int> hc(h_width, -1);
+            for (int j = 0; j < L.dout; ++j) hc[j] = j;
+            add_part(*cur, 1, 0, h_width, 0, n_pad, 1, push_weight(w + L.w2, L.dout, ch.first, ch.second, n_pad, hc, h_width));
+            if (L.has_fc0) add_part(*cur, 0, in_col, k_in, 0, n_pad, 0, push_weight(w + L.w0, L.din, ch.first, ch.second, n_pad, in_cols, k_in));
+            Phase &out = add(os.action, 1);
+            out.d_col = 0;
+            out.n = n_pad;
+            out.cols = ch.second;
+            out.dst_col = os.out_col + ch.first;
             out.residual = !L.has_fc0;
-            out.cols = L.dout;
+            out.res_col = in_col + ch.first;
+            out.store_feat = os.store_feat;
+            out.out_sel = os.out_sel;
+            out.out_ld = os.out_ld;
+            out.bias_off = push_bias(w + L.b2, L.has_fc0 ? w + L.b0 : nullptr, ch.first, ch.second, n_pad);
             cur = &out;
         }
         return cur;
+    }
+
+    // First ResLayer of a stack whose input is wider than 256 columns (always din != dout, dout = 128): the input
+    // arrives as two K-chunks through X[0:...).  `first` is the phase whose action produced chunk A (256 columns,
+    // source columns cols_a of the layer input); chunk B (cols_b, padded to kb) is produced by `action_b`.
+    Phase *wide_first_layer(const ResLayerDesc &L, Phase *first, const std::vector<int> &cols_a, int action_b,
+                            const std::vector<int> &cols_b, int kb, int out_col, Phase **phase_b) {
+        const int n = 128;   // dout
+        add_part(*first, 0, 0, 256, 0, n, 1, push_weight(w + L.w1, L.din, 0, L.dout, n, cols_a, 256));
+        add_part(*first, 0, 0, 256, 128, n, 1, push_weight(w + L.w0, L.din, 0, L.dout, n, cols_a, 256));
+        Phase &pb = add(action_b, 1);
+        add_part(pb, 0, 0, kb, 0, n, 0, push_weight(w + L.w1, L.din, 0, L.dout, n, cols_b, kb));
+        add_part(pb, 0, 0, kb, 128, n, 0, push_weight(w + L.w0, L.din, 0, L.dout, n, cols_b, kb));
+        if (phase_b) *phase_b = &pb;
+        Phase &hid = add(kActHiddenS, 1);     // H -> X[0:128) (chunk B has been consumed)
+        hid.d_col = 0;
+        hid.n = n;
+        hid.dst_col = 0;
+        hid.bias_off = push_bias(w + L.b1, nullptr, 0, L.dout, n);
+        add_part(hid, 0, 0, n, 128, n, 0, push_weight(w + L.w2, L.dout, 0, L.dout, n, iota(L.dout), n));
+        Phase &out = add(kActOut, 1);
+        out.d_col = 128;
+        out.n = n;
+        out.cols = L.dout;
+        out.dst_col = out_col;
+        out.bias_off = push_bias(w + L.b2, w + L.b0, 0, L.dout, n);
+        return &out;
     }
 };
 
@@ -540,92 +683,116 @@ static int upload(const Builder &b, Program **d_prog, unsigned char **d_w, float
 using namespace cppf;
 using namespace cppf::tc;
 
+// Appends a stack whose layers all take <= 256 input columns.  The layer outputs alternate so that a layer that
+// widens 128 -> 256 finds its input in X[128:256) and can write its first output chunk to X[0:128) while the
+// second GEMM still reads the input.
+static Phase *append_stack(Builder &b, const StackDesc &s, int first_layer, Phase *cur, int in_col, const Builder::OutSpec &last) {
+    for (int l = first_layer; l < s.n_layers; ++l) {
+        const ResLayerDesc &L = s.layer[l];
+        Builder::OutSpec os;
+        if (l == s.n_layers - 1) {
+            os = last;
+        } else {
+            const ResLayerDesc &nx = s.layer[l + 1];
+            // the next layer widens beyond its input and has a projection: park this output in the upper half
+            os.out_col = (nx.has_fc0 && nx.dout > 128 && L.dout <= 128) ? 128 : 0;
+        }
+        cur = b.res_layer(L, cur, in_col, os);
+        in_col = os.out_col;
+    }
+    return cur;
+}
+
 extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, void **state) {
     *state = nullptr;
     const HeadsModel &m = *model;
-    if (m.arity != 5) return CPPF_ERR_UNSUPPORTED;   // the tile layouts below assume 10 pairs (4P = 40, 3P = 30)
+    if (m.arity != 5) return CPPF_ERR_UNSUPPORTED;   // the tile layouts below assume 5-point tuples (10 pairs)
     State *st = new State{};
     st->model = m;
     // ---- per-point program -------------------------------------------------------------------------------
     Builder pb;
     pb.w = w;
-    if (m.branch == 0) {   // shot_encoder: [n,352] -> [n,64] bf16
+    if (m.branch == 0) {   // shot_encoder: [n,352] -> [n,64] bf16; first layer 352 = 256 + 96
         Phase *cur = &pb.add(kActLoadRows, 0);
-        cur->dst_buf = 0;
-        cur->cols = CPPF_SHOT_DIM;
-        cur = pb.stack(m.shot_encoder, cur, Builder::pad16(CPPF_SHOT_DIM), nullptr);
-        cur->action = kActFinal;
-        cur->out_sel = 2;
-        cur->out_ld = 64;
-        cur->cols = 64;
+        cur->src_col = 0;
+        cur->cols = 256;
+        cur->width = 256;
+        Phase *pbb = nullptr;
+        cur = pb.wide_first_layer(m.shot_encoder.layer[0], cur, Builder::iota(256), kActLoadRows, Builder::iota(96, 256), 96, 0, &pbb);
+        pbb->src_col = 256;
+        pbb->cols = 96;
+        pbb->width = 96;
+        Builder::OutSpec last;
+        last.action = kActFinal;
+        last.out_sel = 2;
+        last.out_ld = 64;
+        cur = append_stack(pb, m.shot_encoder, 1, cur, 0, last);
         st->point_cols = 64;
     } else {               // desc_transform (train_dino.py:80,95), hoisted per point: Linear 1024 -> 256 as four K-chunks
         const LinearDesc &L = m.desc_transform;
         for (int c = 0; c < 4; ++c) {
             Phase &ph = pb.add(kActLoadRows, c > 0);     // X is refilled only after the previous chunk's MMAs retired
-            ph.dst_buf = 0;
-            ph.chunk = c;
+            ph.src_col = c * 256;
             ph.cols = 256;
-            ph.has_mma = 1;
-            ph.acc_prev = c > 0;
-            ph.n = 256;
-            ph.n_parts = 1;
-            ph.part[0] = Part{0, 256, Builder::slabs(256)};
-            std::vector<int> cols(256);
-            for (int k = 0; k < 256; ++k) cols[k] = c * 256 + k;
-            pb.push_weight_cols(w + L.w, 256, L.din, 256, 256, cols);
-            ph.bias_off = pb.push_bias(w + L.b, nullptr, 256, 256);
+            ph.width = 256;
+            Builder::add_part(ph, 0, 0, 256, 0, 256, c == 0, pb.push_weight(w + L.w, L.din, 0, 256, 256, Builder::iota(256, c * 256), 256));
         }
         Phase &fin = pb.add(kActFinal, 1);
+        fin.d_col = 0;
+        fin.n = 256;
+        fin.cols = 256;
+        fin.dst_col = 0;
         fin.out_sel = 2;
         fin.out_ld = 256;
-        fin.cols = 256;
+        fin.bias_off = pb.push_bias(w + L.b, nullptr, 0, 256, 256);
         st->point_cols = 256;
     }
     // ---- per-tuple program -------------------------------------------------------------------------------
     Builder tb;
     tb.w = w;
     Phase *cur;
+    const ResLayerDesc &T0 = m.tuple_encoder.layer[0];
     if (m.branch == 0) {
-        cur = &tb.add(kActEncodeShot, 0);
-        cur = tb.stack(m.tuple_encoder, cur, Builder::pad16(m.tuple_encoder.in_dim()), nullptr);
+        // tuple_encoder.0 input (train_shot.py:75-83) = [coords 30 | normals 10 | feats 5x64]; chunk A = feats of
+        // slots 0..3 (source columns 40..295), chunk B = [feats of slot 4 (296..359) | coords+normals (0..39) | pad 8]
+        cur = &tb.add(kActEncodeShotA, 0);
+        std::vector<int> cols_b = Builder::iota(64, 296);
+        for (int k = 0; k < 40; ++k) cols_b.push_back(k);
+        cur = tb.wide_first_layer(T0, cur, Builder::iota(256, 40), kActEncodeShotB, cols_b, 112, 0, nullptr);
     } else {
-        // desc_pair_transform over the 5 gathered (already transformed) descriptors (train_dino.py:95-96), then
-        // the tile is [pair 256 | coords 30 | pad 2]: tuple_encoder.0's input columns are permuted to match
+        // desc_pair_transform over the 5 gathered (already transformed) descriptors (train_dino.py:95-96): five
+        // K-chunks into one 256-wide accumulator; its output is chunk A of tuple_encoder.0 ([coords 30 | pair 256])
         const LinearDesc &L = m.desc_pair_transform;
         for (int c = 0; c < m.arity; ++c) {
             Phase &ph = tb.add(kActGather, c > 0);
-            ph.dst_buf = 0;
-            ph.chunk = c;
-            ph.has_mma = 1;
-            ph.acc_prev = c > 0;
-            ph.n = 256;
-            ph.n_parts = 1;
-            ph.part[0] = Part{0, 256, Builder::slabs(256)};
-            std::vector<int> cols(256);
-            for (int k = 0; k < 256; ++k) cols[k] = c * 256 + k;
-            tb.push_weight_cols(w + L.w, 256, L.din, 256, 256, cols);
-            ph.bias_off = tb.push_bias(w + L.b, nullptr, 256, 256);
+            ph.src_col = c;
+            Builder::add_part(ph, 0, 0, 256, 0, 256, c == 0, tb.push_weight(w + L.w, L.din, 0, 256, 256, Builder::iota(256, c * 256), 256));
         }
-        cur = &tb.add(kActPairOut, 1);
-        const int geo = 3 * m.n_pairs;
-        std::vector<int> perm;
-        for (int k = 0; k < 256; ++k) perm.push_back(geo + k);
-        for (int k = 0; k < geo; ++k) perm.push_back(k);
-        cur = tb.stack(m.tuple_encoder, cur, Builder::pad16(256 + geo), &perm);
+        Phase &pair = tb.add(kActOut, 1);
+        pair.d_col = 0;
+        pair.n = 256;
+        pair.cols = 256;
+        pair.dst_col = 0;
+        pair.bias_off = tb.push_bias(w + L.b, nullptr, 0, 256, 256);
+        cur = tb.wide_first_layer(T0, &pair, Builder::iota(256, 30), kActCoordsB, Builder::iota(30), 32, 0, nullptr);
     }
-    cur->store_feat = 1;                         // feat = tuple_encoder output, needed by both heads
-    cur = tb.stack(m.logit_encoder, cur, 256, nullptr);
-    cur->action = kActFinal;                     // logits [T,192] float32
-    cur->out_sel = 0;
-    cur->out_ld = 192;
-    cur->cols = 192;
-    cur->reload_feat = 1;
-    cur = tb.stack(m.scale_encoder, cur, 256, nullptr);
-    cur->action = kActFinal;                     // scale [T,3] float32
-    cur->out_sel = 1;
-    cur->out_ld = 3;
-    cur->cols = 3;
+    {
+        Builder::OutSpec feat;      // tuple_encoder output = the feature both heads read: keep a bf16 copy
+        feat.store_feat = 1;
+        // layers 1..4 are 128 -> 128; layer 5 widens to 256: append_stack parks layer 4's output in X[128:256)
+        cur = append_stack(tb, m.tuple_encoder, 1, cur, 0, feat);
+        Builder::OutSpec logits;
+        logits.action = kActFinal;
+        logits.out_sel = 0;
+        logits.out_ld = 192;
+        cur = append_stack(tb, m.logit_encoder, 0, cur, 0, logits);
+        cur->reload_feat = 1;       // the last logits chunk reloads the feature for the scale head
+        Builder::OutSpec scale;
+        scale.action = kActFinal;
+        scale.out_sel = 1;
+        scale.out_ld = 3;
+        cur = append_stack(tb, m.scale_encoder, 0, cur, 0, scale);
+    }
     if (pb.prog.n_phases > kMaxPhases || tb.prog.n_phases > kMaxPhases) {
         delete st;
         return CPPF_ERR_UNSUPPORTED;
@@ -672,6 +839,10 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
     __nv_bfloat16 *point_feat = static_cast<__nv_bfloat16 *>(ws);
     __nv_bfloat16 *feat_scratch = reinterpret_cast<__nv_bfloat16 *>(static_cast<unsigned char *>(ws) + tc_align(2 * static_cast<size_t>(st->point_cols) * n));
     const int sms = device_info().sm_count;
+    auto blocks_for = [&](int64_t rows) {
+        const int64_t tiles = (rows + kRows - 1) / kRows;
+        return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((tiles + kSlots - 1) / kSlots, sms)));
+    };
     {
         Args a{};
         a.rows = n;
@@ -681,8 +852,7 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.weights = st->d_point_w;
         a.bias = st->d_point_b;
         a.out_bf16 = point_feat;
-        const int blocks = static_cast<int>(std::min<int64_t>((n + kRows - 1) / kRows, sms));
-        chain_tc_kernel<<<blocks, kThreads, kSmemTotal, s>>>(st->d_point_prog, a);
+        chain_tc_kernel<<<blocks_for(n), kThreads, kSmemTotal, s>>>(st->d_point_prog, a);
         CPPF_LAUNCH_CHECK();
     }
     if (T == 0) return CPPF_OK;
@@ -699,8 +869,7 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.feat_scratch = feat_scratch;
         a.out0 = logits;
         a.out1 = scale;
-        const int blocks = static_cast<int>(std::min<int64_t>((T + kRows - 1) / kRows, sms));
-        chain_tc_kernel<<<blocks, kThreads, kSmemTotal, s>>>(st->d_tuple_prog, a);
+        chain_tc_kernel<<<blocks_for(T), kThreads, kSmemTotal, s>>>(st->d_tuple_prog, a);
         CPPF_LAUNCH_CHECK();
     }
     return CPPF_OK;
