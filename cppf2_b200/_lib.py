@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcppf_b200.so")
+LIB_PATH = os.environ.get("CPPF_B200_LIB") or os.path.join(_HERE, "libcppf_b200.so")   # override: experiment builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 CPPF_STATUS_GRID_OVERFLOW = 1

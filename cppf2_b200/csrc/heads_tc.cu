@@ -24,6 +24,10 @@
 #include <cstring>
 #include <vector>
 
+#ifndef CPPF_TC_EXP
+#define CPPF_TC_EXP 0      // timing experiments only (tools/heads_profile.py): bit 0 no bias loads, 1 issuer sleeps when idle,
+#endif                     // 2 no Final stores, 3 no TMEM loads, 4 no feature spill
+
 namespace cppf {
 namespace tc {
 
@@ -36,7 +40,7 @@ constexpr int kStages = 5;
 constexpr int kSlabBytes = 16384;          // N<=128: 64 K-columns, N=256: 32 K-columns
 constexpr int kSlotWarps = 8;
 constexpr int kEpiWarps = kSlots * kSlotWarps;
-constexpr int kThreads = (kEpiWarps + 2) * 32;        // 576
+constexpr int kThreads = (kEpiWarps + 1 + kSlots) * 32;   // 608: epilogue warps, weight producer, one MMA issuer per slot
 constexpr int kTmemCols = 512;
 constexpr int kSlotTmem = 256;             // TMEM columns per slot: D at +0 (and +128), H at +128
 constexpr int kHTmem = 128;
@@ -44,7 +48,10 @@ constexpr int kMaxPhases = 48;
 
 constexpr int kSmemX = 0;
 constexpr int kSmemRing = kSmemX + kSlots * kXBytes;              // 131072
-constexpr int kSmemBar = kSmemRing + kStages * kSlabBytes;        // 212992
+constexpr int kIdxStride = 5;              // staged tuple indices per row (the tile layouts assume 5-point tuples)
+constexpr int kSmemIdx = kSmemRing + kStages * kSlabBytes;        // 212992: int32 [kSlots][128][kIdxStride]
+constexpr int kSmemOnes = kSmemIdx + kSlots * kRows * kIdxStride * 4;   // 128 x 16 bf16 operand: columns 0,1 = 1, rest 0
+constexpr int kSmemBar = kSmemOnes + 2 * kPlane;
 constexpr int kSmemTotal = kSmemBar + 256;
 
 // ---- program description (built on the host, read by every role) ---------------------------------------
@@ -60,8 +67,9 @@ enum Action : int {
     kActFinal = 8,        // global output = D + b
 };
 
-struct Part {             // one A operand x one weight matrix, accumulated into D[d_col : d_col + n)
-    int a_tmem;           // 0: A = X in shared memory, 1: A = H in TMEM
+struct Part {             // one A operand x one weight matrix, accumulated into D[d_col : d_col + n)   (host only)
+    int a_tmem;           // 0: A = X in shared memory, 1: A = H in TMEM, 2: A = the constant ones operand (bias part:
+                          //    B = [hi(bias) | lo(bias) | 0 ...], so that D += bias to ~16 mantissa bits)
     int a_col;            // first column of the operand (bf16 elements)
     int k_cols;           // multiple of 16
     int d_col;            // accumulator column offset inside the slot
@@ -70,11 +78,30 @@ struct Part {             // one A operand x one weight matrix, accumulated into
     int64_t w_off;        // bytes, into the program's slab stream
 };
 
+// One slab of the weight stream = one TMA copy = up to four MMAs per slot.  Built on the host so that the single
+// issuing warp does nothing per slab but test two barriers and fire the MMAs.
+struct Slab {
+    uint32_t a_lo;        // A in shared memory: low descriptor word relative to the slot's X buffer; in TMEM: column offset
+    uint32_t idesc;
+    uint16_t n;           // UMMA N: B-descriptor LBO = 16 n bytes, K-step = 32 n bytes
+    uint16_t d_col;
+    uint16_t bytes16;     // slab size / 16
+    uint8_t n_mma;        // 1..4
+    uint8_t flags;
+};
+enum : uint8_t {
+    kSlabATmem = 1,       // A operand in TMEM
+    kSlabFirst = 2,       // first slab of a phase: wait for the slot's operand
+    kSlabLast = 4,        // last slab of a phase: signal the slot's epilogue
+    kSlabAcc = 8,         // the first MMA accumulates (else it overwrites D)
+    kSlabOnes = 16,       // A = the constant ones operand (bias rows as B)
+};
+constexpr int kMaxSlabs = 256;
+
 struct Phase {
     int action;           // what the slot's epilogue warps do before the phase's MMAs
     int wait_done;        // the action first waits for the slot's previous MMAs
     int n_parts;          // 0: no MMA follows the action
-    Part part[2];
     // action parameters
     int src_col;          // LoadRows: first source column; Gather: tuple slot
     int cols;             // LoadRows: valid source columns; Final: valid output columns of this chunk
@@ -85,13 +112,14 @@ struct Phase {
     int store_feat, reload_feat;
     int out_sel;          // Final: 0 = out0 (float32), 1 = out1 (float32), 2 = point features (bf16)
     int out_ld;
-    int64_t bias_off;     // floats, into the bias blob (start of this chunk)
 };
 
 struct Program {
     int n_phases;
+    int n_slabs;
     int gather_cols;
     Phase phase[kMaxPhases];
+    Slab slab[kMaxSlabs];
 };
 
 struct Args {
@@ -103,10 +131,10 @@ struct Args {
     IdxView idx;
     int arity;
     const unsigned char *weights;       // slab stream of this program
-    const float *bias;
     __nv_bfloat16 *feat_scratch;        // [rows][256] bf16
     float *out0, *out1;
     __nv_bfloat16 *out_bf16;
+    long long *prof;                    // optional [gridDim.x][64] cycle counters (cppf_debug_heads_tc_profile)
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------
@@ -127,6 +155,17 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok));
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
@@ -136,6 +175,11 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -200,6 +244,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
 }
+// relu fused into the conversion (low half <- a, high half <- b)
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
 __device__ __forceinline__ uint4 pack8(const float v[8]) {
     return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
 }
@@ -228,32 +278,25 @@ __device__ __forceinline__ int64_t tile_of(int round, int slot) {
 template <int NB>
 __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, unsigned char *X, uint32_t t_slot_lane, int row,
                                                int64_t grow, bool live, int c /* column inside the chunk */) {
-    float v[NB];
-    const float *bias = a.bias + ph.bias_off + c;
-    float4 b4[NB / 4];
+    float v[NB];     // the bias is already in the accumulator (ones-operand MMA)
+    if (CPPF_TC_EXP & 8) {
 #pragma unroll
-    for (int j = 0; j < NB / 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4 *>(bias) + j);
-    if (NB == 32) tmem_ld32(t_slot_lane + static_cast<uint32_t>(ph.d_col + c), v);
+        for (int j = 0; j < NB; ++j) v[j] = static_cast<float>(row + j);
+    } else if (NB == 32) tmem_ld32(t_slot_lane + static_cast<uint32_t>(ph.d_col + c), v);
     else tmem_ld8(t_slot_lane + static_cast<uint32_t>(ph.d_col + c), v);
-#pragma unroll
-    for (int j = 0; j < NB / 4; ++j) {
-        v[4 * j] += b4[j].x;
-        v[4 * j + 1] += b4[j].y;
-        v[4 * j + 2] += b4[j].z;
-        v[4 * j + 3] += b4[j].w;
-    }
     if (ph.action == kActHiddenT) {
         uint32_t p[NB / 2];
 #pragma unroll
-        for (int j = 0; j < NB / 2; ++j) p[j] = pack2(fmaxf(v[2 * j], 0.0f), fmaxf(v[2 * j + 1], 0.0f));
+        for (int j = 0; j < NB / 2; ++j) p[j] = pack2_relu(v[2 * j], v[2 * j + 1]);
         const uint32_t h_addr = t_slot_lane + kHTmem + static_cast<uint32_t>((ph.dst_col + c) >> 1);
         if (NB == 32) tmem_st16(h_addr, p);
         else tmem_st4(h_addr, p);
     } else if (ph.action == kActHiddenS) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) v[j] = fmaxf(v[j], 0.0f);
-#pragma unroll
-        for (int j = 0; j < NB / 8; ++j) *reinterpret_cast<uint4 *>(act_chunk(X, row, (ph.dst_col + c) / 8 + j)) = pack8(v + 8 * j);
+        for (int j = 0; j < NB / 8; ++j)
+            *reinterpret_cast<uint4 *>(act_chunk(X, row, (ph.dst_col + c) / 8 + j)) =
+                make_uint4(pack2_relu(v[8 * j], v[8 * j + 1]), pack2_relu(v[8 * j + 2], v[8 * j + 3]), pack2_relu(v[8 * j + 4], v[8 * j + 5]),
+                           pack2_relu(v[8 * j + 6], v[8 * j + 7]));
     } else if (ph.action == kActOut) {
         if (ph.residual) {
 #pragma unroll
@@ -268,9 +311,9 @@ __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, u
         for (int j = 0; j < NB / 8; ++j) {
             const uint4 packed = pack8(v + 8 * j);
             *reinterpret_cast<uint4 *>(act_chunk(X, row, (ph.dst_col + c) / 8 + j)) = packed;
-            if (ph.store_feat && live) __stcg(reinterpret_cast<uint4 *>(a.feat_scratch + grow * 256 + ph.dst_col + c + 8 * j), packed);
+            if (!(CPPF_TC_EXP & 16) && ph.store_feat && live) __stcg(reinterpret_cast<uint4 *>(a.feat_scratch + grow * 256 + ph.dst_col + c + 8 * j), packed);
         }
-    } else if (live) {   // kActFinal
+    } else if (live && !((CPPF_TC_EXP & 4) && ph.out_sel != 2)) {   // kActFinal
         if (ph.out_sel == 2) {
 #pragma unroll
             for (int j = 0; j < NB / 8; ++j)
@@ -290,21 +333,22 @@ __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, u
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__restrict__ prog_g, Args a) {
+// The program lives in kernel-parameter (constant) space: every field the MMA issuer and the producer read is a
+// uniform-datapath load indexed by warp-uniform counters, which is what lets tcgen05.mma / cp.async.bulk take their
+// descriptors from uniform registers without per-lane "waterfall" loops (tools/probes/probe_mma_rate.cu: 64 cycles
+// per M128 N128 K16 MMA when issued that way, 160-400 when issued from lane-divergent code).
+__global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_constant__ Program prog, const __grid_constant__ Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ Program prog;
     __shared__ uint32_t s_tmem_base;
     const uint32_t ring0 = smem_u32(smem + kSmemRing);
     const uint32_t bar0 = smem_u32(smem + kSmemBar);
     const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * kStages, bar_act = bar0 + 16 * kStages, bar_done = bar_act + 8 * kSlots;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < static_cast<int>(sizeof(Program) / 4); i += kThreads)
-        reinterpret_cast<uint32_t *>(&prog)[i] = reinterpret_cast<const uint32_t *>(prog_g)[i];
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, kSlots);     // a slab is shared: both slots' MMAs must retire before it is refilled
         }
         for (int s = 0; s < kSlots; ++s) {
             mbar_init(bar_act + 8 * s, kSlotWarps);
@@ -312,6 +356,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < 2 * kRows) {   // ones operand, K-major core-matrix layout like X: plane 0 = columns 0..7, plane 1 = columns 8..15
+        const uint32_t one2 = 0x3f803f80u;   // bf16 (1, 1)
+        *reinterpret_cast<uint4 *>(smem + kSmemOnes + tid * 16) = tid < kRows ? make_uint4(one2, 0, 0, 0) : make_uint4(0, 0, 0, 0);
+    }
+    fence_async_smem();
     if (warp == 0) {  // the whole TMEM: two slots x 256 columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -320,77 +369,108 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
+    if (tmem != 0) __trap();     // one CTA per SM owning all 512 columns: the allocation starts at lane 0, column 0
     const int64_t n_tiles = (a.rows + kRows - 1) / kRows;
     const int n_rounds = static_cast<int>((n_tiles + static_cast<int64_t>(kSlots) * gridDim.x - 1) / (static_cast<int64_t>(kSlots) * gridDim.x));
 
     if (warp == kEpiWarps) {
         // =============================== weight producer ===============================================
-        if (lane == 0) {
-            uint32_t seq = 0;
-            for (int round = 0; round < n_rounds; ++round)
-                for (int p = 0; p < prog.n_phases; ++p) {
-                    const Phase &ph = prog.phase[p];
-                    if (ph.n_parts == 0) continue;
-                    for (int s = 0; s < kSlots; ++s) {
-                        if (tile_of(round, s) >= n_tiles) continue;
-                        for (int q = 0; q < ph.n_parts; ++q) {
-                            const Part &pt = ph.part[q];
-                            const int slab_k = pt.n <= 128 ? 64 : 32;
-                            const unsigned char *src = a.weights + pt.w_off;
-                            for (int k_left = pt.k_cols; k_left > 0; k_left -= slab_k, ++seq) {
-                                const int cols = k_left < slab_k ? k_left : slab_k;
-                                const uint32_t bytes = static_cast<uint32_t>(pt.n) * 2u * cols;
-                                const uint32_t stage = seq % kStages, turn = seq / kStages;
-                                mbar_wait(bar_empty + 8 * stage, (turn & 1u) ^ 1u);
-                                mbar_expect_tx(bar_full + 8 * stage, bytes);
-                                bulk_load(ring0 + stage * kSlabBytes, src, bytes, bar_full + 8 * stage);
-                                src += bytes;
-                            }
-                        }
-                    }
+        // One pass over the slab stream per round; every slab serves both slots of the round.  The whole warp runs
+        // the (uniform) loop; the elected lane issues the copies.
+        const bool leader = elect_one();
+        uint32_t seq = 0;
+        long long t_wait = 0;
+        const long long t_begin = clock64();
+        for (int round = 0; round < n_rounds; ++round) {
+            if (tile_of(round, 0) >= n_tiles) break;
+            const unsigned char *src = a.weights;
+            for (int i = 0; i < prog.n_slabs; ++i, ++seq) {
+                const uint32_t bytes = static_cast<uint32_t>(prog.slab[i].bytes16) << 4;
+                const uint32_t stage = seq % kStages, turn = seq / kStages;
+                const long long t0 = clock64();
+                mbar_wait(bar_empty + 8 * stage, (turn & 1u) ^ 1u);
+                t_wait += clock64() - t0;
+                if (leader) {
+                    mbar_expect_tx(bar_full + 8 * stage, bytes);
+                    bulk_load(ring0 + stage * kSlabBytes, src, bytes, bar_full + 8 * stage);
                 }
+                __syncwarp();
+                src += bytes;
+            }
         }
-    } else if (warp == kEpiWarps + 1) {
-        // =============================== MMA issuer =====================================================
-        if (lane == 0) {
-            uint32_t seq = 0, act_seq[kSlots] = {0, 0};
-            for (int round = 0; round < n_rounds; ++round)
-                for (int p = 0; p < prog.n_phases; ++p) {
-                    const Phase &ph = prog.phase[p];
-                    if (ph.n_parts == 0) continue;
-                    for (int s = 0; s < kSlots; ++s) {
-                        if (tile_of(round, s) >= n_tiles) continue;
-                        mbar_wait(bar_act + 8 * s, act_seq[s] & 1u);   // the slot's A operand is ready, its D is free
-                        ++act_seq[s];
-                        tc_fence_after();
-                        const uint32_t t_slot = tmem + static_cast<uint32_t>(s * kSlotTmem);
-                        const uint32_t x_base = smem_u32(smem + kSmemX + s * kXBytes);
-                        for (int q = 0; q < ph.n_parts; ++q) {
-                            const Part &pt = ph.part[q];
-                            const int slab_k = pt.n <= 128 ? 64 : 32;
-                            const uint32_t idesc = instr_desc(pt.n);
-                            const uint32_t b_plane = static_cast<uint32_t>(pt.n) * 16u;
-                            const uint32_t d_addr = t_slot + static_cast<uint32_t>(pt.d_col);
-                            uint32_t accumulate = pt.init ? 0u : 1u;
-                            for (int k_done = 0; k_done < pt.k_cols; k_done += slab_k, ++seq) {
-                                const int cols = pt.k_cols - k_done < slab_k ? pt.k_cols - k_done : slab_k;
-                                const uint32_t stage = seq % kStages, turn = seq / kStages;
-                                mbar_wait(bar_full + 8 * stage, turn & 1u);
-                                tc_fence_after();
-                                const uint32_t b_base = ring0 + stage * kSlabBytes;
-                                for (int k = 0; k < cols; k += 16) {
-                                    const uint64_t bd = smem_desc(b_base + (k >> 3) * b_plane, b_plane, 128);
-                                    const int ak = pt.a_col + k_done + k;
-                                    if (pt.a_tmem) umma_ts(d_addr, t_slot + kHTmem + static_cast<uint32_t>(ak >> 1), bd, idesc, accumulate);
-                                    else umma_ss(d_addr, smem_desc(x_base + (ak >> 3) * kPlane, kPlane, 128), bd, idesc, accumulate);
-                                    accumulate = 1;
-                                }
-                                umma_commit(bar_empty + 8 * stage);   // slab consumed once these MMAs retire
-                            }
-                        }
-                        umma_commit(bar_done + 8 * s);
-                    }
+        if (a.prof && leader) {
+            a.prof[blockIdx.x * 64 + 4] = clock64() - t_begin;
+            a.prof[blockIdx.x * 64 + 5] = t_wait;
+        }
+    } else if (warp > kEpiWarps) {
+        // =============================== MMA issuers (one warp per slot) ================================
+        // Each slot has its own issuing warp walking the slab list in order with blocking waits, exactly like a GEMM
+        // main loop; the two warps interleave on the tensor pipe by themselves, and a slab is released to the producer
+        // when both have retired their MMAs on it (bar_empty counts two).  The warp runs converged on warp-uniform
+        // state (loop counters, kernel-parameter loads), so every descriptor lives in uniform registers; only the
+        // tcgen05 instructions are predicated on the elected lane.
+        const int s = warp - (kEpiWarps + 1);
+        const bool leader = elect_one();
+        long long t_act = 0, t_full = 0, t_issue = 0, n_steps = 0;
+        const long long t_begin = clock64();
+        constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);    // SBO = 128 B, descriptor version bit 46
+        const uint32_t ones_lo = (smem_u32(smem + kSmemOnes) >> 4) | (static_cast<uint32_t>(kPlane >> 4) << 16);
+        const uint32_t x_lo = smem_u32(smem + kSmemX + s * kXBytes) >> 4;
+        const uint32_t t_slot = static_cast<uint32_t>(s * kSlotTmem);     // TMEM base is 0: the CTA owns all 512 columns (checked above)
+        uint32_t stage = 0, turn = 0, act_par = 0;
+        for (int round = 0; round < n_rounds; ++round) {
+            if (tile_of(round, s) >= n_tiles) break;
+            // slot 1 never runs a round that slot 0 skips; slot 0 releases the slabs alone in rounds slot 1 skips
+            const bool other_active = s == 1 || tile_of(round, 1) < n_tiles;
+            for (int i = 0; i < prog.n_slabs; ++i) {
+                const Slab &sl = prog.slab[i];
+                const uint32_t flags = sl.flags;
+                long long t0 = clock64();
+                if (flags & kSlabFirst) {        // the slot's A operand is ready and its accumulator is free
+                    mbar_wait(bar_act + 8 * s, act_par);
+                    act_par ^= 1u;
                 }
+                long long t1 = clock64();
+                mbar_wait(bar_full + 8 * stage, turn);
+                tc_fence_after();
+                long long t2 = clock64();
+                if (leader) {
+                    const uint32_t n = sl.n, n_mma = sl.n_mma, idesc = sl.idesc;
+                    const uint32_t d_addr = t_slot + sl.d_col;
+                    const uint32_t b_lo = ((ring0 + stage * kSlabBytes) >> 4) | (n << 16);     // LBO = plane of n rows x 16 B
+                    const uint32_t a_lo = (flags & kSlabATmem) ? t_slot + sl.a_lo : (flags & kSlabOnes) ? ones_lo : x_lo + sl.a_lo;
+                    const uint32_t a_step = (flags & kSlabATmem) ? 8u : static_cast<uint32_t>((2 * kPlane) >> 4);
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 4; ++ks) {
+                        if (ks < n_mma && !(CPPF_TC_EXP & 32)) {
+                            const uint64_t bd = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + ks * 2u * n);
+                            const uint32_t acc = (ks > 0 || (flags & kSlabAcc)) ? 1u : 0u;
+                            if (flags & kSlabATmem) umma_ts(d_addr, a_lo + ks * a_step, bd, idesc, acc);
+                            else umma_ss(d_addr, (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + ks * a_step), bd, idesc, acc);
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * stage);                 // this slot is done with the slab once these MMAs retire
+                    if (!other_active) mbar_arrive(bar_empty + 8 * stage);
+                    if (flags & kSlabLast) umma_commit(bar_done + 8 * s);
+                }
+                __syncwarp();
+                if (++stage == kStages) {
+                    stage = 0;
+                    turn ^= 1u;
+                }
+                t_act += t1 - t0;
+                t_full += t2 - t1;
+                t_issue += clock64() - t2;
+                ++n_steps;
+            }
+        }
+        if (a.prof && leader) {
+            long long *o = a.prof + blockIdx.x * 64 + 40 + 8 * s;
+            o[0] = clock64() - t_begin;
+            o[1] = t_act;
+            o[2] = t_full;
+            o[3] = t_issue;
+            o[4] = n_steps;
         }
     } else {
         // =============================== prologue / epilogue warps of one slot ===========================
@@ -398,78 +478,101 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__
         const int row = (sw & 3) * 32 + lane;          // TMEM lane == tile row  (warp % 4 selects the lane quadrant)
         const int half = sw >> 2;                      // which half of the chunk's columns this thread handles
         unsigned char *X = smem + kSmemX + slot * kXBytes;
+        const uint32_t x_u32 = smem_u32(X);
+        int *idx_s = reinterpret_cast<int *>(smem + kSmemIdx) + slot * kRows * kIdxStride;
         const uint32_t t_slot_lane = tmem + static_cast<uint32_t>(slot * kSlotTmem) + (static_cast<uint32_t>((sw & 3) * 32) << 16);
         // (8 rows x 4 chunks) per warp pass for the row movers: conflict-free 16-byte shared stores, whole 32 B sectors
         const int mv_r = lane & 7, mv_c = lane >> 3;
         uint32_t done_seq = 0;
+        long long t_done = 0, t_actn[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t_arrive = 0;
+        const long long t_begin = clock64();
         for (int round = 0; round < n_rounds; ++round) {
             const int64_t tile = tile_of(round, slot);
             if (tile >= n_tiles) break;
             const int64_t row_base = tile * kRows;
             const int64_t grow = row_base + row;
             const bool live = grow < a.rows;
+            if (a.idx.ptr != nullptr) {
+                // the tile's tuple indices, once: every gather below reads them from shared memory
+                for (int e = stid; e < kRows * a.arity; e += kSlotWarps * 32) {
+                    const int r = e / a.arity, k = e - r * a.arity;
+                    idx_s[r * kIdxStride + k] = row_base + r < a.rows ? static_cast<int>(a.idx.at(row_base + r, k)) : 0;
+                }
+                named_bar(1 + slot, kSlotWarps * 32);
+            }
             for (int p = 0; p < prog.n_phases; ++p) {
                 const Phase &ph = prog.phase[p];
+                long long t0 = clock64();
                 if (ph.wait_done) {
                     mbar_wait(bar_done + 8 * slot, done_seq & 1u);
                     ++done_seq;
                     tc_fence_after();
                 }
+                long long t1 = clock64();
+                t_done += t1 - t0;
                 switch (ph.action) {
                     case kActLoadRows: {
                         const int cb_n = ph.width >> 5;                  // blocks of 4 chunks
-                        for (int it = sw; it < 16 * cb_n; it += kSlotWarps) {
-                            const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
-                            float v[8];
-                            const int64_t gr = row_base + r;
+                        for (int it0 = sw; it0 < 16 * cb_n; it0 += 4 * kSlotWarps) {
+                            float4 lo[4], hi[4];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-                            if (gr < a.rows && c8 * 8 < ph.cols) {      // cols is a multiple of 8
-                                const float4 *src = reinterpret_cast<const float4 *>(a.x + gr * a.x_ld + ph.src_col + c8 * 8);
-                                const float4 lo = __ldg(src), hi = __ldg(src + 1);
-                                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-                                v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+                            for (int u = 0; u < 4; ++u) {               // four independent row segments in flight
+                                const int it = it0 + u * kSlotWarps;
+                                const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
+                                const int64_t gr = row_base + r;
+                                lo[u] = hi[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                if (it < 16 * cb_n && gr < a.rows && c8 * 8 < ph.cols) {      // cols is a multiple of 8
+                                    const float4 *src = reinterpret_cast<const float4 *>(a.x + gr * a.x_ld + ph.src_col + c8 * 8);
+                                    lo[u] = __ldg(src);
+                                    hi[u] = __ldg(src + 1);
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int it = it0 + u * kSlotWarps;
+                                if (it >= 16 * cb_n) break;
+                                const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
+                                float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] = (v[j] == v[j]) ? v[j] : 0.0f;   // NaN rows of invalid SHOT points count as zeros (eval.py:215)
+                                *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = pack8(v);
                             }
-                            *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = pack8(v);
                         }
                         break;
                     }
                     case kActEncodeShotA:
                     case kActGather: {
-                        // 32 chunks of 8 bf16 per row: SHOT = features of tuple slots 0..3 (64 wide each), DINO = one 256-wide row
+                        // 32 chunks of 8 bf16 per row: SHOT = features of tuple slots 0..3 (64 wide each), DINO = one 256-wide
+                        // row; asynchronous 16-byte copies straight into the operand layout, all in flight at once
                         for (int it = sw; it < 16 * 8; it += kSlotWarps) {
                             const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
-                            uint4 v = make_uint4(0, 0, 0, 0);
-                            if (row_base + r < a.rows) {
-                                const __nv_bfloat16 *src = ph.action == kActGather
-                                                               ? a.point_feat + a.idx.at(row_base + r, ph.src_col) * 256 + c8 * 8
-                                                               : a.point_feat + a.idx.at(row_base + r, c8 >> 3) * 64 + (c8 & 7) * 8;
-                                v = __ldg(reinterpret_cast<const uint4 *>(src));
-                            }
-                            *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = v;
+                            const bool ok = row_base + r < a.rows;
+                            const __nv_bfloat16 *src = ph.action == kActGather
+                                                           ? a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + ph.src_col]) * 256 + c8 * 8
+                                                           : a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + (c8 >> 3)]) * 64 + (c8 & 7) * 8;
+                            cp_async16(x_u32 + c8 * kPlane + r * 16, src, ok ? 16u : 0u);
                         }
+                        cp_async_wait_all();
                         break;
                     }
                     case kActEncodeShotB: {
                         for (int it = sw; it < 16 * 2; it += kSlotWarps) {   // features of tuple slot 4 -> columns 0..63
                             const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
-                            uint4 v = make_uint4(0, 0, 0, 0);
-                            if (row_base + r < a.rows) v = __ldg(reinterpret_cast<const uint4 *>(a.point_feat + a.idx.at(row_base + r, 4) * 64 + c8 * 8));
-                            *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = v;
+                            const bool ok = row_base + r < a.rows;
+                            cp_async16(x_u32 + c8 * kPlane + r * 16, a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + 4]) * 64 + c8 * 8, ok ? 16u : 0u);
                         }
                         if (stid < kRows) {   // geometry of row `stid`: coords -> columns 64..93, normals -> 94..103, zeros -> 104..111
                             const int64_t g = row_base + stid;
                             if (g < a.rows) {
                                 int64_t pt[8];
-                                for (int k = 0; k < a.arity; ++k) pt[k] = a.idx.at(g, k);
+                                for (int k = 0; k < a.arity; ++k) pt[k] = idx_s[stid * kIdxStride + k];
                                 encode_tuple_geometry(a.pc, a.normal, pt, a.arity, true, [&](int col, float v) { put_elem(X, stid, 64 + col, v); });
                             } else {
                                 for (int c = 64; c < 104; ++c) put_elem(X, stid, c, 0.0f);
                             }
                             *reinterpret_cast<uint4 *>(act_chunk(X, stid, 13)) = make_uint4(0, 0, 0, 0);
                         }
+                        cp_async_wait_all();
                         break;
                     }
                     case kActCoordsB: {
@@ -478,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__
                             *reinterpret_cast<uint4 *>(act_chunk(X, stid, 3)) = make_uint4(0, 0, 0, 0);
                             if (g < a.rows) {
                                 int64_t pt[8];
-                                for (int k = 0; k < a.arity; ++k) pt[k] = a.idx.at(g, k);
+                                for (int k = 0; k < a.arity; ++k) pt[k] = idx_s[stid * kIdxStride + k];
                                 encode_tuple_geometry(a.pc, a.normal, pt, a.arity, false, [&](int col, float v) { put_elem(X, stid, col, v); });
                             } else {
                                 for (int c = 0; c < 30; ++c) put_elem(X, stid, c, 0.0f);
@@ -502,22 +605,32 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__
                             // X <- the spilled tuple feature (written by this slot's own threads in an earlier phase)
                             for (int it = sw; it < 16 * 8; it += kSlotWarps) {
                                 const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
-                                uint4 v = make_uint4(0, 0, 0, 0);
-                                if (row_base + r < a.rows) v = __ldcg(reinterpret_cast<const uint4 *>(a.feat_scratch + (row_base + r) * 256 + c8 * 8));
-                                *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = v;
+                                const bool ok = row_base + r < a.rows;
+                                cp_async16(x_u32 + c8 * kPlane + r * 16, a.feat_scratch + (ok ? row_base + r : row_base) * 256 + c8 * 8, ok ? 16u : 0u);
                             }
+                            cp_async_wait_all();
                         }
                         break;
                     }
                     default: break;
                 }
+                t0 = clock64();
+                t_actn[ph.action] += t0 - t1;
                 if (ph.n_parts) {
-                    fence_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
+                    if (ph.action != kActHiddenT) fence_async_smem();      // generic-proxy writes to X -> visible to the tensor core's async proxy
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_act + 8 * slot);
                 }
+                t_arrive += clock64() - t0;
             }
+        }
+        if (a.prof && sw == 0 && lane == 0) {
+            long long *o = a.prof + blockIdx.x * 64 + 8 + 16 * slot;
+            o[0] = clock64() - t_begin;
+            o[1] = t_done;
+            for (int k = 0; k < 9; ++k) o[2 + k] = t_actn[k];
+            o[11] = t_arrive;
         }
     }
     tc_fence_before();
@@ -531,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const Program *__
 struct Builder {
     Program prog{};
     std::vector<uint16_t> stream;     // bf16 bits of the slab stream
-    std::vector<float> bias;
+    std::vector<std::vector<Part>> parts = std::vector<std::vector<Part>>(kMaxPhases);   // per phase, in stream order
     const float *w;
 
     static uint16_t bf16_bits(float f) {
@@ -558,10 +671,21 @@ struct Builder {
         }
         return static_cast<int64_t>(off) * 2;
     }
-    int64_t push_bias(const float *a, const float *b, int n0, int n_real, int n_pad) {
-        const int64_t off = static_cast<int64_t>(bias.size());
-        for (int i = 0; i < n_pad; ++i) bias.push_back(i < n_real ? a[n0 + i] + (b ? b[n0 + i] : 0.0f) : 0.0f);
-        return off;
+    // Bias of the accumulator chunk D[d_col : d_col + n_pad) of phase `ph`: one more K-step of 16 whose B rows are
+    // k = 0: bf16(bias), k = 1: bf16(bias - bf16(bias)) and whose A operand is the constant ones matrix.
+    void add_bias(Phase &ph, int d_col, const float *a, const float *b, int n0, int n_real, int n_pad) {
+        const size_t off = stream.size();
+        stream.resize(off + static_cast<size_t>(n_pad) * 16, 0);
+        for (int n = 0; n < n_real; ++n) {
+            const float v = a[n0 + n] + (b ? b[n0 + n] : 0.0f);
+            const uint16_t hi = bf16_bits(v);
+            uint32_t hb = static_cast<uint32_t>(hi) << 16;
+            float hf;
+            memcpy(&hf, &hb, 4);
+            stream[off + static_cast<size_t>(n) * 8 + 0] = hi;
+            stream[off + static_cast<size_t>(n) * 8 + 1] = bf16_bits(v - hf);
+        }
+        add_part(ph, 2, 0, 16, d_col, n_pad, 0, static_cast<int64_t>(off) * 2);
     }
     static std::vector<int> iota(int n, int start = 0) {
         std::vector<int> v(n);
@@ -576,8 +700,48 @@ struct Builder {
         ph.wait_done = wait_done;
         return ph;
     }
-    static void add_part(Phase &ph, int a_tmem, int a_col, int k_cols, int d_col, int n, int init, int64_t w_off) {
-        ph.part[ph.n_parts++] = Part{a_tmem, a_col, k_cols, d_col, n, init, w_off};
+    void add_part(Phase &ph, int a_tmem, int a_col, int k_cols, int d_col, int n, int init, int64_t w_off) {
+        parts[&ph - prog.phase].push_back(Part{a_tmem, a_col, k_cols, d_col, n, init, w_off});
+        ++ph.n_parts;
+    }
+
+    // Phases -> the slab list the producer and the MMA issuer walk.  Returns false when it does not fit.
+    bool finalize() {
+        int64_t expect = 0;
+        prog.n_slabs = 0;
+        for (int p = 0; p < prog.n_phases; ++p) {
+            const std::vector<Part> &ps = parts[p];
+            for (size_t q = 0; q < ps.size(); ++q) {
+                const Part &pt = ps[q];
+                if (pt.w_off != expect) return false;               // the stream must be consumed in the order it was written
+                const int slab_k = pt.n <= 128 ? 64 : 32;
+                for (int k_done = 0; k_done < pt.k_cols; k_done += slab_k) {
+                    if (prog.n_slabs >= kMaxSlabs) return false;
+                    const int cols = pt.k_cols - k_done < slab_k ? pt.k_cols - k_done : slab_k;
+                    Slab &sl = prog.slab[prog.n_slabs++];
+                    sl = Slab{};
+                    sl.n = static_cast<uint16_t>(pt.n);
+                    sl.d_col = static_cast<uint16_t>(pt.d_col);
+                    sl.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(pt.n >> 3) << 17) | (static_cast<uint32_t>(kRows >> 4) << 24);
+                    sl.n_mma = static_cast<uint8_t>(cols / 16);
+                    sl.bytes16 = static_cast<uint16_t>(pt.n * 2 * cols / 16);
+                    const int col = pt.a_col + k_done;
+                    if (pt.a_tmem == 1) {
+                        sl.flags |= kSlabATmem;
+                        sl.a_lo = static_cast<uint32_t>(kHTmem + (col >> 1));
+                    } else if (pt.a_tmem == 2) {
+                        sl.flags |= kSlabOnes;
+                    } else {
+                        sl.a_lo = (static_cast<uint32_t>((col >> 3) * kPlane) >> 4) | (static_cast<uint32_t>(kPlane >> 4) << 16);
+                    }
+                    if (!(pt.init && k_done == 0)) sl.flags |= kSlabAcc;
+                    if (q == 0 && k_done == 0) sl.flags |= kSlabFirst;
+                    if (q + 1 == ps.size() && k_done + cols >= pt.k_cols) sl.flags |= kSlabLast;
+                    expect += static_cast<int64_t>(pt.n) * 2 * cols;
+                }
+            }
+        }
+        return expect == static_cast<int64_t>(stream.size()) * 2;
     }
 
     // ResLayer whose input (din <= 256 columns) sits in X at in_col; `cur` is the phase whose action produced it.
@@ -603,7 +767,7 @@ struct Builder {
             hid.d_col = 0;
             hid.n = n_pad;
             hid.dst_col = ch.first;
-            hid.bias_off = push_bias(w + L.b1, nullptr, ch.first, ch.second, n_pad);
+            add_bias(*cur, 0, w + L.b1, nullptr, ch.first, ch.second, n_pad);
             cur = &hid;
             h_width = ch.first + n_pad;
         }
@@ -615,6 +779,7 @@ struct Builder {
             for (int j = 0; j < L.dout; ++j) hc[j] = j;
             add_part(*cur, 1, 0, h_width, 0, n_pad, 1, push_weight(w + L.w2, L.dout, ch.first, ch.second, n_pad, hc, h_width));
             if (L.has_fc0) add_part(*cur, 0, in_col, k_in, 0, n_pad, 0, push_weight(w + L.w0, L.din, ch.first, ch.second, n_pad, in_cols, k_in));
+            add_bias(*cur, 0, w + L.b2, L.has_fc0 ? w + L.b0 : nullptr, ch.first, ch.second, n_pad);
             Phase &out = add(os.action, 1);
             out.d_col = 0;
             out.n = n_pad;
@@ -625,7 +790,6 @@ struct Builder {
             out.store_feat = os.store_feat;
             out.out_sel = os.out_sel;
             out.out_ld = os.out_ld;
-            out.bias_off = push_bias(w + L.b2, L.has_fc0 ? w + L.b0 : nullptr, ch.first, ch.second, n_pad);
             cur = &out;
         }
         return cur;
@@ -642,38 +806,34 @@ struct Builder {
         Phase &pb = add(action_b, 1);
         add_part(pb, 0, 0, kb, 0, n, 0, push_weight(w + L.w1, L.din, 0, L.dout, n, cols_b, kb));
         add_part(pb, 0, 0, kb, 128, n, 0, push_weight(w + L.w0, L.din, 0, L.dout, n, cols_b, kb));
+        add_bias(pb, 0, w + L.b1, nullptr, 0, L.dout, n);
         if (phase_b) *phase_b = &pb;
         Phase &hid = add(kActHiddenS, 1);     // H -> X[0:128) (chunk B has been consumed)
         hid.d_col = 0;
         hid.n = n;
         hid.dst_col = 0;
-        hid.bias_off = push_bias(w + L.b1, nullptr, 0, L.dout, n);
         add_part(hid, 0, 0, n, 128, n, 0, push_weight(w + L.w2, L.dout, 0, L.dout, n, iota(L.dout), n));
+        add_bias(hid, 128, w + L.b2, w + L.b0, 0, L.dout, n);
         Phase &out = add(kActOut, 1);
         out.d_col = 128;
         out.n = n;
         out.cols = L.dout;
         out.dst_col = out_col;
-        out.bias_off = push_bias(w + L.b2, w + L.b0, 0, L.dout, n);
         return &out;
     }
 };
 
 struct State {
     HeadsModel model;
-    Program *d_point_prog, *d_tuple_prog;
+    Program point_prog, tuple_prog;     // passed by value as kernel parameters
     unsigned char *d_point_w, *d_tuple_w;
-    float *d_point_b, *d_tuple_b;
     int point_cols;
 };
 
-static int upload(const Builder &b, Program **d_prog, unsigned char **d_w, float **d_b) {
-    CPPF_CUDA_TRY(cudaMalloc(d_prog, sizeof(Program)));
-    CPPF_CUDA_TRY(cudaMemcpy(*d_prog, &b.prog, sizeof(Program), cudaMemcpyHostToDevice));
+static int upload(const Builder &b, Program *prog, unsigned char **d_w) {
+    *prog = b.prog;
     CPPF_CUDA_TRY(cudaMalloc(d_w, b.stream.size() * 2 + 16));
     CPPF_CUDA_TRY(cudaMemcpy(*d_w, b.stream.data(), b.stream.size() * 2, cudaMemcpyHostToDevice));
-    CPPF_CUDA_TRY(cudaMalloc(d_b, b.bias.size() * 4 + 16));
-    CPPF_CUDA_TRY(cudaMemcpy(*d_b, b.bias.data(), b.bias.size() * 4, cudaMemcpyHostToDevice));
     return CPPF_OK;
 }
 
@@ -735,7 +895,7 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
             ph.src_col = c * 256;
             ph.cols = 256;
             ph.width = 256;
-            Builder::add_part(ph, 0, 0, 256, 0, 256, c == 0, pb.push_weight(w + L.w, L.din, 0, 256, 256, Builder::iota(256, c * 256), 256));
+            pb.add_part(ph, 0, 0, 256, 0, 256, c == 0, pb.push_weight(w + L.w, L.din, 0, 256, 256, Builder::iota(256, c * 256), 256));
         }
         Phase &fin = pb.add(kActFinal, 1);
         fin.d_col = 0;
@@ -744,7 +904,7 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         fin.dst_col = 0;
         fin.out_sel = 2;
         fin.out_ld = 256;
-        fin.bias_off = pb.push_bias(w + L.b, nullptr, 0, 256, 256);
+        pb.add_bias(pb.prog.phase[pb.prog.n_phases - 2], 0, w + L.b, nullptr, 0, 256, 256);
         st->point_cols = 256;
     }
     // ---- per-tuple program -------------------------------------------------------------------------------
@@ -766,14 +926,14 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         for (int c = 0; c < m.arity; ++c) {
             Phase &ph = tb.add(kActGather, c > 0);
             ph.src_col = c;
-            Builder::add_part(ph, 0, 0, 256, 0, 256, c == 0, tb.push_weight(w + L.w, L.din, 0, 256, 256, Builder::iota(256, c * 256), 256));
+            tb.add_part(ph, 0, 0, 256, 0, 256, c == 0, tb.push_weight(w + L.w, L.din, 0, 256, 256, Builder::iota(256, c * 256), 256));
         }
         Phase &pair = tb.add(kActOut, 1);
         pair.d_col = 0;
         pair.n = 256;
         pair.cols = 256;
         pair.dst_col = 0;
-        pair.bias_off = tb.push_bias(w + L.b, nullptr, 0, 256, 256);
+        tb.add_bias(tb.prog.phase[tb.prog.n_phases - 2], 0, w + L.b, nullptr, 0, 256, 256);
         cur = tb.wide_first_layer(T0, &pair, Builder::iota(256, 30), kActCoordsB, Builder::iota(30), 32, 0, nullptr);
     }
     {
@@ -793,13 +953,13 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         scale.out_ld = 3;
         cur = append_stack(tb, m.scale_encoder, 0, cur, 0, scale);
     }
-    if (pb.prog.n_phases > kMaxPhases || tb.prog.n_phases > kMaxPhases) {
+    if (pb.prog.n_phases > kMaxPhases || tb.prog.n_phases > kMaxPhases || !pb.finalize() || !tb.finalize()) {
         delete st;
         return CPPF_ERR_UNSUPPORTED;
     }
     pb.prog.gather_cols = tb.prog.gather_cols = st->point_cols;
-    int rc = upload(pb, &st->d_point_prog, &st->d_point_w, &st->d_point_b);
-    if (rc == CPPF_OK) rc = upload(tb, &st->d_tuple_prog, &st->d_tuple_w, &st->d_tuple_b);
+    int rc = upload(pb, &st->point_prog, &st->d_point_w);
+    if (rc == CPPF_OK) rc = upload(tb, &st->tuple_prog, &st->d_tuple_w);
     if (rc != CPPF_OK) {
         delete st;
         return rc;
@@ -809,15 +969,15 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
     return CPPF_OK;
 }
 
+static long long *g_tc_prof = nullptr;
+// Debug hook: device buffer of [148][64] int64 cycle counters filled by the next launches (nullptr switches it off).
+CPPF_API void cppf_debug_heads_tc_profile(void *dev_counters) { g_tc_prof = static_cast<long long *>(dev_counters); }
+
 extern "C" void cppf_heads_tc_destroy(void *state) {
     State *st = static_cast<State *>(state);
     if (!st) return;
-    cudaFree(st->d_point_prog);
-    cudaFree(st->d_tuple_prog);
     cudaFree(st->d_point_w);
     cudaFree(st->d_tuple_w);
-    cudaFree(st->d_point_b);
-    cudaFree(st->d_tuple_b);
     delete st;
 }
 
@@ -841,7 +1001,8 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
     const int sms = device_info().sm_count;
     auto blocks_for = [&](int64_t rows) {
         const int64_t tiles = (rows + kRows - 1) / kRows;
-        return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((tiles + kSlots - 1) / kSlots, sms)));
+        // every SM gets a CTA; tile_of() fills the first slots of all CTAs before any second slot
+        return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, sms)));
     };
     {
         Args a{};
@@ -850,9 +1011,9 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.x_ld = st->model.branch == 0 ? CPPF_SHOT_DIM : 1024;
         a.arity = st->model.arity;
         a.weights = st->d_point_w;
-        a.bias = st->d_point_b;
         a.out_bf16 = point_feat;
-        chain_tc_kernel<<<blocks_for(n), kThreads, kSmemTotal, s>>>(st->d_point_prog, a);
+        a.prof = nullptr;
+        chain_tc_kernel<<<blocks_for(n), kThreads, kSmemTotal, s>>>(st->point_prog, a);
         CPPF_LAUNCH_CHECK();
     }
     if (T == 0) return CPPF_OK;
@@ -865,11 +1026,11 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.idx = IdxView{idx, idx_stride, idx_is_i64};
         a.arity = st->model.arity;
         a.weights = st->d_tuple_w;
-        a.bias = st->d_tuple_b;
         a.feat_scratch = feat_scratch;
         a.out0 = logits;
         a.out1 = scale;
-        chain_tc_kernel<<<blocks_for(T), kThreads, kSmemTotal, s>>>(st->d_tuple_prog, a);
+        a.prof = g_tc_prof;
+        chain_tc_kernel<<<blocks_for(T), kThreads, kSmemTotal, s>>>(st->tuple_prog, a);
         CPPF_LAUNCH_CHECK();
     }
     return CPPF_OK;
