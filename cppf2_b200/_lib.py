@@ -71,8 +71,10 @@ SIGNATURES = {
     "cppf_vote_rotation": (I, [P, P, I, I64, P, I64, P, P, I, P, P, P]),
     "cppf_sphere_hist": (I, [P, I64, P, P, I, F, I, P, P]),
     "cppf_sphere_band": (I, [I, F]),
-    "cppf_rotation_hist": (I, [P, P, I, I64, P, I64, _IP, I, P, P, I64, P, P, D, P, P, I, P, I, F, I, P, P]),
-    "cppf_rotation_hist_part": (I, [P, P, I, I64, P, I64, _IP, I, P, P, I64, P, P, D, P, P, I, P, I, F, I, P, I, I, P]),
+    "cppf_rotation_hist": (I, [P, P, I, I64, P, I64, _IP, I, P, P, I64, P, P, D, P, P, I, P, I, F, I, P, I, P, P]),
+    "cppf_rotation_hist_part": (I, [P, P, I, I64, P, I64, _IP, I, P, P, I64, P, P, D, P, P, I, P, I, F, I, P, I, P, I, I, P]),
+    "cppf_sphere_lut_bytes": (I64, [I]),
+    "cppf_sphere_lut_build": (I, [P, I, F, I, P]),
     "cppf_pose_workspace_bytes": (I64, [I64]),
     "cppf_pose_finalize": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, I64, P]),
     "cppf_shot_workspace_bytes": (I64, [I64]),

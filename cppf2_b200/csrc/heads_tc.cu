@@ -268,6 +268,66 @@ __device__ __forceinline__ void put_elem(unsigned char *buf, int row, int col, f
     reinterpret_cast<__nv_bfloat16 *>(act_chunk(buf, row, col >> 3))[col & 7] = __float2bfloat16_rn(v);
 }
 
+// Geometry columns of the 5-point tuple encoding (prepare_tuple_inputs, train_shot.py:75-83 / train_dino.py:91-97) for
+// one row, written as whole 16-byte chunks: 30 pair differences (+ 10 |n_i . n_j| for the SHOT branch), same float32
+// operations as encode_tuple_geometry.  All 15 (30) point loads are issued before the first use; two threads share a
+// row (`part` selects which chunks a thread stores).
+__device__ __forceinline__ void tuple_geometry_chunks(const float *__restrict__ pc, const float *__restrict__ normal,
+                                                      const int *__restrict__ idx_row, bool live, bool with_normals, int part,
+                                                      unsigned char *X, int row, int first_chunk) {
+    float pt[5][3], nr[5][3];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) pt[k][c] = live ? __ldg(pc + 3 * static_cast<int64_t>(idx_row[k]) + c) : 0.0f;
+    const bool need_normals = with_normals && part == 1;
+    if (need_normals) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {   // NaN normals of points with < 3 neighbours count as zeros (eval.py:216)
+                const float v = live ? __ldg(normal + 3 * static_cast<int64_t>(idx_row[k]) + c) : 0.0f;
+                nr[k][c] = (v == v) ? v : 0.0f;
+            }
+    }
+    float v[48];
+    int col = 0, pair = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 5; ++j) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[col++] = __fsub_rn(pt[i][c], pt[j][c]);
+            if (need_normals) {
+                const float *a = nr[i], *b = nr[j];
+                const float d = __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
+                const float e = __fadd_rn(__fadd_rn(__fmul_rn(-a[0], b[0]), __fmul_rn(-a[1], b[1])), __fmul_rn(-a[2], b[2]));
+                v[30 + pair] = fmaxf(d, e);
+            }
+            ++pair;
+        }
+#pragma unroll
+    for (int c = with_normals ? 40 : 30; c < 48; ++c) v[c] = 0.0f;
+    // constant register indices only (a `part`-dependent index would send v[] to local memory)
+    if (with_normals) {       // 40 columns + 8 zeros = 6 chunks: part 0 stores chunks 0..2 (coords 0..23), part 1 chunks 3..5
+        if (part == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) *reinterpret_cast<uint4 *>(act_chunk(X, row, first_chunk + j)) = pack8(v + 8 * j);
+        } else {
+#pragma unroll
+            for (int j = 3; j < 6; ++j) *reinterpret_cast<uint4 *>(act_chunk(X, row, first_chunk + j)) = pack8(v + 8 * j);
+        }
+    } else {                  // 30 columns + 2 zeros = 4 chunks: two each
+        if (part == 0) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) *reinterpret_cast<uint4 *>(act_chunk(X, row, first_chunk + j)) = pack8(v + 8 * j);
+        } else {
+#pragma unroll
+            for (int j = 2; j < 4; ++j) *reinterpret_cast<uint4 *>(act_chunk(X, row, first_chunk + j)) = pack8(v + 8 * j);
+        }
+    }
+}
+
 // Static tile assignment: round r gives slot s of CTA b the tile (r*kSlots + s)*gridDim.x + b, so that a
 // partial last round leaves whole second slots idle instead of half of the CTAs.
 __device__ __forceinline__ int64_t tile_of(int round, int slot) {
@@ -561,31 +621,17 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                             const bool ok = row_base + r < a.rows;
                             cp_async16(x_u32 + c8 * kPlane + r * 16, a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + 4]) * 64 + c8 * 8, ok ? 16u : 0u);
                         }
-                        if (stid < kRows) {   // geometry of row `stid`: coords -> columns 64..93, normals -> 94..103, zeros -> 104..111
-                            const int64_t g = row_base + stid;
-                            if (g < a.rows) {
-                                int64_t pt[8];
-                                for (int k = 0; k < a.arity; ++k) pt[k] = idx_s[stid * kIdxStride + k];
-                                encode_tuple_geometry(a.pc, a.normal, pt, a.arity, true, [&](int col, float v) { put_elem(X, stid, 64 + col, v); });
-                            } else {
-                                for (int c = 64; c < 104; ++c) put_elem(X, stid, c, 0.0f);
-                            }
-                            *reinterpret_cast<uint4 *>(act_chunk(X, stid, 13)) = make_uint4(0, 0, 0, 0);
+                        {   // geometry of row stid % 128: coords -> columns 64..93, normals -> 94..103, zeros -> 104..111
+                            const int r = stid & (kRows - 1);
+                            tuple_geometry_chunks(a.pc, a.normal, idx_s + r * kIdxStride, row_base + r < a.rows, true, stid >> 7, X, r, 8);
                         }
                         cp_async_wait_all();
                         break;
                     }
                     case kActCoordsB: {
-                        if (stid < kRows) {   // coords -> columns 0..29, zeros -> 30..31
-                            const int64_t g = row_base + stid;
-                            *reinterpret_cast<uint4 *>(act_chunk(X, stid, 3)) = make_uint4(0, 0, 0, 0);
-                            if (g < a.rows) {
-                                int64_t pt[8];
-                                for (int k = 0; k < a.arity; ++k) pt[k] = idx_s[stid * kIdxStride + k];
-                                encode_tuple_geometry(a.pc, a.normal, pt, a.arity, false, [&](int col, float v) { put_elem(X, stid, col, v); });
-                            } else {
-                                for (int c = 0; c < 30; ++c) put_elem(X, stid, c, 0.0f);
-                            }
+                        {   // coords -> columns 0..29, zeros -> 30..31
+                            const int r = stid & (kRows - 1);
+                            tuple_geometry_chunks(a.pc, a.normal, idx_s + r * kIdxStride, row_base + r < a.rows, false, stid >> 7, X, r, 0);
                         }
                         break;
                     }

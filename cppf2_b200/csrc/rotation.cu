@@ -56,6 +56,41 @@ __device__ __forceinline__ void band_vote(const float p[3], double w, const floa
     }
 }
 
+// Cube-map lookup of the lattice points a direction can possibly hit.  The table (cppf_sphere_lut_build) lists, for
+// every cell of a 6 x G x G cube map, up to kLutCap lattice points within (cell radius + tolerance + margin) of the
+// cell centre -- a superset of the points whose test can succeed -- so the exact reference test below runs on 0-4
+// points instead of the 2*band+1 of the latitude band; the set of hits, hence the histogram, is the same.
+constexpr int kLutCap = 4;
+constexpr uint32_t kLutMagic = 0x4c555431u;   // "LUT1"
+
+__device__ __forceinline__ int cube_cell(const float p[3], int G) {
+    const float ax = fabsf(p[0]), ay = fabsf(p[1]), az = fabsf(p[2]);
+    const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+    const float m = axis == 0 ? p[0] : (axis == 1 ? p[1] : p[2]);
+    const float a = axis == 0 ? p[1] : (axis == 1 ? p[2] : p[0]);
+    const float b = axis == 0 ? p[2] : (axis == 1 ? p[0] : p[1]);
+    const float inv = 1.0f / fabsf(m);
+    const float half_g = 0.5f * static_cast<float>(G);
+    int iu = static_cast<int>((a * inv + 1.0f) * half_g);     // NaN / inf saturate and are clamped: such rows hit nothing anyway
+    int iv = static_cast<int>((b * inv + 1.0f) * half_g);
+    iu = min(max(iu, 0), G - 1);
+    iv = min(max(iv, 0), G - 1);
+    return ((2 * axis + (m < 0.0f ? 1 : 0)) * G + iv) * G + iu;
+}
+
+__device__ __forceinline__ void lut_vote(const float p[3], double w, const float *__restrict__ s_sphere, float cos_thr,
+                                         const uint2 *__restrict__ lut_cells, int G, double *__restrict__ bins) {
+    const uint2 e = __ldg(lut_cells + cube_cell(p, G));
+    const uint32_t word[2] = {e.x, e.y};
+#pragma unroll
+    for (int k = 0; k < kLutCap; ++k) {
+        const uint32_t i = (word[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+        if (i == 0xffffu) break;     // entries are packed front to back
+        const float d = __fmaf_rn(p[2], s_sphere[3 * i + 2], __fmaf_rn(p[1], s_sphere[3 * i + 1], __fmul_rn(p[0], s_sphere[3 * i])));
+        if (d > cos_thr) atomicAdd(&bins[i], w);
+    }
+}
+
 // ---- materialising vote_rotation (drop-in shim) ----------------------------------------------------
 __global__ void __launch_bounds__(256) vote_rotation_kernel(const float *__restrict__ pc, IdxView idx,
                                                             const float *__restrict__ preds_rot, int64_t M,
@@ -119,7 +154,7 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
     const int32_t *__restrict__ kept_list, const int64_t *__restrict__ kept_count, int64_t M,
     const int32_t *__restrict__ imp, const cppf_backvote_summary *__restrict__ summary, double margin,
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R, const float *__restrict__ sphere, int S,
-    float cos_thr, int band, double *__restrict__ counts, int part, int n_parts) {
+    float cos_thr, int band, const uint2 *__restrict__ lut_cells, int lut_g, double *__restrict__ counts, int part, int n_parts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_bins = reinterpret_cast<double *>(smem_raw);                   // [n_theta][S]
     float *s_sphere = reinterpret_cast<float *>(s_bins + cols.n * S);        // [S][3]
@@ -157,7 +192,8 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
             for (int r = lane; r < R; r += 32) {
                 float p[3];
                 rotation_candidate(f, s_cos[r], s_sin[r], p);
-                band_vote(p, w, s_sphere, S, cos_thr, band, half_sm1, bins);
+                if (lut_cells) lut_vote(p, w, s_sphere, cos_thr, lut_cells, lut_g, bins);
+                else band_vote(p, w, s_sphere, S, cos_thr, band, half_sm1, bins);
             }
         }
     }
@@ -204,17 +240,74 @@ CPPF_API int cppf_sphere_hist(const float *pred, int64_t rows, const double *wt,
     return CPPF_OK;
 }
 
+// Host-side builder of the cube-map lookup table.  Layout: uint32 header[4] = {magic, G, cap, S}, then 6*G*G cells of
+// `cap` uint16 lattice indices (0xffff = empty, packed front to back).  A lattice point s belongs to a cell when
+// angle(cell centre, s) <= cell radius + acos(cos_thr) + margin, the margin (1e-3 rad) covering float32 rounding of the
+// device-side cell assignment, of the dot product and of |p| != 1.  Returns CPPF_ERR_UNSUPPORTED when a cell would
+// need more than `cap` entries (the caller retries with a finer G or falls back to the latitude band).
+CPPF_API int64_t cppf_sphere_lut_bytes(int G) { return G < 1 ? 0 : 16 + static_cast<int64_t>(6) * G * G * kLutCap * 2; }
+
+CPPF_API int cppf_sphere_lut_build(const float *sphere_host, int S, float cos_thr, int G, void *lut_host) {
+    if (!sphere_host || !lut_host || S < 1 || S >= 0xffff || G < 1 || G > 1024) return CPPF_ERR_INVALID_ARGUMENT;
+    uint32_t *hdr = static_cast<uint32_t *>(lut_host);
+    hdr[0] = kLutMagic;
+    hdr[1] = static_cast<uint32_t>(G);
+    hdr[2] = kLutCap;
+    hdr[3] = static_cast<uint32_t>(S);
+    uint16_t *cells = reinterpret_cast<uint16_t *>(hdr + 4);
+    const double tol = acos(fmin(1.0, fmax(-1.0, static_cast<double>(cos_thr)))) + 1e-3;
+    auto dir_of = [](int axis, int neg, double u, double v, double out[3]) {
+        double q[3];
+        q[axis] = neg ? -1.0 : 1.0;
+        q[(axis + 1) % 3] = u;
+        q[(axis + 2) % 3] = v;
+        const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+        out[0] = q[0] / n;
+        out[1] = q[1] / n;
+        out[2] = q[2] / n;
+    };
+    for (int face = 0; face < 6; ++face)
+        for (int iv = 0; iv < G; ++iv)
+            for (int iu = 0; iu < G; ++iu) {
+                const int axis = face >> 1, neg = face & 1;
+                const double u0 = -1.0 + 2.0 * iu / G, u1 = -1.0 + 2.0 * (iu + 1) / G;
+                const double v0 = -1.0 + 2.0 * iv / G, v1 = -1.0 + 2.0 * (iv + 1) / G;
+                double c[3], q[3];
+                dir_of(axis, neg, 0.5 * (u0 + u1), 0.5 * (v0 + v1), c);
+                double min_dot = 1.0;
+                const double cu[4] = {u0, u1, u0, u1}, cv[4] = {v0, v0, v1, v1};
+                for (int k = 0; k < 4; ++k) {
+                    dir_of(axis, neg, cu[k], cv[k], q);
+                    min_dot = fmin(min_dot, c[0] * q[0] + c[1] * q[1] + c[2] * q[2]);
+                }
+                const double reach = acos(fmin(1.0, fmax(-1.0, min_dot))) + tol;
+                const double cos_reach = reach >= 3.141592653589793 ? -2.0 : cos(reach);
+                uint16_t *cell = cells + (static_cast<size_t>(face * G + iv) * G + iu) * kLutCap;
+                int n = 0;
+                for (int k = 0; k < kLutCap; ++k) cell[k] = 0xffff;
+                for (int i = 0; i < S; ++i) {
+                    const double sx = sphere_host[3 * i], sy = sphere_host[3 * i + 1], sz = sphere_host[3 * i + 2];
+                    const double sn = sqrt(sx * sx + sy * sy + sz * sz);
+                    if (sn > 0.0 && (c[0] * sx + c[1] * sy + c[2] * sz) / sn < cos_reach) continue;
+                    if (n == kLutCap) return CPPF_ERR_UNSUPPORTED;
+                    cell[n++] = static_cast<uint16_t>(i);
+                }
+            }
+    return CPPF_OK;
+}
+
 CPPF_API int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *theta,
                                      int64_t theta_stride, const int *theta_cols_host, int n_theta, const int32_t *kept_list,
                                      const int64_t *kept_count, int64_t M, const int32_t *imp,
                                      const cppf_backvote_summary *summary, double margin, const float *cos_tab,
                                      const float *sin_tab, int R, const float *sphere, int S, float cos_thr, int band,
-                                     double *counts, int part, int n_parts, void *stream) {
+                                     const void *lut, int lut_g, double *counts, int part, int n_parts, void *stream) {
     if (!pc || !idx || !theta || !theta_cols_host || !cos_tab || !sin_tab || !sphere || !counts)
         return CPPF_ERR_INVALID_ARGUMENT;
     if (n_parts < 1 || part < 0 || part >= n_parts) return CPPF_ERR_INVALID_ARGUMENT;
     if (n_theta < 1 || n_theta > kMaxTheta || M < 0 || R <= 0 || S < 1 || idx_stride < 2) return CPPF_ERR_INVALID_ARGUMENT;
     if (imp && !summary) return CPPF_ERR_INVALID_ARGUMENT;
+    if (lut && lut_g < 1) return CPPF_ERR_INVALID_ARGUMENT;
     if (M == 0) return CPPF_OK;
     ThetaCols cols;
     cols.n = n_theta;
@@ -225,11 +318,13 @@ CPPF_API int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_i
     if (smem > 48 * 1024)
         CPPF_CUDA_TRY(cudaFuncSetAttribute(rotation_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     IdxView iv{idx, idx_stride, idx_is_i64};
-    // one warp per kept tuple; the kept count is only known on the device, so size for M/8 (ratio 0.1) at least
+    // one warp per kept tuple at a time; the kept count is only known on the device, so size for M/8 (ratio 0.1).  With the
+    // lookup table a tuple is cheap and the per-CTA bin flush dominates: two CTAs per SM, several tuples per warp.
     const int64_t guess = (kept_list ? (M / 8 + 1) : M) / n_parts + 1;
-    rotation_hist_kernel<<<grid_for(guess * 32, 256, 4), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    const uint2 *cells = lut ? reinterpret_cast<const uint2 *>(static_cast<const unsigned char *>(lut) + 16) : nullptr;
+    rotation_hist_kernel<<<grid_for(guess * 32, 256, lut ? 2 : 4), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         pc, iv, theta, theta_stride, cols, kept_list, kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere, S,
-        cos_thr, band, counts, part, n_parts);
+        cos_thr, band, cells, lut_g, counts, part, n_parts);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }
@@ -239,8 +334,8 @@ CPPF_API int cppf_rotation_hist(const float *pc, const void *idx, int idx_is_i64
                                 const int64_t *kept_count, int64_t M, const int32_t *imp,
                                 const cppf_backvote_summary *summary, double margin, const float *cos_tab,
                                 const float *sin_tab, int R, const float *sphere, int S, float cos_thr, int band,
-                                double *counts, void *stream) {
+                                const void *lut, int lut_g, double *counts, void *stream) {
     return cppf_rotation_hist_part(pc, idx, idx_is_i64, idx_stride, theta, theta_stride, theta_cols_host, n_theta, kept_list,
-                                   kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere, S, cos_thr, band, counts,
-                                   0, 1, stream);
+                                   kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere, S, cos_thr, band, lut, lut_g,
+                                   counts, 0, 1, stream);
 }

@@ -21,8 +21,8 @@ import torch
 from . import _lib
 from ._lib import BackvoteSummary, Center, GridGeom, Pose, check
 from .hostmath import percentile_plan
-from .voting import (angle_tables, cos_threshold, device_index_tensor, idx_args, read_struct, sphere_points, stream_ptr,
-                     struct_tensor, to_device)
+from .voting import (angle_tables, cos_threshold, device_index_tensor, idx_args, read_struct, sphere_lut, sphere_points,
+                     stream_ptr, struct_tensor, to_device)
 
 
 @dataclass
@@ -146,6 +146,7 @@ class PoseVoter:
         sphere = sphere_points(S, self.device)
         thr = cos_threshold(cfg.angle_tol)
         band = lib.cppf_sphere_band(S, thr)
+        lut, lut_g = sphere_lut(S, thr, self.device)
         launches = 0
 
         # decode (eval.py:225-235)
@@ -191,7 +192,8 @@ class PoseVoter:
         check(lib.cppf_rotation_hist(pc.data_ptr(), ip, i64, istr, self.targets_rot.data_ptr(), 3, cols, 2,
                                      self.kept_list.data_ptr(), kept_count_ptr, T, self.imp.data_ptr(),
                                      self.summary.data_ptr(), float(cfg.imp_wt_margin), ct.data_ptr(), st.data_ptr(), R,
-                                     sphere.data_ptr(), S, thr, band, self.counts.data_ptr(), s), "cppf_rotation_hist")
+                                     sphere.data_ptr(), S, thr, band, None if lut is None else lut.data_ptr(), lut_g,
+                                     self.counts.data_ptr(), s), "cppf_rotation_hist")
         launches += 2
         # pose assembly (eval.py:284-313, 358-363)
         so = None

@@ -32,8 +32,8 @@ from . import _lib
 from ._lib import BackvoteSummary, Center, GridGeom, Pose, check
 from .hostmath import percentile_plan
 from .pipeline import PoseResult, PoseVoter, VoteConfig
-from .voting import (angle_tables, cos_threshold, device_index_tensor, idx_args, read_struct, sphere_points, stream_ptr,
-                     to_device)
+from .voting import (angle_tables, cos_threshold, device_index_tensor, idx_args, read_struct, sphere_lut, sphere_points,
+                     stream_ptr, to_device)
 
 
 def shard_bounds(n_items: int, world: int, rank: int):
@@ -165,12 +165,13 @@ class CudaStages:
         sphere = sphere_points(S, self.device)
         thr = cos_threshold(cfg.angle_tol)
         cols = (C.c_int * 2)(0, 2)
+        lut, lut_g = sphere_lut(S, thr, self.device)
         kept_count_ptr = v.summary.data_ptr() + BackvoteSummary.kept.offset
         check(lib.cppf_rotation_hist_part(self.pc.data_ptr(), ip, i64, istr, rot.data_ptr(), 3, cols, 2,
                                           v.kept_list.data_ptr(), kept_count_ptr, idx.shape[0], v.imp.data_ptr(),
                                           v.summary.data_ptr(), float(cfg.imp_wt_margin), ct.data_ptr(), st.data_ptr(),
                                           int(cfg.num_rots), sphere.data_ptr(), S, thr, lib.cppf_sphere_band(S, thr),
-                                          v.counts.data_ptr(), int(part), int(n_parts), s), "cppf_rotation_hist_part")
+                                          None if lut is None else lut.data_ptr(), lut_g, v.counts.data_ptr(), int(part), int(n_parts), s), "cppf_rotation_hist_part")
         return v.counts
 
     def finalize(self, pc, idx, bins, scales, counts, cfg, scale_override=None) -> PoseResult:

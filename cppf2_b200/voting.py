@@ -112,6 +112,30 @@ def sphere_points(samples: int, device=None) -> torch.Tensor:
     return _sphere_cache[key]
 
 
+_lut_cache = {}
+
+
+def sphere_lut(samples: int, cos_thr: float, device=None):
+    """(device table, G) of the cube-map lookup that narrows the sphere test to <= 4 lattice points per
+    direction (cppf_sphere_lut_build, host-built once per (S, threshold, device)); (None, 0) when no cube
+    resolution fits the 4-entry cells, in which case the kernels use the latitude band."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (int(samples), float(cos_thr), str(device))
+    if key not in _lut_cache:
+        lib = _lib.load()
+        sph = np.ascontiguousarray(np.array(fibonacci_sphere(samples), dtype=np.float32))
+        entry = (None, 0)
+        for g in (32, 48, 64, 96, 128):
+            buf = np.empty(int(lib.cppf_sphere_lut_bytes(g)), dtype=np.uint8)
+            rc = lib.cppf_sphere_lut_build(sph.ctypes.data, int(samples), float(cos_thr), g, buf.ctypes.data)
+            if rc == 0:
+                entry = (torch.from_numpy(buf).to(device), g)
+                break
+        _lut_cache[key] = entry
+    return _lut_cache[key]
+
+
 def cos_threshold(angle_tol: float) -> float:
     """float32(cos(2*angle_tol deg)): eval.py:45 compares in float32."""
     return float(np.float32(np.cos(2 * angle_tol / 180 * np.pi)))

@@ -187,7 +187,14 @@ int cppf_rotation_hist(const float *pc, const void *idx, int idx_is_i64, int64_t
                        int64_t theta_stride, const int *theta_cols_host, int n_theta, const int32_t *kept_list,
                        const int64_t *kept_count, int64_t M, const int32_t *imp, const cppf_backvote_summary *summary,
                        double margin, const float *cos_tab, const float *sin_tab, int R, const float *sphere, int S,
-                       float cos_thr, int band, double *counts, void *stream);
+                       float cos_thr, int band, const void *lut, int lut_g, double *counts, void *stream);
+/* Optional accelerator of the sphere test: a cube-map lookup table (6 x G x G cells, each listing the <= 4 lattice
+ * points a direction inside the cell can hit -- a conservative superset, so the reference test eval.py:45 gives the
+ * same hits as against all S points).  Built on the HOST from the host copy of `sphere`; the caller uploads the
+ * cppf_sphere_lut_bytes(G) bytes and passes the device pointer as `lut` with `lut_g` = G (lut = NULL: latitude band).
+ * cppf_sphere_lut_build returns CPPF_ERR_UNSUPPORTED when some cell needs more than 4 entries (use a finer G). */
+int64_t cppf_sphere_lut_bytes(int G);
+int cppf_sphere_lut_build(const float *sphere_host, int S, float cos_thr, int G, void *lut_host);
 /* Same over the kept items congruent to `part` modulo `n_parts`: in a tuple-sharded run every
  * rank votes its share of the global kept list and the [n_theta,S] bins are summed by one all-reduce. */
 int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *theta,
@@ -195,7 +202,7 @@ int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_is_i64, in
                             const int64_t *kept_count, int64_t M, const int32_t *imp,
                             const cppf_backvote_summary *summary, double margin, const float *cos_tab,
                             const float *sin_tab, int R, const float *sphere, int S, float cos_thr, int band,
-                            double *counts, int part, int n_parts, void *stream);
+                            const void *lut, int lut_g, double *counts, int part, int n_parts, void *stream);
 
 /* ---- pose assembly ------------------------------------------------------------------------------
  * replaces eval.py:284-313 (top-1 directions, Gram-Schmidt, scale median) and :358-363 (branch loss). */

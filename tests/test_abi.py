@@ -60,3 +60,47 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.CppfError):
         _lib.load()
+
+
+def test_sphere_lut_is_a_superset_of_every_possible_hit():
+    """Host-built cube-map lookup (cppf_sphere_lut_build): for random and adversarial directions, every lattice
+    point passing the reference test dot > cos_thr (eval.py:45) is listed in the direction's cell."""
+    import numpy as np
+    from cppf2_b200 import _lib
+    from cppf2_b200.voting import cos_threshold, fibonacci_sphere
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for S, tol in ((720, 1.0), (360, 2.0), (1440, 0.5)):
+        sph = np.ascontiguousarray(np.array(fibonacci_sphere(S), dtype=np.float32))
+        thr = cos_threshold(tol)
+        built = None
+        for g in (32, 48, 64, 96, 128):
+            buf = np.empty(int(lib.cppf_sphere_lut_bytes(g)), dtype=np.uint8)
+            if lib.cppf_sphere_lut_build(sph.ctypes.data, S, thr, g, buf.ctypes.data) == 0:
+                built = (g, buf)
+                break
+        assert built is not None
+        g, buf = built
+        hdr = buf[:16].view(np.uint32)
+        assert hdr[1] == g and hdr[2] == 4 and hdr[3] == S
+        cells = buf[16:].view(np.uint16).reshape(6, g, g, 4)
+        p = rng.standard_normal((300000, 3)).astype(np.float32)
+        p /= np.linalg.norm(p, axis=-1, keepdims=True)
+        # directions on cube edges / corners / cell borders and right on top of lattice points
+        edge = np.float32([[1, 1, 0], [1, -1, 0.3], [1, 1, 1], [-1, 1, -1], [0, 0, 1], [0, -1, 0], [1, 0.5, 0.25], [1, 0.0625, -0.125]])
+        p = np.concatenate([p, edge / np.linalg.norm(edge, axis=-1, keepdims=True), sph]).astype(np.float32)
+        # numpy restatement of the device-side cell assignment (rotation.cu: cube_cell)
+        a = np.abs(p)
+        axis = np.where((a[:, 0] >= a[:, 1]) & (a[:, 0] >= a[:, 2]), 0, np.where(a[:, 1] >= a[:, 2], 1, 2))
+        rows = np.arange(p.shape[0])
+        m = p[rows, axis]
+        u = p[rows, (axis + 1) % 3] / np.abs(m)
+        v = p[rows, (axis + 2) % 3] / np.abs(m)
+        iu = np.clip(((u + 1) * np.float32(0.5 * g)).astype(np.int64), 0, g - 1)
+        iv = np.clip(((v + 1) * np.float32(0.5 * g)).astype(np.int64), 0, g - 1)
+        listed = cells[2 * axis + (m < 0), iv, iu]                      # [rows, 4]
+        dots = p @ sph.T                                                  # float32
+        hit_r, hit_s = np.nonzero(dots > np.float32(thr))
+        assert hit_r.size > 0
+        ok = (listed[hit_r] == hit_s[:, None].astype(np.uint16)).any(-1)
+        assert ok.all(), f"S={S}: {np.count_nonzero(~ok)} hits missing from the lookup table"

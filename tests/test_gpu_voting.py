@@ -230,6 +230,38 @@ def test_sphere_hist_band_equals_brute_force(V):
         assert np.array_equal(out[0], out[1]) and out[0].sum() > 0
 
 
+def test_rotation_hist_lookup_table_equals_band(V):
+    """The fused rotation vote gives the same bins through the cube-map lookup table as through the latitude band
+    (same hit set; float64 sums in a different order)."""
+    import ctypes as C
+    from cppf2_b200 import _lib, synth
+    from cppf2_b200.voting import angle_tables, cos_threshold, sphere_lut, sphere_points, stream_ptr
+    lib = _lib.load()
+    pc = synth.half_cylinder_cloud(3000, seed=5)
+    rng = np.random.default_rng(9)
+    M, R = 6000, 180
+    idx = torch.from_numpy(rng.integers(0, pc.shape[0], (M, 2)).astype(np.int64)).cuda()
+    theta = torch.from_numpy(rng.uniform(0, np.pi, (M, 3)).astype(np.float32)).cuda()
+    theta[:3, 0] = torch.tensor([np.pi / 2, 0.0, np.pi], dtype=torch.float32)    # tan blow-up / zero
+    pc_d = torch.from_numpy(pc).cuda()
+    ct, st = angle_tables(R)
+    for S, tol in ((720, 1.0), (1440, 0.5)):
+        sph, thr = sphere_points(S), cos_threshold(tol)
+        lut, g = sphere_lut(S, thr)
+        assert lut is not None and g > 0
+        cols = (C.c_int * 2)(0, 2)
+        out = []
+        for table in (None, lut):
+            counts = torch.zeros((2, S), dtype=torch.float64, device="cuda")
+            _lib.check(lib.cppf_rotation_hist(pc_d.data_ptr(), idx.data_ptr(), 1, 2, theta.data_ptr(), 3, cols, 2, None, None, M,
+                                              None, None, 0.01, ct.data_ptr(), st.data_ptr(), R, sph.data_ptr(), S, thr,
+                                              lib.cppf_sphere_band(S, thr), None if table is None else table.data_ptr(), g,
+                                              counts.data_ptr(), stream_ptr()))
+            out.append(counts.cpu().numpy())
+        assert out[0].sum() > 0
+        np.testing.assert_array_equal(out[0], out[1])     # unit weights: integer-valued float64 sums are exact
+
+
 def test_pose_chain_matches_reference_instance(golden, oracle):
     from cppf2_b200.pipeline import PoseVoter, VoteConfig
     g = golden("instance")
