@@ -87,6 +87,7 @@ SIGNATURES = {
     "cppf_heads_has_tc": (I, [P]),
     "cppf_heads_workspace_bytes": (I64, [P, I64, I64, I]),
     "cppf_heads_forward": (I, [P, I, P, I64, P, I, I64, I64, P, P, P, P, P, I64, P]),
+    "cppf_heads_forward_sampled": (I, [P, I, P, I64, P, I, I64, I64, P, P, P, U64, P, P, P, I64, P]),
 }
 
 _lib = None

@@ -110,6 +110,16 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Counter-based uniform in [0,1) for the multinomial draw of row `ctr` (splitmix64 finaliser, 24 mantissa bits): the
+// stand-alone sampler (targets.cu) and the sampling epilogue of the heads (heads_tc.cu) draw the same numbers.
+__device__ __forceinline__ float uniform_from_counter(uint64_t seed, uint64_t ctr) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (ctr + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

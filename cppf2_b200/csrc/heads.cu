@@ -362,7 +362,8 @@ extern "C" void cppf_heads_tc_destroy(void *state);
 extern "C" int64_t cppf_heads_tc_workspace_bytes(const void *state, int64_t T, int64_t n);
 extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t n, const void *idx, int idx_is_i64,
                                      int64_t idx_stride, int64_t T, const float *feat, const float *normal, float *logits,
-                                     float *scale, void *ws, int64_t ws_bytes, void *stream);
+                                     float *scale, unsigned char *bins, const float *u01, unsigned long long seed, void *ws,
+                                     int64_t ws_bytes, void *stream);
 
 CPPF_API int cppf_heads_create(int branch, int num_more, const float *weights_host, int64_t n_floats, cppf_heads **out) {
     if ((branch != 0 && branch != 1) || num_more < 0 || num_more > 6 || !weights_host || !out) return CPPF_ERR_INVALID_ARGUMENT;
@@ -446,6 +447,20 @@ CPPF_API int64_t cppf_heads_workspace_bytes(const cppf_heads *h, int64_t T, int6
                                 align256(sizeof(float) * 256 * static_cast<size_t>(T)) + 256);
 }
 
+CPPF_API int cppf_heads_forward_sampled(const cppf_heads *h, int precision, const float *pc, int64_t n, const void *idx,
+                                        int idx_is_i64, int64_t idx_stride, int64_t T, const float *feat, const float *normal,
+                                        const float *u01, uint64_t seed, uint8_t *bins, float *scale, void *ws, int64_t ws_bytes,
+                                        void *stream) {
+    if (!h || !pc || !feat || !bins || !scale || !ws || n <= 0 || T < 0) return CPPF_ERR_INVALID_ARGUMENT;
+    if (T > 0 && !idx) return CPPF_ERR_INVALID_ARGUMENT;
+    if (h->model.branch == 0 && !normal) return CPPF_ERR_INVALID_ARGUMENT;
+    if (idx_stride < h->model.arity) return CPPF_ERR_INVALID_ARGUMENT;
+    // the draw is an epilogue of the tensor-core kernel only; the float32 path keeps the two-call form
+    if (precision != 1 || !h->tc) return CPPF_ERR_UNSUPPORTED;
+    return cppf_heads_tc_forward(h->tc, pc, n, idx, idx_is_i64, idx_stride, T, feat, normal, nullptr, scale, bins, u01, seed, ws,
+                                 ws_bytes, stream);
+}
+
 CPPF_API int cppf_heads_forward(const cppf_heads *h, int precision, const float *pc, int64_t n, const void *idx, int idx_is_i64,
                                 int64_t idx_stride, int64_t T, const float *feat, const float *normal, float *logits,
                                 float *scale, void *ws, int64_t ws_bytes, void *stream) {
@@ -455,8 +470,8 @@ CPPF_API int cppf_heads_forward(const cppf_heads *h, int precision, const float 
     if (idx_stride < h->model.arity) return CPPF_ERR_INVALID_ARGUMENT;
     if (precision == 1) {
         if (!h->tc) return CPPF_ERR_UNSUPPORTED;
-        return cppf_heads_tc_forward(h->tc, pc, n, idx, idx_is_i64, idx_stride, T, feat, normal, logits, scale, ws, ws_bytes,
-                                     stream);
+        return cppf_heads_tc_forward(h->tc, pc, n, idx, idx_is_i64, idx_stride, T, feat, normal, logits, scale, nullptr, nullptr, 0,
+                                     ws, ws_bytes, stream);
     }
     if (precision != 0) return CPPF_ERR_INVALID_ARGUMENT;
     if (ws_bytes < cppf_heads_workspace_bytes(h, T, n, 0)) return CPPF_ERR_WORKSPACE;

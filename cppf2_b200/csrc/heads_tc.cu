@@ -134,6 +134,9 @@ struct Args {
     __nv_bfloat16 *feat_scratch;        // [rows][256] bf16
     float *out0, *out1;
     __nv_bfloat16 *out_bf16;
+    unsigned char *bins;                // non-null: out0 is not written; the logits epilogue draws one bin per (row, coord)
+    const float *u01;                   // [rows][6] injected uniforms or nullptr (counter-based generator keyed by seed)
+    unsigned long long seed;
     long long *prof;                    // optional [gridDim.x][64] cycle counters (cppf_debug_heads_tc_profile)
 };
 
@@ -372,6 +375,27 @@ __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, u
             const uint4 packed = pack8(v + 8 * j);
             *reinterpret_cast<uint4 *>(act_chunk(X, row, (ph.dst_col + c) / 8 + j)) = packed;
             if (!(CPPF_TC_EXP & 16) && ph.store_feat && live) __stcg(reinterpret_cast<uint4 *>(a.feat_scratch + grow * 256 + ph.dst_col + c + 8 * j), packed);
+        }
+    } else if (NB == 32 && ph.out_sel == 0 && a.bins != nullptr) {
+        // kActFinal of the logits with the decode fused in (eval.py:225-229): the 32 columns of this batch are the 32
+        // bins of coordinate (dst_col + c) / 32 of this row; softmax numerators, running sum, one inverse-CDF draw
+        if (live) {
+            float m = v[0];
+#pragma unroll
+            for (int j = 1; j < NB; ++j) m = fmaxf(m, v[j]);
+            float run = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                run += expf(v[j] - m);
+                v[j] = run;
+            }
+            const int64_t r6 = grow * 6 + ((ph.dst_col + c) >> 5);
+            const float u = a.u01 ? __ldg(a.u01 + r6) : uniform_from_counter(a.seed, static_cast<uint64_t>(r6));
+            const float cut = u * run;
+            int b = 0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) b += v[j] <= cut ? 1 : 0;
+            a.bins[r6] = static_cast<unsigned char>(b < 32 ? b : 31);
         }
     } else if (live && !((CPPF_TC_EXP & 4) && ph.out_sel != 2)) {   // kActFinal
         if (ph.out_sel == 2) {
@@ -1037,9 +1061,11 @@ extern "C" int64_t cppf_heads_tc_workspace_bytes(const void *state, int64_t T, i
 
 extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t n, const void *idx, int idx_is_i64,
                                      int64_t idx_stride, int64_t T, const float *feat, const float *normal, float *logits,
-                                     float *scale, void *ws, int64_t ws_bytes, void *stream) {
+                                     float *scale, unsigned char *bins, const float *u01, unsigned long long seed, void *ws,
+                                     int64_t ws_bytes, void *stream) {
     const State *st = static_cast<const State *>(state);
     if (!st) return CPPF_ERR_UNSUPPORTED;
+    if (!logits && !bins) return CPPF_ERR_INVALID_ARGUMENT;
     if (ws_bytes < cppf_heads_tc_workspace_bytes(state, T, n)) return CPPF_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     __nv_bfloat16 *point_feat = static_cast<__nv_bfloat16 *>(ws);
@@ -1075,6 +1101,9 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.feat_scratch = feat_scratch;
         a.out0 = logits;
         a.out1 = scale;
+        a.bins = bins;
+        a.u01 = u01;
+        a.seed = seed;
         a.prof = g_tc_prof;
         chain_tc_kernel<<<blocks_for(T), kThreads, kSmemTotal, s>>>(st->tuple_prog, a);
         CPPF_LAUNCH_CHECK();

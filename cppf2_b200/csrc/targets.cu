@@ -103,14 +103,6 @@ __global__ void __launch_bounds__(256) decode_targets_kernel(const float *__rest
 // softmax + one multinomial draw per row: one warp per row of `num_bins` (<= 32) logits, lane = bin,
 // coalesced 128 B row reads, softmax and inclusive CDF by shuffles, draw = #(cdf <= u*total).
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float uniform_from_counter(uint64_t seed, uint64_t ctr) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (ctr + 1);  // splitmix64 finaliser
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);  // [0,1)
-}
-
 __global__ void __launch_bounds__(256) sample_bins_kernel(const float *__restrict__ logits, int64_t rows, int num_bins,
                                                           const float *__restrict__ u01, uint64_t seed,
                                                           uint8_t *__restrict__ bins) {

@@ -136,18 +136,27 @@ class PoseEstimator:
                 model = heads.get(branch)
                 if model is None or (branch == "dino" and inst.desc is None):
                     continue
-                self._mark("heads_" + branch, True)
-                if branch == "dino":
-                    logits, scales = model(pc, to_device(inst.desc, torch.float32, self.device), idx)
-                else:
-                    logits, scales = model(pc, idx, desc352, normals)
-                self._mark("heads_" + branch, False)
-                launches += 4
                 slot = pose_buf[2 * i + b]
                 inj = None if draws is None else draws[i].get(branch)
+                vote_seed = self.seed + 7919 * (2 * i + b)
+                # bf16 tensor-core heads draw the bins in their own epilogue (no [T,6,32] logits in HBM) unless the
+                # caller injects the draws; the float32 heads keep forward + cppf_sample_bins
+                fused = inj is None and getattr(model, "precision", 0) == 1
+                self._mark("heads_" + branch, True)
+                logits = None
+                if branch == "dino":
+                    args = (pc, to_device(inst.desc, torch.float32, self.device), idx)
+                else:
+                    args = (pc, idx, desc352, normals)
+                if fused:
+                    inj, scales = model.forward_sampled(*args, seed=vote_seed)
+                else:
+                    logits, scales = model(*args)
+                self._mark("heads_" + branch, False)
+                launches += 2 if getattr(model, "precision", 0) == 1 else 4
                 self._mark("vote_" + branch, True)
                 self.voter.vote(pc, idx, vc, pred_scales=scales, bins=inj, logits=None if inj is not None else logits,
-                                seed=self.seed + 7919 * (2 * i + b), cells_hint=cells_hint, pose_out=slot,
+                                seed=vote_seed, cells_hint=cells_hint, pose_out=slot,
                                 scale_override=scale_from_dino if branch == "shot" else None)
                 self._mark("vote_" + branch, False)
                 launches += self.voter.launches

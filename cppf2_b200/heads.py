@@ -125,7 +125,9 @@ class BeyondCPPF:
         self._handle = handle
         self._device = device
 
-    def _run(self, points, idx, feat, normal):
+    def _run(self, points, idx, feat, normal, sample=None):
+        """sample = None: (logits, scale) like the reference's forward.  sample = dict(u01=..., seed=...): the decode of
+        eval.py:225-229 runs as the epilogue of the logits head and (bins u8 [T,6], scale) come back instead."""
         lib = _lib.load()
         pc = to_device(points, torch.float32)
         dev = pc.device
@@ -134,12 +136,21 @@ class BeyondCPPF:
         feat = to_device(feat, torch.float32, dev)
         nrm = None if normal is None else to_device(normal, torch.float32, dev)
         T, n = idx.shape[0], pc.shape[0]
-        logits = torch.empty((T, 6, 32), dtype=torch.float32, device=dev)
         scale = torch.empty((T, 3), dtype=torch.float32, device=dev)
         need = int(lib.cppf_heads_workspace_bytes(self._handle, T, n, self.precision))
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         ip, i64, istr = idx_args(idx)
+        if sample is not None:
+            u01 = sample.get("u01")
+            u01 = None if u01 is None else to_device(u01, torch.float32, dev)
+            bins = torch.empty((T, 6), dtype=torch.uint8, device=dev)
+            check(lib.cppf_heads_forward_sampled(self._handle, self.precision, pc.data_ptr(), n, ip, i64, istr, T, feat.data_ptr(),
+                                                 None if nrm is None else nrm.data_ptr(), None if u01 is None else u01.data_ptr(),
+                                                 int(sample.get("seed", 0)), bins.data_ptr(), scale.data_ptr(),
+                                                 self._ws.data_ptr(), self._ws.numel(), stream_ptr()), "cppf_heads_forward_sampled")
+            return bins, scale
+        logits = torch.empty((T, 6, 32), dtype=torch.float32, device=dev)
         check(lib.cppf_heads_forward(self._handle, self.precision, pc.data_ptr(), n, ip, i64, istr, T, feat.data_ptr(),
                                      None if nrm is None else nrm.data_ptr(), logits.data_ptr(), scale.data_ptr(),
                                      self._ws.data_ptr(), self._ws.numel(), stream_ptr()), "cppf_heads_forward")
@@ -156,6 +167,10 @@ class BeyondCPPFSHOT(BeyondCPPF):
     def forward(self, points, point_idxs_all, shot_feat, normal):
         return self._run(points, point_idxs_all, shot_feat, normal)
 
+    def forward_sampled(self, points, point_idxs_all, shot_feat, normal, u01=None, seed: int = 0):
+        """forward + softmax + one multinomial draw per (tuple, coordinate) (eval.py:221-229) in one kernel chain."""
+        return self._run(points, point_idxs_all, shot_feat, normal, sample=dict(u01=u01, seed=seed))
+
 
 class BeyondCPPFDINO(BeyondCPPF):
     """train_dino.py:58-133.  forward(points [N,3], point_descs [N,1024], point_idxs_all [T,5])."""
@@ -163,3 +178,6 @@ class BeyondCPPFDINO(BeyondCPPF):
 
     def forward(self, points, point_descs, point_idxs_all):
         return self._run(points, point_idxs_all, point_descs, None)
+
+    def forward_sampled(self, points, point_descs, point_idxs_all, u01=None, seed: int = 0):
+        return self._run(points, point_idxs_all, point_descs, None, sample=dict(u01=u01, seed=seed))

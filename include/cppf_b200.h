@@ -255,6 +255,15 @@ int cppf_heads_forward(const cppf_heads *h, int precision, const float *pc, int6
                        int64_t idx_stride, int64_t T, const float *feat, const float *normal, float *logits,
                        float *scale, void *ws, int64_t ws_bytes, void *stream);
 
+/* The same forward with the decode of eval.py:225-229 fused into the logits epilogue (precision 1 only, else
+ * CPPF_ERR_UNSUPPORTED): softmax over the 32 bins of each of the 6 coordinates and one inverse-CDF draw per
+ * (tuple, coordinate), uniforms from u01 f32 [T,6] or, when NULL, the counter-based generator of cppf_sample_bins
+ * keyed by `seed`.  Writes bins u8 [T,6] and scale f32 [T,3]; the [T,6,32] logits never reach HBM. */
+int cppf_heads_forward_sampled(const cppf_heads *h, int precision, const float *pc, int64_t n, const void *idx,
+                               int idx_is_i64, int64_t idx_stride, int64_t T, const float *feat, const float *normal,
+                               const float *u01, uint64_t seed, uint8_t *bins, float *scale, void *ws, int64_t ws_bytes,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,3 +148,44 @@ def test_bf16_tensor_core_dino_head(n, t):
           f"scale max err {err_scale:.2e}")
     assert err_cls <= 5e-3 * rng_cls + 1e-4 and err_scale <= 5e-3 * rng_scale + 1e-4
     assert float((cls - want_cls).abs().mean()) <= 5e-4 * rng_cls
+
+
+@pytest.mark.parametrize("branch", ["shot", "dino"])
+@pytest.mark.parametrize("n,t,inject", [(900, 5000, True), (4096, 50000, False), (333, 77, True)])
+def test_fused_sampling_epilogue_equals_forward_then_sample_bins(branch, n, t, inject):
+    """cppf_heads_forward_sampled (decode fused into the logits epilogue, eval.py:221-229) draws the bins that
+    cppf_sample_bins draws from the logits of cppf_heads_forward with the same uniforms: same kernel, same
+    accumulators; the running sum is sequential instead of a warp scan, so a draw may differ only when u*total
+    sits within float32 rounding of a CDF step.  The scale head output must be identical."""
+    from cppf2_b200 import _lib
+    from cppf2_b200.heads import BeyondCPPFDINO, BeyondCPPFSHOT
+    from cppf2_b200.voting import stream_ptr
+    lib = _lib.load()
+    pc, idx, shot, normal, desc = make_inputs(n, t, seed=n + 3)
+    m = (BeyondCPPFSHOT if branch == "shot" else BeyondCPPFDINO)(dict(num_more=3), precision=1).cuda()
+    m.load_state_dict(init_state_dict(branch, 77))
+    if not _tc_available(m):
+        pytest.skip("library built without the tcgen05 heads")
+    tpc, tidx = torch.from_numpy(pc).cuda(), torch.from_numpy(idx).cuda()
+    args = (tpc, tidx, torch.from_numpy(shot).cuda(), torch.from_numpy(normal).cuda()) if branch == "shot" else \
+           (tpc, torch.from_numpy(desc).cuda(), tidx)
+    u01 = torch.rand((t, 6), generator=torch.Generator().manual_seed(5)).cuda() if inject else None
+    seed = 4242
+    logits, scale = m(*args)
+    want = torch.empty((t, 6), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.cppf_sample_bins(logits.data_ptr(), t, 32, None if u01 is None else u01.data_ptr(), seed, want.data_ptr(),
+                                    stream_ptr()))
+    bins, scale2 = m.forward_sampled(*args, u01=u01, seed=seed)
+    torch.cuda.synchronize()
+    assert bins.shape == (t, 6) and bins.dtype == torch.uint8
+    assert torch.equal(scale, scale2)
+    mismatch = (bins != want)
+    frac = mismatch.float().mean().item()
+    assert frac < 1e-4, f"{frac:.2e} of the draws differ"
+    if mismatch.any() and inject:      # every differing draw sits on a CDF step
+        p = torch.softmax(logits.double(), -1).cumsum(-1)
+        gap = (p - u01.double()[..., None]).abs().min(-1)[0]
+        assert (gap[mismatch] < 1e-5).all()
+    # the draws follow the logits: the mean log-probability of the drawn bins beats a uniform draw
+    logp = torch.log_softmax(logits, -1).gather(-1, bins.long()[..., None]).mean().item()
+    assert logp > float(np.log(1 / 32)) - 1e-3
