@@ -268,15 +268,14 @@ def main():
     for inst in raw:
         pc_p, desc_p = torch.from_numpy(inst["pc"]).pin_memory(), torch.from_numpy(inst["desc"]).pin_memory()
         host_instances.append((pc_p, desc_p, inst))
-        h2d += pc_p.numel() * 4 + desc_p.numel() * 4 + NUM_PAIRS * 5 * 4
-    idx_pinned = [torch.empty((NUM_PAIRS, 5), dtype=torch.int32).pin_memory() for _ in raw]
-    erng = np.random.default_rng(200 + rank)
+        h2d += pc_p.numel() * 4 + desc_p.numel() * 4
 
     def e2e_step():
+        # the public call: pinned host clouds + descriptors in, poses out; tuple indices (eval.py:207) are drawn on the
+        # device by the estimator (point_idxs=None), uploads run on its copy stream ahead of the kernels
         insts = []
         for k, (pc_p, desc_p, inst) in enumerate(host_instances):
-            idx_pinned[k].numpy()[...] = erng.integers(0, pc_p.shape[0], (NUM_PAIRS, 5), dtype=np.int32)   # eval.py:207
-            it = Instance(pc=pc_p, category=inst["category"], desc=desc_p, point_idxs=idx_pinned[k].to(dev, non_blocking=True))
+            it = Instance(pc=pc_p, category=inst["category"], desc=desc_p, point_idxs=None)
             it.cells_hint = dev_instances[k].cells_hint
             insts.append(it)
         return est.estimate(insts)

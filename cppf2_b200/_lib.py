@@ -59,6 +59,7 @@ SIGNATURES = {
     "cppf_vote_center_smem_cells": (I64, []),
     "cppf_grid_argmax": (I, [P, P, D, P, P]),
     "cppf_grid_to_i64": (I, [P, P, P, P]),
+    "cppf_sample_tuples": (I, [I64, I64, I, U64, P, P]),
     "cppf_sample_bins": (I, [P, I64, I, P, U64, P, P]),
     "cppf_decode_targets": (I, [P, P, I, I64, P, I64, I, _DP, P, P, P, P, P]),
     "cppf_generate_targets": (I, [P, I64, _DP, P, P, P, P]),

@@ -131,9 +131,34 @@ __global__ void __launch_bounds__(256) sample_bins_kernel(const float *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tuple sampling (eval.py:207: np.random.randint(0, N, (T, K)), with replacement): one counter-based
+// 64-bit draw per index, mapped to [0, n) by multiply-shift.  Host-sampled indices remain injectable
+// everywhere; this is the default when the caller passes none, and saves the 4*T*K-byte upload.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_tuples_kernel(int64_t n, int64_t count, uint64_t seed, int32_t *__restrict__ idx) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(i) + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        idx[i] = static_cast<int32_t>(__umul64hi(z, static_cast<uint64_t>(n)));
+    }
+}
+
 }  // namespace cppf
 
 using namespace cppf;
+
+CPPF_API int cppf_sample_tuples(int64_t n, int64_t T, int arity, uint64_t seed, int32_t *idx, void *stream) {
+    if (!idx || n < 1 || n > 0x7fffffff || T < 0 || arity < 1) return CPPF_ERR_INVALID_ARGUMENT;
+    if (T == 0) return CPPF_OK;
+    const int64_t count = T * arity;
+    sample_tuples_kernel<<<grid_for(count, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, count, seed, idx);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
 
 static Axes axes_from_host(const double *axes_host) {
     Axes ax;

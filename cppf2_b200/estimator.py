@@ -25,10 +25,10 @@ import numpy as np
 import torch
 
 from . import _lib, shot
-from ._lib import Pose
+from ._lib import Pose, check
 from .heads import BeyondCPPFDINO, BeyondCPPFSHOT
 from .pipeline import PoseResult, PoseVoter, VoteConfig
-from .voting import to_device
+from .voting import stream_ptr, to_device
 
 SYMMETRIC_Y = ("can", "bottle", "bowl")   # loss on the y coordinate only (eval.py:360-361)
 
@@ -96,6 +96,8 @@ class PoseEstimator:
         self.pose_bytes = C.sizeof(Pose)
         self.timing_hook = None        # optional callable(stage: str, begin: bool) for bench.py's per-kernel events
         self.launches = 0
+        self.copy_stream = torch.cuda.Stream(device=self.device)   # uploads of instance i+1 overlap the kernels of instance i
+        self._idx_pool: List[torch.Tensor] = []                      # device-sampled tuple indices, one buffer per instance slot
 
     def vote_config(self, category: str) -> VoteConfig:
         cfg = self.cfgs[category]
@@ -109,22 +111,73 @@ class PoseEstimator:
         if self.timing_hook is not None:
             self.timing_hook(stage, begin)
 
-    def enqueue(self, instances: Sequence[Instance], pose_buf: torch.Tensor, draws: Optional[List[dict]] = None) -> List[dict]:
+    def _sample_tuples(self, slot: int, n: int) -> torch.Tensor:
+        """eval.py:207 on the device (cppf_sample_tuples): no host RNG pass, no 4*T*5-byte upload."""
+        while len(self._idx_pool) <= slot:
+            self._idx_pool.append(torch.empty((self.num_pairs, 5), dtype=torch.int32, device=self.device))
+        idx = self._idx_pool[slot]
+        self._draws += 1
+        check(_lib.load().cppf_sample_tuples(n, self.num_pairs, 5, (self.seed << 32) + self._draws, idx.data_ptr(),
+                                            stream_ptr()), "cppf_sample_tuples")
+        return idx
+
+    _draws = 0
+
+    def stage(self, instances: Sequence[Instance]) -> List[dict]:
+        """Starts the host->device copies of every instance on the copy stream (pinned sources make them asynchronous)
+        and returns, per instance, the device tensors plus the event the compute stream has to wait for."""
+        compute = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(compute)      # buffers recycled by the allocator may still be read by queued kernels
+        staged = []
+        with torch.cuda.stream(self.copy_stream):
+            for inst in instances:
+                vc = self.vote_config(inst.category)
+                host_pc = inst.pc if isinstance(inst.pc, np.ndarray) else (inst.pc.numpy() if not inst.pc.is_cuda else None)
+                cells_hint = getattr(inst, "cells_hint", None)
+                if cells_hint is None and host_pc is not None:
+                    cells_hint = PoseVoter.grid_cells_on_host(host_pc, vc.res)
+                item = dict(pc=to_device(inst.pc, torch.float32, self.device), cells_hint=cells_hint, desc=None, idx=None)
+                if inst.desc is not None:
+                    item["desc"] = to_device(inst.desc, torch.float32, self.device)
+                if inst.point_idxs is not None:
+                    pi = inst.point_idxs
+                    item["idx"] = pi if isinstance(pi, torch.Tensor) and pi.is_cuda else \
+                        to_device(pi, torch.int32 if pi.dtype in (np.int32, torch.int32) else torch.int64, self.device)
+                for t in (item["pc"], item["desc"], item["idx"]):
+                    if t is not None:
+                        t.record_stream(compute)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                item["ready"] = ev
+                staged.append(item)
+        return staged
+
+    def enqueue(self, instances: Sequence[Instance], pose_buf: torch.Tensor, draws: Optional[List[dict]] = None,
+                staged: Optional[List[dict]] = None) -> List[dict]:
         """Queues every kernel of the frame on the current stream.  pose_buf: uint8 CUDA [len(instances)*2, sizeof(pose)].
         `draws[i][branch]` may inject the multinomial draws (uint8 [T,6]) of an (instance, branch) for parity runs.
-        Inputs may already be device tensors (device-resident benchmarking) or host arrays (copied here)."""
+        Inputs may already be device tensors (device-resident benchmarking) or host arrays (`staged` = self.stage(...)
+        uploads them on the copy stream; without it they are copied here, in stream order)."""
         plan = []
         launches = 0
         for i, inst in enumerate(instances):
             vc = self.vote_config(inst.category)
-            on_host = isinstance(inst.pc, np.ndarray)
-            cells_hint = PoseVoter.grid_cells_on_host(inst.pc, vc.res) if on_host else getattr(inst, "cells_hint", None)
-            pc = to_device(inst.pc, torch.float32, self.device)
+            if staged is not None:
+                st = staged[i]
+                torch.cuda.current_stream(self.device).wait_event(st["ready"])
+                pc, cells_hint, idx, desc_dev = st["pc"], st["cells_hint"], st["idx"], st["desc"]
+            else:
+                on_host = isinstance(inst.pc, np.ndarray)
+                cells_hint = PoseVoter.grid_cells_on_host(inst.pc, vc.res) if on_host else getattr(inst, "cells_hint", None)
+                pc = to_device(inst.pc, torch.float32, self.device)
+                idx = inst.point_idxs
+                if idx is not None and not isinstance(idx, torch.Tensor):
+                    idx = to_device(idx, torch.int32 if idx.dtype == np.int32 else torch.int64, self.device)
+                desc_dev = None if inst.desc is None else to_device(inst.desc, torch.float32, self.device)
             n = pc.shape[0]
-            idx = inst.point_idxs
-            if idx is None:   # eval.py:207; int32 halves the H2D traffic of the 2 MB index matrix
-                idx = self.rng.integers(0, n, (self.num_pairs, 5), dtype=np.int32)
-            idx = idx if isinstance(idx, torch.Tensor) else to_device(idx, torch.int32 if idx.dtype == np.int32 else torch.int64, self.device)
+            if idx is None:
+                idx = self._sample_tuples(i, n)
+                launches += 1
             heads = self.models[inst.category]
             self._mark("shot", True)
             desc352, normals = shot.compute_device(pc, vc.res * 10, vc.res * 10)      # eval.py:210
@@ -134,7 +187,7 @@ class PoseEstimator:
             scale_from_dino = None
             for b, branch in enumerate(("dino", "shot")):                              # eval.py:219
                 model = heads.get(branch)
-                if model is None or (branch == "dino" and inst.desc is None):
+                if model is None or (branch == "dino" and desc_dev is None):
                     continue
                 slot = pose_buf[2 * i + b]
                 inj = None if draws is None else draws[i].get(branch)
@@ -145,7 +198,7 @@ class PoseEstimator:
                 self._mark("heads_" + branch, True)
                 logits = None
                 if branch == "dino":
-                    args = (pc, to_device(inst.desc, torch.float32, self.device), idx)
+                    args = (pc, desc_dev, idx)
                 else:
                     args = (pc, idx, desc352, normals)
                 if fused:
@@ -183,7 +236,7 @@ class PoseEstimator:
     def estimate(self, instances: Sequence[Instance], draws: Optional[List[dict]] = None) -> List[Optional[InstancePose]]:
         """Host arrays in, poses out: H2D of clouds / descriptors / tuple indices, the kernel chain, one D2H."""
         pose_buf = torch.zeros((len(instances) * 2, self.pose_bytes), dtype=torch.uint8, device=self.device)
-        plan = self.enqueue(instances, pose_buf, draws)
+        plan = self.enqueue(instances, pose_buf, draws, staged=self.stage(instances))
         pose_host = pose_buf.cpu().numpy()     # the frame's only device->host copy (synchronises the stream)
         return self.collect(plan, pose_host)
 

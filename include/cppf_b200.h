@@ -112,6 +112,11 @@ int cppf_grid_to_i64(const uint32_t *grid, const cppf_grid_geom *geom, int64_t *
  * replaces eval.py:225-235 (softmax, multinomial, pair scale) and generate_target_pairs,
  * dataset.py:118-135 (float64 where the reference is float64).                                        */
 
+/* Tuple sampling, eval.py:207 (np.random.randint(0, N, (T, K)), with replacement): idx i32 [T,arity] drawn on the
+ * device from a counter-based generator keyed by `seed`.  Host-sampled indices stay injectable in every call that
+ * takes `idx`; this is the default of the frame driver when the caller supplies none. */
+int cppf_sample_tuples(int64_t n, int64_t T, int arity, uint64_t seed, int32_t *idx, void *stream);
+
 /* logits [T,6,num_bins] f32 -> bins uint8 [T,6].  One draw per (tuple, coordinate) by inverse CDF of
  * softmax(logits): with u01 [T,6] given the draw is the first bin whose cumulative probability exceeds
  * u; with u01 == NULL uniforms come from a counter-based generator keyed by (seed, tuple, coordinate). */

@@ -353,3 +353,26 @@ def test_sample_bins_inverse_cdf():
     _lib.check(lib.cppf_sample_bins(sharp.data_ptr(), 20000, 32, None, 1234, out.data_ptr(), stream_ptr()))
     frac5 = (out == 5).float().mean().item()
     assert set(out.unique().tolist()) <= {5, 9} and 0.48 < frac5 < 0.52
+
+
+def test_sample_tuples_on_device():
+    """cppf_sample_tuples (eval.py:207): in range, deterministic per seed, different across seeds, uniform."""
+    from cppf2_b200 import _lib
+    from cppf2_b200.voting import stream_ptr
+    lib = _lib.load()
+    n, T = 2731, 50000
+    a = torch.empty((T, 5), dtype=torch.int32, device="cuda")
+    b = torch.empty_like(a)
+    c = torch.empty_like(a)
+    _lib.check(lib.cppf_sample_tuples(n, T, 5, 7, a.data_ptr(), stream_ptr()))
+    _lib.check(lib.cppf_sample_tuples(n, T, 5, 7, b.data_ptr(), stream_ptr()))
+    _lib.check(lib.cppf_sample_tuples(n, T, 5, 8, c.data_ptr(), stream_ptr()))
+    assert int(a.min()) >= 0 and int(a.max()) < n
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    counts = torch.bincount(a.flatten().long(), minlength=n).float()
+    expect = T * 5 / n
+    assert abs(float(counts.mean()) - expect) < 1e-3 and float(counts.std()) < 1.3 * expect ** 0.5   # Poisson-like spread
+    assert int(counts.min()) > 0
+    # columns are independent draws: tuples repeating a point are rare but allowed (with replacement)
+    same01 = (a[:, 0] == a[:, 1]).float().mean().item()
+    assert same01 < 5.0 / n
