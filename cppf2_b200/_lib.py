@@ -44,6 +44,22 @@ class Pose(C.Structure):
                 ("count_right", C.c_float), ("kept", C.c_int64), ("status", C.c_uint32), ("pad", C.c_uint32)]
 
 
+class VoteParams(C.Structure):
+    _fields_ = [("res", C.c_double), ("num_rots", C.c_int), ("num_bins", C.c_int), ("sphere_bins", C.c_int),
+                ("cos_thr", C.c_float), ("band", C.c_int), ("lut_g", C.c_int), ("up_loc", C.c_int), ("right_loc", C.c_int),
+                ("loss_y_only", C.c_int), ("pad0", C.c_int), ("lut", C.c_void_p), ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),
+                ("sphere", C.c_void_p), ("axes", C.c_double * 9), ("imp_margin", C.c_double), ("rank_lo", C.c_int64),
+                ("gamma", C.c_float), ("pad", C.c_int)]
+
+
+class VoteBuffers(C.Structure):
+    _fields_ = [("grid", C.c_void_p), ("grid_capacity", C.c_int64), ("geom", C.c_void_p), ("center", C.c_void_p),
+                ("summary", C.c_void_p), ("status", C.c_void_p), ("targets_tr", C.c_void_p), ("targets_rot", C.c_void_p),
+                ("errs", C.c_void_p), ("keep", C.c_void_p), ("kept_list", C.c_void_p), ("imp", C.c_void_p),
+                ("counts", C.c_void_p), ("ws_backvote", C.c_void_p), ("ws_backvote_bytes", C.c_int64),
+                ("ws_pose", C.c_void_p), ("ws_pose_bytes", C.c_int64)]
+
+
 P, I, I64, F, D, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
 _DP = C.POINTER(C.c_double)
 _IP = C.POINTER(C.c_int)
@@ -76,6 +92,7 @@ SIGNATURES = {
     "cppf_rotation_hist_part": (I, [P, P, I, I64, P, I64, _IP, I, P, P, I64, P, P, D, P, P, I, P, I, F, I, P, I, P, I, I, P]),
     "cppf_sphere_lut_bytes": (I64, [I]),
     "cppf_sphere_lut_build": (I, [P, I, F, I, P]),
+    "cppf_vote_chain": (I, [P, I64, P, I, I64, I64, P, P, P, I64, P, P, P, P]),
     "cppf_pose_workspace_bytes": (I64, [I64]),
     "cppf_pose_finalize": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, I64, P]),
     "cppf_shot_workspace_bytes": (I64, [I64]),

@@ -18,6 +18,7 @@ backbone (descriptors are an input), and the optional Adam refinement (opt=False
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -85,14 +86,19 @@ class PoseEstimator:
 
     def __init__(self, models: Dict[str, Dict[str, object]], cfgs: Dict[str, dict], num_pairs: int = 50000,
                  num_rots: int = 180, angle_tol: float = 1.0, backproj_ratio: float = 0.1, imp_wt_margin: float = 0.01,
-                 seed: int = 0, max_points: int = 50000, device=None):
+                 seed: int = 0, max_points: int = 50000, device=None, n_streams: Optional[int] = None):
         self.models, self.cfgs = models, cfgs
         self.num_pairs, self.num_rots = int(num_pairs), int(num_rots)
         self.angle_tol, self.backproj_ratio, self.imp_wt_margin = angle_tol, backproj_ratio, imp_wt_margin
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rng = np.random.default_rng(seed)
         self.seed = int(seed)
-        self.voter = PoseVoter(self.num_pairs, max_points, device=self.device)
+        # Instances are independent (eval.py:153): instance i runs on lane i % n_streams, each lane a CUDA stream with its
+        # own voter buffers, so the small latency-bound kernels of one instance fill the SMs another leaves idle.
+        self.n_streams = max(1, int(n_streams if n_streams is not None else os.environ.get("CPPF_STREAMS", "6")))
+        self.voters = [PoseVoter(self.num_pairs, max_points, device=self.device) for _ in range(self.n_streams)]
+        self.voter = self.voters[0]
+        self.lanes = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)] if self.n_streams > 1 else []
         self.pose_bytes = C.sizeof(Pose)
         self.timing_hook = None        # optional callable(stage: str, begin: bool) for bench.py's per-kernel events
         self.launches = 0
@@ -145,7 +151,8 @@ class PoseEstimator:
                         to_device(pi, torch.int32 if pi.dtype in (np.int32, torch.int32) else torch.int64, self.device)
                 for t in (item["pc"], item["desc"], item["idx"]):
                     if t is not None:
-                        t.record_stream(compute)
+                        for st in [compute] + self.lanes:
+                            t.record_stream(st)
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
                 item["ready"] = ev
@@ -160,65 +167,82 @@ class PoseEstimator:
         uploads them on the copy stream; without it they are copied here, in stream order)."""
         plan = []
         launches = 0
+        main = torch.cuda.current_stream(self.device)
+        if self.lanes:                                  # fork: every lane starts after what is already queued on the caller's stream
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for lane in self.lanes:
+                lane.wait_event(fork)
         for i, inst in enumerate(instances):
-            vc = self.vote_config(inst.category)
-            if staged is not None:
-                st = staged[i]
-                torch.cuda.current_stream(self.device).wait_event(st["ready"])
-                pc, cells_hint, idx, desc_dev = st["pc"], st["cells_hint"], st["idx"], st["desc"]
-            else:
-                on_host = isinstance(inst.pc, np.ndarray)
-                cells_hint = PoseVoter.grid_cells_on_host(inst.pc, vc.res) if on_host else getattr(inst, "cells_hint", None)
-                pc = to_device(inst.pc, torch.float32, self.device)
-                idx = inst.point_idxs
-                if idx is not None and not isinstance(idx, torch.Tensor):
-                    idx = to_device(idx, torch.int32 if idx.dtype == np.int32 else torch.int64, self.device)
-                desc_dev = None if inst.desc is None else to_device(inst.desc, torch.float32, self.device)
-            n = pc.shape[0]
-            if idx is None:
-                idx = self._sample_tuples(i, n)
-                launches += 1
-            heads = self.models[inst.category]
-            self._mark("shot", True)
-            desc352, normals = shot.compute_device(pc, vc.res * 10, vc.res * 10)      # eval.py:210
-            self._mark("shot", False)
-            launches += 9
-            slots = {}
-            scale_from_dino = None
-            for b, branch in enumerate(("dino", "shot")):                              # eval.py:219
-                model = heads.get(branch)
-                if model is None or (branch == "dino" and desc_dev is None):
-                    continue
-                slot = pose_buf[2 * i + b]
-                inj = None if draws is None else draws[i].get(branch)
-                vote_seed = self.seed + 7919 * (2 * i + b)
-                # bf16 tensor-core heads draw the bins in their own epilogue (no [T,6,32] logits in HBM) unless the
-                # caller injects the draws; the float32 heads keep forward + cppf_sample_bins
-                fused = inj is None and getattr(model, "precision", 0) == 1
-                self._mark("heads_" + branch, True)
-                logits = None
-                if branch == "dino":
-                    args = (pc, desc_dev, idx)
-                else:
-                    args = (pc, idx, desc352, normals)
-                if fused:
-                    inj, scales = model.forward_sampled(*args, seed=vote_seed)
-                else:
-                    logits, scales = model(*args)
-                self._mark("heads_" + branch, False)
-                launches += 2 if getattr(model, "precision", 0) == 1 else 4
-                self._mark("vote_" + branch, True)
-                self.voter.vote(pc, idx, vc, pred_scales=scales, bins=inj, logits=None if inj is not None else logits,
-                                seed=vote_seed, cells_hint=cells_hint, pose_out=slot,
-                                scale_override=scale_from_dino if branch == "shot" else None)
-                self._mark("vote_" + branch, False)
-                launches += self.voter.launches
-                if branch == "dino":   # the SHOT branch reuses the DINO branch's scale (eval.py:308-310)
-                    scale_from_dino = PoseVoter.scale_ptr_of(slot)
-                slots[branch] = 2 * i + b
-            plan.append(dict(slots=slots, category=inst.category))
+            with torch.cuda.stream(self.lanes[i % self.n_streams] if self.lanes else main):
+                n_l, item = self._enqueue_instance(i, inst, pose_buf, draws, None if staged is None else staged[i])
+            launches += n_l
+            plan.append(item)
+        for lane in self.lanes:                         # join: the caller's stream continues after every lane
+            ev = torch.cuda.Event()
+            ev.record(lane)
+            main.wait_event(ev)
         self.launches = launches
         return plan
+
+    def _enqueue_instance(self, i: int, inst: Instance, pose_buf: torch.Tensor, draws, st):
+        voter = self.voters[i % self.n_streams]
+        launches = 0
+        vc = self.vote_config(inst.category)
+        if st is not None:
+            torch.cuda.current_stream(self.device).wait_event(st["ready"])
+            pc, cells_hint, idx, desc_dev = st["pc"], st["cells_hint"], st["idx"], st["desc"]
+        else:
+            on_host = isinstance(inst.pc, np.ndarray)
+            cells_hint = PoseVoter.grid_cells_on_host(inst.pc, vc.res) if on_host else getattr(inst, "cells_hint", None)
+            pc = to_device(inst.pc, torch.float32, self.device)
+            idx = inst.point_idxs
+            if idx is not None and not isinstance(idx, torch.Tensor):
+                idx = to_device(idx, torch.int32 if idx.dtype == np.int32 else torch.int64, self.device)
+            desc_dev = None if inst.desc is None else to_device(inst.desc, torch.float32, self.device)
+        n = pc.shape[0]
+        if idx is None:
+            idx = self._sample_tuples(i, n)
+            launches += 1
+        heads = self.models[inst.category]
+        self._mark("shot", True)
+        desc352, normals = shot.compute_device(pc, vc.res * 10, vc.res * 10)      # eval.py:210
+        self._mark("shot", False)
+        launches += 9
+        slots = {}
+        scale_from_dino = None
+        for b, branch in enumerate(("dino", "shot")):                              # eval.py:219
+            model = heads.get(branch)
+            if model is None or (branch == "dino" and desc_dev is None):
+                continue
+            slot = pose_buf[2 * i + b]
+            inj = None if draws is None else draws[i].get(branch)
+            vote_seed = self.seed + 7919 * (2 * i + b)
+            # bf16 tensor-core heads draw the bins in their own epilogue (no [T,6,32] logits in HBM) unless the
+            # caller injects the draws; the float32 heads keep forward + cppf_sample_bins
+            fused = inj is None and getattr(model, "precision", 0) == 1
+            self._mark("heads_" + branch, True)
+            logits = None
+            if branch == "dino":
+                args = (pc, desc_dev, idx)
+            else:
+                args = (pc, idx, desc352, normals)
+            if fused:
+                inj, scales = model.forward_sampled(*args, seed=vote_seed)
+            else:
+                logits, scales = model(*args)
+            self._mark("heads_" + branch, False)
+            launches += 2 if getattr(model, "precision", 0) == 1 else 4
+            self._mark("vote_" + branch, True)
+            voter.vote(pc, idx, vc, pred_scales=scales, bins=inj, logits=None if inj is not None else logits,
+                       seed=vote_seed, cells_hint=cells_hint, pose_out=slot,
+                       scale_override=scale_from_dino if branch == "shot" else None)
+            self._mark("vote_" + branch, False)
+            launches += voter.launches
+            if branch == "dino":   # the SHOT branch reuses the DINO branch's scale (eval.py:308-310)
+                scale_from_dino = PoseVoter.scale_ptr_of(slot)
+            slots[branch] = 2 * i + b
+        return launches, dict(slots=slots, category=inst.category)
 
     def collect(self, plan: List[dict], pose_host: np.ndarray) -> List[Optional[InstancePose]]:
         """Ensemble selection on the host from the pose records (eval.py:358-372)."""

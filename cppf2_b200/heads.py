@@ -46,7 +46,7 @@ class BeyondCPPF:
         self._state: Dict[str, np.ndarray] = {}
         self._handle = None
         self._device = None
-        self._ws = None
+        self._ws_by_stream: Dict[tuple, torch.Tensor] = {}
         self.load_state_dict(init_state_dict(self.branch, seed=0, num_more=self.num_more))
 
     # -- nn.Module-like surface the reference scripts touch ------------------------------------------------
@@ -138,8 +138,11 @@ class BeyondCPPF:
         T, n = idx.shape[0], pc.shape[0]
         scale = torch.empty((T, 3), dtype=torch.float32, device=dev)
         need = int(lib.cppf_heads_workspace_bytes(self._handle, T, n, self.precision))
-        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        # one scratch per (device, stream): the frame driver runs instances of the same category on several streams
+        key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._ws_by_stream.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._ws_by_stream[key] = torch.empty(need, dtype=torch.uint8, device=dev)
         ip, i64, istr = idx_args(idx)
         if sample is not None:
             u01 = sample.get("u01")
@@ -148,12 +151,12 @@ class BeyondCPPF:
             check(lib.cppf_heads_forward_sampled(self._handle, self.precision, pc.data_ptr(), n, ip, i64, istr, T, feat.data_ptr(),
                                                  None if nrm is None else nrm.data_ptr(), None if u01 is None else u01.data_ptr(),
                                                  int(sample.get("seed", 0)), bins.data_ptr(), scale.data_ptr(),
-                                                 self._ws.data_ptr(), self._ws.numel(), stream_ptr()), "cppf_heads_forward_sampled")
+                                                 ws.data_ptr(), ws.numel(), stream_ptr()), "cppf_heads_forward_sampled")
             return bins, scale
         logits = torch.empty((T, 6, 32), dtype=torch.float32, device=dev)
         check(lib.cppf_heads_forward(self._handle, self.precision, pc.data_ptr(), n, ip, i64, istr, T, feat.data_ptr(),
                                      None if nrm is None else nrm.data_ptr(), logits.data_ptr(), scale.data_ptr(),
-                                     self._ws.data_ptr(), self._ws.numel(), stream_ptr()), "cppf_heads_forward")
+                                     ws.data_ptr(), ws.numel(), stream_ptr()), "cppf_heads_forward")
         return logits, scale
 
     def __call__(self, *args, **kwargs):

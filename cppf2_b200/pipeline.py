@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BackvoteSummary, Center, GridGeom, Pose, check
+from ._lib import BackvoteSummary, Center, GridGeom, Pose, VoteBuffers, VoteParams, check
 from .hostmath import percentile_plan
 from .voting import (angle_tables, cos_threshold, device_index_tensor, idx_args, read_struct, sphere_lut, sphere_points,
                      stream_ptr, struct_tensor, to_device)
@@ -102,6 +102,63 @@ class PoseVoter:
         self.ws_backvote = torch.empty(int(self.lib.cppf_backvote_workspace_bytes(T, self.max_points)), dtype=torch.uint8, device=d)
         self.ws_pose = torch.empty(int(self.lib.cppf_pose_workspace_bytes(T)), dtype=torch.uint8, device=d)
         self.launches = 0   # kernels + memset nodes enqueued by the last vote() call
+        self._params_cache = {}
+        self._buffers = None
+
+    def _vote_buffers(self, S: int) -> VoteBuffers:
+        if self.counts.shape != (2, S):
+            self.counts = torch.empty((2, S), dtype=torch.float64, device=self.device)
+            self._buffers = None
+        key = (self.grid.data_ptr(), self.counts.data_ptr(), self.errs.data_ptr())
+        if self._buffers is None or self._buffers[0] != key:
+            b = VoteBuffers(grid=self.grid.data_ptr(), grid_capacity=self.grid.numel(), geom=self.geom.data_ptr(),
+                            center=self.center.data_ptr(), summary=self.summary.data_ptr(), status=self.status.data_ptr(),
+                            targets_tr=self.targets_tr.data_ptr(), targets_rot=self.targets_rot.data_ptr(),
+                            errs=self.errs.data_ptr(), keep=self.keep.data_ptr(), kept_list=self.kept_list.data_ptr(),
+                            imp=self.imp.data_ptr(), counts=self.counts.data_ptr(), ws_backvote=self.ws_backvote.data_ptr(),
+                            ws_backvote_bytes=self.ws_backvote.numel(), ws_pose=self.ws_pose.data_ptr(),
+                            ws_pose_bytes=self.ws_pose.numel())
+            self._buffers = (key, b)
+        return self._buffers[1]
+
+    def _vote_params(self, cfg: "VoteConfig", T: int) -> VoteParams:
+        key = (cfg.res, tuple(cfg.up), tuple(cfg.right), tuple(cfg.front), cfg.num_rots, cfg.angle_tol, cfg.backproj_ratio,
+               cfg.imp_wt_margin, cfg.num_bins, cfg.loss_y_only, T)
+        p = self._params_cache.get(key)
+        if p is None:
+            S = cfg.num_sphere
+            thr = cos_threshold(cfg.angle_tol)
+            ct, st = angle_tables(int(cfg.num_rots), self.device)
+            sphere = sphere_points(S, self.device)
+            lut, lut_g = sphere_lut(S, thr, self.device)
+            rank_lo, gamma = percentile_plan(T, cfg.backproj_ratio)
+            p = VoteParams(res=float(cfg.res), num_rots=int(cfg.num_rots), num_bins=int(cfg.num_bins), sphere_bins=S, cos_thr=thr,
+                           band=self.lib.cppf_sphere_band(S, thr), lut_g=lut_g,
+                           up_loc=int(np.where(np.asarray(cfg.up))[0][0]), right_loc=int(np.where(np.asarray(cfg.right))[0][0]),
+                           loss_y_only=int(cfg.loss_y_only), lut=None if lut is None else lut.data_ptr(), cos_tab=ct.data_ptr(),
+                           sin_tab=st.data_ptr(), sphere=sphere.data_ptr(),
+                           axes=_lib.axes_array(cfg.up, cfg.front, cfg.right),   # call-site order, eval.py:237-240
+                           imp_margin=float(cfg.imp_wt_margin), rank_lo=int(rank_lo), gamma=float(gamma))
+            self._params_cache[key] = p
+        return p
+
+    def vote_bins(self, pc: torch.Tensor, idx: torch.Tensor, cfg: "VoteConfig", bins: torch.Tensor, pred_scales, scale_override,
+                  cells_hint: Optional[int], pose_out: Optional[torch.Tensor]):
+        """The whole chain from the drawn bins to the pose record in ONE host call (cppf_vote_chain): device tensors only,
+        same kernels and buffers as vote()."""
+        T, N = idx.shape[0], pc.shape[0]
+        self._ensure(T, N, cells_hint)
+        ip, i64, istr = idx_args(idx)
+        params, bufs = self._vote_params(cfg, T), self._vote_buffers(cfg.num_sphere)
+        check(self.lib.cppf_vote_chain(pc.data_ptr(), N, ip, i64, istr, T, bins.data_ptr(),
+                                       None if pred_scales is None else pred_scales.data_ptr(),
+                                       None if scale_override is None else scale_override.data_ptr(), int(cells_hint or 0),
+                                       C.byref(params), C.byref(bufs), (self.pose if pose_out is None else pose_out).data_ptr(),
+                                       stream_ptr()), "cppf_vote_chain")
+        self.launches = 24
+        self._live = (pc, idx, bins, pred_scales, scale_override)
+        self._T = T
+        return self
 
     # -- helpers -------------------------------------------------------------------------------------
     def _ensure(self, T: int, N: int, cells_hint: Optional[int]):
@@ -137,85 +194,26 @@ class PoseVoter:
         pc = to_device(pc, torch.float32, self.device)
         idx = device_index_tensor(point_idxs_all, self.device)
         T, N = idx.shape[0], pc.shape[0]
-        self._ensure(T, N, cells_hint)
-        s = stream_ptr()
-        ip, i64, istr = idx_args(idx)
-        R = int(cfg.num_rots)
-        ct, st = angle_tables(R, self.device)
-        S = cfg.num_sphere
-        sphere = sphere_points(S, self.device)
-        thr = cos_threshold(cfg.angle_tol)
-        band = lib.cppf_sphere_band(S, thr)
-        lut, lut_g = sphere_lut(S, thr, self.device)
-        launches = 0
-
-        # decode (eval.py:225-235)
         if (bins is None) == (logits is None):
             raise ValueError("give exactly one of bins / logits")
-        if logits is not None:
+        self._ensure(T, N, cells_hint)
+        if logits is not None:                         # decode (eval.py:225-229): softmax + one multinomial draw
             lg = to_device(logits, torch.float32, self.device)
             u = None if u01 is None else to_device(u01, torch.float32, self.device)
             check(lib.cppf_sample_bins(lg.data_ptr(), T, cfg.num_bins, None if u is None else u.data_ptr(), int(seed),
-                                       self.bins.data_ptr(), s), "cppf_sample_bins")
-            bins_t = self.bins
-            launches += 1
+                                       self.bins.data_ptr(), stream_ptr()), "cppf_sample_bins")
+            bins_t = self.bins[:T]
         else:
             bins_t = to_device(bins, torch.uint8, self.device)
-        # call-site order (eval.py:237-240): positional (up, front, right) -> column 2 is the angle to `right`
-        axes = _lib.axes_array(cfg.up, cfg.front, cfg.right)
-        check(lib.cppf_decode_targets(pc.data_ptr(), ip, i64, istr, bins_t.data_ptr(), T, cfg.num_bins, axes,
-                                      self.targets_tr.data_ptr(), self.targets_rot.data_ptr(), None, None, s),
-              "cppf_decode_targets")
-        # centre vote (train_dino.py:171-215)
-        check(lib.cppf_cloud_bounds(pc.data_ptr(), N, float(cfg.res), self.geom.data_ptr(), s), "cppf_cloud_bounds")
-        self.status.zero_()
-        check(lib.cppf_vote_center(pc.data_ptr(), N, ip, i64, istr, self.targets_tr.data_ptr(), T, ct.data_ptr(),
-                                   st.data_ptr(), R, self.geom.data_ptr(), self.grid.data_ptr(), self.grid.numel(),
-                                   int(cells_hint or 0), 0, self.status.data_ptr(), s), "cppf_vote_center")
-        check(lib.cppf_grid_argmax(self.grid.data_ptr(), self.geom.data_ptr(), float(cfg.res), self.center.data_ptr(), s),
-              "cppf_grid_argmax")
-        launches += 1 + 1 + 1 + 2 + 2
-        # back-vote filter (eval.py:251-275)
-        rank_lo, gamma = percentile_plan(T, cfg.backproj_ratio)
-        check(lib.cppf_backvote_filter(pc.data_ptr(), N, ip, i64, istr, self.targets_tr.data_ptr(), T, axes,
-                                       self.center.data_ptr(), rank_lo, float(gamma), self.errs.data_ptr(),
-                                       self.keep.data_ptr(), self.kept_list.data_ptr(), self.imp.data_ptr(),
-                                       self.summary.data_ptr(), self.ws_backvote.data_ptr(), self.ws_backvote.numel(), s),
-              "cppf_backvote_filter")
-        launches += 1 + 2 + 5 + 2 + 1 + 1
-        # rotation votes for the angle to `up` (column 0) and to `right` (column 2) (eval.py:277-293)
-        if self.counts.shape != (2, S):
-            self.counts = torch.empty((2, S), dtype=torch.float64, device=self.device)
-        self.counts.zero_()
-        cols = (C.c_int * 2)(0, 2)
-        kept_count_ptr = self.summary.data_ptr() + BackvoteSummary.kept.offset
-        check(lib.cppf_rotation_hist(pc.data_ptr(), ip, i64, istr, self.targets_rot.data_ptr(), 3, cols, 2,
-                                     self.kept_list.data_ptr(), kept_count_ptr, T, self.imp.data_ptr(),
-                                     self.summary.data_ptr(), float(cfg.imp_wt_margin), ct.data_ptr(), st.data_ptr(), R,
-                                     sphere.data_ptr(), S, thr, band, None if lut is None else lut.data_ptr(), lut_g,
-                                     self.counts.data_ptr(), s), "cppf_rotation_hist")
-        launches += 2
-        # pose assembly (eval.py:284-313, 358-363)
         so = None
-        if scale_override is not None:
+        if scale_override is not None:   # the reference reuses the DINO-branch scale in the SHOT branch (eval.py:308-310)
             so = to_device(np.asarray(scale_override, dtype=np.float32) if not isinstance(scale_override, torch.Tensor)
                            else scale_override, torch.float32, self.device)
         ps = None if pred_scales is None else to_device(pred_scales, torch.float32, self.device)
         if ps is None and so is None:
             raise ValueError("pred_scales or scale_override is required")
-        up_loc = int(np.where(np.asarray(cfg.up))[0][0])
-        right_loc = int(np.where(np.asarray(cfg.right))[0][0])
-        check(lib.cppf_pose_finalize(pc.data_ptr(), ip, i64, istr, bins_t.data_ptr(), cfg.num_bins,
-                                     None if ps is None else ps.data_ptr(), self.kept_list.data_ptr(),
-                                     self.summary.data_ptr(), self.counts.data_ptr(), sphere.data_ptr(), S,
-                                     self.center.data_ptr(), up_loc, right_loc, int(cfg.loss_y_only),
-                                     None if so is None else so.data_ptr(),
-                                     (self.pose if pose_out is None else pose_out).data_ptr(), self.ws_pose.data_ptr(),
-                                     self.ws_pose.numel(), s), "cppf_pose_finalize")
-        launches += 4
-        self.launches = launches
-        self._live = (pc, idx, bins_t, ps, so)  # keep inputs alive until the stream has consumed them
-        self._T = T
+        self.vote_bins(pc, idx, cfg, bins_t, ps, so, cells_hint, pose_out)
+        self.launches += 0 if logits is None else 1
         return self
 
     @staticmethod

@@ -24,7 +24,7 @@ _ws_cache = {}
 def _workspace(n: int, device) -> torch.Tensor:
     lib = _lib.load()
     need = int(lib.cppf_shot_workspace_bytes(n))
-    key = str(device)
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)   # one scratch per stream: instances may overlap
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=device)

@@ -219,6 +219,55 @@ int cppf_pose_finalize(const float *pc, const void *idx, int idx_is_i64, int64_t
                        const float *scale_override /* 3 floats or NULL: eval.py:308 reuses the DINO scale */,
                        cppf_pose *pose, void *ws, int64_t ws_bytes, void *stream);
 
+/* ---- the whole vote chain in one call ------------------------------------------------------------
+ * The body of the instance loop after the heads, eval.py:230-313 and :358-363: cppf_decode_targets ->
+ * cppf_cloud_bounds -> cppf_vote_center -> cppf_grid_argmax -> cppf_backvote_filter -> cppf_rotation_hist
+ * (angle columns 0 and 2) -> cppf_pose_finalize, enqueued on `stream` from one host call.  Every pointer in both
+ * structs is a DEVICE pointer to a caller-owned buffer except `axes` (host values).                   */
+typedef struct cppf_vote_params {
+    double res;                 /* cfg.res (eval.py:172): the Python float; the grid geometry uses float32(res), the voted
+                                   centre lo + cell*res the float64 value (train_dino.py:213) */
+    int num_rots, num_bins;     /* 180, 32 */
+    int sphere_bins;            /* S = fibonacci lattice size (eval.py:79) */
+    float cos_thr;              /* float32(cos(2*angle_tol)) */
+    int band;                   /* cppf_sphere_band(S, cos_thr) */
+    int lut_g;                  /* cube-map resolution of `lut` (ignored when lut == NULL) */
+    int up_loc, right_loc, loss_y_only;
+    const void *lut;            /* cppf_sphere_lut_build table or NULL */
+    const float *cos_tab, *sin_tab;   /* [num_rots], torch-CPU values */
+    const float *sphere;        /* [S,3] */
+    double axes[9];             /* positional (up, right, front) of dataset.py:118 as passed at eval.py:237-240 */
+    double imp_margin;          /* eval.py:275: 0.01 */
+    int64_t rank_lo;            /* floor(ratio*(T-1)) */
+    float gamma;                /* fractional part of ratio*(T-1) */
+    int pad;
+} cppf_vote_params;
+
+typedef struct cppf_vote_buffers {
+    uint32_t *grid;             /* [grid_capacity] */
+    int64_t grid_capacity;
+    cppf_grid_geom *geom;
+    cppf_center *center;
+    cppf_backvote_summary *summary;
+    uint32_t *status;
+    float *targets_tr;          /* [T,2] */
+    float *targets_rot;         /* [T,3] */
+    float *errs;                /* [T] */
+    uint8_t *keep;              /* [T] */
+    int32_t *kept_list;         /* [T] */
+    int32_t *imp;               /* [n] */
+    double *counts;             /* [2,S] */
+    void *ws_backvote;
+    int64_t ws_backvote_bytes;  /* cppf_backvote_workspace_bytes(T, n) */
+    void *ws_pose;
+    int64_t ws_pose_bytes;      /* cppf_pose_workspace_bytes(T) */
+} cppf_vote_buffers;
+
+/* bins u8 [T,6] are the multinomial draws (cppf_sample_bins / cppf_heads_forward_sampled / injected). */
+int cppf_vote_chain(const float *pc, int64_t n, const void *idx, int idx_is_i64, int64_t idx_stride, int64_t T,
+                    const uint8_t *bins, const float *pred_scales, const float *scale_override, int64_t cells_hint,
+                    const cppf_vote_params *params, const cppf_vote_buffers *buffers, cppf_pose *pose_out, void *stream);
+
 /* ---- SHOT descriptor ----------------------------------------------------------------------------
  * replaces shot.compute / shot.estimate_normal, src_shot/shot.cpp:12-42, :45-100 (PCL NormalEstimation +
  * SHOTEstimation<SHOT352>, radius search, viewpoint at the origin, NaN rows for invalid points).       */
