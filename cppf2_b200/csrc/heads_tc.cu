@@ -421,6 +421,14 @@ __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, u
 // uniform-datapath load indexed by warp-uniform counters, which is what lets tcgen05.mma / cp.async.bulk take their
 // descriptors from uniform registers without per-lane "waterfall" loops (tools/probes/probe_mma_rate.cu: 64 cycles
 // per M128 N128 K16 MMA when issued that way, 160-400 when issued from lane-divergent code).
+// clock64() is read only by the profiling instantiation (cppf_debug_heads_tc_profile); the production one carries no counters
+template <bool kProf>
+__device__ __forceinline__ long long prof_clock() {
+    if constexpr (kProf) return clock64();
+    else return 0;
+}
+
+template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_constant__ Program prog, const __grid_constant__ Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t s_tmem_base;
@@ -464,16 +472,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         const bool leader = elect_one();
         uint32_t seq = 0;
         long long t_wait = 0;
-        const long long t_begin = clock64();
+        const long long t_begin = prof_clock<kProf>();
         for (int round = 0; round < n_rounds; ++round) {
             if (tile_of(round, 0) >= n_tiles) break;
             const unsigned char *src = a.weights;
             for (int i = 0; i < prog.n_slabs; ++i, ++seq) {
                 const uint32_t bytes = static_cast<uint32_t>(prog.slab[i].bytes16) << 4;
                 const uint32_t stage = seq % kStages, turn = seq / kStages;
-                const long long t0 = clock64();
+                const long long t0 = prof_clock<kProf>();
                 mbar_wait(bar_empty + 8 * stage, (turn & 1u) ^ 1u);
-                t_wait += clock64() - t0;
+                t_wait += prof_clock<kProf>() - t0;
                 if (leader) {
                     mbar_expect_tx(bar_full + 8 * stage, bytes);
                     bulk_load(ring0 + stage * kSlabBytes, src, bytes, bar_full + 8 * stage);
@@ -482,8 +490,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                 src += bytes;
             }
         }
-        if (a.prof && leader) {
-            a.prof[blockIdx.x * 64 + 4] = clock64() - t_begin;
+        if (kProf && a.prof && leader) {
+            a.prof[blockIdx.x * 64 + 4] = prof_clock<kProf>() - t_begin;
             a.prof[blockIdx.x * 64 + 5] = t_wait;
         }
     } else if (warp > kEpiWarps) {
@@ -496,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         const int s = warp - (kEpiWarps + 1);
         const bool leader = elect_one();
         long long t_act = 0, t_full = 0, t_issue = 0, n_steps = 0;
-        const long long t_begin = clock64();
+        const long long t_begin = prof_clock<kProf>();
         constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);    // SBO = 128 B, descriptor version bit 46
         const uint32_t ones_lo = (smem_u32(smem + kSmemOnes) >> 4) | (static_cast<uint32_t>(kPlane >> 4) << 16);
         const uint32_t x_lo = smem_u32(smem + kSmemX + s * kXBytes) >> 4;
@@ -509,15 +517,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             for (int i = 0; i < prog.n_slabs; ++i) {
                 const Slab &sl = prog.slab[i];
                 const uint32_t flags = sl.flags;
-                long long t0 = clock64();
+                long long t0 = prof_clock<kProf>();
                 if (flags & kSlabFirst) {        // the slot's A operand is ready and its accumulator is free
                     mbar_wait(bar_act + 8 * s, act_par);
                     act_par ^= 1u;
                 }
-                long long t1 = clock64();
+                long long t1 = prof_clock<kProf>();
                 mbar_wait(bar_full + 8 * stage, turn);
                 tc_fence_after();
-                long long t2 = clock64();
+                long long t2 = prof_clock<kProf>();
                 if (leader) {
                     const uint32_t n = sl.n, n_mma = sl.n_mma, idesc = sl.idesc;
                     const uint32_t d_addr = t_slot + sl.d_col;
@@ -544,13 +552,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                 }
                 t_act += t1 - t0;
                 t_full += t2 - t1;
-                t_issue += clock64() - t2;
+                t_issue += prof_clock<kProf>() - t2;
                 ++n_steps;
             }
         }
-        if (a.prof && leader) {
+        if (kProf && a.prof && leader) {
             long long *o = a.prof + blockIdx.x * 64 + 40 + 8 * s;
-            o[0] = clock64() - t_begin;
+            o[0] = prof_clock<kProf>() - t_begin;
             o[1] = t_act;
             o[2] = t_full;
             o[3] = t_issue;
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         const int mv_r = lane & 7, mv_c = lane >> 3;
         uint32_t done_seq = 0;
         long long t_done = 0, t_actn[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t_arrive = 0;
-        const long long t_begin = clock64();
+        const long long t_begin = prof_clock<kProf>();
         for (int round = 0; round < n_rounds; ++round) {
             const int64_t tile = tile_of(round, slot);
             if (tile >= n_tiles) break;
@@ -586,13 +594,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             }
             for (int p = 0; p < prog.n_phases; ++p) {
                 const Phase &ph = prog.phase[p];
-                long long t0 = clock64();
+                long long t0 = prof_clock<kProf>();
                 if (ph.wait_done) {
                     mbar_wait(bar_done + 8 * slot, done_seq & 1u);
                     ++done_seq;
                     tc_fence_after();
                 }
-                long long t1 = clock64();
+                long long t1 = prof_clock<kProf>();
                 t_done += t1 - t0;
                 switch (ph.action) {
                     case kActLoadRows: {
@@ -684,20 +692,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                     }
                     default: break;
                 }
-                t0 = clock64();
-                t_actn[ph.action] += t0 - t1;
+                t0 = prof_clock<kProf>();
+                if (kProf) t_actn[ph.action] += t0 - t1;
                 if (ph.n_parts) {
                     if (ph.action != kActHiddenT) fence_async_smem();      // generic-proxy writes to X -> visible to the tensor core's async proxy
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_act + 8 * slot);
                 }
-                t_arrive += clock64() - t0;
+                t_arrive += prof_clock<kProf>() - t0;
             }
         }
-        if (a.prof && sw == 0 && lane == 0) {
+        if (kProf && a.prof && sw == 0 && lane == 0) {
             long long *o = a.prof + blockIdx.x * 64 + 8 + 16 * slot;
-            o[0] = clock64() - t_begin;
+            o[0] = prof_clock<kProf>() - t_begin;
             o[1] = t_done;
             for (int k = 0; k < 9; ++k) o[2 + k] = t_actn[k];
             o[11] = t_arrive;
@@ -1034,7 +1042,8 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         delete st;
         return rc;
     }
-    CPPF_CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    CPPF_CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    CPPF_CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     *state = st;
     return CPPF_OK;
 }
@@ -1085,7 +1094,7 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.weights = st->d_point_w;
         a.out_bf16 = point_feat;
         a.prof = nullptr;
-        chain_tc_kernel<<<blocks_for(n), kThreads, kSmemTotal, s>>>(st->point_prog, a);
+        chain_tc_kernel<false><<<blocks_for(n), kThreads, kSmemTotal, s>>>(st->point_prog, a);
         CPPF_LAUNCH_CHECK();
     }
     if (T == 0) return CPPF_OK;
@@ -1105,7 +1114,8 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.u01 = u01;
         a.seed = seed;
         a.prof = g_tc_prof;
-        chain_tc_kernel<<<blocks_for(T), kThreads, kSmemTotal, s>>>(st->tuple_prog, a);
+        if (a.prof) chain_tc_kernel<true><<<blocks_for(T), kThreads, kSmemTotal, s>>>(st->tuple_prog, a);
+        else chain_tc_kernel<false><<<blocks_for(T), kThreads, kSmemTotal, s>>>(st->tuple_prog, a);
         CPPF_LAUNCH_CHECK();
     }
     return CPPF_OK;
