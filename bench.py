@@ -47,6 +47,16 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def heads_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per tuple-program launch of the heads kernel, from the committed
+    `ncu --set full` capture (profiles/r01_heads_ncu_full.json); None when the summary is absent."""
+    path = os.path.join(ROOT, "profiles", "r01_heads_ncu_full.json")
+    try:
+        return json.load(open(path))["traffic_bytes_per_tuple_launch_mean"]
+    except Exception:
+        return None
+
+
 def build_frame(frame_id: int):
     """Synthetic frame -> per-instance clouds exactly as eval.py:185-201 prepares them (host, untimed)."""
     from cppf2_b200 import synth
@@ -333,7 +343,9 @@ def main():
         peak = peaks["bf16_sustained"]
         ach = kernels["heads"]["achieved_tflops"]
         roofline = {"kernel": "heads (ResLayer chains, %s)" % {0: "fp32 CUDA cores", 1: "bf16 tcgen05", 2: "SHOT bf16 tcgen05 + DINO fp32 CUDA cores"}[precision], "bound": "tensor",
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained"}
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": heads_traffic(),
+                    "traffic_note": "DRAM bytes per tuple-program launch (ncu --set full, profiles/r01_heads_ncu_full.md)",
+                    "peak_source": peaks["source"] + ", sustained"}
     elif vote_ms >= shot_ms:
         ach = kernels["vote_chain"]["alg_GBps"]
         roofline = {"kernel": "vote chain (decode, centre vote, back-vote, rotation, pose)", "bound": "hbm", "achieved": ach,

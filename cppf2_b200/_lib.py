@@ -92,6 +92,10 @@ SIGNATURES = {
     "cppf_rotation_hist_part": (I, [P, P, I, I64, P, I64, _IP, I, P, P, I64, P, P, D, P, P, I, P, I, F, I, P, I, P, I, I, P]),
     "cppf_sphere_lut_bytes": (I64, [I]),
     "cppf_sphere_lut_build": (I, [P, I, F, I, P]),
+    "cppf_cloud_workspace_bytes": (I64, [I64]),
+    "cppf_backproject": (I, [P, I, D, P, I, I, _DP, P, P, P, P, I64, P]),
+    "cppf_voxel_downsample": (I, [P, I64, D, P, U64, P, P, P, P, P, P, I64, P]),
+    "cppf_gather_points": (I, [P, P, I64, P, P, P, P]),
     "cppf_vote_chain": (I, [P, I64, P, I, I64, I64, P, P, P, I64, P, P, P, P]),
     "cppf_pose_workspace_bytes": (I64, [I64]),
     "cppf_pose_finalize": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, I64, P]),

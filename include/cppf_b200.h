@@ -219,6 +219,31 @@ int cppf_pose_finalize(const float *pc, const void *idx, int idx_is_i64, int64_t
                        const float *scale_override /* 3 floats or NULL: eval.py:308 reuses the DINO scale */,
                        cppf_pose *pose, void *ws, int64_t ws_bytes, void *stream);
 
+/* ---- instance cloud preparation (the step in front of SHOT) -----------------------
+ * replaces backproject (utils/util.py:2586-2607, with the callers' un-flip of x and y, eval.py:185-189), downsample
+ * (utils/util.py:39-46: Open3D voxel_down_sample_and_trace + np.random.choice) and the 50 000-point cap
+ * (eval.py:195-198).  ws sized by cppf_cloud_workspace_bytes(n) with n = H*W resp. the number of points.  */
+int64_t cppf_cloud_workspace_bytes(int64_t n);
+
+/* depth [H,W] uint16 (depth_is_u16) or float32, divided by depth_div (1000 for REAL275 millimetres; 1 = as is);
+ * mask u8 [H,W]; kinv_host = the 9 doubles of np.linalg.inv(intrinsics), row-major.  Outputs in row-major pixel
+ * order (np.where): pc f32 [H*W,3] capacity, pix i32 [H*W] = row*W + col of each point, *count (device). */
+int cppf_backproject(const void *depth, int depth_is_u16, double depth_div, const uint8_t *mask, int H, int W,
+                     const double *kinv_host, float *pc, int32_t *pix, int64_t *count, void *ws, int64_t ws_bytes,
+                     void *stream);
+
+/* One member per occupied voxel of size `res` (Open3D grid: origin = min bound - res/2, float64).  The member with
+ * the smallest (priority, index) wins: priority = prio[i] (f32 in [0,1), injectable) or a counter-based draw keyed
+ * by `seed`.  Outputs in ascending index order: pc_out f32 [n,3] capacity, kept_idx i32 [n], *count (device);
+ * side_in/side_out (i32 [n], optional) carry a per-point payload (the pixel index) along. */
+int cppf_voxel_downsample(const float *pc, int64_t n, double res, const float *prio, uint64_t seed, float *pc_out,
+                          int32_t *kept_idx, int64_t *count, const int32_t *side_in, int32_t *side_out, void *ws,
+                          int64_t ws_bytes, void *stream);
+
+/* pc_out[j] = pc[idx[j]], j < m (the 50 000-point cap: idx from cppf_sample_tuples(n, 50000, 1, ...)). */
+int cppf_gather_points(const float *pc, const int32_t *idx, int64_t m, float *pc_out, const int32_t *side_in,
+                       int32_t *side_out, void *stream);
+
 /* ---- the whole vote chain in one call ------------------------------------------------------------
  * The body of the instance loop after the heads, eval.py:230-313 and :358-363: cppf_decode_targets ->
  * cppf_cloud_bounds -> cppf_vote_center -> cppf_grid_argmax -> cppf_backvote_filter -> cppf_rotation_hist

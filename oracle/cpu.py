@@ -306,3 +306,35 @@ def shot_lrf(pc, shot_r: float):
     margins = np.zeros((pc.shape[0], 2), np.int32)
     lib().oracle_shot_lrf(pc, pc.shape[0], float(shot_r), rf, margins)
     return rf, margins
+
+
+# ---- instance cloud preparation -- plain numpy restatements -------------------------------------
+def backproject(depth_m, intrinsics, instance_mask):
+    """utils/util.py:2586-2607 followed by the callers' un-flip of x and y (eval.py:185-189): float32 camera-frame
+    points of the masked, valid-depth pixels in np.where order, and their (rows, cols).  Pinned by
+    tests/golden/backproject.npz (minted from the reference's own function)."""
+    kinv = np.linalg.inv(np.asarray(intrinsics, dtype=np.float64))
+    final = np.logical_and(instance_mask, depth_m > 0)
+    rows, cols = np.where(final)
+    uv1 = np.stack([cols, rows, np.ones_like(cols)], 0).astype(np.float64)
+    xyz = (kinv @ uv1).T
+    z = np.asarray(depth_m, dtype=np.float64)[rows, cols]
+    pts = xyz * z[:, None] / xyz[:, -1:]
+    return pts.astype(np.float32), (rows, cols)
+
+
+def voxel_downsample(pc, res: float, prio) -> np.ndarray:
+    """utils/util.py:39-46 restated: Open3D 0.18 `voxel_down_sample_and_trace(res, min_bound, max_bound)` bins point p
+    into voxel floor((p - (min_bound - res/2)) / res) (float64; VoxelDownSampleAndTrace in open3d/geometry/PointCloud.cpp),
+    then one member per voxel is drawn.  Open3D is not installable here (parity unpinned for the binning; the draw is
+    injected): the member with the smallest (prio, index) represents its voxel.  Returns kept indices, ascending
+    (Open3D's own order is that of an unordered_map and carries no meaning)."""
+    p = np.asarray(pc, dtype=np.float32).astype(np.float64)
+    lo = p.min(0) - 0.5 * float(res)
+    vox = np.floor((p - lo) / float(res)).astype(np.int64)
+    _, inv = np.unique(vox, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    order = np.lexsort((np.arange(p.shape[0]), np.asarray(prio, dtype=np.float32), inv))
+    first = np.ones(order.shape[0], bool)
+    first[1:] = inv[order][1:] != inv[order][:-1]
+    return np.sort(order[first])

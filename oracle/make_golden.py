@@ -308,9 +308,25 @@ def mint_percentile():
     save("percentile", **cases)
 
 
+def mint_backproject(ref):
+    """The reference's own backproject (utils/util.py:2586-2607) on a synthetic REAL275-shaped depth frame, followed by
+    the callers' un-flip and float32 cast (eval.py:185-189)."""
+    from cppf2_b200 import synth
+    frame = synth.synth_real275_frame(3, 3)
+    depth = frame["depth"].astype(np.uint16)
+    mask = frame["masks"][0]
+    pts, idxs = ref.backproject(depth / 1000., synth.REAL275_K, mask)
+    pts[:, 0] = -pts[:, 0]
+    pts[:, 1] = -pts[:, 1]
+    # a small crop keeps the fixture tiny; the crop must contain the whole mask
+    save("backproject", depth=depth, mask=np.packbits(mask), mask_shape=np.array(mask.shape), K=synth.REAL275_K,
+         pc=pts.astype(np.float32), rows=idxs[0].astype(np.int32), cols=idxs[1].astype(np.int32))
+
+
 def main():
     torch.set_grad_enabled(False)
     ref = load_reference()
+    mint_backproject(ref)
     mint_vote_center(ref)
     mint_targets(ref)
     mint_rotation(ref)

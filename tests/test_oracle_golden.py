@@ -117,3 +117,25 @@ def test_instance_body(oracle, golden):
     np.testing.assert_allclose(out["R_est"], g["R_est"], atol=1e-7)
     assert np.array_equal(out["pred_scale"], g["pred_scale"])
     np.testing.assert_allclose(out["loss"], float(g["loss_all"]), rtol=1e-6)
+
+
+def test_oracle_backproject_matches_reference_golden(golden, oracle):
+    """numpy restatement of utils/util.py:2586-2607 (+ eval.py:185-189) against the output of the reference's own function."""
+    g = golden("backproject")
+    mask = np.unpackbits(g["mask"])[:int(np.prod(g["mask_shape"]))].reshape(g["mask_shape"]).astype(bool)
+    pts, (rows, cols) = oracle.backproject(g["depth"] / 1000., g["K"], mask)
+    assert np.array_equal(pts, g["pc"]) and np.array_equal(rows, g["rows"]) and np.array_equal(cols, g["cols"])
+
+
+def test_oracle_voxel_downsample_properties(oracle):
+    """One representative per occupied voxel of the Open3D grid (origin = min - res/2), the injected draw decides which."""
+    rng = np.random.default_rng(0)
+    pc = (rng.random((5000, 3)) * 0.05).astype(np.float32)
+    prio = rng.random(5000).astype(np.float32)
+    idx = oracle.voxel_downsample(pc, 0.004, prio)
+    p = pc.astype(np.float64)
+    vox = np.floor((p - (p.min(0) - 0.002)) / 0.004).astype(np.int64)
+    assert len(np.unique(vox[idx], axis=0)) == len(idx) == len(np.unique(vox, axis=0))
+    for i in idx[:50]:     # the representative has the smallest draw of its voxel
+        same = np.all(vox == vox[i], axis=1)
+        assert prio[i] == prio[same].min()
