@@ -257,6 +257,41 @@ class PoseEstimator:
             out.append(InstancePose(RT=r.RT, scale=r.unit_scale, branch=best, loss=r.loss, results=results))
         return out
 
+    def estimate_frame(self, depth, masks, categories: Sequence[str], intrinsics, desc_fn=None, depth_div: float = 1000.0,
+                       frame_seed: int = 0) -> List[Optional[InstancePose]]:
+        """The frame loop of eval.py:153-372 from the raw inputs: depth [H,W] (uint16 millimetres or float32), one boolean
+        mask [H,W] and one category per detection.  Depth and masks are uploaded once; back-projection, voxel
+        down-sampling and the 50 000-point cap (eval.py:185-201) run on the device (cppf2_b200.cloud), then the instance
+        loop.  `desc_fn(i, pix)` returns the [N,1024] key-point descriptors of instance i at the kept pixels `pix`
+        (row*W + col, CUDA int32) -- the DINOv2 backbone is not part of this path; None runs the SHOT branch only.
+        Instances with fewer than 50 valid pixels or an extent above 1000 voxels are skipped like the reference does."""
+        from . import cloud
+        dev = self.device
+        d = depth if isinstance(depth, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(depth))
+        d = d.to(dev, non_blocking=True)
+        m = [(x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))).to(dev, non_blocking=True) for x in masks]
+        res = [self.vote_config(c).res for c in categories]
+        clouds = cloud.prepare_instance_clouds(d, m, intrinsics, res, depth_div=depth_div, seed=self.seed * 8191 + frame_seed)
+        instances, where = [], []
+        for i, item in enumerate(clouds):
+            if item is None:
+                continue
+            pc, pix = item
+            desc = None if desc_fn is None else desc_fn(i, pix)
+            instances.append(Instance(pc=pc, category=categories[i], desc=desc, point_idxs=None))
+            where.append(i)
+        out: List[Optional[InstancePose]] = [None] * len(masks)
+        if not instances:
+            return out
+        pose_buf = torch.zeros((len(instances) * 2, self.pose_bytes), dtype=torch.uint8, device=dev)
+        plan = self.enqueue(instances, pose_buf)
+        poses = self.collect(plan, pose_buf.cpu().numpy())
+        for i, p in zip(where, poses):
+            if p is not None and any(r.status & _lib.CPPF_STATUS_GRID_GUARD for r in p.results.values()):
+                p = None                                                   # eval.py:200
+            out[i] = p
+        return out
+
     def estimate(self, instances: Sequence[Instance], draws: Optional[List[dict]] = None) -> List[Optional[InstancePose]]:
         """Host arrays in, poses out: H2D of clouds / descriptors / tuple indices, the kernel chain, one D2H."""
         pose_buf = torch.zeros((len(instances) * 2, self.pose_bytes), dtype=torch.uint8, device=self.device)

@@ -56,3 +56,27 @@ def test_estimator_device_rng_and_shot_only():
     assert set(a.results) == {"shot"}
     # the scale comes from the SHOT head itself when the DINO branch is absent (reference would raise NameError)
     assert np.isfinite(a.scale).all()
+
+
+def test_estimate_frame_from_depth_and_masks():
+    """eval.py:153-372 from the raw frame: device back-projection / voxel down-sampling, then the instance loop."""
+    from cppf2_b200.estimator import PoseEstimator, build_models
+    frame = synth.synth_real275_frame(2, 3)
+    cats = sorted(set(frame["cats"]))
+    models, cfgs = build_models(cats, precision=1)
+    est = PoseEstimator(models, cfgs, num_pairs=8192, seed=1)
+    pool = torch.nn.functional.normalize(torch.randn((50000, 1024), device="cuda"), dim=-1)
+    masks = list(frame["masks"]) + [np.zeros_like(frame["masks"][0])]           # an empty detection is skipped
+    got = est.estimate_frame(frame["depth"].astype(np.uint16), masks, list(frame["cats"]) + [frame["cats"][0]], synth.REAL275_K,
+                             desc_fn=lambda i, pix: pool[: pix.shape[0]])
+    assert len(got) == 4 and got[3] is None
+    for i, p in enumerate(got[:3]):
+        n_pix = int((frame["masks"][i] & (frame["depth"] > 0)).sum())
+        if n_pix < 50:
+            assert p is None
+            continue
+        assert p is not None and np.isfinite(p.RT).all() and p.branch in ("dino", "shot")
+        # the voted translation lies inside the instance's back-projected extent (plus one object diameter)
+        rows, cols = np.where(frame["masks"][i] & (frame["depth"] > 0))
+        z = frame["depth"][rows, cols] / 1000.0
+        assert z.min() - 0.6 < p.RT[2, 3] < z.max() + 0.6

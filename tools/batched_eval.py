@@ -1,0 +1,87 @@
+"""BASELINE config 5 -- batched eval: synthetic REAL275-shaped frames sharded by frame across the ranks, end to end
+from (depth, masks) in pinned host memory to (RT, scale) per instance, frames/s = frames / max-over-ranks time.
+
+    python tools/batched_eval.py [--frames 256] [--gpus N]          (N > 1: launch under torchrun, one rank per GPU)
+
+Every rank owns frames rank, rank+world, ...; no data-path collective (frames are independent, eval.py:132); the final
+gather of the pose records is one all_gather_object.  DINO descriptors are seeded unit-norm stand-ins taken from a
+device-resident pool (the DINOv2 backbone is out of scope), heads are random-init (no checkpoints in the mount).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cppf2_b200 import synth  # noqa: E402
+from cppf2_b200.estimator import PoseEstimator, build_models  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--instances", type=int, default=6)
+    args = ap.parse_args()
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mine = list(range(rank, args.frames, world))
+    # synthetic frames are rendered once on the host (untimed) into pinned buffers
+    frames = []
+    cats_all = set()
+    for f in mine:
+        fr = synth.synth_real275_frame(1000 + f, args.instances)
+        frames.append(dict(depth=torch.from_numpy(fr["depth"].astype(np.uint16)).pin_memory(),
+                           masks=[torch.from_numpy(m).pin_memory() for m in fr["masks"]], cats=fr["cats"]))
+        cats_all.update(fr["cats"])
+    all_cats = sorted(cats_all)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, all_cats)
+        all_cats = sorted(set(c for g in gathered for c in g))
+    models, cfgs = build_models(all_cats, precision=1)
+    est = PoseEstimator(models, cfgs, num_pairs=50000, num_rots=180, seed=rank)
+    pool = torch.nn.functional.normalize(torch.randn((50000, 1024), device=dev, generator=torch.Generator(dev).manual_seed(7)), dim=-1)
+
+    def desc_fn(i, pix):
+        return pool[: pix.shape[0]]
+
+    def run(fr, k):
+        return est.estimate_frame(fr["depth"], fr["masks"], fr["cats"], synth.REAL275_K, desc_fn=desc_fn, frame_seed=k)
+
+    for k in range(min(3, len(frames))):
+        run(frames[k], k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    poses = [run(fr, k) for k, fr in enumerate(frames)]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n_inst = sum(1 for p in poses for q in p if q is not None)
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        c = torch.tensor([n_inst], device=dev, dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        n_inst = int(c.item())
+    if rank == 0:
+        print(json.dumps({"config": "batched eval, synthetic REAL275 frames sharded by frame", "frames": args.frames, "n_gpus": world,
+                          "instances_posed": n_inst, "seconds": dt, "frames_per_sec": args.frames / dt,
+                          "tuples_per_sec": n_inst * 2 * 50000 / dt,
+                          "h2d_bytes_per_frame": 640 * 480 * 2 + args.instances * 640 * 480, "scaling": "weak (frames sharded, no collective)"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

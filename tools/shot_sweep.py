@@ -1,0 +1,71 @@
+"""BASELINE config 3 -- SHOT-352 descriptor extraction sweep, 10k-200k points per cloud, against the PCL-semantics CPU
+restatement (oracle/shot_oracle.cpp; PCL itself is not installable here) single-threaded (faithful: the reference uses the
+non-OpenMP PCL classes, shot.cpp:25,82) and with all host threads.
+
+    python tools/shot_sweep.py [--sizes 10000,20000,50000,100000,200000] [--cpu-max 50000]
+
+Cloud: points on a torus whose area gives ~pi*10^2 neighbours inside the radius (res = 2 mm, radii 20 mm), jittered
+along the normal, centred 1 m in front of the camera.  Reports points/s, the algorithmic GB/s
+(1432 B/point) and the fraction of the HBM peak, one JSON line per size.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cppf2_b200 import shot  # noqa: E402
+
+
+def torus_cloud(n, res=0.002, seed=7):
+    rng = np.random.default_rng(seed)
+    area = n * res * res                      # one point per res^2
+    r = np.sqrt(area / (4 * np.pi ** 2 * 4))  # torus R = 4 r: area = 4 pi^2 R r
+    R = 4 * r
+    u, v = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    rr = r + rng.uniform(-res / 4, res / 4, n)
+    p = np.stack([(R + rr * np.cos(v)) * np.cos(u), (R + rr * np.cos(v)) * np.sin(u), rr * np.sin(v) + 1.0], -1)
+    return p.astype(np.float32)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="10000,20000,50000,100000,200000")
+    ap.add_argument("--cpu-max", type=int, default=50000, help="largest cloud the single-thread CPU leg runs on")
+    args = ap.parse_args()
+    peaks_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    hbm = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+    from oracle import cpu as oracle
+    for n in [int(s) for s in args.sizes.split(",")]:
+        pc = torus_cloud(n)
+        d = torch.from_numpy(pc).cuda()
+        for _ in range(3):
+            shot.compute_device(d, 0.02, 0.02)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            desc, normals = shot.compute_device(d, 0.02, 0.02)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        line = {"points": n, "gpu_ms": ms, "gpu_points_per_sec": n / ms * 1e3, "alg_GBps": n * 1432 / ms / 1e6,
+                "hbm_frac": n * 1432 / ms / 1e6 / hbm, "valid_rows": int((~torch.isnan(desc[:, 0])).sum())}
+        if n <= args.cpu_max:
+            t0 = time.perf_counter()
+            oracle.shot_compute(pc, 0.02, 0.02, threads=1)
+            line["cpu_1thread_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle.shot_compute(pc, 0.02, 0.02, threads=os.cpu_count() or 1)
+        line["cpu_all_threads_s"] = time.perf_counter() - t0
+        line["cpu_threads"] = os.cpu_count()
+        line["speedup_vs_all_threads"] = line["cpu_all_threads_s"] * 1e3 / ms
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
