@@ -125,7 +125,7 @@ def run_cpu_instance(inst, sds, rng, timings=None):
                              sym_y_only=inst["category"] in ("can", "bottle", "bowl"))
 
 
-def reference_arm(args):
+def reference_arm(args, emit=print):
     """The reference's CPU implementation of the path (oracle port), all host threads, one instance per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -148,7 +148,7 @@ def reference_arm(args):
     value = per * args.steps / dt
     sample = (f"1 instance x 2 branches x {NUM_PAIRS} tuples per step (of the {N_INSTANCES}-instance frame); stage seconds "
               + ", ".join(f"{k} {v:.2f}" for k, v in timings.items()))
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    emit(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": workload_config(),
@@ -173,8 +173,16 @@ def main():
     ap.add_argument("--precision", type=int, default=int(os.environ.get("CPPF_PRECISION", "-1")), help="heads: 0 fp32, 1 bf16 tcgen05, -1 best available")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: anything a library prints at C level (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str):
+        os.write(real_stdout, (line + "\n").encode())
+
     if args.impl == "reference":
-        return reference_arm(args)
+        return reference_arm(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -388,7 +396,7 @@ def main():
             "gpu_launches": launches * args.steps,
             "pose_check": {"finite": bool(all(p is not None and np.isfinite(p.RT).all() for p in poses)),
                            "branches": [p.branch for p in poses if p is not None]}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
