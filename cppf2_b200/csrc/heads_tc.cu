@@ -65,6 +65,7 @@ enum Action : int {
     kActHiddenS = 6,      // X[dst_col : +n) = relu(D + b)    (bf16 -> shared memory; first layers)
     kActOut = 7,          // X[dst_col : +n) = D + b (+ X[res_col : +n))   (optionally spilled to the feature scratch)
     kActFinal = 8,        // global output = D + b
+    kActOutT = 9,         // Y[dst_col : +n) = D + b          (bf16 -> TMEM, no relu: a layer output that stays in tensor memory)
 };
 
 struct Part {             // one A operand x one weight matrix, accumulated into D[d_col : d_col + n)   (host only)
@@ -347,10 +348,15 @@ __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, u
         for (int j = 0; j < NB; ++j) v[j] = static_cast<float>(row + j);
     } else if (NB == 32) tmem_ld32(t_slot_lane + static_cast<uint32_t>(ph.d_col + c), v);
     else tmem_ld8(t_slot_lane + static_cast<uint32_t>(ph.d_col + c), v);
-    if (ph.action == kActHiddenT) {
+    if (ph.action == kActHiddenT || ph.action == kActOutT) {
         uint32_t p[NB / 2];
+        if (ph.action == kActHiddenT) {
 #pragma unroll
-        for (int j = 0; j < NB / 2; ++j) p[j] = pack2_relu(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < NB / 2; ++j) p[j] = pack2_relu(v[2 * j], v[2 * j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NB / 2; ++j) p[j] = pack2(v[2 * j], v[2 * j + 1]);
+        }
         const uint32_t h_addr = t_slot_lane + kHTmem + static_cast<uint32_t>((ph.dst_col + c) >> 1);
         if (NB == 32) tmem_st16(h_addr, p);
         else tmem_st4(h_addr, p);
@@ -576,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         // (8 rows x 4 chunks) per warp pass for the row movers: conflict-free 16-byte shared stores, whole 32 B sectors
         const int mv_r = lane & 7, mv_c = lane >> 3;
         uint32_t done_seq = 0;
-        long long t_done = 0, t_actn[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t_arrive = 0;
+        long long t_done = 0, t_actn[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_arrive = 0;
         const long long t_begin = prof_clock<kProf>();
         for (int round = 0; round < n_rounds; ++round) {
             const int64_t tile = tile_of(round, slot);
@@ -668,6 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                         break;
                     }
                     case kActHiddenT:
+                    case kActOutT:
                     case kActHiddenS:
                     case kActOut:
                     case kActFinal: {
@@ -678,7 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                         } else {
                             epilogue_batch<8>(ph, a, X, t_slot_lane, row, grow, live, c0);
                         }
-                        if (ph.action == kActHiddenT) tmem_st_wait();
+                        if (ph.action == kActHiddenT || ph.action == kActOutT) tmem_st_wait();
                         if (ph.action == kActFinal && ph.reload_feat) {
                             // X <- the spilled tuple feature (written by this slot's own threads in an earlier phase)
                             for (int it = sw; it < 16 * 8; it += kSlotWarps) {
@@ -695,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                 t0 = prof_clock<kProf>();
                 if (kProf) t_actn[ph.action] += t0 - t1;
                 if (ph.n_parts) {
-                    if (ph.action != kActHiddenT) fence_async_smem();      // generic-proxy writes to X -> visible to the tensor core's async proxy
+                    if (ph.action != kActHiddenT && ph.action != kActOutT) fence_async_smem();   // generic-proxy writes to X -> visible to the tensor core's async proxy
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_act + 8 * slot);
@@ -707,8 +714,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             long long *o = a.prof + blockIdx.x * 64 + 8 + 16 * slot;
             o[0] = prof_clock<kProf>() - t_begin;
             o[1] = t_done;
-            for (int k = 0; k < 9; ++k) o[2 + k] = t_actn[k];
-            o[11] = t_arrive;
+            for (int k = 0; k < 10; ++k) o[2 + k] = t_actn[k];
+            o[12] = t_arrive;
         }
     }
     tc_fence_before();
@@ -831,7 +838,9 @@ struct Builder {
         int store_feat = 0;
         int out_sel = 0, out_ld = 0;
     };
-    Phase *res_layer(const ResLayerDesc &L, Phase *cur, int in_col, const OutSpec &os) {
+    // in_tmem: the layer input is a bf16 activation in tensor memory (column in_col of the H/Y space, i.e. Y = 128..255),
+    // fed to fc1 and fc0 as the A operand from TMEM; din must then be a multiple of 16 (no zero padding in TMEM).
+    Phase *res_layer(const ResLayerDesc &L, Phase *cur, int in_col, const OutSpec &os, int in_tmem = 0) {
         const int k_in = pad16(L.din);
         const std::vector<int> in_cols = iota(L.din);
         // hidden / output chunks of at most 128 columns
@@ -840,7 +849,7 @@ struct Builder {
         int h_width = 0;
         for (auto &ch : chunks) {
             const int n_pad = chunk_pad(ch.second);
-            add_part(*cur, 0, in_col, k_in, 0, n_pad, 1, push_weight(w + L.w1, L.din, ch.first, ch.second, n_pad, in_cols, k_in));
+            add_part(*cur, in_tmem, in_col, k_in, 0, n_pad, 1, push_weight(w + L.w1, L.din, ch.first, ch.second, n_pad, in_cols, k_in));
             Phase &hid = add(kActHiddenT, 1);
             hid.d_col = 0;
             hid.n = n_pad;
@@ -856,7 +865,7 @@ struct Builder {
             std::vector<int> hc(h_width, -1);
             for (int j = 0; j < L.dout; ++j) hc[j] = j;
             add_part(*cur, 1, 0, h_width, 0, n_pad, 1, push_weight(w + L.w2, L.dout, ch.first, ch.second, n_pad, hc, h_width));
-            if (L.has_fc0) add_part(*cur, 0, in_col, k_in, 0, n_pad, 0, push_weight(w + L.w0, L.din, ch.first, ch.second, n_pad, in_cols, k_in));
+            if (L.has_fc0) add_part(*cur, in_tmem, in_col, k_in, 0, n_pad, 0, push_weight(w + L.w0, L.din, ch.first, ch.second, n_pad, in_cols, k_in));
             add_bias(*cur, 0, w + L.b2, L.has_fc0 ? w + L.b0 : nullptr, ch.first, ch.second, n_pad);
             Phase &out = add(os.action, 1);
             out.d_col = 0;
@@ -1015,21 +1024,37 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         cur = tb.wide_first_layer(T0, &pair, Builder::iota(256, 30), kActCoordsB, Builder::iota(30), 32, 0, nullptr);
     }
     {
-        Builder::OutSpec feat;      // tuple_encoder output = the feature both heads read: keep a bf16 copy
-        feat.store_feat = 1;
+        // tuple_encoder output = the feature both heads read, left in X[0:256).  The scale head runs FIRST and keeps its
+        // layer outputs in tensor memory (Y, the 64 spare TMEM columns next to H), so X still holds the feature when the
+        // logit head starts: no spill of the feature to global memory, no reload.
+        Builder::OutSpec feat;
         // layers 1..4 are 128 -> 128; layer 5 widens to 256: append_stack parks layer 4's output in X[128:256)
         cur = append_stack(tb, m.tuple_encoder, 1, cur, 0, feat);
+        const StackDesc &S = m.scale_encoder;
+        bool scale_in_tmem = S.n_layers >= 2;
+        for (int l = 1; l < S.n_layers; ++l) scale_in_tmem = scale_in_tmem && S.layer[l].has_fc0 && S.layer[l].din % 16 == 0 && S.layer[l].din <= 128;
+        scale_in_tmem = scale_in_tmem && S.layer[0].has_fc0 && S.layer[0].dout <= 128;
+        if (!scale_in_tmem) {
+            delete st;
+            return CPPF_ERR_UNSUPPORTED;
+        }
+        for (int l = 0; l < S.n_layers; ++l) {
+            Builder::OutSpec os;
+            if (l == S.n_layers - 1) {
+                os.action = kActFinal;
+                os.out_sel = 1;
+                os.out_ld = 3;
+            } else {
+                os.action = kActOutT;
+                os.out_col = 128;          // Y
+            }
+            cur = l == 0 ? tb.res_layer(S.layer[l], cur, 0, os, 0) : tb.res_layer(S.layer[l], cur, 128, os, 1);
+        }
         Builder::OutSpec logits;
         logits.action = kActFinal;
         logits.out_sel = 0;
         logits.out_ld = 192;
         cur = append_stack(tb, m.logit_encoder, 0, cur, 0, logits);
-        cur->reload_feat = 1;       // the last logits chunk reloads the feature for the scale head
-        Builder::OutSpec scale;
-        scale.action = kActFinal;
-        scale.out_sel = 1;
-        scale.out_ld = 3;
-        cur = append_stack(tb, m.scale_encoder, 0, cur, 0, scale);
     }
     if (pb.prog.n_phases > kMaxPhases || tb.prog.n_phases > kMaxPhases || !pb.finalize() || !tb.finalize()) {
         delete st;

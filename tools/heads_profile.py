@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cppf2_b200 import _lib, synth  # noqa: E402
 from cppf2_b200.heads import BeyondCPPFDINO, BeyondCPPFSHOT  # noqa: E402
 
-ACTIONS = ["LoadRows", "EncShotA", "EncShotB", "Gather", "CoordsB", "HiddenT", "HiddenS", "Out", "Final"]
+ACTIONS = ["LoadRows", "EncShotA", "EncShotB", "Gather", "CoordsB", "HiddenT", "HiddenS", "Out", "Final", "OutT"]
 
 
 def main():
@@ -62,9 +62,9 @@ def main():
             print(f"  mma issuer s{sl}: total {o[0] / 1e3:8.1f}  wait_operand {o[1] / 1e3:8.1f}  wait_weights {o[2] / 1e3:8.1f}  issue {o[3] / 1e3:8.1f}  steps {o[4]:.0f} -> issue {o[3] / st:.0f} cycles/step")
         print(f"  producer   : total {m[4] / 1e3:8.1f}  wait_free_stage {m[5] / 1e3:8.1f}")
         for s in range(2):
-            o = m[8 + 16 * s: 8 + 16 * s + 12]
-            acts = "  ".join(f"{ACTIONS[k]} {o[2 + k] / 1e3:.1f}" for k in range(9) if o[2 + k] > 0)
-            print(f"  epilogue s{s}: total {o[0] / 1e3:8.1f}  wait_mma {o[1] / 1e3:8.1f}  arrive {o[11] / 1e3:6.1f}  | {acts}")
+            o = m[8 + 16 * s: 8 + 16 * s + 13]
+            acts = "  ".join(f"{ACTIONS[k]} {o[2 + k] / 1e3:.1f}" for k in range(10) if o[2 + k] > 0)
+            print(f"  epilogue s{s}: total {o[0] / 1e3:8.1f}  wait_mma {o[1] / 1e3:8.1f}  arrive {o[12] / 1e3:6.1f}  | {acts}")
 
 
 if __name__ == "__main__":
