@@ -21,6 +21,7 @@
 #include "heads_common.cuh"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -1105,10 +1106,20 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
     __nv_bfloat16 *point_feat = static_cast<__nv_bfloat16 *>(ws);
     __nv_bfloat16 *feat_scratch = reinterpret_cast<__nv_bfloat16 *>(static_cast<unsigned char *>(ws) + tc_align(2 * static_cast<size_t>(st->point_cols) * n));
     const int sms = device_info().sm_count;
+    // Grid: the fewest CTAs that still finish in the minimal number of rounds (a round = one tile in each of a CTA's
+    // two slots).  T = 50 000 is 391 tiles = 1.32 rounds of 148 x 2 slots: 148 CTAs would run a full round and then a
+    // round with 95 half-empty CTAs (one slot idle, no MMA/epilogue overlap); 98 CTAs run two full rounds and leave
+    // 50 SMs to the kernels of the other instances' streams.  CPPF_TC_GRID=full restores one CTA per SM.
+    static const bool grid_full = [] {
+        const char *e = getenv("CPPF_TC_GRID");
+        return e && e[0] == 'f';
+    }();
     auto blocks_for = [&](int64_t rows) {
         const int64_t tiles = (rows + kRows - 1) / kRows;
-        // every SM gets a CTA; tile_of() fills the first slots of all CTAs before any second slot
-        return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, sms)));
+        if (grid_full || tiles <= sms) return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, sms)));   // small: latency first
+        const int64_t rounds = std::max<int64_t>(1, (tiles + static_cast<int64_t>(kSlots) * sms - 1) / (static_cast<int64_t>(kSlots) * sms));
+        const int64_t per_cta = rounds * kSlots;
+        return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((tiles + per_cta - 1) / per_cta, sms)));
     };
     {
         Args a{};

@@ -133,7 +133,8 @@ class PoseEstimator:
         """Starts the host->device copies of every instance on the copy stream (pinned sources make them asynchronous)
         and returns, per instance, the device tensors plus the event the compute stream has to wait for."""
         compute = torch.cuda.current_stream(self.device)
-        self.copy_stream.wait_stream(compute)      # buffers recycled by the allocator may still be read by queued kernels
+        # no wait on the compute stream here: every staged tensor is record_stream()-ed on the streams that read it, so the
+        # allocator cannot recycle it early, and the copies of frame k+1 may run under the kernels of frame k
         staged = []
         with torch.cuda.stream(self.copy_stream):
             for inst in instances:
@@ -292,12 +293,34 @@ class PoseEstimator:
             out[i] = p
         return out
 
+    def submit(self, instances: Sequence[Instance], draws: Optional[List[dict]] = None) -> "PendingFrame":
+        """Asynchronous form of `estimate`: starts the uploads, queues the kernels and the pose read-back (into pinned host
+        memory) and returns at once; `.result()` waits for that frame only.  Keeping one frame in flight ahead lets the
+        host work and the uploads of frame k+1 overlap the kernels of frame k."""
+        pose_buf = torch.zeros((len(instances) * 2, self.pose_bytes), dtype=torch.uint8, device=self.device)
+        staged = self.stage(instances)
+        plan = self.enqueue(instances, pose_buf, draws, staged=staged)
+        pose_host = torch.empty(pose_buf.shape, dtype=torch.uint8, pin_memory=True)
+        pose_host.copy_(pose_buf, non_blocking=True)     # the frame's only device->host copy
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        return PendingFrame(self, plan, pose_host, done, (pose_buf, staged))
+
     def estimate(self, instances: Sequence[Instance], draws: Optional[List[dict]] = None) -> List[Optional[InstancePose]]:
         """Host arrays in, poses out: H2D of clouds / descriptors / tuple indices, the kernel chain, one D2H."""
-        pose_buf = torch.zeros((len(instances) * 2, self.pose_bytes), dtype=torch.uint8, device=self.device)
-        plan = self.enqueue(instances, pose_buf, draws, staged=self.stage(instances))
-        pose_host = pose_buf.cpu().numpy()     # the frame's only device->host copy (synchronises the stream)
-        return self.collect(plan, pose_host)
+        return self.submit(instances, draws).result()
+
+
+class PendingFrame:
+    """A frame queued by PoseEstimator.submit(): result() blocks until its pose records have reached the host."""
+
+    def __init__(self, est: PoseEstimator, plan, pose_host: torch.Tensor, done: torch.cuda.Event, keepalive):
+        self._est, self._plan, self._pose_host, self._done, self._keep = est, plan, pose_host, done, keepalive
+
+    def result(self) -> List[Optional[InstancePose]]:
+        self._done.synchronize()
+        self._keep = None
+        return self._est.collect(self._plan, self._pose_host.numpy())
 
 
 def build_models(categories: Sequence[str], branches=("dino", "shot"), precision: int = 0, ckpt_root: Optional[str] = None,

@@ -32,15 +32,17 @@ def main():
     for _ in range(3):
         est.estimate(insts)
     torch.cuda.synchronize()
-    # enqueue-only time (no final synchronisation): what the host must get through per frame
-    t0 = time.perf_counter()
+    # enqueue-only time with an empty queue (synchronise, enqueue one frame, read the clock before the GPU finishes):
+    # what the host must get through per frame
+    host = []
     for _ in range(steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         pose_buf = torch.zeros((len(insts) * 2, est.pose_bytes), dtype=torch.uint8, device=est.device)
         est.enqueue(insts, pose_buf, staged=est.stage(insts))
-    t1 = time.perf_counter()
+        host.append(time.perf_counter() - t0)
     torch.cuda.synchronize()
-    t2 = time.perf_counter()
-    print(f"host enqueue {1e3 * (t1 - t0) / steps:.2f} ms/frame; drain {1e3 * (t2 - t1):.2f} ms after {steps} frames")
+    print(f"host enqueue (stage + enqueue, empty queue): median {1e3 * sorted(host)[len(host) // 2]:.2f} ms/frame, launches {est.launches}")
     pr = cProfile.Profile()
     pr.enable()
     for _ in range(steps):
