@@ -96,6 +96,7 @@ SIGNATURES = {
     "cppf_backproject": (I, [P, I, D, P, I, I, _DP, P, P, P, P, I64, P]),
     "cppf_voxel_downsample": (I, [P, I64, D, P, U64, P, P, P, P, P, P, I64, P]),
     "cppf_gather_points": (I, [P, P, I64, P, P, P, P]),
+    "cppf_interpolate_features": (I, [P, I, I, I, I64, I64, I64, P, I64, F, I, P, P]),
     "cppf_vote_chain": (I, [P, I64, P, I, I64, I64, P, P, P, I64, P, P, P, P]),
     "cppf_pose_workspace_bytes": (I64, [I64]),
     "cppf_pose_finalize": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, I64, P]),

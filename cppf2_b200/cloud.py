@@ -148,3 +148,21 @@ def downsample(pc, res, prio=None, seed: int = 0):
     """utils/util.py:39-46: one random member per occupied voxel; returns the kept indices (ascending)."""
     _, kept, count, _ = voxel_downsample_device(torch.from_numpy(np.ascontiguousarray(pc, dtype=np.float32)).cuda(), res, prio=prio, seed=seed)
     return kept[:int(count.item())].cpu().numpy().astype(np.int64)
+
+
+def interpolate_features(descriptors, pts, strides=8, normalize=True):
+    """dataset.py:40-59: descriptors [1,C,h,w] (any strides: the reference passes the permuted ViT token view),
+    pts [1,n,2] (x, y) -> [1,C,n] like the reference (a transposed view of the kernel's [n,C] rows; the caller's
+    `[0].T` (dataset.py:79) then yields contiguous [n,C])."""
+    lib = _lib.load()
+    d = descriptors if isinstance(descriptors, torch.Tensor) else torch.from_numpy(np.asarray(descriptors))
+    d = d.cuda().float() if not d.is_cuda else d.float()
+    p = pts if isinstance(pts, torch.Tensor) else torch.from_numpy(np.asarray(pts))
+    p = p.to(d.device, torch.float32).reshape(-1, 2).contiguous()
+    if d.dim() != 4 or d.shape[0] != 1:
+        raise ValueError("descriptors must be [1,C,h,w]")
+    _, C, h, w = d.shape
+    out = torch.empty((p.shape[0], C), dtype=torch.float32, device=d.device)
+    check(lib.cppf_interpolate_features(d.data_ptr(), C, h, w, d.stride(1), d.stride(2), d.stride(3), p.data_ptr(), p.shape[0],
+                                        float(strides), int(bool(normalize)), out.data_ptr(), stream_ptr()), "cppf_interpolate_features")
+    return out.T.unsqueeze(0)

@@ -244,6 +244,14 @@ int cppf_voxel_downsample(const float *pc, int64_t n, double res, const float *p
 int cppf_gather_points(const float *pc, const int32_t *idx, int64_t m, float *pc_out, const int32_t *side_in,
                        int32_t *side_out, void *stream);
 
+/* ---- key-point descriptor sampling ------------------------------------------------
+ * replaces interpolate_features, dataset.py:40-59: bilinear grid_sample (align_corners=False, zero padding) of the
+ * patch-token map desc f32 [C,h,w] (element strides given, so the ViT's [h*w,C] layout is read in place) at the
+ * key-points pts f32 [n,2] = (x, y) in pixels of the (cropped) image, `stride` = image pixels per token, followed by
+ * F.normalize over the channels when `normalize`.  out f32 [n,C]. */
+int cppf_interpolate_features(const float *desc, int C, int h, int w, int64_t stride_c, int64_t stride_h, int64_t stride_w,
+                              const float *pts, int64_t n, float stride, int normalize, float *out, void *stream);
+
 /* ---- the whole vote chain in one call ------------------------------------------------------------
  * The body of the instance loop after the heads, eval.py:230-313 and :358-363: cppf_decode_targets ->
  * cppf_cloud_bounds -> cppf_vote_center -> cppf_grid_argmax -> cppf_backvote_filter -> cppf_rotation_hist

@@ -323,10 +323,27 @@ def mint_backproject(ref):
          pc=pts.astype(np.float32), rows=idxs[0].astype(np.int32), cols=idxs[1].astype(np.int32))
 
 
+def mint_interp_features(ref):
+    """The reference's own interpolate_features (dataset.py:40-59) on a random token map in the ViT's native [h*w, C]
+    layout seen through the permuted [1,C,h,w] view, key-points including image corners and out-of-range positions."""
+    import importlib
+    ds = importlib.import_module("dataset")
+    g = torch.Generator().manual_seed(3)
+    C, h, w, stride = 64, 18, 18, 256 / 18
+    tokens = torch.randn(h * w, C, generator=g)
+    raw = tokens.reshape(1, h, w, C).permute(0, 3, 1, 2)
+    pts = torch.rand(1, 200, 2, generator=g) * 256
+    pts[0, :4] = torch.tensor([[0., 0.], [255.9, 255.9], [-3., 10.], [128., 300.]])
+    save("interp_features", tokens=tokens.numpy(), h=np.array(h), w=np.array(w), stride=np.array(stride, dtype=np.float64), pts=pts.numpy(),
+         out=ds.interpolate_features(raw, pts, strides=stride, normalize=True)[0].T.numpy(),
+         out_raw=ds.interpolate_features(raw, pts, strides=stride, normalize=False)[0].T.numpy())
+
+
 def main():
     torch.set_grad_enabled(False)
     ref = load_reference()
     mint_backproject(ref)
+    mint_interp_features(ref)
     mint_vote_center(ref)
     mint_targets(ref)
     mint_rotation(ref)

@@ -96,3 +96,20 @@ def test_prepare_instance_clouds_frame():
         z = frame["depth"][rows, cols] / 1000.0
         np.testing.assert_allclose(pc[:, 2].cpu().numpy(), z, rtol=1e-6)
         assert frame["masks"][i][rows, cols].all()
+
+
+def test_interpolate_features_matches_reference_golden(golden):
+    """dataset.py:40-59 (bilinear grid_sample, align_corners=False, zero padding, then F.normalize) against the output of
+    the reference's own function; the token map is passed as the permuted view of the ViT layout, like the reference does."""
+    from cppf2_b200 import cloud
+    g = golden("interp_features")
+    h, w, C = int(g["h"]), int(g["w"]), g["tokens"].shape[1]
+    tokens = torch.from_numpy(g["tokens"]).cuda()
+    raw = tokens.reshape(1, h, w, C).permute(0, 3, 1, 2)           # [1,C,h,w], channel stride 1
+    pts = torch.from_numpy(g["pts"]).cuda()
+    got = cloud.interpolate_features(raw, pts, strides=float(g["stride"]), normalize=True)
+    assert got.shape == (1, C, pts.shape[1])
+    np.testing.assert_allclose(got[0].T.cpu().numpy(), g["out"], rtol=1e-5, atol=2e-6)
+    got_raw = cloud.interpolate_features(raw.contiguous(), pts, strides=float(g["stride"]), normalize=False)   # channel-major copy
+    np.testing.assert_allclose(got_raw[0].T.cpu().numpy(), g["out_raw"], rtol=1e-5, atol=2e-6)
+    assert np.all(got_raw[0].T.cpu().numpy()[3] == 0)               # key-point below the image: zero padding
