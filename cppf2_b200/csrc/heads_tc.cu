@@ -1110,10 +1110,11 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
     // two slots).  T = 50 000 is 391 tiles = 1.32 rounds of 148 x 2 slots: 148 CTAs would run a full round and then a
     // round with 95 half-empty CTAs (one slot idle, no MMA/epilogue overlap); 98 CTAs run two full rounds and leave
     // 50 SMs to the kernels of the other instances' streams.  CPPF_TC_GRID=full restores one CTA per SM.
-    static const bool grid_full = [] {
+    static const char grid_mode = [] {
         const char *e = getenv("CPPF_TC_GRID");
-        return e && e[0] == 'f';
+        return e ? e[0] : 'b';
     }();
+    const bool grid_full = grid_mode == 'f';
     auto blocks_for = [&](int64_t rows) {
         const int64_t tiles = (rows + kRows - 1) / kRows;
         if (grid_full || tiles <= sms) return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, sms)));   // small: latency first
