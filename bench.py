@@ -381,7 +381,7 @@ def main():
 
     # ---- CPU baseline: the oracle port on this box's host cores, one full frame ----------------------------------
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (bench contract)
         from oracle import cpu as oracle
         torch.set_num_threads(os.cpu_count() or 1)
         oracle.set_num_threads(os.cpu_count() or 1)

@@ -101,6 +101,86 @@ __global__ void __launch_bounds__(128, 1) probe(int n, int iters, long long *out
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+// SS / TS MMA rate under competing shared-memory traffic: warps 2.. store (or load) 16 B per lane in a loop with `gap`
+// dependent ALU operations between accesses, into a region the MMAs do not touch.
+template <int mode>
+__global__ void __launch_bounds__(256, 1) probe_traffic(int n, int iters, int gap, int loads, long long *out) {
+    extern __shared__ __align__(1024) unsigned char smem[];   // 128 KB of operands + 32 KB traffic region
+    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ volatile int s_stop;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 163840 / 16; i += 256) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        s_stop = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    if (warp == 1) {
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        const uint32_t idesc = instr_desc(n);
+        const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem) + 65536;
+        uint64_t bd[8], ad[8];
+#pragma unroll
+        for (uint32_t ks = 0; ks < 8; ++ks) {
+            bd[ks] = desc_noswz(b_base + ks * 2 * (n * 16), n * 16, 128);
+            ad[ks] = desc_noswz(a_base + ks * 4096, 2048, 128);
+        }
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i += 8) {
+            if (leader) {
+#pragma unroll
+                for (uint32_t ks = 0; ks < 8; ++ks) {
+                    if (mode & 1) mma_ts(tmem, tmem + 256 + ks * 8, bd[ks], idesc, (i + ks) > 0);
+                    else mma_ss(tmem, ad[ks], bd[ks], idesc, (i + ks) > 0);
+                }
+            }
+            __syncwarp();
+        }
+        if (leader) commit(smem_u32(&bar[0]));
+        __syncwarp();
+        wait(smem_u32(&bar[0]), 0);
+        const long long t2 = clock64();
+        if (leader) {
+            out[blockIdx.x * 2] = t2 - t0;
+            out[blockIdx.x * 2 + 1] = t2 - t0;
+        }
+        s_stop = 1;
+    } else if (warp >= 2) {
+        unsigned char *region = smem + 131072;
+        uint4 v = make_uint4(tid, 1, 2, 3);
+        uint32_t acc = tid;
+        int it = 0;
+        while (!s_stop) {
+            unsigned char *p = region + ((it & 15) * 2048) + ((tid - 64) & 127) * 16;
+            if (loads) {
+                uint32_t r0, r1, r2, r3;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+                acc += r0;
+            } else {
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+            for (int g = 0; g < gap; ++g) acc = acc * 1664525u + 1013904223u;
+            ++it;
+        }
+        if (acc == 0x12345u) out[0] = acc;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 // Round trip of one dependent step: `burst` MMAs -> commit -> (another warp) wait -> tcgen05.ld -> arrive -> issuer wait.
 __global__ void __launch_bounds__(160, 1) roundtrip(int n, int burst, int iters, int with_epilogue, long long *out) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -160,6 +240,22 @@ __global__ void __launch_bounds__(160, 1) roundtrip(int n, int burst, int iters,
 }
 
 int main() {
+    {
+        long long *d;
+        cudaMalloc(&d, 148 * 2 * 8);
+        for (int mode = 0; mode < 2; ++mode)
+            for (int loads = 0; loads < 2; ++loads)
+                for (int gap : {0, 8, 32, 128}) {
+                    auto k = mode == 0 ? probe_traffic<0> : probe_traffic<1>;
+                    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 163840);
+                    k<<<148, 256, 163840>>>(128, 2048, gap, loads, d);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    long long h[2];
+                    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+                    printf("traffic probe %s N=128, 6 warps of %s with %3d ALU ops between: %.1f cyc/MMA [%s]\n", mode ? "TS" : "SS", loads ? "ld.shared.v4" : "st.shared.v4",
+                           gap, h[0] / 2048.0, cudaGetErrorString(e));
+                }
+    }
     {
         long long *d;
         cudaMalloc(&d, 148 * 2 * 8);
