@@ -102,6 +102,10 @@ class PoseEstimator:
         self.pose_bytes = C.sizeof(Pose)
         self.timing_hook = None        # optional callable(stage: str, begin: bool) for bench.py's per-kernel events
         self.launches = 0
+        self._pose_ring: Dict[int, List[torch.Tensor]] = {}
+        self._pose_next = 0
+        self.host_threads = max(1, int(os.environ.get("CPPF_HOST_THREADS", "1")))
+        self._pool = None
         self.copy_stream = torch.cuda.Stream(device=self.device)   # uploads of instance i+1 overlap the kernels of instance i
         self._idx_pool: List[torch.Tensor] = []                      # device-sampled tuple indices, one buffer per instance slot
 
@@ -122,12 +126,11 @@ class PoseEstimator:
         while len(self._idx_pool) <= slot:
             self._idx_pool.append(torch.empty((self.num_pairs, 5), dtype=torch.int32, device=self.device))
         idx = self._idx_pool[slot]
-        self._draws += 1
-        check(_lib.load().cppf_sample_tuples(n, self.num_pairs, 5, (self.seed << 32) + self._draws, idx.data_ptr(),
+        check(_lib.load().cppf_sample_tuples(n, self.num_pairs, 5, (self.seed << 40) + (self._frames << 8) + slot, idx.data_ptr(),
                                             stream_ptr()), "cppf_sample_tuples")
         return idx
 
-    _draws = 0
+    _frames = 0
 
     def stage(self, instances: Sequence[Instance]) -> List[dict]:
         """Starts the host->device copies of every instance on the copy stream (pinned sources make them asynchronous)
@@ -168,15 +171,30 @@ class PoseEstimator:
         uploads them on the copy stream; without it they are copied here, in stream order)."""
         plan = []
         launches = 0
+        self._frames += 1
+        while len(self._idx_pool) < len(instances):     # per-slot index buffers exist before any worker thread needs one
+            self._idx_pool.append(torch.empty((self.num_pairs, 5), dtype=torch.int32, device=self.device))
         main = torch.cuda.current_stream(self.device)
         if self.lanes:                                  # fork: every lane starts after what is already queued on the caller's stream
             fork = torch.cuda.Event()
             fork.record(main)
             for lane in self.lanes:
                 lane.wait_event(fork)
-        for i, inst in enumerate(instances):
+        def one(i):
             with torch.cuda.stream(self.lanes[i % self.n_streams] if self.lanes else main):
-                n_l, item = self._enqueue_instance(i, inst, pose_buf, draws, None if staged is None else staged[i])
+                return self._enqueue_instance(i, instances[i], pose_buf, draws, None if staged is None else staged[i])
+
+        if self.host_threads > 1 and self.lanes and self.timing_hook is None and len(instances) > 1:
+            # the lanes are independent streams: enqueue them from a few host threads (ctypes and torch release the GIL
+            # inside the launch calls, which are most of the host time of a frame)
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                dev_index = self.device.index
+                self._pool = ThreadPoolExecutor(self.host_threads, initializer=lambda: torch.cuda.set_device(dev_index))
+            results = list(self._pool.map(one, range(len(instances))))
+        else:
+            results = [one(i) for i in range(len(instances))]
+        for n_l, item in results:
             launches += n_l
             plan.append(item)
         for lane in self.lanes:                         # join: the caller's stream continues after every lane
@@ -300,11 +318,20 @@ class PoseEstimator:
         pose_buf = torch.zeros((len(instances) * 2, self.pose_bytes), dtype=torch.uint8, device=self.device)
         staged = self.stage(instances)
         plan = self.enqueue(instances, pose_buf, draws, staged=staged)
-        pose_host = torch.empty(pose_buf.shape, dtype=torch.uint8, pin_memory=True)
+        pose_host = self._pinned_pose(pose_buf.shape[0])
         pose_host.copy_(pose_buf, non_blocking=True)     # the frame's only device->host copy
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(self.device))
         return PendingFrame(self, plan, pose_host, done, (pose_buf, staged))
+
+    def _pinned_pose(self, rows: int) -> torch.Tensor:
+        """Pinned read-back buffers are recycled round-robin (4 frames may be in flight) instead of allocated per frame."""
+        ring = self._pose_ring.setdefault(rows, [])
+        if len(ring) < 4:
+            ring.append(torch.empty((rows, self.pose_bytes), dtype=torch.uint8, pin_memory=True))
+            return ring[-1]
+        self._pose_next = (self._pose_next + 1) % 4
+        return ring[self._pose_next]
 
     def estimate(self, instances: Sequence[Instance], draws: Optional[List[dict]] = None) -> List[Optional[InstancePose]]:
         """Host arrays in, poses out: H2D of clouds / descriptors / tuple indices, the kernel chain, one D2H."""
