@@ -125,11 +125,33 @@ def run_cpu_instance(inst, sds, rng, timings=None):
                              sym_y_only=inst["category"] in ("can", "bottle", "bowl"))
 
 
+def reference_shot_sweep(emit):
+    """CPU leg of BASELINE config 3 (tools/shot_sweep.py drives the CUDA leg): the PCL-semantics SHOT restatement on the
+    host cores, single-threaded (faithful to shot.cpp:25,82) up to 50k points and with all threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from shot_sweep import torus_cloud
+    from oracle import cpu as oracle
+    for n in (10000, 20000, 50000, 100000, 200000):
+        pc = torus_cloud(n)
+        line = {"impl": "reference", "config": "SHOT sweep (BASELINE configs[2]), CPU port", "points": n, "cpu_threads": os.cpu_count()}
+        if n <= 50000:
+            t0 = time.perf_counter()
+            oracle.shot_compute(pc, 0.02, 0.02, threads=1)
+            line["cpu_1thread_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle.shot_compute(pc, 0.02, 0.02, threads=os.cpu_count() or 1)
+        line["cpu_all_threads_s"] = time.perf_counter() - t0
+        line["cpu_points_per_sec"] = n / line["cpu_all_threads_s"]
+        emit(json.dumps(line))
+
+
 def reference_arm(args, emit=print):
     """The reference's CPU implementation of the path (oracle port), all host threads, one instance per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if getattr(args, "shot_sweep", False):
+        return reference_shot_sweep(emit)
     import torch
     from oracle import cpu as oracle
     torch.set_num_threads(os.cpu_count() or 1)
@@ -172,6 +194,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=int(os.environ.get("CPPF_PRECISION", "-1")), help="heads: 0 fp32, 1 bf16 tcgen05, -1 best available")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shot-sweep", action="store_true", help="with --impl reference: CPU leg of the SHOT sweep (config 3)")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: anything a library prints at C level (NCCL's version banner) goes to stderr
     sys.stdout.flush()

@@ -1,8 +1,9 @@
-"""BASELINE config 3 -- SHOT-352 descriptor extraction sweep, 10k-200k points per cloud, against the PCL-semantics CPU
-restatement (oracle/shot_oracle.cpp; PCL itself is not installable here) single-threaded (faithful: the reference uses the
-non-OpenMP PCL classes, shot.cpp:25,82) and with all host threads.
+"""BASELINE config 3 -- SHOT-352 descriptor extraction sweep, 10k-200k points per cloud.  The CPU side of the comparison
+(the PCL-semantics restatement on the host cores, single-threaded like the reference's non-OpenMP PCL classes,
+shot.cpp:25,82, and with all threads) is timed by `python bench.py --impl reference --shot-sweep`, the one place outside
+the tests that may execute oracle/; this tool only drives the CUDA path.
 
-    python tools/shot_sweep.py [--sizes 10000,20000,50000,100000,200000] [--cpu-max 50000]
+    python tools/shot_sweep.py [--sizes 10000,20000,50000,100000,200000]
 
 Cloud: points on a torus whose area gives ~pi*10^2 neighbours inside the radius (res = 2 mm, radii 20 mm), jittered
 along the normal, centred 1 m in front of the camera.  Reports points/s, the algorithmic GB/s
@@ -35,11 +36,9 @@ def torus_cloud(n, res=0.002, seed=7):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="10000,20000,50000,100000,200000")
-    ap.add_argument("--cpu-max", type=int, default=50000, help="largest cloud the single-thread CPU leg runs on")
     args = ap.parse_args()
     peaks_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     hbm = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
-    from oracle import cpu as oracle
     for n in [int(s) for s in args.sizes.split(",")]:
         pc = torus_cloud(n)
         d = torch.from_numpy(pc).cuda()
@@ -55,15 +54,6 @@ def main():
         ms = a.elapsed_time(b) / 10
         line = {"points": n, "gpu_ms": ms, "gpu_points_per_sec": n / ms * 1e3, "alg_GBps": n * 1432 / ms / 1e6,
                 "hbm_frac": n * 1432 / ms / 1e6 / hbm, "valid_rows": int((~torch.isnan(desc[:, 0])).sum())}
-        if n <= args.cpu_max:
-            t0 = time.perf_counter()
-            oracle.shot_compute(pc, 0.02, 0.02, threads=1)
-            line["cpu_1thread_s"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        oracle.shot_compute(pc, 0.02, 0.02, threads=os.cpu_count() or 1)
-        line["cpu_all_threads_s"] = time.perf_counter() - t0
-        line["cpu_threads"] = os.cpu_count()
-        line["speedup_vs_all_threads"] = line["cpu_all_threads_s"] * 1e3 / ms
         print(json.dumps(line), flush=True)
 
 
