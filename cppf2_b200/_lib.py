@@ -60,6 +60,15 @@ class VoteBuffers(C.Structure):
                 ("ws_pose", C.c_void_p), ("ws_pose_bytes", C.c_int64)]
 
 
+class InstanceIO(C.Structure):
+    _fields_ = [("pc", C.c_void_p), ("n", C.c_int64), ("idx", C.c_void_p), ("idx_is_i64", C.c_int), ("pad0", C.c_int),
+                ("idx_stride", C.c_int64), ("T", C.c_int64), ("dino_desc", C.c_void_p), ("heads_dino", C.c_void_p),
+                ("heads_shot", C.c_void_p), ("normal_r", C.c_float), ("shot_r", C.c_float), ("shot_desc", C.c_void_p),
+                ("normals", C.c_void_p), ("ws_shot", C.c_void_p), ("ws_shot_bytes", C.c_int64), ("bins", C.c_void_p),
+                ("scales", C.c_void_p), ("ws_heads", C.c_void_p), ("ws_heads_bytes", C.c_int64), ("seed_dino", C.c_uint64),
+                ("seed_shot", C.c_uint64), ("cells_hint", C.c_int64), ("pose_dino", C.c_void_p), ("pose_shot", C.c_void_p)]
+
+
 P, I, I64, F, D, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
 _DP = C.POINTER(C.c_double)
 _IP = C.POINTER(C.c_int)
@@ -98,6 +107,7 @@ SIGNATURES = {
     "cppf_gather_points": (I, [P, P, I64, P, P, P, P]),
     "cppf_interpolate_features": (I, [P, I, I, I, I64, I64, I64, P, I64, F, I, P, P]),
     "cppf_vote_chain": (I, [P, I64, P, I, I64, I64, P, P, P, I64, P, P, P, P]),
+    "cppf_instance_pose": (I, [P, P, P, P]),
     "cppf_pose_workspace_bytes": (I64, [I64]),
     "cppf_pose_finalize": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, I64, P]),
     "cppf_shot_workspace_bytes": (I64, [I64]),

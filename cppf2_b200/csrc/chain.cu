@@ -45,3 +45,34 @@ CPPF_API int cppf_vote_chain(const float *pc, int64_t n, const void *idx, int id
                               p->sphere, p->sphere_bins, b->center, p->up_loc, p->right_loc, p->loss_y_only, scale_override, pose_out,
                               b->ws_pose, b->ws_pose_bytes, stream);
 }
+
+// One host call per INSTANCE (eval.py:203-372 for one detection): SHOT-352 + normals, then per branch the heads with the decode
+// fused in and the vote chain.  The DINO branch runs first; the SHOT branch reuses its scale (eval.py:308-310).  Host glue
+// only -- about 60 kernel launches leave from one C call instead of ~10 foreign-function calls of the Python driver.
+CPPF_API int cppf_instance_pose(const cppf_instance_io *io, const cppf_vote_params *p, const cppf_vote_buffers *b, void *stream) {
+    if (!io || !p || !b || !io->pc || !io->idx || io->n <= 0 || io->T <= 0) return CPPF_ERR_INVALID_ARGUMENT;
+    const bool run_dino = io->heads_dino != nullptr && io->dino_desc != nullptr;
+    const bool run_shot = io->heads_shot != nullptr;
+    if (!run_dino && !run_shot) return CPPF_ERR_INVALID_ARGUMENT;
+    if (!io->bins || !io->scales || !io->ws_heads) return CPPF_ERR_INVALID_ARGUMENT;
+    if (run_dino && !io->pose_dino) return CPPF_ERR_INVALID_ARGUMENT;
+    if (run_shot && (!io->pose_shot || !io->shot_desc || !io->normals || !io->ws_shot)) return CPPF_ERR_INVALID_ARGUMENT;
+    uint8_t *bins_dino = io->bins, *bins_shot = io->bins + io->T * 6;
+    float *scale_dino = io->scales, *scale_shot = io->scales + io->T * 3;
+    if (run_shot)   // eval.py:210; queued first so that its small kernels overlap the previous instance's tail
+        CPPF_TRY(cppf_shot_compute_ex(io->pc, io->n, io->normal_r, io->shot_r, io->shot_desc, io->normals, nullptr, 1, nullptr, io->ws_shot,
+                                      io->ws_shot_bytes, stream));
+    if (run_dino) {
+        CPPF_TRY(cppf_heads_forward_sampled(io->heads_dino, 1, io->pc, io->n, io->idx, io->idx_is_i64, io->idx_stride, io->T, io->dino_desc,
+                                            nullptr, nullptr, io->seed_dino, bins_dino, scale_dino, io->ws_heads, io->ws_heads_bytes, stream));
+        CPPF_TRY(cppf_vote_chain(io->pc, io->n, io->idx, io->idx_is_i64, io->idx_stride, io->T, bins_dino, scale_dino, nullptr,
+                                 io->cells_hint, p, b, io->pose_dino, stream));
+    }
+    if (run_shot) {
+        CPPF_TRY(cppf_heads_forward_sampled(io->heads_shot, 1, io->pc, io->n, io->idx, io->idx_is_i64, io->idx_stride, io->T, io->shot_desc,
+                                            io->normals, nullptr, io->seed_shot, bins_shot, scale_shot, io->ws_heads, io->ws_heads_bytes, stream));
+        CPPF_TRY(cppf_vote_chain(io->pc, io->n, io->idx, io->idx_is_i64, io->idx_stride, io->T, bins_shot, scale_shot,
+                                 run_dino ? io->pose_dino->scale : nullptr, io->cells_hint, p, b, io->pose_shot, stream));
+    }
+    return CPPF_OK;
+}

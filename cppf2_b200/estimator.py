@@ -29,7 +29,7 @@ from . import _lib, shot
 from ._lib import Pose, check
 from .heads import BeyondCPPFDINO, BeyondCPPFSHOT
 from .pipeline import PoseResult, PoseVoter, VoteConfig
-from .voting import stream_ptr, to_device
+from .voting import idx_args, stream_ptr, to_device
 
 SYMMETRIC_Y = ("can", "bottle", "bowl")   # loss on the y coordinate only (eval.py:360-361)
 
@@ -102,6 +102,8 @@ class PoseEstimator:
         self.pose_bytes = C.sizeof(Pose)
         self.timing_hook = None        # optional callable(stage: str, begin: bool) for bench.py's per-kernel events
         self.launches = 0
+        self._lane_bufs: Dict[int, dict] = {}
+        self.one_call = os.environ.get("CPPF_ONE_CALL", "1") != "0"      # cppf_instance_pose per instance (bf16 heads, no injected draws)
         self._pose_ring: Dict[int, List[torch.Tensor]] = {}
         self._pose_next = 0
         self.host_threads = max(1, int(os.environ.get("CPPF_HOST_THREADS", "1")))
@@ -204,6 +206,59 @@ class PoseEstimator:
         self.launches = launches
         return plan
 
+    def _lane_buffers(self, lane: int, n: int, heads: dict) -> dict:
+        """Per-lane device buffers of the one-call instance path, grown on demand and reused across frames."""
+        lib = _lib.load()
+        buf = self._lane_bufs.get(lane)
+        T = self.num_pairs
+        need_heads = max([int(lib.cppf_heads_workspace_bytes(m._handle, T, n, 1)) for m in heads.values()] + [256])
+        if buf is None or buf["cap"] < n or buf["ws_heads"].numel() < need_heads:
+            cap = max(n, 4096 if buf is None else buf["cap"])
+            d = self.device
+            buf = dict(cap=cap, shot_desc=torch.empty((cap, 352), dtype=torch.float32, device=d),
+                       normals=torch.empty((cap, 3), dtype=torch.float32, device=d),
+                       ws_shot=torch.empty(int(lib.cppf_shot_workspace_bytes(cap)), dtype=torch.uint8, device=d),
+                       bins=torch.empty((2, T, 6), dtype=torch.uint8, device=d),
+                       scales=torch.empty((2, T, 3), dtype=torch.float32, device=d),
+                       ws_heads=torch.empty(max(need_heads, max(int(lib.cppf_heads_workspace_bytes(m._handle, T, cap, 1))
+                                                                for m in heads.values())), dtype=torch.uint8, device=d))
+            self._lane_bufs[lane] = buf
+        return buf
+
+    def _instance_one_call(self, i: int, lane: int, voter: PoseVoter, vc: VoteConfig, heads: dict, pc, idx, desc_dev, cells_hint,
+                           pose_buf: torch.Tensor):
+        """cppf_instance_pose: SHOT, both heads (decode fused in) and both vote chains of one instance from one host call."""
+        lib = _lib.load()
+        n, T = pc.shape[0], idx.shape[0]
+        dino = heads.get("dino") if desc_dev is not None else None
+        sh = heads.get("shot")
+        for m in (dino, sh):
+            if m is not None:
+                m._ensure(self.device)
+        live = {k: m for k, m in (("dino", dino), ("shot", sh)) if m is not None}
+        buf = self._lane_buffers(lane, n, live)
+        voter._ensure(T, n, cells_hint)
+        params, vbufs = voter._vote_params(vc, T), voter._vote_buffers(vc.num_sphere)
+        ip, i64, istr = idx_args(idx)
+        slot_d, slot_s = pose_buf[2 * i], pose_buf[2 * i + 1]
+        io = _lib.InstanceIO(pc=pc.data_ptr(), n=n, idx=ip, idx_is_i64=i64, idx_stride=istr, T=T,
+                             dino_desc=None if dino is None else desc_dev.data_ptr(),
+                             heads_dino=None if dino is None else dino._handle, heads_shot=None if sh is None else sh._handle,
+                             normal_r=float(vc.res * 10), shot_r=float(vc.res * 10), shot_desc=buf["shot_desc"].data_ptr(),
+                             normals=buf["normals"].data_ptr(), ws_shot=buf["ws_shot"].data_ptr(), ws_shot_bytes=buf["ws_shot"].numel(),
+                             bins=buf["bins"].data_ptr(), scales=buf["scales"].data_ptr(), ws_heads=buf["ws_heads"].data_ptr(),
+                             ws_heads_bytes=buf["ws_heads"].numel(), seed_dino=self.seed + 7919 * (2 * i),
+                             seed_shot=self.seed + 7919 * (2 * i + 1), cells_hint=int(cells_hint or 0),
+                             pose_dino=slot_d.data_ptr(), pose_shot=slot_s.data_ptr())
+        check(lib.cppf_instance_pose(C.byref(io), C.byref(params), C.byref(vbufs), stream_ptr()), "cppf_instance_pose")
+        voter._live = (pc, idx, desc_dev)
+        slots = {}
+        if dino is not None:
+            slots["dino"] = 2 * i
+        if sh is not None:
+            slots["shot"] = 2 * i + 1
+        return (9 if sh is not None else 0) + 26 * len(slots), slots
+
     def _enqueue_instance(self, i: int, inst: Instance, pose_buf: torch.Tensor, draws, st):
         voter = self.voters[i % self.n_streams]
         launches = 0
@@ -224,6 +279,10 @@ class PoseEstimator:
             idx = self._sample_tuples(i, n)
             launches += 1
         heads = self.models[inst.category]
+        if (draws is None and self.timing_hook is None and self.one_call and heads
+                and all(getattr(m, "precision", 0) == 1 for m in heads.values())):
+            n_l, slots = self._instance_one_call(i, i % self.n_streams, voter, vc, heads, pc, idx, desc_dev, cells_hint, pose_buf)
+            return launches + n_l, dict(slots=slots, category=inst.category)
         self._mark("shot", True)
         desc352, normals = shot.compute_device(pc, vc.res * 10, vc.res * 10)      # eval.py:210
         self._mark("shot", False)

@@ -301,6 +301,39 @@ int cppf_vote_chain(const float *pc, int64_t n, const void *idx, int idx_is_i64,
                     const uint8_t *bins, const float *pred_scales, const float *scale_override, int64_t cells_hint,
                     const cppf_vote_params *params, const cppf_vote_buffers *buffers, cppf_pose *pose_out, void *stream);
 
+/* ---- one instance in one call ------------------------------------------------------------------------
+ * The body of the instance loop, eval.py:203-372, for one detection: SHOT-352 + normals, then for the DINO branch
+ * (when heads_dino and dino_desc are given) and the SHOT branch (when heads_shot is given): heads with the decode
+ * fused in (cppf_heads_forward_sampled, precision 1) and cppf_vote_chain; the SHOT branch reuses the DINO branch's
+ * scale (eval.py:308-310).  All pointers are device pointers to caller-owned buffers. */
+struct cppf_heads;
+typedef struct cppf_instance_io {
+    const float *pc;            /* [n,3] */
+    int64_t n;
+    const void *idx;            /* [T, >= 5] tuple indices */
+    int idx_is_i64;
+    int pad0;
+    int64_t idx_stride;
+    int64_t T;
+    const float *dino_desc;     /* [n,1024] or NULL */
+    const struct cppf_heads *heads_dino, *heads_shot;   /* either may be NULL */
+    float normal_r, shot_r;     /* 10 * res (eval.py:210) */
+    float *shot_desc;           /* out [n,352] */
+    float *normals;             /* out [n,3] */
+    void *ws_shot;
+    int64_t ws_shot_bytes;      /* cppf_shot_workspace_bytes(n) */
+    uint8_t *bins;              /* out [2][T,6]: DINO draws, then SHOT draws */
+    float *scales;              /* out [2][T,3] */
+    void *ws_heads;
+    int64_t ws_heads_bytes;     /* max over the branches of cppf_heads_workspace_bytes(h, T, n, 1) */
+    uint64_t seed_dino, seed_shot;
+    int64_t cells_hint;
+    cppf_pose *pose_dino, *pose_shot;
+} cppf_instance_io;
+
+int cppf_instance_pose(const cppf_instance_io *io, const cppf_vote_params *params, const cppf_vote_buffers *buffers,
+                       void *stream);
+
 /* ---- SHOT descriptor ----------------------------------------------------------------------------
  * replaces shot.compute / shot.estimate_normal, src_shot/shot.cpp:12-42, :45-100 (PCL NormalEstimation +
  * SHOTEstimation<SHOT352>, radius search, viewpoint at the origin, NaN rows for invalid points).       */

@@ -80,3 +80,30 @@ def test_estimate_frame_from_depth_and_masks():
         rows, cols = np.where(frame["masks"][i] & (frame["depth"] > 0))
         z = frame["depth"][rows, cols] / 1000.0
         assert z.min() - 0.6 < p.RT[2, 3] < z.max() + 0.6
+
+
+def test_one_call_instance_path_equals_python_sequence():
+    """cppf_instance_pose (one host call per instance) queues the same kernels with the same seeds as the Python sequence
+    of shot.compute / forward_sampled / vote: identical translations, kept counts, bins and scales; rotations equal up to the
+    float64 summation order of the sphere bins."""
+    from cppf2_b200.estimator import Instance, PoseEstimator, build_models
+    cats = ["mug", "laptop"]
+    models, cfgs = build_models(cats, precision=1, seed=5)
+    est = PoseEstimator(models, cfgs, num_pairs=20000, max_points=4000, seed=11)
+    instances = []
+    for i, cat in enumerate(cats):
+        pc = synth.half_cylinder_cloud(2200 + 500 * i, seed=60 + i, jitter=0.0005)
+        instances.append(Instance(pc=pc, category=cat, desc=synth.unit_descriptors(pc.shape[0], 1024, seed=70 + i),
+                                  point_idxs=synth.sample_tuples(pc.shape[0], 20000, 5, seed=80 + i)))
+    assert est.one_call
+    a = est.estimate(instances)
+    est.one_call = False
+    b = est.estimate(instances)
+    for x, y in zip(a, b):
+        assert x.branch == y.branch
+        for br in ("dino", "shot"):
+            r, o = x.results[br], y.results[br]
+            assert np.array_equal(r.t, o.t) and r.kept == o.kept and r.bin_up == o.bin_up and r.bin_right == o.bin_right
+            assert np.array_equal(r.scale, o.scale)
+            np.testing.assert_allclose(r.R, o.R, atol=1e-9)
+            np.testing.assert_allclose(r.loss, o.loss, rtol=1e-9)
