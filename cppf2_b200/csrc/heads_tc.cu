@@ -82,14 +82,12 @@ struct Part {             // one A operand x one weight matrix, accumulated into
 
 // One slab of the weight stream = one TMA copy = up to four MMAs per slot.  Built on the host so that the single
 // issuing warp does nothing per slab but test two barriers and fire the MMAs.
-struct Slab {
+struct Slab {             // 16 bytes: the issuer reads a slab with ONE 128-bit uniform constant load
     uint32_t a_lo;        // A in shared memory: low descriptor word relative to the slot's X buffer; in TMEM: column offset
     uint32_t idesc;
-    uint16_t n;           // UMMA N: B-descriptor LBO = 16 n bytes, K-step = 32 n bytes
-    uint16_t d_col;
-    uint16_t bytes16;     // slab size / 16
-    uint8_t n_mma;        // 1..4
-    uint8_t flags;
+    uint32_t nd;          // (n << 16) | d_col.  n = UMMA N: B-descriptor LBO = 16 n bytes (the field value is n), K-step = 32 n bytes
+    uint32_t misc;        // bytes16 | n_mma << 16 | flags << 24   (slab size / 16, 1..4 MMAs)
+    __host__ __device__ uint32_t bytes() const { return (misc & 0xffffu) << 4; }
 };
 enum : uint8_t {
     kSlabATmem = 1,       // A operand in TMEM
@@ -484,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             if (tile_of(round, 0) >= n_tiles) break;
             const unsigned char *src = a.weights;
             for (int i = 0; i < prog.n_slabs; ++i, ++seq) {
-                const uint32_t bytes = static_cast<uint32_t>(prog.slab[i].bytes16) << 4;
+                const uint32_t bytes = prog.slab[i].bytes();
                 const uint32_t stage = seq % kStages, turn = seq / kStages;
                 const long long t0 = prof_clock<kProf>();
                 mbar_wait(bar_empty + 8 * stage, (turn & 1u) ^ 1u);
@@ -515,6 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);    // SBO = 128 B, descriptor version bit 46
         const uint32_t ones_lo = (smem_u32(smem + kSmemOnes) >> 4) | (static_cast<uint32_t>(kPlane >> 4) << 16);
         const uint32_t x_lo = smem_u32(smem + kSmemX + s * kXBytes) >> 4;
+        const uint32_t ring_lo = ring0 >> 4;
         const uint32_t t_slot = static_cast<uint32_t>(s * kSlotTmem);     // TMEM base is 0: the CTA owns all 512 columns (checked above)
         uint32_t stage = 0, turn = 0, act_par = 0;
         for (int round = 0; round < n_rounds; ++round) {
@@ -522,30 +521,46 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             // slot 1 never runs a round that slot 0 skips; slot 0 releases the slabs alone in rounds slot 1 skips
             const bool other_active = s == 1 || tile_of(round, 1) < n_tiles;
             for (int i = 0; i < prog.n_slabs; ++i) {
-                const Slab &sl = prog.slab[i];
-                const uint32_t flags = sl.flags;
+                const uint4 w = *reinterpret_cast<const uint4 *>(&prog.slab[i]);      // a_lo, idesc, nd, misc
+                const uint32_t flags = w.w >> 24;
                 long long t0 = prof_clock<kProf>();
                 if (flags & kSlabFirst) {        // the slot's A operand is ready and its accumulator is free
                     mbar_wait(bar_act + 8 * s, act_par);
                     act_par ^= 1u;
+                    tc_fence_after();            // the epilogue's tcgen05.ld/st of this slot are ordered before the MMAs below
                 }
                 long long t1 = prof_clock<kProf>();
+                // weights arrive through the async proxy (cp.async.bulk, complete_tx on this barrier): no tcgen05 fence needed
                 mbar_wait(bar_full + 8 * stage, turn);
-                tc_fence_after();
                 long long t2 = prof_clock<kProf>();
-                if (leader) {
-                    const uint32_t n = sl.n, n_mma = sl.n_mma, idesc = sl.idesc;
-                    const uint32_t d_addr = t_slot + sl.d_col;
-                    const uint32_t b_lo = ((ring0 + stage * kSlabBytes) >> 4) | (n << 16);     // LBO = plane of n rows x 16 B
-                    const uint32_t a_lo = (flags & kSlabATmem) ? t_slot + sl.a_lo : (flags & kSlabOnes) ? ones_lo : x_lo + sl.a_lo;
-                    const uint32_t a_step = (flags & kSlabATmem) ? 8u : static_cast<uint32_t>((2 * kPlane) >> 4);
-#pragma unroll
-                    for (uint32_t ks = 0; ks < 4; ++ks) {
-                        if (ks < n_mma && !(CPPF_TC_EXP & 32)) {
-                            const uint64_t bd = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + ks * 2u * n);
-                            const uint32_t acc = (ks > 0 || (flags & kSlabAcc)) ? 1u : 0u;
-                            if (flags & kSlabATmem) umma_ts(d_addr, a_lo + ks * a_step, bd, idesc, acc);
-                            else umma_ss(d_addr, (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + ks * a_step), bd, idesc, acc);
+                if (leader && !(CPPF_TC_EXP & 32)) {
+                    // every value below is warp-uniform: descriptors stay in uniform registers, a handful of adds per MMA
+                    const uint32_t idesc = w.y, n_mma = (w.w >> 16) & 0xffu;
+                    const uint32_t d_addr = t_slot + (w.z & 0xffffu);
+                    const uint32_t b_lo = (ring_lo + stage * static_cast<uint32_t>(kSlabBytes >> 4)) | (w.z & 0xffff0000u);   // LBO field = n
+                    const uint32_t b_step = (w.z >> 16) << 1;                                  // 32 n bytes per K = 16 step
+                    const uint32_t acc0 = (flags >> 3) & 1u;                                   // kSlabAcc
+                    constexpr uint64_t kHi = static_cast<uint64_t>(kDescHi) << 32;
+                    if (flags & kSlabATmem) {
+                        const uint32_t a0 = t_slot + w.x;
+                        umma_ts(d_addr, a0, kHi | b_lo, idesc, acc0);
+                        if (n_mma > 1) {
+                            umma_ts(d_addr, a0 + 8u, kHi | (b_lo + b_step), idesc, 1u);
+                            if (n_mma > 2) {
+                                umma_ts(d_addr, a0 + 16u, kHi | (b_lo + 2u * b_step), idesc, 1u);
+                                if (n_mma > 3) umma_ts(d_addr, a0 + 24u, kHi | (b_lo + 3u * b_step), idesc, 1u);
+                            }
+                        }
+                    } else {
+                        constexpr uint32_t kAStep = static_cast<uint32_t>((2 * kPlane) >> 4);
+                        const uint32_t a0 = ((flags & kSlabOnes) ? ones_lo : x_lo) + w.x;
+                        umma_ss(d_addr, kHi | a0, kHi | b_lo, idesc, acc0);
+                        if (n_mma > 1) {
+                            umma_ss(d_addr, kHi | (a0 + kAStep), kHi | (b_lo + b_step), idesc, 1u);
+                            if (n_mma > 2) {
+                                umma_ss(d_addr, kHi | (a0 + 2u * kAStep), kHi | (b_lo + 2u * b_step), idesc, 1u);
+                                if (n_mma > 3) umma_ss(d_addr, kHi | (a0 + 3u * kAStep), kHi | (b_lo + 3u * b_step), idesc, 1u);
+                            }
                         }
                     }
                     umma_commit(bar_empty + 8 * stage);                 // this slot is done with the slab once these MMAs retire
@@ -806,23 +821,22 @@ struct Builder {
                     const int cols = pt.k_cols - k_done < slab_k ? pt.k_cols - k_done : slab_k;
                     Slab &sl = prog.slab[prog.n_slabs++];
                     sl = Slab{};
-                    sl.n = static_cast<uint16_t>(pt.n);
-                    sl.d_col = static_cast<uint16_t>(pt.d_col);
+                    sl.nd = (static_cast<uint32_t>(pt.n) << 16) | static_cast<uint32_t>(pt.d_col);
                     sl.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(pt.n >> 3) << 17) | (static_cast<uint32_t>(kRows >> 4) << 24);
-                    sl.n_mma = static_cast<uint8_t>(cols / 16);
-                    sl.bytes16 = static_cast<uint16_t>(pt.n * 2 * cols / 16);
+                    uint32_t flags = 0;
                     const int col = pt.a_col + k_done;
                     if (pt.a_tmem == 1) {
-                        sl.flags |= kSlabATmem;
+                        flags |= kSlabATmem;
                         sl.a_lo = static_cast<uint32_t>(kHTmem + (col >> 1));
                     } else if (pt.a_tmem == 2) {
-                        sl.flags |= kSlabOnes;
+                        flags |= kSlabOnes;
                     } else {
                         sl.a_lo = (static_cast<uint32_t>((col >> 3) * kPlane) >> 4) | (static_cast<uint32_t>(kPlane >> 4) << 16);
                     }
-                    if (!(pt.init && k_done == 0)) sl.flags |= kSlabAcc;
-                    if (q == 0 && k_done == 0) sl.flags |= kSlabFirst;
-                    if (q + 1 == ps.size() && k_done + cols >= pt.k_cols) sl.flags |= kSlabLast;
+                    if (!(pt.init && k_done == 0)) flags |= kSlabAcc;
+                    if (q == 0 && k_done == 0) flags |= kSlabFirst;
+                    if (q + 1 == ps.size() && k_done + cols >= pt.k_cols) flags |= kSlabLast;
+                    sl.misc = static_cast<uint32_t>(pt.n * 2 * cols / 16) | (static_cast<uint32_t>(cols / 16) << 16) | (flags << 24);
                     expect += static_cast<int64_t>(pt.n) * 2 * cols;
                 }
             }
