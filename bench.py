@@ -434,7 +434,12 @@ def main():
     heads_ms = stage_ms.get("heads_shot", 0.0) + stage_ms.get("heads_dino", 0.0)
     vote_ms = stage_ms.get("vote_shot", 0.0) + stage_ms.get("vote_dino", 0.0)
     shot_ms = stage_ms.get("shot", 0.0)
-    flops = 2.0 * (macs_per_tuple("shot") + macs_per_tuple("dino")) * NUM_PAIRS * n_inst + 2.0 * (258048 + 262144) * n_pts
+    # flops EXECUTED: the tensor-core DINO head evaluates desc_pair_transform (256 x 1280 + 256 bias) per point instead of
+    # per tuple (linearity, csrc/heads_tc.cu kActGatherSum), so those MACs move from the tuple count to the point count
+    pair_macs = 256 * 1280 + 256
+    hoisted = precision == 1
+    flops = 2.0 * (macs_per_tuple("shot") + macs_per_tuple("dino") - (pair_macs if hoisted else 0)) * NUM_PAIRS * n_inst \
+        + 2.0 * (258048 + 262144 + (pair_macs if hoisted else 0)) * n_pts
     vote_bytes = 2 * n_inst * (NUM_PAIRS * 24) + 2 * n_pts * 12
     shot_bytes = n_pts * 1432
     kernels = {

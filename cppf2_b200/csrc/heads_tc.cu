@@ -67,6 +67,7 @@ enum Action : int {
     kActOut = 7,          // X[dst_col : +n) = D + b (+ X[res_col : +n))   (optionally spilled to the feature scratch)
     kActFinal = 8,        // global output = D + b
     kActOutT = 9,         // Y[dst_col : +n) = D + b          (bf16 -> TMEM, no relu: a layer output that stays in tensor memory)
+    kActGatherSum = 10,   // X[0:256) = sum over the tuple's points k of the per-point row block G[idx_k][256 k : 256 k + 256)
 };
 
 struct Part {             // one A operand x one weight matrix, accumulated into D[d_col : d_col + n)   (host only)
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         // (8 rows x 4 chunks) per warp pass for the row movers: conflict-free 16-byte shared stores, whole 32 B sectors
         const int mv_r = lane & 7, mv_c = lane >> 3;
         uint32_t done_seq = 0;
-        long long t_done = 0, t_actn[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_arrive = 0;
+        long long t_done = 0, t_actn[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_arrive = 0;
         const long long t_begin = prof_clock<kProf>();
         for (int round = 0; round < n_rounds; ++round) {
             const int64_t tile = tile_of(round, slot);
@@ -654,24 +655,33 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                         }
                         break;
                     }
-                    case kActEncodeShotA:
-                    case kActGather: {
-                        // 32 chunks of 8 bf16 per row: SHOT = features of tuple slots 0..3 (64 wide each), DINO = one 256-wide
-                        // row; asynchronous 16-byte copies straight into the operand layout, all in flight at once
-                        for (int it = sw; it < 16 * 8; it += kSlotWarps) {
-                            const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
+                    case kActEncodeShotA: {
+                        // features (64 bf16 = one 128-byte line per point) of tuple slots 0..3 -> X[0:256): a warp pass copies the
+                        // whole lines of 4 rows (see kActGatherSum for why not 8 half lines); asynchronous 16-byte copies
+                        // straight into the operand layout, all in flight at once
+                        for (int it = sw; it < 32 * 4; it += kSlotWarps) {
+                            const int r = (it & 31) * 4 + (lane >> 3), k = it >> 5, c8 = k * 8 + (lane & 7);
                             const bool ok = row_base + r < a.rows;
-                            const __nv_bfloat16 *src = ph.action == kActGather
-                                                           ? a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + ph.src_col]) * 256 + c8 * 8
-                                                           : a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + (c8 >> 3)]) * 64 + (c8 & 7) * 8;
-                            cp_async16(x_u32 + c8 * kPlane + r * 16, src, ok ? 16u : 0u);
+                            cp_async16(x_u32 + c8 * kPlane + r * 16, a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + k]) * 64 + (lane & 7) * 8,
+                                       ok ? 16u : 0u);
+                        }
+                        cp_async_wait_all();
+                        break;
+                    }
+                    case kActGather: {
+                        // one 256-wide per-point row (tuple slot src_col) -> X[0:256)
+                        for (int it = sw; it < 32 * 4; it += kSlotWarps) {
+                            const int r = (it & 31) * 4 + (lane >> 3), c8 = (it >> 5) * 8 + (lane & 7);
+                            const bool ok = row_base + r < a.rows;
+                            cp_async16(x_u32 + c8 * kPlane + r * 16,
+                                       a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + ph.src_col]) * prog.gather_cols + c8 * 8, ok ? 16u : 0u);
                         }
                         cp_async_wait_all();
                         break;
                     }
                     case kActEncodeShotB: {
-                        for (int it = sw; it < 16 * 2; it += kSlotWarps) {   // features of tuple slot 4 -> columns 0..63
-                            const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
+                        for (int it = sw; it < 32; it += kSlotWarps) {   // features of tuple slot 4 -> columns 0..63, whole lines
+                            const int r = it * 4 + (lane >> 3), c8 = lane & 7;
                             const bool ok = row_base + r < a.rows;
                             cp_async16(x_u32 + c8 * kPlane + r * 16, a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + 4]) * 64 + c8 * 8, ok ? 16u : 0u);
                         }
@@ -680,6 +690,34 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                             tuple_geometry_chunks(a.pc, a.normal, idx_s + r * kIdxStride, row_base + r < a.rows, true, stid >> 7, X, r, 8);
                         }
                         cp_async_wait_all();
+                        break;
+                    }
+                    case kActGatherSum: {
+                        // desc_pair_transform by linearity (train_dino.py:95-96): W [256, 5*256] applied to the concatenation of
+                        // the 5 transformed descriptors = sum_k W_k f(desc[idx_k]); the per-point program has stored
+                        // G[n][256 k : 256 k + 256) = W_k f(desc_n) (+ bias in block 0) as bf16, so a tuple costs five 512-byte row
+                        // gathers and no tensor work.  Sum in float32, one rounding to bf16 into the operand layout.
+                        const int64_t ld = prog.gather_cols;
+#pragma unroll 1
+                        for (int it = sw; it < 32 * 4; it += kSlotWarps) {
+                            // a warp pass = 4 rows x 128 contiguous bytes: whole 128-byte lines per L2 request (a 64-byte
+                            // half-line mapping moves the same sectors with twice the requests); the shared-memory stores
+                            // then land 2-way conflicted, which is the cheaper side
+                            const int r = (it & 31) * 4 + (lane >> 3), c8 = (it >> 5) * 8 + (lane & 7);
+                            uint4 g[5];
+#pragma unroll
+                            for (int k = 0; k < 5; ++k)          // five independent 16-byte loads in flight per lane
+                                g[k] = __ldg(reinterpret_cast<const uint4 *>(a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + k]) * ld + k * 256 + c8 * 8));
+                            float acc[8], v[8];
+                            unpack8(g[0], acc);
+#pragma unroll
+                            for (int k = 1; k < 5; ++k) {
+                                unpack8(g[k], v);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                            }
+                            *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = row_base + r < a.rows ? pack8(acc) : make_uint4(0, 0, 0, 0);
+                        }
                         break;
                     }
                     case kActCoordsB: {
@@ -732,6 +770,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             o[1] = t_done;
             for (int k = 0; k < 10; ++k) o[2 + k] = t_actn[k];
             o[12] = t_arrive;
+            o[13] = t_actn[10];
         }
     }
     tc_fence_before();
@@ -990,8 +1029,13 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         last.out_ld = 64;
         cur = append_stack(pb, m.shot_encoder, 1, cur, 0, last);
         st->point_cols = 64;
-    } else {               // desc_transform (train_dino.py:80,95), hoisted per point: Linear 1024 -> 256 as four K-chunks
+    } else {
+        // desc_transform (train_dino.py:80,95) hoisted per point: Linear 1024 -> 256 as four K-chunks, output f kept in X as
+        // bf16; then desc_pair_transform (train_dino.py:81,96) hoisted too: its weight [256, 5*256] splits into five
+        // 256x256 blocks W_k, one per tuple slot, and G[n][256 k : 256 k + 256) = W_k f_n (+ bias in block 0) is stored per
+        // point, so that the tuple program only gathers and sums (kActGatherSum): N << 5 T makes this ~18x fewer MACs.
         const LinearDesc &L = m.desc_transform;
+        const LinearDesc &P = m.desc_pair_transform;
         for (int c = 0; c < 4; ++c) {
             Phase &ph = pb.add(kActLoadRows, c > 0);     // X is refilled only after the previous chunk's MMAs retired
             ph.src_col = c * 256;
@@ -999,15 +1043,24 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
             ph.width = 256;
             pb.add_part(ph, 0, 0, 256, 0, 256, c == 0, pb.push_weight(w + L.w, L.din, 0, 256, 256, Builder::iota(256, c * 256), 256));
         }
-        Phase &fin = pb.add(kActFinal, 1);
-        fin.d_col = 0;
-        fin.n = 256;
-        fin.cols = 256;
-        fin.dst_col = 0;
-        fin.out_sel = 2;
-        fin.out_ld = 256;
-        pb.add_bias(pb.prog.phase[pb.prog.n_phases - 2], 0, w + L.b, nullptr, 0, 256, 256);
-        st->point_cols = 256;
+        pb.add_bias(pb.prog.phase[pb.prog.n_phases - 1], 0, w + L.b, nullptr, 0, 256, 256);
+        Phase *cur = &pb.add(kActOut, 1);                // X[0:256) = bf16(f)
+        cur->d_col = 0;
+        cur->n = 256;
+        cur->cols = 256;
+        cur->dst_col = 0;
+        for (int k = 0; k < m.arity; ++k) {
+            pb.add_part(*cur, 0, 0, 256, 0, 256, 1, pb.push_weight(w + P.w, P.din, 0, 256, 256, Builder::iota(256, k * 256), 256));
+            if (k == 0) pb.add_bias(*cur, 0, w + P.b, nullptr, 0, 256, 256);
+            cur = &pb.add(kActFinal, 1);                 // stores block k while (for k < 4) block k + 1 is not yet issued
+            cur->d_col = 0;
+            cur->n = 256;
+            cur->cols = 256;
+            cur->dst_col = k * 256;
+            cur->out_sel = 2;
+            cur->out_ld = 256 * m.arity;
+        }
+        st->point_cols = 256 * m.arity;
     }
     // ---- per-tuple program -------------------------------------------------------------------------------
     Builder tb;
@@ -1022,20 +1075,9 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         for (int k = 0; k < 40; ++k) cols_b.push_back(k);
         cur = tb.wide_first_layer(T0, cur, Builder::iota(256, 40), kActEncodeShotB, cols_b, 112, 0, nullptr);
     } else {
-        // desc_pair_transform over the 5 gathered (already transformed) descriptors (train_dino.py:95-96): five
-        // K-chunks into one 256-wide accumulator; its output is chunk A of tuple_encoder.0 ([coords 30 | pair 256])
-        const LinearDesc &L = m.desc_pair_transform;
-        for (int c = 0; c < m.arity; ++c) {
-            Phase &ph = tb.add(kActGather, c > 0);
-            ph.src_col = c;
-            tb.add_part(ph, 0, 0, 256, 0, 256, c == 0, tb.push_weight(w + L.w, L.din, 0, 256, 256, Builder::iota(256, c * 256), 256));
-        }
-        Phase &pair = tb.add(kActOut, 1);
-        pair.d_col = 0;
-        pair.n = 256;
-        pair.cols = 256;
-        pair.dst_col = 0;
-        tb.add_bias(tb.prog.phase[tb.prog.n_phases - 2], 0, w + L.b, nullptr, 0, 256, 256);
+        // desc_pair_transform of the 5 gathered descriptors = sum of 5 per-point row blocks (kActGatherSum, see the
+        // per-point program); its output is chunk A of tuple_encoder.0 ([coords 30 | pair 256])
+        Phase &pair = tb.add(kActGatherSum, 0);
         cur = tb.wide_first_layer(T0, &pair, Builder::iota(256, 30), kActCoordsB, Builder::iota(30), 32, 0, nullptr);
     }
     {

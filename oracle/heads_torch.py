@@ -51,8 +51,17 @@ class Ref:
         feat = self.stack(x, "tuple_encoder")
         return self.stack(feat, "logit_encoder").reshape(feat.shape[0], 6, -1), self.stack(feat, "scale_encoder")
 
-    def forward_dino(self, points, descs, idx):
+    def forward_dino(self, points, descs, idx, hoist_pair=False):
+        """hoist_pair: desc_pair_transform evaluated per point and slot, W_k f(desc_n) (+ bias in block 0), each block
+        rounded like the tensor-core path stores it, then gathered and summed per tuple -- the same linear map
+        (train_dino.py:95-96) with the rounding points of csrc/heads_tc.cu's kActGatherSum."""
         td = self.linear(descs, "desc_transform")
-        pair = self.linear(torch.cat([td[idx[:, i]] for i in range(self.k)], -1), "desc_pair_transform")
+        if hoist_pair:
+            W, b = self.sd["desc_pair_transform.weight"], self.sd["desc_pair_transform.bias"]
+            d = td.shape[1]
+            blocks = [self.q(F.linear(self.q(td), self.q(W[:, k * d:(k + 1) * d]), b if k == 0 else None)) for k in range(self.k)]
+            pair = sum(blocks[k][idx[:, k]] for k in range(self.k))
+        else:
+            pair = self.linear(torch.cat([td[idx[:, i]] for i in range(self.k)], -1), "desc_pair_transform")
         feat = self.stack(torch.cat([self.coords(points, idx), pair], -1), "tuple_encoder")
         return self.stack(feat, "logit_encoder").reshape(feat.shape[0], 6, -1), self.stack(feat, "scale_encoder")

@@ -139,15 +139,23 @@ def test_bf16_tensor_core_dino_head(n, t):
     cls, scale = m(tpc, tdesc, tidx)
     torch.cuda.synchronize()
     with torch.no_grad():
-        want_cls, want_scale = Ref("dino", sd, emulate_bf16=True, device="cuda").forward_dino(tpc, tdesc, tidx)
+        # the tensor-core path evaluates desc_pair_transform per point and slot (linearity, kActGatherSum): the bf16-emulated
+        # reference with the same rounding points is the tight one; the as-written evaluation order is bounded too
+        want_cls, want_scale = Ref("dino", sd, emulate_bf16=True, device="cuda").forward_dino(tpc, tdesc, tidx, hoist_pair=True)
+        asw_cls, _ = Ref("dino", sd, emulate_bf16=True, device="cuda").forward_dino(tpc, tdesc, tidx)
         f32_cls, _ = Ref("dino", sd, device="cuda").forward_dino(tpc, tdesc, tidx)
+        f32_hoist, _ = Ref("dino", sd, device="cuda").forward_dino(tpc, tdesc, tidx, hoist_pair=True)
     rng_cls = float(want_cls.max() - want_cls.min())
     rng_scale = float(want_scale.max() - want_scale.min()) + 1e-3
     err_cls, err_scale = float((cls - want_cls).abs().max()), float((scale - want_scale).abs().max())
-    print(f"DINO T={t}: logits range {rng_cls:.3f}, max |tc - bf16 ref| {err_cls:.2e}, |tc - fp32 ref| {float((cls - f32_cls).abs().max()):.2e}; "
-          f"scale max err {err_scale:.2e}")
+    print(f"DINO T={t}: logits range {rng_cls:.3f}, max |tc - bf16 ref| {err_cls:.2e} (mean {float((cls - want_cls).abs().mean()):.2e}), "
+          f"|tc - bf16 ref as written| {float((cls - asw_cls).abs().max()):.2e} (mean {float((cls - asw_cls).abs().mean()):.2e}), "
+          f"|tc - fp32 ref| {float((cls - f32_cls).abs().max()):.2e}; scale max err {err_scale:.2e}")
+    assert float((f32_hoist - f32_cls).abs().max()) <= 2e-5 * rng_cls + 1e-6     # the hoisted form is the same linear map
     assert err_cls <= 5e-3 * rng_cls + 1e-4 and err_scale <= 5e-3 * rng_scale + 1e-4
     assert float((cls - want_cls).abs().mean()) <= 5e-4 * rng_cls
+    assert float((cls - asw_cls).abs().max()) <= 5e-3 * rng_cls + 1e-4 and float((cls - asw_cls).abs().mean()) <= 1e-3 * rng_cls
+    assert float((cls - f32_cls).abs().max()) < 0.05 * rng_cls
 
 
 @pytest.mark.parametrize("branch", ["shot", "dino"])

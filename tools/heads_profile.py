@@ -62,8 +62,10 @@ def main():
             print(f"  mma issuer s{sl}: total {o[0] / 1e3:8.1f}  wait_operand {o[1] / 1e3:8.1f}  wait_weights {o[2] / 1e3:8.1f}  issue {o[3] / 1e3:8.1f}  steps {o[4]:.0f} -> issue {o[3] / st:.0f} cycles/step")
         print(f"  producer   : total {m[4] / 1e3:8.1f}  wait_free_stage {m[5] / 1e3:8.1f}")
         for s in range(2):
-            o = m[8 + 16 * s: 8 + 16 * s + 13]
+            o = m[8 + 16 * s: 8 + 16 * s + 14]
             acts = "  ".join(f"{ACTIONS[k]} {o[2 + k] / 1e3:.1f}" for k in range(10) if o[2 + k] > 0)
+            if o[13] > 0:
+                acts += f"  GatherSum {o[13] / 1e3:.1f}"
             print(f"  epilogue s{s}: total {o[0] / 1e3:8.1f}  wait_mma {o[1] / 1e3:8.1f}  arrive {o[12] / 1e3:6.1f}  | {acts}")
 
 
