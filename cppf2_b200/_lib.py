@@ -17,6 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 CPPF_STATUS_GRID_OVERFLOW = 1
 CPPF_STATUS_GRID_GUARD = 2
 CPPF_STATUS_EMPTY = 4
+CPPF_STATUS_REFINED = 8
 
 
 class CppfError(RuntimeError):
@@ -49,7 +50,7 @@ class VoteParams(C.Structure):
                 ("cos_thr", C.c_float), ("band", C.c_int), ("lut_g", C.c_int), ("up_loc", C.c_int), ("right_loc", C.c_int),
                 ("loss_y_only", C.c_int), ("pad0", C.c_int), ("lut", C.c_void_p), ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),
                 ("sphere", C.c_void_p), ("axes", C.c_double * 9), ("imp_margin", C.c_double), ("rank_lo", C.c_int64),
-                ("gamma", C.c_float), ("pad", C.c_int)]
+                ("gamma", C.c_float), ("refine_iters", C.c_int), ("refine_lr", C.c_float), ("pad", C.c_int)]
 
 
 class VoteBuffers(C.Structure):
@@ -110,6 +111,7 @@ SIGNATURES = {
     "cppf_instance_pose": (I, [P, P, P, P]),
     "cppf_pose_workspace_bytes": (I64, [I64]),
     "cppf_pose_finalize": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, I64, P]),
+    "cppf_pose_finalize_refine": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, I, F, I64, P, P, I64, P]),
     "cppf_shot_workspace_bytes": (I64, [I64]),
     "cppf_shot_compute": (I, [P, I64, F, F, P, P, P, I64, P]),
     "cppf_estimate_normal": (I, [P, I64, F, P, P, I64, P]),

@@ -40,10 +40,10 @@ CPPF_API int cppf_vote_chain(const float *pc, int64_t n, const void *idx, int id
     CPPF_TRY(cppf_rotation_hist(pc, idx, idx_is_i64, idx_stride, b->targets_rot, 3, cols, 2, b->kept_list, &b->summary->kept, T,
                                 b->imp, b->summary, p->imp_margin, p->cos_tab, p->sin_tab, p->num_rots, p->sphere, p->sphere_bins,
                                 p->cos_thr, p->band, p->lut, p->lut_g, b->counts, stream));
-    // pose assembly (eval.py:284-313, 358-363)
-    return cppf_pose_finalize(pc, idx, idx_is_i64, idx_stride, bins, p->num_bins, pred_scales, b->kept_list, b->summary, b->counts,
-                              p->sphere, p->sphere_bins, b->center, p->up_loc, p->right_loc, p->loss_y_only, scale_override, pose_out,
-                              b->ws_pose, b->ws_pose_bytes, stream);
+    // pose assembly (eval.py:284-313), optional refinement (eval.py:319-355), branch loss (eval.py:358-363)
+    return cppf_pose_finalize_refine(pc, idx, idx_is_i64, idx_stride, bins, p->num_bins, pred_scales, b->kept_list, b->summary, b->counts,
+                                     p->sphere, p->sphere_bins, b->center, p->up_loc, p->right_loc, p->loss_y_only, scale_override,
+                                     p->refine_iters, p->refine_lr, T, pose_out, b->ws_pose, b->ws_pose_bytes, stream);
 }
 
 // One host call per INSTANCE (eval.py:203-372 for one detection): SHOT-352 + normals, then per branch the heads with the decode

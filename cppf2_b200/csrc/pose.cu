@@ -137,6 +137,175 @@ __global__ void __launch_bounds__(1024) scale_median_kernel(const float *__restr
     }
 }
 
+// ---- online pose refinement (eval.py:319-355, `opt=True`) ---------------------------------------------
+// 100 Adam steps (torch.optim.Adam defaults, lr 1e-2) on the translation (3) and a raw quaternion (x, y, z, w), started at
+// (T_est, identity), minimising mean |((pc - t) @ (Q(q) R_est))[pair] - pred_pairs_scaled| over the kept pairs (the y
+// column only for the symmetric categories).  lietorch semantics restated in oracle/refine_torch.py: Q is the rotation
+// of the NORMALISED quaternion, its gradient is the left-perturbation tangent sum_i Q[:,i] x G[:,i] stored in slots
+// x, y, z (slot w is zero, so w never moves), scaled by pi/180 before the optimiser step.
+// The reference launches ~15 kernels per step; here one CTA carries the whole loop: the 2M (point, target) rows are
+// compacted once into a scratch the L1 keeps, each step is one pass over them with 12 float64 sums (9 of d_j*sign_k,
+// 3 of sign_k) reduced through shuffles + shared memory, and every thread repeats the scalar update redundantly, which
+// saves the broadcast.  Per-element arithmetic is float32 like torch's; the sums are float64, so the result does not
+// depend on the reduction order beyond one float32 rounding (the reference's own order is unspecified: cuBLAS + atomics).
+struct RefineRow {
+    float p[3];
+    float y[3];
+};
+
+__global__ void __launch_bounds__(512, 1) pose_refine_kernel(const float *__restrict__ pc, IdxView idx,
+                                                              const uint8_t *__restrict__ bins, int num_bins,
+                                                              const int32_t *__restrict__ kept_list,
+                                                              const cppf_backvote_summary *__restrict__ summary,
+                                                              int loss_y_only, int iters, float lr,
+                                                              RefineRow *__restrict__ rows, cppf_pose *__restrict__ pose) {
+    __shared__ double s_part[16][12];
+    __shared__ double s_tot[12];
+    const int64_t M = summary->kept;
+    if (M <= 0 || iters <= 0) return;
+    const int64_t n_rows = 2 * M;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // (1) compact: point and scaled prediction of both ends of every kept pair (eval.py:231-235 for the scaling)
+    const float denom = static_cast<float>(num_bins - 1);
+    for (int64_t i = tid; i < M; i += blockDim.x) {
+        const int64_t m = kept_list[i];
+        const int64_t ia = idx.at(m, 0), ib = idx.at(m, 1);
+        float p[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) p[k] = __fsub_rn(__fdiv_rn(static_cast<float>(bins[6 * m + k]), denom), 0.5f);
+        const float a[3] = {pc[3 * ia], pc[3 * ia + 1], pc[3 * ia + 2]};
+        const float b[3] = {pc[3 * ib], pc[3 * ib + 1], pc[3 * ib + 2]};
+        const float real = norm3_numpy(__fsub_rn(b[0], a[0]), __fsub_rn(b[1], a[1]), __fsub_rn(b[2], a[2]));
+        const float pn = norm3_torch(__fsub_rn(p[3], p[0]), __fsub_rn(p[4], p[1]), __fsub_rn(p[5], p[2]));
+        const float sc = __fdiv_rn(real, pn < 1e-7f ? 1e-7f : pn);
+        RefineRow ra, rb;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ra.p[k] = a[k];
+            rb.p[k] = b[k];
+            ra.y[k] = __fmul_rn(p[k], sc);
+            rb.y[k] = __fmul_rn(p[3 + k], sc);
+        }
+        rows[2 * i] = ra;
+        rows[2 * i + 1] = rb;
+    }
+    __syncthreads();
+    // (2) the optimiser state, replicated in every thread
+    float R0[9], t[3], q[4] = {0.f, 0.f, 0.f, 1.f};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R0[i] = static_cast<float>(pose->R[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = static_cast<float>(pose->t[i]);
+    float m_t[3] = {0.f, 0.f, 0.f}, v_t[3] = {0.f, 0.f, 0.f}, m_q[3] = {0.f, 0.f, 0.f}, v_q[3] = {0.f, 0.f, 0.f};
+    const double beta1 = 0.9, beta2 = 0.999;
+    double b1_pow = 1.0, b2_pow = 1.0;
+    const float inv_cnt = 1.0f / (static_cast<float>(n_rows) * (loss_y_only ? 1.0f : 3.0f));
+    float Q[9], rot[9];
+    auto quat_matrix = [&](const float *qq, float *out) {      // column i = v + w (2 u x v) + u x (2 u x v), v = e_i
+        const float n = sqrtf(qq[0] * qq[0] + qq[1] * qq[1] + qq[2] * qq[2] + qq[3] * qq[3]);
+        const float u[3] = {qq[0] / n, qq[1] / n, qq[2] / n}, w = qq[3] / n;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float v[3] = {i == 0 ? 1.f : 0.f, i == 1 ? 1.f : 0.f, i == 2 ? 1.f : 0.f};
+            float uv[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) uv[k] += uv[k];
+            const float c2[3] = {u[1] * uv[2] - u[2] * uv[1], u[2] * uv[0] - u[0] * uv[2], u[0] * uv[1] - u[1] * uv[0]};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) out[3 * k + i] = v[k] + w * uv[k] + c2[k];
+        }
+    };
+    auto matmul3 = [](const float *A, const float *B, float *C) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    };
+    for (int it = 1; it <= iters; ++it) {
+        quat_matrix(q, Q);
+        matmul3(Q, R0, rot);                                   // rot = Q @ R_est
+        double acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+        for (int64_t i = tid; i < n_rows; i += blockDim.x) {
+            const RefineRow r = rows[i];
+            const float d[3] = {r.p[0] - t[0], r.p[1] - t[1], r.p[2] - t[2]};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (loss_y_only && k != 1) continue;
+                const float c = d[0] * rot[k] + d[1] * rot[3 + k] + d[2] * rot[6 + k];
+                const float e = c - r.y[k];
+                const float sg = e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f);      // torch: d|x|/dx = sign(x), 0 at 0
+                acc[9 + k] += static_cast<double>(sg);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[3 * j + k] += static_cast<double>(d[j] * sg);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) s_part[wid][k] = acc[k];
+        }
+        __syncthreads();
+        if (wid == 0) {
+            const int n_w = blockDim.x >> 5;
+            for (int k = 0; k < 12; ++k) {
+                double v = lane < n_w ? s_part[lane][k] : 0.0;
+                v = warp_sum(v);
+                if (lane == 0) s_tot[k] = v;
+            }
+        }
+        __syncthreads();
+        // gradients (float32 like the reference's autograd): g_rot = (pc - t)^T @ (sign / cnt), g_t = -sum_rows (sign / cnt) @ rot^T
+        float g_rot[9], g_t[3], G[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g_rot[k] = static_cast<float>(s_tot[k]) * inv_cnt;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            g_t[j] = -(rot[3 * j] * static_cast<float>(s_tot[9]) + rot[3 * j + 1] * static_cast<float>(s_tot[10]) +
+                       rot[3 * j + 2] * static_cast<float>(s_tot[11])) * inv_cnt;
+        // dL/dQ = g_rot @ R_est^T
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) G[3 * i + j] = g_rot[3 * i] * R0[3 * j] + g_rot[3 * i + 1] * R0[3 * j + 1] + g_rot[3 * i + 2] * R0[3 * j + 2];
+        float g_q[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {                           // sum_i Q[:,i] x G[:,i]
+            const float a0 = Q[i], a1 = Q[3 + i], a2 = Q[6 + i], b0 = G[i], b1 = G[3 + i], b2 = G[6 + i];
+            g_q[0] += a1 * b2 - a2 * b1;
+            g_q[1] += a2 * b0 - a0 * b2;
+            g_q[2] += a0 * b1 - a1 * b0;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g_q[k] = g_q[k] / 180.f * 3.14159274f;      // delta_rot.grad / 180 * np.pi
+        // torch.optim.Adam, single-tensor path, float32 parameters
+        b1_pow *= beta1;
+        b2_pow *= beta2;
+        const float step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - b1_pow));
+        const float bc2_sqrt = static_cast<float>(sqrt(1.0 - b2_pow));
+        auto adam = [&](float &p, float &m, float &v, float g) {
+            m = m + (g - m) * 0.1f;                              // exp_avg.lerp_(grad, 1 - beta1)
+            v = v * 0.999f + 0.001f * g * g;                     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+            const float den = sqrtf(v) / bc2_sqrt + 1e-8f;
+            p = p - step_size * (m / den);
+        };
+#pragma unroll
+        for (int k = 0; k < 3; ++k) adam(t[k], m_t[k], v_t[k], g_t[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) adam(q[k], m_q[k], v_q[k], g_q[k]);
+        // q[3] has a zero gradient in every step: exp_avg = exp_avg_sq = 0, update 0 / (0 + eps) = 0
+    }
+    if (tid == 0) {
+        quat_matrix(q, Q);
+        matmul3(Q, R0, rot);
+        for (int i = 0; i < 9; ++i) pose->R[i] = static_cast<double>(rot[i]);
+        for (int i = 0; i < 3; ++i) pose->t[i] = static_cast<double>(t[i]);
+        pose->status |= CPPF_STATUS_REFINED;
+    }
+}
+
 // ---- branch loss: mean clip(|canon(pc[pair]) - pred_pairs|, 0, 0.1) over kept pairs (eval.py:358-363) -
 __global__ void __launch_bounds__(256) pose_loss_kernel(const float *__restrict__ pc, IdxView idx,
                                                         const uint8_t *__restrict__ bins, int num_bins,
@@ -199,8 +368,8 @@ __global__ void __launch_bounds__(256) pose_loss_kernel(const float *__restrict_
 using namespace cppf;
 
 CPPF_API int64_t cppf_pose_workspace_bytes(int64_t T) {
-    (void)T;
-    return 256;
+    // PoseScratch + the refinement's compacted rows (2 per kept pair, at most T pairs)
+    return 256 + static_cast<int64_t>(sizeof(RefineRow)) * 2 * (T > 0 ? T : 0);
 }
 
 CPPF_API int cppf_pose_finalize(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride,
@@ -208,12 +377,23 @@ CPPF_API int cppf_pose_finalize(const float *pc, const void *idx, int idx_is_i64
                                 const cppf_backvote_summary *summary, const double *counts, const float *sphere, int S,
                                 const cppf_center *center, int up_loc, int right_loc, int loss_y_only,
                                 const float *scale_override, cppf_pose *pose, void *ws, int64_t ws_bytes, void *stream) {
+    return cppf_pose_finalize_refine(pc, idx, idx_is_i64, idx_stride, bins, num_bins, pred_scales, kept_list, summary, counts, sphere, S,
+                                     center, up_loc, right_loc, loss_y_only, scale_override, 0, 0.0f, 0, pose, ws, ws_bytes, stream);
+}
+
+CPPF_API int cppf_pose_finalize_refine(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride,
+                                       const uint8_t *bins, int num_bins, const float *pred_scales, const int32_t *kept_list,
+                                       const cppf_backvote_summary *summary, const double *counts, const float *sphere, int S,
+                                       const cppf_center *center, int up_loc, int right_loc, int loss_y_only,
+                                       const float *scale_override, int refine_iters, float refine_lr, int64_t T, cppf_pose *pose,
+                                       void *ws, int64_t ws_bytes, void *stream) {
     if (!pc || !idx || !bins || !kept_list || !summary || !counts || !sphere || !center || !pose || !ws)
         return CPPF_ERR_INVALID_ARGUMENT;
     if (!pred_scales && !scale_override) return CPPF_ERR_INVALID_ARGUMENT;
     if (up_loc < 0 || up_loc > 2 || right_loc < 0 || right_loc > 2 || up_loc == right_loc || S < 1 || idx_stride < 2)
         return CPPF_ERR_INVALID_ARGUMENT;
-    if (ws_bytes < cppf_pose_workspace_bytes(0)) return CPPF_ERR_WORKSPACE;
+    if (refine_iters < 0 || (refine_iters > 0 && !(refine_lr > 0.0f))) return CPPF_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < cppf_pose_workspace_bytes(refine_iters > 0 ? T : 0)) return CPPF_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PoseScratch *scratch = static_cast<PoseScratch *>(ws);
     CPPF_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(PoseScratch), s));
@@ -222,6 +402,11 @@ CPPF_API int cppf_pose_finalize(const float *pc, const void *idx, int idx_is_i64
     scale_median_kernel<<<3, 1024, 0, s>>>(pred_scales, kept_list, summary, scale_override, pose);
     CPPF_LAUNCH_CHECK();
     IdxView iv{idx, idx_stride, idx_is_i64};
+    if (refine_iters > 0) {      // eval.py:319-355: after R_est / scale are assembled, before the branch loss
+        RefineRow *rows = reinterpret_cast<RefineRow *>(static_cast<unsigned char *>(ws) + 256);
+        pose_refine_kernel<<<1, 512, 0, s>>>(pc, iv, bins, num_bins, kept_list, summary, loss_y_only, refine_iters, refine_lr, rows, pose);
+        CPPF_LAUNCH_CHECK();
+    }
     pose_loss_kernel<<<device_info().sm_count, 256, 0, s>>>(pc, iv, bins, num_bins, kept_list, summary, loss_y_only, pose,
                                                            scratch);
     CPPF_LAUNCH_CHECK();

@@ -86,10 +86,11 @@ class PoseEstimator:
 
     def __init__(self, models: Dict[str, Dict[str, object]], cfgs: Dict[str, dict], num_pairs: int = 50000,
                  num_rots: int = 180, angle_tol: float = 1.0, backproj_ratio: float = 0.1, imp_wt_margin: float = 0.01,
-                 seed: int = 0, max_points: int = 50000, device=None, n_streams: Optional[int] = None):
+                 seed: int = 0, max_points: int = 50000, device=None, n_streams: Optional[int] = None, opt: bool = False):
         self.models, self.cfgs = models, cfgs
         self.num_pairs, self.num_rots = int(num_pairs), int(num_rots)
         self.angle_tol, self.backproj_ratio, self.imp_wt_margin = angle_tol, backproj_ratio, imp_wt_margin
+        self.opt = bool(opt)            # eval.py:62: online refinement of (R, t) per (instance, branch), eval.py:319-355
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rng = np.random.default_rng(seed)
         self.seed = int(seed)
@@ -117,7 +118,7 @@ class PoseEstimator:
         return VoteConfig(res=float(g("res", 0.002)), up=tuple(g("up", (0, 1, 0))), right=tuple(g("right", (1, 0, 0))),
                           front=tuple(g("front", (0, 0, 1))), num_rots=self.num_rots, angle_tol=self.angle_tol,
                           backproj_ratio=self.backproj_ratio, imp_wt_margin=self.imp_wt_margin,
-                          loss_y_only=category in SYMMETRIC_Y)
+                          loss_y_only=category in SYMMETRIC_Y, opt=self.opt)
 
     def _mark(self, stage: str, begin: bool):
         if self.timing_hook is not None:
@@ -257,7 +258,7 @@ class PoseEstimator:
             slots["dino"] = 2 * i
         if sh is not None:
             slots["shot"] = 2 * i + 1
-        return (9 if sh is not None else 0) + 26 * len(slots), slots
+        return (9 if sh is not None else 0) + (26 + (1 if self.opt else 0)) * len(slots), slots
 
     def _enqueue_instance(self, i: int, inst: Instance, pose_buf: torch.Tensor, draws, st):
         voter = self.voters[i % self.n_streams]

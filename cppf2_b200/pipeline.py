@@ -38,6 +38,9 @@ class VoteConfig:
     imp_wt_margin: float = 0.01
     num_bins: int = 32
     loss_y_only: bool = False       # can / bottle / bowl: symmetric about y (eval.py:360-361)
+    opt: bool = False               # online refinement (eval.py:62 `opt`, :319-355); the reference's default is True
+    opt_iters: int = 100            # eval.py:326
+    opt_lr: float = 1e-2            # eval.py:324
 
     @property
     def num_sphere(self) -> int:
@@ -123,7 +126,7 @@ class PoseVoter:
 
     def _vote_params(self, cfg: "VoteConfig", T: int) -> VoteParams:
         key = (cfg.res, tuple(cfg.up), tuple(cfg.right), tuple(cfg.front), cfg.num_rots, cfg.angle_tol, cfg.backproj_ratio,
-               cfg.imp_wt_margin, cfg.num_bins, cfg.loss_y_only, T)
+               cfg.imp_wt_margin, cfg.num_bins, cfg.loss_y_only, T, cfg.opt, cfg.opt_iters, cfg.opt_lr)
         p = self._params_cache.get(key)
         if p is None:
             S = cfg.num_sphere
@@ -138,7 +141,8 @@ class PoseVoter:
                            loss_y_only=int(cfg.loss_y_only), lut=None if lut is None else lut.data_ptr(), cos_tab=ct.data_ptr(),
                            sin_tab=st.data_ptr(), sphere=sphere.data_ptr(),
                            axes=_lib.axes_array(cfg.up, cfg.front, cfg.right),   # call-site order, eval.py:237-240
-                           imp_margin=float(cfg.imp_wt_margin), rank_lo=int(rank_lo), gamma=float(gamma))
+                           imp_margin=float(cfg.imp_wt_margin), rank_lo=int(rank_lo), gamma=float(gamma),
+                           refine_iters=int(cfg.opt_iters) if cfg.opt else 0, refine_lr=float(cfg.opt_lr))
             self._params_cache[key] = p
         return p
 
@@ -155,7 +159,7 @@ class PoseVoter:
                                        None if scale_override is None else scale_override.data_ptr(), int(cells_hint or 0),
                                        C.byref(params), C.byref(bufs), (self.pose if pose_out is None else pose_out).data_ptr(),
                                        stream_ptr()), "cppf_vote_chain")
-        self.launches = 24
+        self.launches = 24 + (1 if cfg.opt else 0)
         self._live = (pc, idx, bins, pred_scales, scale_override)
         self._T = T
         return self

@@ -34,6 +34,7 @@ extern "C" {
 #define CPPF_STATUS_GRID_OVERFLOW 1u   /* gx*gy*gz exceeds the grid buffer handed to cppf_vote_center */
 #define CPPF_STATUS_GRID_GUARD 2u      /* extent/res > 1000 on some axis: the reference skips the instance (eval.py:200) */
 #define CPPF_STATUS_EMPTY 4u           /* no tuple survived a stage (empty cloud, no kept pair) */
+#define CPPF_STATUS_REFINED 8u         /* R and t went through the online refinement (eval.py:319-355) */
 
 #define CPPF_SHOT_DIM 352
 #define CPPF_NUM_BINS 32
@@ -219,6 +220,19 @@ int cppf_pose_finalize(const float *pc, const void *idx, int idx_is_i64, int64_t
                        const float *scale_override /* 3 floats or NULL: eval.py:308 reuses the DINO scale */,
                        cppf_pose *pose, void *ws, int64_t ws_bytes, void *stream);
 
+/* Same with the reference's online refinement (eval.py:319-355, `opt=True`, its default) between the pose assembly and
+ * the branch loss when refine_iters > 0: refine_iters Adam steps (reference: 100, lr 1e-2) on (t, quaternion) minimising
+ * the L1 distance between the canonicalised kept pairs and the scaled predictions, in one single-CTA kernel.  R and t of
+ * *pose are then the refined float32 values and CPPF_STATUS_REFINED is raised.  T = number of tuples (sizes the scratch:
+ * ws_bytes >= cppf_pose_workspace_bytes(T)).  lietorch (SO3) is not part of the reference tree: its semantics are restated,
+ * parity unpinned (oracle/refine_torch.py). */
+int cppf_pose_finalize_refine(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const uint8_t *bins,
+                              int num_bins, const float *pred_scales, const int32_t *kept_list,
+                              const cppf_backvote_summary *summary, const double *counts, const float *sphere, int S,
+                              const cppf_center *center, int up_loc, int right_loc, int loss_y_only,
+                              const float *scale_override, int refine_iters, float refine_lr, int64_t T, cppf_pose *pose,
+                              void *ws, int64_t ws_bytes, void *stream);
+
 /* ---- instance cloud preparation (the step in front of SHOT) -----------------------
  * replaces backproject (utils/util.py:2586-2607, with the callers' un-flip of x and y, eval.py:185-189), downsample
  * (utils/util.py:39-46: Open3D voxel_down_sample_and_trace + np.random.choice) and the 50 000-point cap
@@ -273,6 +287,8 @@ typedef struct cppf_vote_params {
     double imp_margin;          /* eval.py:275: 0.01 */
     int64_t rank_lo;            /* floor(ratio*(T-1)) */
     float gamma;                /* fractional part of ratio*(T-1) */
+    int refine_iters;           /* 0 = opt=False; the reference's opt=True runs 100 (eval.py:326) */
+    float refine_lr;            /* 1e-2 (eval.py:324) */
     int pad;
 } cppf_vote_params;
 
