@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=int(os.environ.get("CPPF_PRECISION", "-1")), help="heads: 0 fp32, 1 bf16 tcgen05, -1 best available")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="store_true", help="run the online pose refinement (eval.py:319-355) in every (instance, branch); "
+                    "off by default: the CPU arm and the published tolerance are defined without it")
     ap.add_argument("--shot-sweep", action="store_true", help="with --impl reference: CPU leg of the SHOT sweep (config 3)")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: anything a library prints at C level (NCCL's version banner) goes to stderr
@@ -277,7 +279,7 @@ def main():
             m.precision = 1 if (has_tc and args.precision != 0) else 0
             used.add((m.branch, m.precision))
     precision = 1 if all(p == 1 for _, p in used) else (0 if all(p == 0 for _, p in used) else 2)
-    est = PoseEstimator(models, cfgs, num_pairs=NUM_PAIRS, num_rots=NUM_ROTS, seed=rank)
+    est = PoseEstimator(models, cfgs, num_pairs=NUM_PAIRS, num_rots=NUM_ROTS, seed=rank, opt=args.opt)
     n_inst = len(raw)
     tuples_per_step = 2 * NUM_PAIRS * n_inst
 
@@ -322,7 +324,7 @@ def main():
 
     # per-kernel durations for the roofline: the same steps on ONE stream (no overlap between instances), CUDA events
     # around each stage on the launching stream
-    est1 = PoseEstimator(models, cfgs, num_pairs=NUM_PAIRS, num_rots=NUM_ROTS, seed=rank, n_streams=1)
+    est1 = PoseEstimator(models, cfgs, num_pairs=NUM_PAIRS, num_rots=NUM_ROTS, seed=rank, n_streams=1, opt=args.opt)
     stage_events = {}
 
     def hook(stage, begin):
@@ -487,7 +489,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {0: "f32", 1: "bf16", 2: "bf16 (SHOT head, tcgen05) + f32 (DINO head)"}[precision], "data": "synthetic", "config": workload_config(),
-            "frames_per_sec": world * 1e3 / ms_per_step, "instances": n_inst, "points": n_pts,
+            "frames_per_sec": world * 1e3 / ms_per_step, "instances": n_inst, "points": n_pts, "refinement": bool(args.opt),
             "roofline": roofline, "kernels": kernels,
             "kernel_timing": {"how": "same steps on one stream (instances serialised), CUDA events per stage on the launching stream",
                               "ms_per_step_serial": serial_ms, "streams_in_timed_run": est.n_streams}, "cpu_baseline": cpu_baseline, "clocks": clocks,

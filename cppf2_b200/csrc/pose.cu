@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(1024) scale_median_kernel(const float *__restr
 // 3 of sign_k) reduced through shuffles + shared memory, and every thread repeats the scalar update redundantly, which
 // saves the broadcast.  Per-element arithmetic is float32 like torch's; the sums are float64, so the result does not
 // depend on the reduction order beyond one float32 rounding (the reference's own order is unspecified: cuBLAS + atomics).
-struct RefineRow {
+struct __align__(8) RefineRow {
     float p[3];
     float y[3];
 };
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(512, 1) pose_refine_kernel(const float *__rest
                                                               RefineRow *__restrict__ rows, cppf_pose *__restrict__ pose) {
     __shared__ double s_part[16][12];
     __shared__ double s_tot[12];
+    __shared__ float s_pose[12];                                // rot (9) and t (3) of the current step
     const int64_t M = summary->kept;
     if (M <= 0 || iters <= 0) return;
     const int64_t n_rows = 2 * M;
@@ -221,9 +222,29 @@ __global__ void __launch_bounds__(512, 1) pose_refine_kernel(const float *__rest
 #pragma unroll
             for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
     };
-    for (int it = 1; it <= iters; ++it) {
+    // warp 0 owns the optimiser state and publishes (rot, t) through shared memory; the other warps only sweep rows.
+    // Measured 6.7 us per step at 2M = 10 000 rows: ~3.7 us the row sweep (issue-bound: ~90 instructions per row, 16 warps on
+    // 4 schedulers), ~2.3 us the dependent scalar chain (IEEE sqrt / divisions of Adam and of the quaternion), the rest the
+    // two reductions.  More rows in flight per thread and float32 partial sums did not help (the latter also made the result
+    // depend on the kept list's order).
+    if (wid == 0) {
         quat_matrix(q, Q);
         matmul3(Q, R0, rot);                                   // rot = Q @ R_est
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) s_pose[k] = rot[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s_pose[9 + k] = t[k];
+        }
+    }
+    __syncthreads();
+    for (int it = 1; it <= iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) rot[k] = s_pose[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] = s_pose[9 + k];
+        // float64 from the first add on: the kept list comes out of an atomic compaction in no particular order, and float64
+        // sums of float32 terms make the result independent of it (float32 partials were seen to differ run to run)
         double acc[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) acc[k] = 0.0;
@@ -249,57 +270,64 @@ __global__ void __launch_bounds__(512, 1) pose_refine_kernel(const float *__rest
         }
         __syncthreads();
         if (wid == 0) {
-            const int n_w = blockDim.x >> 5;
-            for (int k = 0; k < 12; ++k) {
-                double v = lane < n_w ? s_part[lane][k] : 0.0;
-                v = warp_sum(v);
-                if (lane == 0) s_tot[k] = v;
+            if (lane < 12) {                                    // one fixed-order sum of the warps' partials per component
+                const int n_w = blockDim.x >> 5;
+                double v = 0.0;
+                for (int w = 0; w < n_w; ++w) v += s_part[w][lane];
+                s_tot[lane] = v;
+            }
+            __syncwarp();
+            // gradients (float32 like the reference's autograd): g_rot = (pc - t)^T @ (sign / cnt), g_t = -sum_rows (sign / cnt) @ rot^T
+            float g_rot[9], g_t[3], G[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g_rot[k] = static_cast<float>(s_tot[k]) * inv_cnt;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                g_t[j] = -(rot[3 * j] * static_cast<float>(s_tot[9]) + rot[3 * j + 1] * static_cast<float>(s_tot[10]) +
+                           rot[3 * j + 2] * static_cast<float>(s_tot[11])) * inv_cnt;
+            // dL/dQ = g_rot @ R_est^T
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) G[3 * i + j] = g_rot[3 * i] * R0[3 * j] + g_rot[3 * i + 1] * R0[3 * j + 1] + g_rot[3 * i + 2] * R0[3 * j + 2];
+            float g_q[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {                           // sum_i Q[:,i] x G[:,i]
+                const float a0 = Q[i], a1 = Q[3 + i], a2 = Q[6 + i], b0 = G[i], b1 = G[3 + i], b2 = G[6 + i];
+                g_q[0] += a1 * b2 - a2 * b1;
+                g_q[1] += a2 * b0 - a0 * b2;
+                g_q[2] += a0 * b1 - a1 * b0;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g_q[k] = g_q[k] / 180.f * 3.14159274f;      // delta_rot.grad / 180 * np.pi
+            // torch.optim.Adam, single-tensor path, float32 parameters
+            b1_pow *= beta1;
+            b2_pow *= beta2;
+            const float step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - b1_pow));
+            const float bc2_sqrt = static_cast<float>(sqrt(1.0 - b2_pow));
+            auto adam = [&](float &p, float &m, float &v, float g) {
+                m = m + (g - m) * 0.1f;                              // exp_avg.lerp_(grad, 1 - beta1)
+                v = v * 0.999f + 0.001f * g * g;                     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+                const float den = sqrtf(v) / bc2_sqrt + 1e-8f;
+                p = p - step_size * (m / den);
+            };
+#pragma unroll
+            for (int k = 0; k < 3; ++k) adam(t[k], m_t[k], v_t[k], g_t[k]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) adam(q[k], m_q[k], v_q[k], g_q[k]);
+            // q[3] has a zero gradient in every step: exp_avg = exp_avg_sq = 0, update 0 / (0 + eps) = 0
+            quat_matrix(q, Q);
+            matmul3(Q, R0, rot);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) s_pose[k] = rot[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s_pose[9 + k] = t[k];
             }
         }
         __syncthreads();
-        // gradients (float32 like the reference's autograd): g_rot = (pc - t)^T @ (sign / cnt), g_t = -sum_rows (sign / cnt) @ rot^T
-        float g_rot[9], g_t[3], G[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) g_rot[k] = static_cast<float>(s_tot[k]) * inv_cnt;
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            g_t[j] = -(rot[3 * j] * static_cast<float>(s_tot[9]) + rot[3 * j + 1] * static_cast<float>(s_tot[10]) +
-                       rot[3 * j + 2] * static_cast<float>(s_tot[11])) * inv_cnt;
-        // dL/dQ = g_rot @ R_est^T
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) G[3 * i + j] = g_rot[3 * i] * R0[3 * j] + g_rot[3 * i + 1] * R0[3 * j + 1] + g_rot[3 * i + 2] * R0[3 * j + 2];
-        float g_q[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {                           // sum_i Q[:,i] x G[:,i]
-            const float a0 = Q[i], a1 = Q[3 + i], a2 = Q[6 + i], b0 = G[i], b1 = G[3 + i], b2 = G[6 + i];
-            g_q[0] += a1 * b2 - a2 * b1;
-            g_q[1] += a2 * b0 - a0 * b2;
-            g_q[2] += a0 * b1 - a1 * b0;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) g_q[k] = g_q[k] / 180.f * 3.14159274f;      // delta_rot.grad / 180 * np.pi
-        // torch.optim.Adam, single-tensor path, float32 parameters
-        b1_pow *= beta1;
-        b2_pow *= beta2;
-        const float step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - b1_pow));
-        const float bc2_sqrt = static_cast<float>(sqrt(1.0 - b2_pow));
-        auto adam = [&](float &p, float &m, float &v, float g) {
-            m = m + (g - m) * 0.1f;                              // exp_avg.lerp_(grad, 1 - beta1)
-            v = v * 0.999f + 0.001f * g * g;                     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-            const float den = sqrtf(v) / bc2_sqrt + 1e-8f;
-            p = p - step_size * (m / den);
-        };
-#pragma unroll
-        for (int k = 0; k < 3; ++k) adam(t[k], m_t[k], v_t[k], g_t[k]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) adam(q[k], m_q[k], v_q[k], g_q[k]);
-        // q[3] has a zero gradient in every step: exp_avg = exp_avg_sq = 0, update 0 / (0 + eps) = 0
     }
-    if (tid == 0) {
-        quat_matrix(q, Q);
-        matmul3(Q, R0, rot);
+    if (tid == 0) {                                             // warp 0 holds the final (rot, t)
         for (int i = 0; i < 9; ++i) pose->R[i] = static_cast<double>(rot[i]);
         for (int i = 0; i < 3; ++i) pose->t[i] = static_cast<double>(t[i]);
         pose->status |= CPPF_STATUS_REFINED;
