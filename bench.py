@@ -49,8 +49,8 @@ def load_peaks():
 
 def heads_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per tuple-program launch of the heads kernel, from the committed
-    `ncu --set full` capture (profiles/r01_heads_ncu_full.json); None when the summary is absent."""
-    path = os.path.join(ROOT, "profiles", "r01_heads_ncu_full.json")
+    `ncu --set full` capture (profiles/r01_heads_v5_ncu_full.json); None when the summary is absent."""
+    path = os.path.join(ROOT, "profiles", "r01_heads_v5_ncu_full.json")
     try:
         return json.load(open(path))["traffic_bytes_per_tuple_launch_mean"]
     except Exception:
@@ -454,7 +454,7 @@ def main():
         ach = kernels["heads"]["achieved_tflops"]
         roofline = {"kernel": "heads (ResLayer chains, %s)" % {0: "fp32 CUDA cores", 1: "bf16 tcgen05", 2: "SHOT bf16 tcgen05 + DINO fp32 CUDA cores"}[precision], "bound": "tensor",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": heads_traffic(),
-                    "traffic_note": "DRAM bytes per tuple-program launch (ncu --set full, profiles/r01_heads_ncu_full.md)",
+                    "traffic_note": "DRAM bytes per tuple-program launch (ncu --set full, profiles/r01_heads_v5_ncu_full.md)",
                     "peak_source": peaks["source"] + ", sustained"}
     elif vote_ms >= shot_ms:
         ach = kernels["vote_chain"]["alg_GBps"]
