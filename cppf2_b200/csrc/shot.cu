@@ -22,6 +22,7 @@ namespace cppf {
 
 constexpr int kShotWarps = 8;                    // key-points in flight per CTA
 constexpr int kShotMaxCells = 1 << 21;           // cell table capacity (coarsened beyond that)
+constexpr int kShotListCap = 768;                // cached neighbours per key-point (more: the cells are swept again)
 
 struct ShotGrid {        // device-resident search grid header
     float lo[3];
@@ -380,6 +381,9 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
     const float4 *__restrict__ normals_sorted, float radius_f, double radius, float *__restrict__ desc,
     float *__restrict__ rf_out) {
     __shared__ float s_hist[kShotWarps][CPPF_SHOT_DIM];
+    // in-radius neighbours found by pass A (positions in the sorted array, sweep order): passes B and C walk this list
+    // instead of sweeping the 27 cells again -- a surface sampled at radius/10 has ~270 neighbours among ~900 candidates
+    __shared__ int s_list[kShotWarps][kShotListCap];
     const ShotGrid g = *gp;
     const int n_sorted = cell_start[g.cells];
     const float radius_sq = static_cast<float>(radius * radius);
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     float *hist = s_hist[wib];
+    int *list = s_list[wib];
     (void)radius_f;
     const REAL r12 = static_cast<REAL>(radius / 2), r14 = static_cast<REAL>(radius / 4), r34 = static_cast<REAL>((radius * 3) / 4);
     const REAL RAD_45 = static_cast<REAL>(0.78539816339744830961566084581988);
@@ -404,25 +409,62 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
         // pass A: weighted scatter matrix in double (shot_lrf.hpp::getLocalRF)
         double cov[6] = {0, 0, 0, 0, 0, 0}, wsum = 0.0;
         int valid = 0, total = 0;
-        for_each_candidate(g, cell_start, sorted, p, lane, [&](int, const float4 &q) {
-            const float d2 = flann_dist2(p, q);
-            if (d2 < radius_sq) {
-                ++total;
-                if (!(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
-                    const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
-                                 vz = static_cast<double>(__fsub_rn(q.z, p[2]));
-                    const double w = radius - sqrt(static_cast<double>(d2));
-                    cov[0] += w * (vx * vx);
-                    cov[1] += w * (vx * vy);
-                    cov[2] += w * (vx * vz);
-                    cov[3] += w * (vy * vy);
-                    cov[4] += w * (vy * vz);
-                    cov[5] += w * (vz * vz);
-                    wsum += w;
-                    ++valid;
+        int n_list = 0;                                  // warp-uniform
+        {
+            const int cx = shot_coord(p[0], g.lo[0], g.inv, g.dim[0]);
+            const int cy = shot_coord(p[1], g.lo[1], g.inv, g.dim[1]);
+            const int cz = shot_coord(p[2], g.lo[2], g.inv, g.dim[2]);
+            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+            for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x)
+                for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+                    const int row = (x * g.dim[1] + y) * g.dim[2];
+                    const int b = cell_start[row + z0], e = cell_start[row + z1 + 1];  // z-neighbours are contiguous
+                    for (int j0 = b; j0 < e; j0 += 32) {     // same visiting order as for_each_candidate, whole warp converged
+                        const int j = j0 + lane;
+                        bool hit = false;
+                        if (j < e) {
+                            const float4 q = sorted[j];
+                            const float d2 = flann_dist2(p, q);
+                            if (d2 < radius_sq) {
+                                hit = true;
+                                ++total;
+                                if (!(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
+                                    const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
+                                                 vz = static_cast<double>(__fsub_rn(q.z, p[2]));
+                                    const double w = radius - sqrt(static_cast<double>(d2));
+                                    cov[0] += w * (vx * vx);
+                                    cov[1] += w * (vx * vy);
+                                    cov[2] += w * (vx * vz);
+                                    cov[3] += w * (vy * vy);
+                                    cov[4] += w * (vy * vz);
+                                    cov[5] += w * (vz * vz);
+                                    wsum += w;
+                                    ++valid;
+                                }
+                            }
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (m) {
+                            const int pos = n_list + __popc(m & ((1u << lane) - 1u));
+                            if (hit && pos < kShotListCap) list[pos] = j;
+                            n_list += __popc(m);
+                        }
+                    }
                 }
+        }
+        __syncwarp();
+        const bool listed = n_list <= kShotListCap;
+        // passes B and C: the cached neighbours when they fit, else the cells again
+        auto for_each_neighbour = [&](auto &&f) {
+            if (listed) {
+                for (int k = lane; k < n_list; k += 32) {
+                    const int j = list[k];
+                    f(j, sorted[j]);
+                }
+            } else {
+                for_each_candidate(g, cell_start, sorted, p, lane, f);
             }
-        });
+        };
 #pragma unroll
         for (int i = 0; i < 6; ++i) cov[i] = warp_sum(cov[i]);
         wsum = warp_sum(wsum);
@@ -441,7 +483,7 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
             double v3[3] = {V[0], V[3], V[6]};  // smallest eigenvalue -> z
             // pass B: sign disambiguation votes
             int plus_t = 0, plus_n = 0;
-            for_each_candidate(g, cell_start, sorted, p, lane, [&](int, const float4 &q) {
+            for_each_neighbour([&](int, const float4 &q) {
                 if (flann_dist2(p, q) < radius_sq && !(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
                     const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
                                  vz = static_cast<double>(__fsub_rn(q.z, p[2]));
@@ -474,7 +516,7 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
         // pass C: histogram (shot.hpp::createBinDistanceShape + interpolateSingleChannel)
         for (int j = lane; j < CPPF_SHOT_DIM; j += 32) hist[j] = 0.0f;
         __syncwarp();
-        for_each_candidate(g, cell_start, sorted, p, lane, [&](int j, const float4 &q) {
+        for_each_neighbour([&](int j, const float4 &q) {
             const float d2 = flann_dist2(p, q);
             if (!(d2 < radius_sq)) return;
             const float4 nq = normals_sorted[j];
