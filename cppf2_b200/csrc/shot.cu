@@ -380,7 +380,13 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
     const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
     const float4 *__restrict__ normals_sorted, float radius_f, double radius, float *__restrict__ desc,
     float *__restrict__ rf_out) {
-    __shared__ float s_hist[kShotWarps][CPPF_SHOT_DIM];
+    // The histogram accumulates in 32-bit fixed point: shared-memory float atomicAdd is a compare-and-swap loop (60 % of this
+    // kernel's stall samples, ncu; so is the 64-bit integer add), the 32-bit integer add is one native ATOMS.ADD.  A neighbour
+    // adds at most 5 over all bins, so with `total` neighbours a scale of 2^k, k = 32 - bits(5 total + 1) (<= 24), cannot
+    // overflow: 2^21 for the ~270 neighbours of a cloud sampled at radius/10.  Each contribution is rounded to 2^-k once;
+    // the sum itself is exact, hence independent of the order the lanes arrive in and identical from run to run (PCL adds in
+    // float in kd-tree order, which nothing pins either).
+    __shared__ unsigned int s_hist[kShotWarps][CPPF_SHOT_DIM];
     // in-radius neighbours found by pass A (positions in the sorted array, sweep order): passes B and C walk this list
     // instead of sweeping the 27 cells again -- a surface sampled at radius/10 has ~270 neighbours among ~900 candidates
     __shared__ int s_list[kShotWarps][kShotListCap];
@@ -391,7 +397,9 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
     const int wib = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    float *hist = s_hist[wib];
+    unsigned int *hist = s_hist[wib];
+    float hist_scale = 1.0f;
+    auto hist_add = [&](int bin_index, float v) { atomicAdd(&hist[bin_index], __float2uint_rn(v * hist_scale)); };
     int *list = s_list[wib];
     (void)radius_f;
     const REAL r12 = static_cast<REAL>(radius / 2), r14 = static_cast<REAL>(radius / 4), r34 = static_cast<REAL>((radius * 3) / 4);
@@ -514,7 +522,12 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
         }
 
         // pass C: histogram (shot.hpp::createBinDistanceShape + interpolateSingleChannel)
-        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) hist[j] = 0.0f;
+        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) hist[j] = 0u;
+        {
+            const unsigned m = 5u * static_cast<unsigned>(total) + 1u;          // total < 2^29 points
+            const int k = min(24, __clz(m));                                    // 32 - bits(m)
+            hist_scale = static_cast<float>(1u << k);
+        }
         __syncwarp();
         for_each_neighbour([&](int j, const float4 &q) {
             const float d2 = flann_dist2(p, q);
@@ -548,16 +561,16 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
             bin -= static_cast<REAL>(step);
             REAL wgt = REAL(1) - (bin < 0 ? -bin : bin);
             if (bin > 0)
-                atomicAdd(&hist[vol + ((step + 1) % 10)], static_cast<float>(bin));
+                hist_add(vol + ((step + 1) % 10), static_cast<float>(bin));
             else
-                atomicAdd(&hist[vol + ((step - 1 + 10) % 10)], -static_cast<float>(bin));
+                hist_add(vol + ((step - 1 + 10) % 10), -static_cast<float>(bin));
             if (distance > r12) {
                 const REAL rd = (distance - r34) / r12;
                 if (distance > r34)
                     wgt += REAL(1) - rd;
                 else {
                     wgt += REAL(1) + rd;
-                    atomicAdd(&hist[(di - 2) * 11 + step], -static_cast<float>(rd));
+                    hist_add((di - 2) * 11 + step, -static_cast<float>(rd));
                 }
             } else {
                 const REAL rd = (distance - r14) / r12;
@@ -565,7 +578,7 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
                     wgt += REAL(1) + rd;
                 else {
                     wgt += REAL(1) - rd;
-                    atomicAdd(&hist[(di + 2) * 11 + step], static_cast<float>(rd));
+                    hist_add((di + 2) * 11 + step, static_cast<float>(rd));
                 }
             }
             REAL ic = zr / distance;
@@ -577,7 +590,7 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
                     wgt += REAL(1) - id;
                 else {
                     wgt += REAL(1) + id;
-                    atomicAdd(&hist[(di + 1) * 11 + step], -static_cast<float>(id));
+                    hist_add((di + 1) * 11 + step, -static_cast<float>(id));
                 }
             } else {
                 const REAL id = (incl - RAD_45) / RAD_90;
@@ -585,7 +598,7 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
                     wgt += REAL(1) + id;
                 else {
                     wgt += REAL(1) - id;
-                    atomicAdd(&hist[(di - 1) * 11 + step], static_cast<float>(id));
+                    hist_add((di - 1) * 11 + step, static_cast<float>(id));
                 }
             }
             if (yr != 0 || xr != 0) {
@@ -595,21 +608,27 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
                 ad = ad < REAL(-0.5) ? REAL(-0.5) : (ad > REAL(0.5) ? REAL(0.5) : ad);
                 if (ad > 0) {
                     wgt += REAL(1) - ad;
-                    atomicAdd(&hist[((di + 4) % 32) * 11 + step], static_cast<float>(ad));
+                    hist_add(((di + 4) % 32) * 11 + step, static_cast<float>(ad));
                 } else {
                     wgt += REAL(1) + ad;
-                    atomicAdd(&hist[((di - 4 + 32) % 32) * 11 + step], -static_cast<float>(ad));
+                    hist_add(((di - 4 + 32) % 32) * 11 + step, -static_cast<float>(ad));
                 }
             }
-            atomicAdd(&hist[vol + step], static_cast<float>(wgt));
+            hist_add(vol + step, static_cast<float>(wgt));
         });
         __syncwarp();
         // normalizeHistogram: float squares accumulated in double, divide by float(norm)
         double acc = 0.0;
-        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) acc += static_cast<double>(hist[j] * hist[j]);
+        float hv[CPPF_SHOT_DIM / 32];
+#pragma unroll
+        for (int u = 0; u < CPPF_SHOT_DIM / 32; ++u) {
+            hv[u] = static_cast<float>(static_cast<double>(hist[lane + 32 * u]) / static_cast<double>(hist_scale));
+            acc += static_cast<double>(hv[u] * hv[u]);
+        }
         acc = warp_sum(acc);
         const float nrm = static_cast<float>(sqrt(acc));
-        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) out[j] = hist[j] / nrm;
+#pragma unroll
+        for (int u = 0; u < CPPF_SHOT_DIM / 32; ++u) out[lane + 32 * u] = hv[u] / nrm;
         __syncwarp();
     }
 }
