@@ -107,3 +107,30 @@ def test_one_call_instance_path_equals_python_sequence():
             assert np.array_equal(r.scale, o.scale)
             np.testing.assert_allclose(r.R, o.R, atol=1e-9)
             np.testing.assert_allclose(r.loss, o.loss, rtol=1e-9)
+
+
+def test_result_pickles_through_the_frame_loop(tmp_path):
+    """eval.py:132-399 around the device path: detection dict in, pred_RTs / pred_scales out, one pickle per frame."""
+    import pickle
+    from cppf2_b200 import results as R, synth
+    from cppf2_b200.estimator import PoseEstimator, build_models
+    frame = synth.synth_real275_frame(3, 3)
+    cat2id = {v: k for k, v in R.ID2CATEGORY.items()}
+    n = len(frame["cats"])
+    res = dict(image_path="data/real/test/scene_9/0007", pred_bboxes=np.zeros((n + 1, 4), np.int32),
+               pred_masks=np.stack(list(frame["masks"]) + [np.zeros_like(frame["masks"][0])], -1),
+               pred_class_ids=np.array([cat2id[c] for c in frame["cats"]] + [0]), gt_RTs=np.zeros((0, 4, 4)),
+               gt_scales=np.zeros((0, 3)), gt_class_ids=np.zeros(0, np.int64))
+    models, cfgs = build_models(sorted(set(frame["cats"])), branches=("shot",), precision=1)
+    est = PoseEstimator(models, cfgs, num_pairs=8192, seed=5)
+    out = R.run_results(est, [res], out_dir=tmp_path, read_depth=lambda p: frame["depth"].astype(np.uint16))
+    assert out[0]["pred_RTs"].shape == (n + 1, 4, 4) and out[0]["pred_scales"].shape == (n + 1, 3)
+    assert np.array_equal(out[0]["pred_RTs"][n], np.eye(4))                       # background detection untouched
+    ran = [i for i in range(n) if not np.array_equal(out[0]["pred_RTs"][i], np.eye(4))]
+    assert ran, "no instance of the synthetic frame produced a pose"
+    for i in ran:
+        RT = out[0]["pred_RTs"][i]
+        assert np.isfinite(RT).all() and 0.3 < RT[2, 3] < 3.0                     # the voted centre lies in front of the camera
+        assert abs(np.linalg.norm(out[0]["pred_scales"][i]) - 1.0) < 1e-5         # scale / ||scale|| (eval.py:371)
+    dumped = pickle.load(open(tmp_path / "real_test_scene_9_0007.pkl", "rb"))
+    assert np.array_equal(dumped["pred_RTs"], out[0]["pred_RTs"])
