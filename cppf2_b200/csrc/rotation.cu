@@ -42,8 +42,9 @@ __device__ __forceinline__ void rotation_candidate(const RotFrame &f, float cr, 
 }
 
 // Tests direction p against the lattice band and adds w to every bin it hits.
-__device__ __forceinline__ void band_vote(const float p[3], double w, const float *__restrict__ s_sphere, int S,
-                                          float cos_thr, int band, float half_sm1, double *__restrict__ bins) {
+template <class Add>
+__device__ __forceinline__ void band_vote(const float p[3], const float *__restrict__ s_sphere, int S,
+                                          float cos_thr, int band, float half_sm1, Add &&add) {
     int lo = 0, hi = S - 1;
     if (band < S) {
         const int ic = __float2int_rn((1.0f - p[1]) * half_sm1);
@@ -52,7 +53,7 @@ __device__ __forceinline__ void band_vote(const float p[3], double w, const floa
     }
     for (int i = lo; i <= hi; ++i) {
         const float d = __fmaf_rn(p[2], s_sphere[3 * i + 2], __fmaf_rn(p[1], s_sphere[3 * i + 1], __fmul_rn(p[0], s_sphere[3 * i])));
-        if (d > cos_thr) atomicAdd(&bins[i], w);
+        if (d > cos_thr) add(i);
     }
 }
 
@@ -78,8 +79,9 @@ __device__ __forceinline__ int cube_cell(const float p[3], int G) {
     return ((2 * axis + (m < 0.0f ? 1 : 0)) * G + iv) * G + iu;
 }
 
-__device__ __forceinline__ void lut_vote(const float p[3], double w, const float *__restrict__ s_sphere, float cos_thr,
-                                         const uint2 *__restrict__ lut_cells, int G, double *__restrict__ bins) {
+template <class Add>
+__device__ __forceinline__ void lut_vote(const float p[3], const float *__restrict__ s_sphere, float cos_thr,
+                                         const uint2 *__restrict__ lut_cells, int G, Add &&add) {
     const uint2 e = __ldg(lut_cells + cube_cell(p, G));
     const uint32_t word[2] = {e.x, e.y};
 #pragma unroll
@@ -87,8 +89,20 @@ __device__ __forceinline__ void lut_vote(const float p[3], double w, const float
         const uint32_t i = (word[k >> 1] >> (16 * (k & 1))) & 0xffffu;
         if (i == 0xffffu) break;     // entries are packed front to back
         const float d = __fmaf_rn(p[2], s_sphere[3 * i + 2], __fmaf_rn(p[1], s_sphere[3 * i + 1], __fmul_rn(p[0], s_sphere[3 * i])));
-        if (d > cos_thr) atomicAdd(&bins[i], w);
+        if (d > cos_thr) add(static_cast<int>(i));
     }
+}
+
+// A weighted bin as two 32-bit limbs of a 32.32 fixed-point sum: shared-memory atomicAdd on a double (and on a 64-bit
+// integer) is a compare-and-swap loop -- a quarter of rotation_hist_kernel's stall samples (ncu) -- while the 32-bit integer
+// add is one native ATOMS.ADD.  The low limb takes the fraction, a wrap of it carries into the high limb together with the
+// integer part; the sum is exact, so it does not depend on the order the lanes arrive in.
+__device__ __forceinline__ void fixed_add(unsigned long long *bin, unsigned long long v) {
+    uint32_t *limb = reinterpret_cast<uint32_t *>(bin);          // little endian: [0] fraction, [1] integer part
+    const uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
+    const uint32_t old = atomicAdd(&limb[0], lo);
+    const uint32_t carry = (old + lo) < old ? 1u : 0u;
+    if (hi + carry) atomicAdd(&limb[1], hi + carry);
 }
 
 // ---- materialising vote_rotation (drop-in shim) ----------------------------------------------------
@@ -134,7 +148,7 @@ __global__ void __launch_bounds__(256) sphere_hist_kernel(const float *__restric
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += stride) {
         const float p[3] = {pred[3 * i], pred[3 * i + 1], pred[3 * i + 2]};
         const double w = wt ? __drcp_rn(wt[i]) : 1.0;
-        band_vote(p, w, s_sphere, S, cos_thr, band, half_sm1, s_bins);
+        band_vote(p, s_sphere, S, cos_thr, band, half_sm1, [&](int i) { atomicAdd(&s_bins[i], w); });
     }
     __syncthreads();
     for (int i = threadIdx.x; i < S; i += blockDim.x)
@@ -156,11 +170,11 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R, const float *__restrict__ sphere, int S,
     float cos_thr, int band, const uint2 *__restrict__ lut_cells, int lut_g, double *__restrict__ counts, int part, int n_parts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_bins = reinterpret_cast<double *>(smem_raw);                   // [n_theta][S]
+    unsigned long long *s_bins = reinterpret_cast<unsigned long long *>(smem_raw);     // [n_theta][S], 32.32 fixed point
     float *s_sphere = reinterpret_cast<float *>(s_bins + cols.n * S);        // [S][3]
     float *s_cos = s_sphere + 3 * S;                                         // [R]
     float *s_sin = s_cos + R;
-    for (int i = threadIdx.x; i < cols.n * S; i += blockDim.x) s_bins[i] = 0.0;
+    for (int i = threadIdx.x; i < cols.n * S; i += blockDim.x) s_bins[i] = 0ull;
     for (int i = threadIdx.x; i < 3 * S; i += blockDim.x) s_sphere[i] = sphere[i];
     for (int i = threadIdx.x; i < R; i += blockDim.x) {
         s_cos[i] = cos_tab[i];
@@ -185,21 +199,25 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
             const double wj = __ddiv_rn(static_cast<double>(imp[ib]), imp_max);
             w = __drcp_rn(__dadd_rn(__dadd_rn(wi, wj), margin));
         }
+        // the pair weight 1 / (imp_i + imp_j + margin) lies in (0, 1 / margin]: rounded once to 2^-32 (relative 5e-10 at
+        // the smallest weight the reference can produce, 1 / 2.01); weights beyond 2^31 saturate
+        const unsigned long long wv = __double2ull_rn(fmin(w, 2147483648.0) * 4294967296.0);
         for (int c = 0; c < cols.n; ++c) {
             RotFrame f;
             if (!rotation_frame(a, b, theta[m * theta_stride + cols.col[c]], f)) break;  // warp-uniform
-            double *bins = s_bins + c * S;
+            unsigned long long *bins = s_bins + c * S;
+            auto add = [&](int i) { fixed_add(&bins[i], wv); };
             for (int r = lane; r < R; r += 32) {
                 float p[3];
                 rotation_candidate(f, s_cos[r], s_sin[r], p);
-                if (lut_cells) lut_vote(p, w, s_sphere, cos_thr, lut_cells, lut_g, bins);
-                else band_vote(p, w, s_sphere, S, cos_thr, band, half_sm1, bins);
+                if (lut_cells) lut_vote(p, s_sphere, cos_thr, lut_cells, lut_g, add);
+                else band_vote(p, s_sphere, S, cos_thr, band, half_sm1, add);
             }
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cols.n * S; i += blockDim.x)
-        if (s_bins[i] != 0.0) atomicAdd(&counts[i], s_bins[i]);
+        if (s_bins[i] != 0ull) atomicAdd(&counts[i], static_cast<double>(s_bins[i]) * (1.0 / 4294967296.0));
 }
 
 }  // namespace cppf
