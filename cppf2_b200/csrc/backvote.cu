@@ -159,6 +159,106 @@ __global__ void __launch_bounds__(256) select_pass_kernel(const float *__restric
     }
 }
 
+// The same selection in ONE launch for the sizes the instance loop runs (T = 50 000): a single 1024-thread CTA makes the
+// four radix passes and the min-greater pass over the errors (200 KB, L2-resident) with its state in shared memory.  Seven
+// launches (two memsets + five passes of ~5 us each, mostly launch latency) become one; results are identical (integer counts).
+constexpr int64_t kSelectSmallMax = 1 << 17;
+
+__global__ void __launch_bounds__(1024) select_small_kernel(const float *__restrict__ errs, int64_t T, int64_t rank_lo, float gamma,
+                                                            cppf_backvote_summary *__restrict__ summary) {
+    __shared__ uint32_t s_hist[256];
+    __shared__ unsigned long long s_cum[256];
+    __shared__ uint32_t s_prefix, s_min;
+    __shared__ unsigned long long s_k, s_below, s_equal;
+    __shared__ int s_digit;
+    const int tid = threadIdx.x, lane = lane_id();
+    if (tid == 0) {
+        s_prefix = 0u;
+        s_k = static_cast<unsigned long long>(rank_lo);
+        s_below = 0ull;
+        s_equal = 0ull;
+        s_min = 0xffffffffu;
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+        if (tid < 256) s_hist[tid] = 0u;
+        if (tid == 0) s_digit = 256;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const int shift = 24 - 8 * pass;
+        const uint32_t decided = pass == 0 ? 0u : ~((1u << (shift + 8)) - 1u);
+        // whole warps iterate together (full-width ballot); four independent loads in flight per thread: one CTA sweeping
+        // 200 KB is bound by L2 latency, not bandwidth
+        for (int64_t base = tid - lane; base < T; base += 4 * blockDim.x) {
+            uint32_t key[4];
+            bool in[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t t = base + u * blockDim.x + lane;
+                in[u] = t < T;
+                key[u] = in[u] ? float_to_key(__ldg(errs + t)) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool in_prefix = in[u] && (key[u] & decided) == (prefix & decided);
+                const uint32_t active = __ballot_sync(0xffffffffu, in_prefix);
+                if (in_prefix) {      // lanes with equal digits elect one leader that adds the group's size (see select_pass_kernel)
+                    const uint32_t digit = (key[u] >> shift) & 0xffu;
+                    const uint32_t peers = __match_any_sync(active, digit);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], static_cast<uint32_t>(__popc(peers)));
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 256) s_cum[tid] = s_hist[tid];
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {                                     // inclusive scan of the 256 bins
+            const unsigned long long add = (tid < 256 && tid >= o) ? s_cum[tid - o] : 0ull;
+            __syncthreads();
+            if (tid < 256) s_cum[tid] += add;
+            __syncthreads();
+        }
+        const unsigned long long k = s_k;
+        if (tid < 256 && s_cum[tid] > k) atomicMin(&s_digit, tid);
+        __syncthreads();
+        if (tid == 0) {
+            int d = s_digit;
+            if (d == 256) d = 255;
+            const unsigned long long cum = d > 0 ? s_cum[d - 1] : 0ull;
+            s_prefix = prefix | (static_cast<uint32_t>(d) << shift);
+            s_k = k - cum;
+            s_below += cum;
+            s_equal = s_cum[d] - cum;
+        }
+        __syncthreads();
+    }
+    const uint32_t prefix = s_prefix;
+    uint32_t local_min = 0xffffffffu;
+#pragma unroll 4
+    for (int64_t t = tid; t < T; t += blockDim.x) {
+        const uint32_t key = float_to_key(__ldg(errs + t));
+        if (key > prefix && key < local_min) local_min = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, local_min, o);
+        local_min = other < local_min ? other : local_min;
+    }
+    if (lane == 0) atomicMin(&s_min, local_min);
+    __syncthreads();
+    if (tid != 0) return;
+    // both order statistics are known (same rules as the last pass of select_pass_kernel)
+    const float s_lo = key_to_float(prefix);
+    float s_hi = s_lo;
+    const unsigned long long next_rank = static_cast<unsigned long long>(rank_lo) + 1ull;
+    if (next_rank >= s_below + s_equal && next_rank < static_cast<unsigned long long>(T)) s_hi = key_to_float(s_min);
+    const float diff = __fsub_rn(s_hi, s_lo);
+    float thr = __fadd_rn(s_lo, __fmul_rn(diff, gamma));
+    if (gamma >= 0.5f) thr = __fsub_rn(s_hi, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+    summary->threshold = thr;
+    summary->s_lo = s_lo;
+    summary->s_hi = s_hi;
+}
+
 __global__ void __launch_bounds__(256) backvote_mask_kernel(const float *__restrict__ errs, IdxView idx, int64_t T,
                                                             const cppf_backvote_summary *__restrict__ summary_in,
                                                             uint8_t *__restrict__ keep, int32_t *__restrict__ kept_list,
@@ -231,6 +331,11 @@ CPPF_API int cppf_backvote_select(const float *errs, int64_t T, int64_t rank_lo,
     if (!errs || !summary || !ws || T <= 0 || rank_lo < 0 || rank_lo >= T) return CPPF_ERR_INVALID_ARGUMENT;
     if (ws_bytes < cppf_backvote_workspace_bytes(T, 0)) return CPPF_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (T <= kSelectSmallMax) {
+        select_small_kernel<<<1, 1024, 0, s>>>(errs, T, rank_lo, gamma, summary);
+        CPPF_LAUNCH_CHECK();
+        return CPPF_OK;
+    }
     SelectState *st = static_cast<SelectState *>(ws);
     CPPF_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(SelectState), s));
     CPPF_CUDA_TRY(cudaMemsetAsync(&st->min_gt, 0xff, sizeof(uint32_t), s));

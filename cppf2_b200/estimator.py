@@ -258,7 +258,8 @@ class PoseEstimator:
             slots["dino"] = 2 * i
         if sh is not None:
             slots["shot"] = 2 * i + 1
-        return (9 if sh is not None else 0) + (26 + (1 if self.opt else 0)) * len(slots), slots
+        chain = (18 if T <= (1 << 17) else 24) + (1 if self.opt else 0)       # PoseVoter.vote_bins' count
+        return (9 if sh is not None else 0) + (2 + chain) * len(slots), slots
 
     def _enqueue_instance(self, i: int, inst: Instance, pose_buf: torch.Tensor, draws, st):
         voter = self.voters[i % self.n_streams]

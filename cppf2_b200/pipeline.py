@@ -159,7 +159,8 @@ class PoseVoter:
                                        None if scale_override is None else scale_override.data_ptr(), int(cells_hint or 0),
                                        C.byref(params), C.byref(bufs), (self.pose if pose_out is None else pose_out).data_ptr(),
                                        stream_ptr()), "cppf_vote_chain")
-        self.launches = 24 + (1 if cfg.opt else 0)
+        # kernels + memset nodes of the chain: the back-vote selection is one launch up to 2^17 tuples, seven above
+        self.launches = (18 if T <= (1 << 17) else 24) + (1 if cfg.opt else 0)
         self._live = (pc, idx, bins, pred_scales, scale_override)
         self._T = T
         return self

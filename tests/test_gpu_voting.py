@@ -304,7 +304,7 @@ def test_pose_chain_matches_reference_instance(golden, oracle):
     np.testing.assert_allclose(res_o.scale, [0.3, 0.4, 0.5], rtol=1e-7)
 
 
-@pytest.mark.parametrize("T", [11, 1000, 20001, 50000])
+@pytest.mark.parametrize("T", [11, 1000, 20001, 50000, 131072, 131073, 300000])   # <= 2^17: one-CTA select, above: one kernel per radix pass
 def test_backvote_percentile_exact(golden, oracle, T):
     """Radix selection + numpy 'linear' interpolation: threshold and kept set equal np.percentile's."""
     from cppf2_b200 import _lib
