@@ -123,6 +123,20 @@ __global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ g
 // ---------------------------------------------------------------------------------------------------
 // the vote kernel
 // ---------------------------------------------------------------------------------------------------
+// a / b with the correctly rounded quotient of IEEE division (what torch computes, train_dino.py:199) for a divisor that is
+// the same for the whole launch: q = a * RN(1/b) followed by two residual corrections in FMA arithmetic -- the sequence the
+// hardware division's fast path runs after its reciprocal refinement, minus the per-call reciprocal and range check (5
+// instructions instead of ~11; three divisions are a quarter of a vote's instructions and the shared-memory mode is issue-bound).
+// The operands here are finite and far from the denormal range (grid coordinates in metres over a voxel size); a NaN stays a
+// NaN.  Bit-exactness of the grids against the torch-CPU golden vectors and the oracle is what the tests check.
+__device__ __forceinline__ float div_by(float a, float b, float inv_b) {
+    float q = __fmul_rn(a, inv_b);
+    float r = __fmaf_rn(-b, q, a);
+    q = __fmaf_rn(r, inv_b, q);
+    r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, inv_b, q);
+}
+
 constexpr int kVoteThreads = 256;
 constexpr int kMaxRotsSmem = 1024;
 
@@ -154,6 +168,7 @@ __global__ void __launch_bounds__(THREADS) vote_center_kernel(
     if (cells > capacity) return;  // flagged by grid_zero_kernel
     if (MODE == 0) grid += (blockIdx.x % replica_count(cells, capacity, replicas_max)) * cells;
     const float res = geom->res;
+    const float inv_res = __frcp_rn(res);      // correctly rounded reciprocal of the launch-wide divisor (see div_by)
     const float lo0 = geom->lo[0], lo1 = geom->lo[1], lo2 = geom->lo[2];
     const int g0 = static_cast<int>(geom->grid_res[0]), g1 = static_cast<int>(geom->grid_res[1]),
               g2 = static_cast<int>(geom->grid_res[2]);
@@ -202,9 +217,9 @@ __global__ void __launch_bounds__(THREADS) vote_center_kernel(
                 const float o0 = __fadd_rn(__fmul_rn(cr, x0), __fmul_rn(sr, y0));
                 const float o1 = __fadd_rn(__fmul_rn(cr, x1), __fmul_rn(sr, y1));
                 const float o2 = __fadd_rn(__fmul_rn(cr, x2), __fmul_rn(sr, y2));
-                const float q0 = __fdiv_rn(__fsub_rn(__fadd_rn(c0, o0), lo0), res);
-                const float q1 = __fdiv_rn(__fsub_rn(__fadd_rn(c1, o1), lo1), res);
-                const float q2 = __fdiv_rn(__fsub_rn(__fadd_rn(c2, o2), lo2), res);
+                const float q0 = div_by(__fsub_rn(__fadd_rn(c0, o0), lo0), res, inv_res);
+                const float q1 = div_by(__fsub_rn(__fadd_rn(c1, o1), lo1), res, inv_res);
+                const float q2 = div_by(__fsub_rn(__fadd_rn(c2, o2), lo2), res, inv_res);
                 const int i0 = __float2int_rz(__fadd_rn(q0, 0.5f));
                 const int i1 = __float2int_rz(__fadd_rn(q1, 0.5f));
                 const int i2 = __float2int_rz(__fadd_rn(q2, 0.5f));
