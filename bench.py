@@ -11,9 +11,12 @@ pose + ensemble selection -- 12 (instance, branch) votes = 600 000 tuples.  Dept
 down-sampling are "next" rows of the scope table and run once, untimed.
 
 metric / value : tuples voted per second, inputs resident in HBM when the timed region starts.
-e2e            : same metric through the public call (PoseEstimator.estimate) with HOST buffers: per step the
-                 clouds, descriptors and freshly sampled tuple indices are copied from pinned host memory and
-                 the pose records are read back.
+e2e            : same metric through the public call (PoseEstimator.submit()/result(), one frame in flight ahead) with
+                 HOST buffers: per step the clouds and descriptors are copied from pinned host memory, the tuple indices
+                 are drawn on the device and the pose records are read back; the faster of two K-step passes.
+roofline       : the heads kernel (tensor-bound): executed flops / CUDA-event time of the heads stages in a second,
+                 single-stream pass; per-stage medians.  clocks: in-process NVML, attached before the warm-up.
+--opt          : with the reference's online refinement (eval.py:319-355) in every (instance, branch).
 N > 1          : one process per GPU (torchrun), frames sharded across ranks, no data-path collective (weak
                  scaling); time is the max over ranks.
 --impl reference: the CPU oracle (oracle/, the port of the reference's path: PCL-semantics SHOT in C++, torch-CPU
