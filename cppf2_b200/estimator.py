@@ -11,9 +11,11 @@ Per instance (category cfg: res, num_more, up/right/front -- eval.py:172,192,210
 Everything after the host hands over (cloud, descriptors, tuple indices) is queued on one CUDA stream;
 the only device->host traffic is one 152-byte pose record per (instance, branch), read once per frame.
 
-Steps of the reference that stay where they were ("next" rows): depth
-back-projection and voxel down-sampling (host numpy, `backproject_host`, `voxel_downsample_host`), the DINOv2
-backbone (descriptors are an input), and the optional Adam refinement (opt=False semantics).
+Steps of the reference that stay outside this driver: the DINOv2 backbone (descriptors are an input), detection and mAP.
+Depth back-projection, voxel down-sampling and the 50 000-point cap run on the device through `estimate_frame`
+(cppf2_b200.cloud; `backproject_host` / `voxel_downsample_host` below are the host forms the benchmark uses to prepare its
+inputs once, untimed); the online Adam refinement (eval.py:319-355) runs on the device when `opt=True` (the reference's
+default; False here, because the published tolerance and the CPU arm are defined without it).
 """
 from __future__ import annotations
 
