@@ -100,5 +100,8 @@ def test_estimator_opt_flag_runs_both_paths_alike():
     assert a is not None and b is not None and a.branch == b.branch
     for br in a.results:
         assert a.results[br].status & 8 and b.results[br].status & 8
-        np.testing.assert_array_equal(a.results[br].R, b.results[br].R)
-        np.testing.assert_array_equal(a.results[br].t, b.results[br].t)
+        # same kernels, same inputs; the kept list leaves the atomic compaction in a different order from launch to launch, and the
+        # float64 row sums make the refinement independent of that order up to a last-bit rounding that a step may or may not
+        # see: equal to well below the float32 resolution of the pose, not necessarily bit for bit
+        np.testing.assert_allclose(a.results[br].R, b.results[br].R, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(a.results[br].t, b.results[br].t, rtol=0, atol=1e-6)
