@@ -161,11 +161,11 @@ def cpu_state_dicts(cats):
             for ci, cat in enumerate(cats)}
 
 
-def run_cpu_instance(inst, sds, rng, timings=None):
+def run_cpu_instance(inst, sds, rng, timings=None, opt=False):
     from oracle.pipeline_cpu import instance_pose_cpu
     idx = rng.integers(0, inst["pc"].shape[0], (NUM_PAIRS, 5)).astype(np.int64)
     return instance_pose_cpu(inst["pc"], idx, inst["cfg"], sds[inst["category"]], desc=inst["desc"], timings=timings,
-                             sym_y_only=inst["category"] in ("can", "bottle", "bowl"))
+                             sym_y_only=inst["category"] in ("can", "bottle", "bowl"), opt=opt)
 
 
 def reference_shot_sweep(emit):
@@ -204,11 +204,11 @@ def reference_arm(args, emit=print):
     rng = np.random.default_rng(0)
     per = 2 * NUM_PAIRS
     for w in range(args.warmup):
-        run_cpu_instance(instances[w % len(instances)], sds, rng)
+        run_cpu_instance(instances[w % len(instances)], sds, rng, opt=getattr(args, "opt", False))
     timings = {}
     t0 = time.perf_counter()
     for k in range(args.steps):
-        run_cpu_instance(instances[k % len(instances)], sds, rng, timings)
+        run_cpu_instance(instances[k % len(instances)], sds, rng, timings, opt=getattr(args, "opt", False))
     dt = time.perf_counter() - t0
     value = per * args.steps / dt
     sample = (f"1 instance x 2 branches x {NUM_PAIRS} tuples per step (of the {N_INSTANCES}-instance frame); stage seconds "
@@ -480,7 +480,7 @@ def main():
         t0 = time.perf_counter()
         n_done = 0
         for inst in raw:
-            run_cpu_instance(inst, sds, crng, timings)
+            run_cpu_instance(inst, sds, crng, timings, opt=args.opt)
             n_done += 1
             if time.perf_counter() - t0 > 30.0:
                 break

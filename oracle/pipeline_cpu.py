@@ -14,8 +14,9 @@ from .heads_torch import Ref
 
 
 def instance_pose_cpu(pc, idx, cfg: dict, state_dicts: dict, desc=None, bins=None, seed=0, threads=0, timings=None,
-                      num_rots=180, sym_y_only=False):
-    """eval.py:207-372 (opt=False) for one instance.  `state_dicts` = {"dino": sd, "shot": sd} (either optional).
+                      num_rots=180, sym_y_only=False, opt=False):
+    """eval.py:207-372 for one instance; `opt` adds the online refinement (eval.py:319-355, oracle/refine_torch.py).
+    `state_dicts` = {"dino": sd, "shot": sd} (either optional).
     `bins[branch]` injects the multinomial draws; otherwise torch.multinomial on the CPU with `seed`.
     Returns {branch: oracle.instance_body dict} plus the winning branch under key "best"."""
     t0 = time.perf_counter()
@@ -27,7 +28,7 @@ def instance_pose_cpu(pc, idx, cfg: dict, state_dicts: dict, desc=None, bins=Non
     t1 = time.perf_counter()
     out, best, best_loss, dino_scale = {}, None, np.inf, None
     tpc, tidx = torch.from_numpy(pc), torch.from_numpy(np.asarray(idx, dtype=np.int64))
-    t_heads = t_vote = 0.0
+    t_heads = t_vote = t_ref_total = 0.0
     for branch in ("dino", "shot"):
         sd = state_dicts.get(branch)
         if sd is None or (branch == "dino" and desc is None):
@@ -51,15 +52,29 @@ def instance_pose_cpu(pc, idx, cfg: dict, state_dicts: dict, desc=None, bins=Non
                                     scale_override=dino_scale if branch == "shot" else None)   # eval.py:308-310
         if branch == "dino":
             dino_scale = body["pred_scale"]
+        t_ref0 = time.perf_counter()
+        if opt and body["pairs_mask"].any():                            # eval.py:319-355, then the loss with the refined pose
+            from .refine_torch import final_loss, refine_pose
+            mask = body["pairs_mask"]
+            pair_idx = np.asarray(idx, dtype=np.int64)[mask][:, :2]
+            scaled = (body["pred_pairs"] * body["pair_scale"][:, None, None]).astype(np.float32)
+            body["T_voted"], body["R_voted"] = body["T_est"], body["R_est"]
+            body["T_est"], body["R_est"] = refine_pose(pc, pair_idx, scaled[mask], body["T_est"], body["R_est"], sym_y_only)
+            body["loss"] = final_loss(pc, pair_idx, body["pred_pairs"][mask], body["T_est"], body["R_est"],
+                                      np.float32(np.linalg.norm(body["pred_scale"])), sym_y_only)
+        t_refine = time.perf_counter() - t_ref0
         body["bins"] = b
         out[branch] = body
         if body["loss"] < best_loss:
             best, best_loss = branch, body["loss"]
         t_heads += tv - th
-        t_vote += time.perf_counter() - tv
+        t_vote += time.perf_counter() - tv - t_refine
+        t_ref_total += t_refine
     out["best"] = best
     if timings is not None:
         timings["shot"] = timings.get("shot", 0.0) + (t1 - t0)
         timings["heads"] = timings.get("heads", 0.0) + t_heads
         timings["vote"] = timings.get("vote", 0.0) + t_vote
+        if opt:
+            timings["refine"] = timings.get("refine", 0.0) + t_ref_total
     return out

@@ -22,24 +22,18 @@ class SO3Matrix(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q):
         qn = q / torch.linalg.vector_norm(q)
-        u, w = qn[:3], qn[3]
-        eye = torch.eye(3, dtype=q.dtype)
-        cols = []
-        for i in range(3):
-            v = eye[i]
-            uv = torch.linalg.cross(u, v)
-            uv = uv + uv
-            cols.append(v + w * uv + torch.linalg.cross(u, uv))
-        Q = torch.stack(cols, dim=1)
+        x, y, z, w = qn.unbind()
+        zero = torch.zeros((), dtype=q.dtype)
+        U = torch.stack([torch.stack([zero, -z, y]), torch.stack([z, zero, -x]), torch.stack([-y, x, zero])])   # U e_i = u x e_i
+        UV = U + U                                               # uv = 2 (u x v), one column per basis vector v = e_i
+        Q = torch.eye(3, dtype=q.dtype) + w * UV + U @ UV        # v + w uv + u x uv
         ctx.save_for_backward(Q)
         return Q
 
     @staticmethod
     def backward(ctx, G):
         (Q,) = ctx.saved_tensors
-        g = torch.zeros(3, dtype=G.dtype)
-        for i in range(3):
-            g = g + torch.linalg.cross(Q[:, i], G[:, i])
+        g = torch.linalg.cross(Q.T, G.T).sum(0)                  # sum_i Q[:, i] x G[:, i]
         return torch.cat([g, torch.zeros(1, dtype=G.dtype)])
 
 
@@ -51,6 +45,9 @@ def refine_pose(pc, pair_idx, pred_pairs_scaled, T_est, R_est, y_only, iters=100
     idx_t = torch.from_numpy(np.ascontiguousarray(pair_idx)).long()
     target = torch.from_numpy(np.ascontiguousarray(pred_pairs_scaled)).float()
     R0 = torch.from_numpy(np.ascontiguousarray(R_est)).float()
+    # a hundred steps of ~20 tiny ops: intra-op threads only add hand-off cost here (4.2 s with 16 threads, 0.13 s with one)
+    n_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
     with torch.enable_grad():
         opt_trans = torch.nn.Parameter(torch.from_numpy(np.ascontiguousarray(T_est)).float(), requires_grad=True)
         delta_rot = torch.tensor([0, 0, 0, 1.], requires_grad=True)
@@ -68,6 +65,7 @@ def refine_pose(pc, pair_idx, pred_pairs_scaled, T_est, R_est, y_only, iters=100
             opt.step()
     T_out = opt_trans.detach().numpy()
     R_out = (SO3Matrix.apply(delta_rot.detach()) @ R0).numpy()
+    torch.set_num_threads(n_threads)
     return T_out, R_out
 
 
