@@ -476,6 +476,9 @@ def main():
         oracle.set_num_threads(os.cpu_count() or 1)
         sds = cpu_state_dicts(cats)
         crng = np.random.default_rng(0)
+        if args.opt:      # torch.optim / autograd initialise lazily on first use (seconds): not part of the path's cost
+            from oracle.refine_torch import refine_pose
+            refine_pose(raw[0]["pc"][:64], np.zeros((8, 2), np.int64), np.zeros((8, 2, 3), np.float32), np.zeros(3), np.eye(3), False, iters=2)
         timings = {}
         t0 = time.perf_counter()
         n_done = 0
