@@ -219,7 +219,7 @@ def reference_arm(args, emit=print):
                       "config": workload_config(),
                       "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0}))
+                      "refinement": bool(getattr(args, "opt", False)), "gpu_launches": 0}))
 
 
 def workload_config():
