@@ -22,18 +22,24 @@ class SO3Matrix(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q):
         qn = q / torch.linalg.vector_norm(q)
-        x, y, z, w = qn.unbind()
-        zero = torch.zeros((), dtype=q.dtype)
-        U = torch.stack([torch.stack([zero, -z, y]), torch.stack([z, zero, -x]), torch.stack([-y, x, zero])])   # U e_i = u x e_i
-        UV = U + U                                               # uv = 2 (u x v), one column per basis vector v = e_i
-        Q = torch.eye(3, dtype=q.dtype) + w * UV + U @ UV        # v + w uv + u x uv
+        u, w = qn[:3], qn[3]
+        eye = torch.eye(3, dtype=q.dtype)
+        cols = []
+        for i in range(3):                                       # Eigen's order of operations, column by column
+            v = eye[i]
+            uv = torch.linalg.cross(u, v)
+            uv = uv + uv
+            cols.append(v + w * uv + torch.linalg.cross(u, uv))
+        Q = torch.stack(cols, dim=1)
         ctx.save_for_backward(Q)
         return Q
 
     @staticmethod
     def backward(ctx, G):
         (Q,) = ctx.saved_tensors
-        g = torch.linalg.cross(Q.T, G.T).sum(0)                  # sum_i Q[:, i] x G[:, i]
+        g = torch.zeros(3, dtype=G.dtype)
+        for i in range(3):
+            g = g + torch.linalg.cross(Q[:, i], G[:, i])
         return torch.cat([g, torch.zeros(1, dtype=G.dtype)])
 
 
