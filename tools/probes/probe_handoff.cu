@@ -116,7 +116,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1) * 32, 1) probe(int n_mma, int 
             uint32_t r[32];
             tmem_ld32(lane_addr, r);
             const long long t_loaded = clock64();
-            sink += r[it & 31];
+            sink += r[0] ^ r[31];               // constant indices: a runtime index would push r[] to local memory
             if (warp == 0 && lane == 0) {       // the issuer's two stamps of this round were written (and fenced) before its commit
                 acc[kFenceArrive] += t_arrive - t0;
                 acc[kIssuerAwake] += s_stamp[1] - t_arrive;        // last of the 4 arrivals is within a few cycles of warp 0's
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128, 1) probe_single(int iters, long long *out
     for (int it = 0; it < iters; ++it) {
         uint32_t r[32];
         tmem_ld32(lane_addr + (it & 3) * 32, r);
-        sink += r[it & 31];
+        sink += r[0] ^ r[31];                   // constant indices (see above)
     }
     long long t2 = clock64();
     if (tid == 0) {
