@@ -31,7 +31,7 @@ class GridGeom(C.Structure):
 
 class Center(C.Structure):
     _fields_ = [("world", C.c_double * 3), ("cell", C.c_int64 * 3), ("linear", C.c_int64), ("votes", C.c_uint32),
-                ("pad", C.c_uint32)]
+                ("status", C.c_uint32), ("cells", C.c_int64)]
 
 
 class BackvoteSummary(C.Structure):
@@ -42,7 +42,7 @@ class BackvoteSummary(C.Structure):
 class Pose(C.Structure):
     _fields_ = [("R", C.c_double * 9), ("t", C.c_double * 3), ("scale", C.c_float * 3), ("scale_norm", C.c_float),
                 ("loss", C.c_double), ("bin_up", C.c_int32), ("bin_right", C.c_int32), ("count_up", C.c_float),
-                ("count_right", C.c_float), ("kept", C.c_int64), ("status", C.c_uint32), ("pad", C.c_uint32)]
+                ("count_right", C.c_float), ("kept", C.c_int64), ("status", C.c_uint32), ("grid_cells", C.c_uint32)]
 
 
 class VoteParams(C.Structure):
@@ -83,8 +83,8 @@ SIGNATURES = {
     "cppf_vote_center": (I, [P, I64, P, I, I64, P, I64, P, P, I, P, P, I64, I64, I, P, P]),
     "cppf_vote_center_ex": (I, [P, I64, P, I, I64, P, I64, P, P, I, P, P, I64, I, P, I, I, I64, P]),
     "cppf_vote_center_smem_cells": (I64, []),
-    "cppf_grid_argmax": (I, [P, P, D, P, P]),
-    "cppf_grid_to_i64": (I, [P, P, P, P]),
+    "cppf_grid_argmax": (I, [P, I64, P, D, P, P, P]),
+    "cppf_grid_to_i64": (I, [P, I64, P, P, P]),
     "cppf_sample_tuples": (I, [I64, I64, I, U64, P, P]),
     "cppf_sample_bins": (I, [P, I64, I, P, U64, P, P]),
     "cppf_decode_targets": (I, [P, P, I, I64, P, I64, I, _DP, P, P, P, P, P]),

@@ -1,25 +1,39 @@
 // Library-level entry points: error strings, version, cached device properties.
 #include "common.cuh"
 
+#include <atomic>
 #include <mutex>
 
 namespace cppf {
 
+// Properties of the CURRENT device, cached per device ordinal (one process may drive several GPUs, and several host
+// threads may get here at once).
 const DeviceInfo &device_info() {
-    static DeviceInfo info{148, 126ll << 20, 10, 0, 227 * 1024};
-    static std::once_flag once;
-    std::call_once(once, [] {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return;
+    constexpr int kMaxDevices = 64;
+    static DeviceInfo info[kMaxDevices];
+    static std::once_flag once[kMaxDevices];
+    static const DeviceInfo fallback{148, 126ll << 20, 10, 0, 227 * 1024};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return fallback;
+    std::call_once(once[dev], [dev] {
+        info[dev] = fallback;
         cudaDeviceProp p;
         if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return;
-        info.sm_count = p.multiProcessorCount;
-        info.l2_bytes = p.l2CacheSize;
-        info.cc_major = p.major;
-        info.cc_minor = p.minor;
-        info.max_smem_optin = static_cast<int>(p.sharedMemPerBlockOptin);
+        info[dev].sm_count = p.multiProcessorCount;
+        info[dev].l2_bytes = p.l2CacheSize;
+        info[dev].cc_major = p.major;
+        info[dev].cc_minor = p.minor;
+        info[dev].max_smem_optin = static_cast<int>(p.sharedMemPerBlockOptin);
     });
-    return info;
+    return info[dev];
+}
+
+// True exactly once per (call site tag, device): the caller then performs its per-device one-time setup.
+bool first_use_on_device(std::atomic<uint64_t> *seen) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const uint64_t bit = 1ull << dev;
+    return (seen->fetch_or(bit) & bit) == 0;
 }
 
 }  // namespace cppf

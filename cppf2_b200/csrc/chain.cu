@@ -30,7 +30,7 @@ CPPF_API int cppf_vote_chain(const float *pc, int64_t n, const void *idx, int id
     CPPF_CUDA_TRY(cudaMemsetAsync(b->status, 0, sizeof(uint32_t), s));
     CPPF_TRY(cppf_vote_center(pc, n, idx, idx_is_i64, idx_stride, b->targets_tr, T, p->cos_tab, p->sin_tab, p->num_rots, b->geom,
                               b->grid, b->grid_capacity, cells_hint, 0, b->status, stream));
-    CPPF_TRY(cppf_grid_argmax(b->grid, b->geom, p->res, b->center, stream));
+    CPPF_TRY(cppf_grid_argmax(b->grid, b->grid_capacity, b->geom, p->res, b->status, b->center, stream));
     // back-vote filter (eval.py:251-275)
     CPPF_TRY(cppf_backvote_filter(pc, n, idx, idx_is_i64, idx_stride, b->targets_tr, T, p->axes, b->center, p->rank_lo, p->gamma,
                                   b->errs, b->keep, b->kept_list, b->imp, b->summary, b->ws_backvote, b->ws_backvote_bytes, stream));

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -30,8 +31,23 @@ struct DeviceInfo {
     int max_smem_optin;
 };
 
-// Cached per process; B200: 148 SMs, ~126 MB L2, 227 KB opt-in shared memory.
+// Properties of the current device, cached per device ordinal; B200: 148 SMs, ~126 MB L2, 227 KB opt-in shared memory.
 const DeviceInfo &device_info();
+
+// Per-device one-time setup (cudaFuncSetAttribute opt-ins): thread-safe, and repeated for every device a process drives.
+// A failed attempt is not remembered as done.
+bool first_use_on_device(std::atomic<uint64_t> *seen);
+#define CPPF_TRY_ONCE_PER_DEVICE(expr)                         \
+    do {                                                       \
+        static std::atomic<uint64_t> _seen{0};                 \
+        if (cppf::first_use_on_device(&_seen)) {               \
+            cudaError_t _e1 = (expr);                          \
+            if (_e1 != cudaSuccess) {                          \
+                _seen.store(0);                                \
+                CPPF_CUDA_TRY(_e1);                            \
+            }                                                  \
+        }                                                      \
+    } while (0)
 
 // Row of the tuple-index matrix, int64 (reference dtype) or int32, arbitrary row stride.
 struct IdxView {

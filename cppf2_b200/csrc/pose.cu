@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(256) pose_directions_kernel(const double *__re
     pose->count_up = s_bestv[0];
     pose->count_right = s_bestv[1];
     pose->kept = summary ? summary->kept : 0;
-    pose->status = (summary && summary->kept == 0) ? CPPF_STATUS_EMPTY : 0u;
+    // every stage's flags end up in the one record the caller reads: the grid stage's (extent guard eval.py:200, overflow of
+    // the grid buffer, empty cloud) arrive through the centre
+    pose->status = ((summary && summary->kept == 0) ? CPPF_STATUS_EMPTY : 0u) | center->status;
+    pose->grid_cells = center->cells > 0xffffffffll ? 0xffffffffu : static_cast<uint32_t>(center->cells);
 }
 
 // ---- lower median of the kept scale predictions, one CTA per axis ------------------------------------

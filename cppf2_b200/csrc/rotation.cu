@@ -187,9 +187,11 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
     const int lane = lane_id();
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    // tuple-sharded runs give every rank the kept items congruent to `part` modulo `n_parts`
-    for (int64_t it = warp * n_parts + part; it < n_items; it += n_warps * n_parts) {
+    // a partitioned run (cppf_rotation_hist_part) votes the TUPLES congruent to `part` modulo `n_parts`: the partition is by
+    // tuple id, not by position in kept_list, whose order (atomic compaction) differs from run to run and rank to rank
+    for (int64_t it = warp; it < n_items; it += n_warps) {
         const int64_t m = kept_list ? static_cast<int64_t>(kept_list[it]) : it;
+        if (n_parts > 1 && m % n_parts != part) continue;      // warp-uniform
         const int64_t ia = idx.at(m, 0), ib = idx.at(m, 1);
         const float a[3] = {pc[3 * ia], pc[3 * ia + 1], pc[3 * ia + 2]};
         const float b[3] = {pc[3 * ib], pc[3 * ib + 1], pc[3 * ib + 2]};
@@ -338,7 +340,7 @@ CPPF_API int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_i
     IdxView iv{idx, idx_stride, idx_is_i64};
     // one warp per kept tuple at a time; the kept count is only known on the device, so size for M/8 (ratio 0.1).  With the
     // lookup table a tuple is cheap and the per-CTA bin flush dominates: two CTAs per SM, several tuples per warp.
-    const int64_t guess = (kept_list ? (M / 8 + 1) : M) / n_parts + 1;
+    const int64_t guess = (kept_list ? (M / 8 + 1) : M) + 1;
     const uint2 *cells = lut ? reinterpret_cast<const uint2 *>(static_cast<const unsigned char *>(lut) + 16) : nullptr;
     rotation_hist_kernel<<<grid_for(guess * 32, 256, lut ? 2 : 4), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         pc, iv, theta, theta_stride, cols, kept_list, kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere, S,

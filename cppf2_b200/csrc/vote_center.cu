@@ -269,12 +269,16 @@ struct CenterScratch {  // lives in the tail of cppf_center (pad fields), zeroed
     unsigned int ticket;
 };
 
-__global__ void __launch_bounds__(256) grid_argmax_kernel(const uint32_t *__restrict__ grid,
+__global__ void __launch_bounds__(256) grid_argmax_kernel(const uint32_t *__restrict__ grid, int64_t capacity,
                                                           const cppf_grid_geom *__restrict__ geom, double res,
+                                                          const uint32_t *__restrict__ status,
                                                           cppf_center *__restrict__ out,
                                                           unsigned long long *__restrict__ key,
                                                           unsigned int *__restrict__ ticket) {
-    const int64_t cells = geom->cells;
+    // a grid larger than the caller's buffer was never voted (grid_zero_kernel raised CPPF_STATUS_GRID_OVERFLOW): nothing to
+    // scan, and nothing may be read past the buffer
+    const bool overflow = geom->cells > capacity;
+    const int64_t cells = overflow ? 0 : geom->cells;
     unsigned long long best = 0ull;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < cells; i += stride) {
@@ -312,13 +316,17 @@ __global__ void __launch_bounds__(256) grid_argmax_kernel(const uint32_t *__rest
         }
         out->linear = lin;
         out->votes = static_cast<uint32_t>(k >> 32);
+        out->cells = geom->cells;
+        // the stage's status travels with the centre into the pose record (pose_directions_kernel): geometry flags
+        // (extent guard, empty cloud), overflow of the caller's grid buffer, and whatever the vote kernels raised
+        out->status = geom->flags | (overflow ? CPPF_STATUS_GRID_OVERFLOW : 0u) | (status ? *status : 0u);
     }
 }
 
-__global__ void __launch_bounds__(256) grid_widen_kernel(const uint32_t *__restrict__ grid,
+__global__ void __launch_bounds__(256) grid_widen_kernel(const uint32_t *__restrict__ grid, int64_t capacity,
                                                          const cppf_grid_geom *__restrict__ geom,
                                                          int64_t *__restrict__ out) {
-    const int64_t cells = geom->cells;
+    const int64_t cells = geom->cells < capacity ? geom->cells : capacity;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < cells; i += stride)
         out[i] = static_cast<int64_t>(grid[i]);
@@ -361,12 +369,9 @@ CPPF_API int cppf_vote_center_ex(const float *pc, int64_t n, const void *idx, in
         const size_t smem = static_cast<size_t>(smem_cells) * sizeof(uint32_t);
         const int smem_max = dev.max_smem_optin - 2 * kMaxRotsSmem * static_cast<int>(sizeof(float)) - 1024;
         if (smem_cells <= 0 || smem > static_cast<size_t>(smem_max)) return CPPF_ERR_UNSUPPORTED;
-        static bool attr_set = false;
-        if (!attr_set) {
-            CPPF_CUDA_TRY(cudaFuncSetAttribute(vote_center_kernel<8, 1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               smem_max));
-            attr_set = true;
-        }
+        // the opt-in is per device and must be taken once, whichever host thread gets here first
+        CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(vote_center_kernel<8, 1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      smem_max));
         int64_t warps = (T + 7) / 8;
         int64_t blocks = (warps + 31) / 32;
         const int64_t per_sm = smem > 100 * 1024 ? 1 : 2;
@@ -416,25 +421,26 @@ CPPF_API int cppf_vote_center(const float *pc, int64_t n, const void *idx, int i
                                grid_capacity, accumulate, status, smem_ok ? 1 : 0, kMaxReplicas, cells_hint, stream);
 }
 
-CPPF_API int cppf_grid_argmax(const uint32_t *grid, const cppf_grid_geom *geom, double res, cppf_center *center,
-                              void *stream) {
-    if (!grid || !geom || !center) return CPPF_ERR_INVALID_ARGUMENT;
+CPPF_API int cppf_grid_argmax(const uint32_t *grid, int64_t grid_capacity, const cppf_grid_geom *geom, double res,
+                              const uint32_t *status, cppf_center *center, void *stream) {
+    if (!grid || !geom || !center || grid_capacity <= 0) return CPPF_ERR_INVALID_ARGUMENT;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CPPF_CUDA_TRY(cudaMemsetAsync(center, 0, sizeof(cppf_center), s));
-    // scratch words live in the struct's tail (`votes` is written last by the finalising thread; `pad`
+    // scratch words live in the struct's tail (`votes` is written last by the finalising thread; `status`
     // doubles as the ticket, `linear` as the packed key until then)
     unsigned long long *key = reinterpret_cast<unsigned long long *>(&center->linear);
-    unsigned int *ticket = reinterpret_cast<unsigned int *>(&center->pad);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(&center->status);
     int blocks = device_info().sm_count * 4;
-    grid_argmax_kernel<<<blocks, 256, 0, s>>>(grid, geom, res, center, key, ticket);
+    grid_argmax_kernel<<<blocks, 256, 0, s>>>(grid, grid_capacity, geom, res, status, center, key, ticket);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }
 
-CPPF_API int cppf_grid_to_i64(const uint32_t *grid, const cppf_grid_geom *geom, int64_t *grid_i64, void *stream) {
-    if (!grid || !geom || !grid_i64) return CPPF_ERR_INVALID_ARGUMENT;
+CPPF_API int cppf_grid_to_i64(const uint32_t *grid, int64_t grid_capacity, const cppf_grid_geom *geom, int64_t *grid_i64,
+                              void *stream) {
+    if (!grid || !geom || !grid_i64 || grid_capacity <= 0) return CPPF_ERR_INVALID_ARGUMENT;
     int blocks = device_info().sm_count * 4;
-    grid_widen_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(grid, geom, grid_i64);
+    grid_widen_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(grid, grid_capacity, geom, grid_i64);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }

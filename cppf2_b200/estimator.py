@@ -107,8 +107,7 @@ class PoseEstimator:
         self.launches = 0
         self._lane_bufs: Dict[int, dict] = {}
         self.one_call = os.environ.get("CPPF_ONE_CALL", "1") != "0"      # cppf_instance_pose per instance (bf16 heads, no injected draws)
-        self._pose_ring: Dict[int, List[torch.Tensor]] = {}
-        self._pose_next = 0
+        self._pose_ring: Dict[int, List[torch.Tensor]] = {}      # free pinned pose buffers by row count
         self.host_threads = max(1, int(os.environ.get("CPPF_HOST_THREADS", "1")))
         self._pool = None
         self.copy_stream = torch.cuda.Stream(device=self.device)   # uploads of instance i+1 overlap the kernels of instance i
@@ -209,16 +208,17 @@ class PoseEstimator:
         self.launches = launches
         return plan
 
-    def _lane_buffers(self, lane: int, n: int, heads: dict) -> dict:
-        """Per-lane device buffers of the one-call instance path, grown on demand and reused across frames."""
+    def _lane_buffers(self, lane: int, n: int, T: int, heads: dict) -> dict:
+        """Per-lane device buffers of the one-call instance path, grown on demand (points AND tuples: an Instance may bring
+        its own point_idxs with more rows than num_pairs) and reused across frames."""
         lib = _lib.load()
         buf = self._lane_bufs.get(lane)
-        T = self.num_pairs
         need_heads = max([int(lib.cppf_heads_workspace_bytes(m._handle, T, n, 1)) for m in heads.values()] + [256])
-        if buf is None or buf["cap"] < n or buf["ws_heads"].numel() < need_heads:
+        if buf is None or buf["cap"] < n or buf["cap_T"] < T or buf["ws_heads"].numel() < need_heads:
             cap = max(n, 4096 if buf is None else buf["cap"])
+            T = max(T, self.num_pairs if buf is None else buf["cap_T"])
             d = self.device
-            buf = dict(cap=cap, shot_desc=torch.empty((cap, 352), dtype=torch.float32, device=d),
+            buf = dict(cap=cap, cap_T=T, shot_desc=torch.empty((cap, 352), dtype=torch.float32, device=d),
                        normals=torch.empty((cap, 3), dtype=torch.float32, device=d),
                        ws_shot=torch.empty(int(lib.cppf_shot_workspace_bytes(cap)), dtype=torch.uint8, device=d),
                        bins=torch.empty((2, T, 6), dtype=torch.uint8, device=d),
@@ -239,7 +239,7 @@ class PoseEstimator:
             if m is not None:
                 m._ensure(self.device)
         live = {k: m for k, m in (("dino", dino), ("shot", sh)) if m is not None}
-        buf = self._lane_buffers(lane, n, live)
+        buf = self._lane_buffers(lane, n, T, live)
         voter._ensure(T, n, cells_hint)
         params, vbufs = voter._vote_params(vc, T), voter._vote_buffers(vc.num_sphere)
         ip, i64, istr = idx_args(idx)
@@ -249,7 +249,8 @@ class PoseEstimator:
                              heads_dino=None if dino is None else dino._handle, heads_shot=None if sh is None else sh._handle,
                              normal_r=float(vc.res * 10), shot_r=float(vc.res * 10), shot_desc=buf["shot_desc"].data_ptr(),
                              normals=buf["normals"].data_ptr(), ws_shot=buf["ws_shot"].data_ptr(), ws_shot_bytes=buf["ws_shot"].numel(),
-                             bins=buf["bins"].data_ptr(), scales=buf["scales"].data_ptr(), ws_heads=buf["ws_heads"].data_ptr(),
+                             bins=buf["bins"].data_ptr(), scales=buf["scales"].data_ptr(),       # [2][T,*] packed at this T: fits, cap_T >= T
+                             ws_heads=buf["ws_heads"].data_ptr(),
                              ws_heads_bytes=buf["ws_heads"].numel(), seed_dino=self.seed + 7919 * (2 * i),
                              seed_shot=self.seed + 7919 * (2 * i + 1), cells_hint=int(cells_hint or 0),
                              pose_dino=slot_d.data_ptr(), pose_shot=slot_s.data_ptr())
@@ -334,10 +335,30 @@ class PoseEstimator:
             if not results:
                 out.append(None)
                 continue
+            if any(r.status & _lib.CPPF_STATUS_GRID_GUARD for r in results.values()):
+                out.append(None)                                                   # extent / res > 1000: skipped, eval.py:200
+                continue
             best = min(results, key=lambda br: (results[br].loss, br != "dino"))   # DINO first on ties, as the '<' does
             r = results[best]
             out.append(InstancePose(RT=r.RT, scale=r.unit_scale, branch=best, loss=r.loss, results=results))
         return out
+
+    @staticmethod
+    def overflowed(poses: Sequence[Optional["InstancePose"]]) -> Dict[int, int]:
+        """{instance index: grid cells needed} of the poses whose centre grid did not fit the voter's buffer."""
+        need = {}
+        for i, p in enumerate(poses):
+            if p is not None:
+                cells = [r.grid_cells for r in p.results.values() if r.status & _lib.CPPF_STATUS_GRID_OVERFLOW]
+                if cells:
+                    need[i] = max(cells)
+        return need
+
+    def _grow_grids(self, cells: int):
+        for v in self.voters:
+            if v.grid.numel() < cells:
+                v.grid = torch.empty(int(cells), dtype=torch.int32, device=self.device)
+                v._buffers = None
 
     def estimate_frame(self, depth, masks, categories: Sequence[str], intrinsics, desc_fn=None, depth_div: float = 1000.0,
                        frame_seed: int = 0) -> List[Optional[InstancePose]]:
@@ -365,12 +386,7 @@ class PoseEstimator:
         out: List[Optional[InstancePose]] = [None] * len(masks)
         if not instances:
             return out
-        pose_buf = torch.zeros((len(instances) * 2, self.pose_bytes), dtype=torch.uint8, device=dev)
-        plan = self.enqueue(instances, pose_buf)
-        poses = self.collect(plan, pose_buf.cpu().numpy())
-        for i, p in zip(where, poses):
-            if p is not None and any(r.status & _lib.CPPF_STATUS_GRID_GUARD for r in p.results.values()):
-                p = None                                                   # eval.py:200
+        for i, p in zip(where, self.estimate(instances)):      # extent guard and grid regrowth: collect() / PendingFrame
             out[i] = p
         return out
 
@@ -385,16 +401,19 @@ class PoseEstimator:
         pose_host.copy_(pose_buf, non_blocking=True)     # the frame's only device->host copy
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(self.device))
-        return PendingFrame(self, plan, pose_host, done, (pose_buf, staged))
+        return PendingFrame(self, plan, pose_host, done, (pose_buf, staged), instances, draws)
 
     def _pinned_pose(self, rows: int) -> torch.Tensor:
-        """Pinned read-back buffers are recycled round-robin (4 frames may be in flight) instead of allocated per frame."""
-        ring = self._pose_ring.setdefault(rows, [])
-        if len(ring) < 4:
-            ring.append(torch.empty((rows, self.pose_bytes), dtype=torch.uint8, pin_memory=True))
-            return ring[-1]
-        self._pose_next = (self._pose_next + 1) % 4
-        return ring[self._pose_next]
+        """Pinned read-back buffer of one frame.  Buffers are pooled per row count and handed back by PendingFrame.result()
+        once the record has been parsed, so a buffer is never reused while its frame is still unread, however many frames
+        the caller keeps in flight."""
+        pool = self._pose_ring.setdefault(rows, [])
+        return pool.pop() if pool else torch.empty((rows, self.pose_bytes), dtype=torch.uint8, pin_memory=True)
+
+    def _release_pose(self, buf: torch.Tensor):
+        pool = self._pose_ring.setdefault(buf.shape[0], [])
+        if len(pool) < 8:
+            pool.append(buf)
 
     def estimate(self, instances: Sequence[Instance], draws: Optional[List[dict]] = None) -> List[Optional[InstancePose]]:
         """Host arrays in, poses out: H2D of clouds / descriptors / tuple indices, the kernel chain, one D2H."""
@@ -404,13 +423,36 @@ class PoseEstimator:
 class PendingFrame:
     """A frame queued by PoseEstimator.submit(): result() blocks until its pose records have reached the host."""
 
-    def __init__(self, est: PoseEstimator, plan, pose_host: torch.Tensor, done: torch.cuda.Event, keepalive):
+    def __init__(self, est: PoseEstimator, plan, pose_host: torch.Tensor, done: torch.cuda.Event, keepalive, instances=None,
+                 draws=None):
         self._est, self._plan, self._pose_host, self._done, self._keep = est, plan, pose_host, done, keepalive
+        self._instances, self._draws, self._out = instances, draws, None
 
     def result(self) -> List[Optional[InstancePose]]:
+        if self._out is not None:
+            return self._out
+        est = self._est
         self._done.synchronize()
         self._keep = None
-        return self._est.collect(self._plan, self._pose_host.numpy())
+        out = est.collect(self._plan, self._pose_host.numpy())
+        est._release_pose(self._pose_host)
+        self._pose_host = None
+        # A centre grid larger than the voter's buffer (a mask bleeding into the background: 0.3 x 0.3 x 1.0 m at 2 mm is
+        # 11 M cells) is flagged by the kernels, never voted: grow the buffers to the size the record names and repeat those
+        # instances.  The reference handles any grid up to the 1000-voxel extent guard (train_dino.py:173, eval.py:200).
+        need = est.overflowed(out)
+        if need and self._instances is not None:
+            est._grow_grids(max(need.values()))
+            which = sorted(need)
+            sub_draws = None if self._draws is None else [self._draws[i] for i in which]
+            redo = est.submit([self._instances[i] for i in which], sub_draws).result()
+            for i, p in zip(which, redo):
+                if p is not None and est.overflowed([p]):
+                    raise _lib.CppfError(f"centre grid of instance {i} ({need[i]} cells) still exceeds the voter's buffer")
+                out[i] = p
+        self._instances = self._draws = None
+        self._out = out
+        return out
 
 
 def build_models(categories: Sequence[str], branches=("dino", "shot"), precision: int = 0, ckpt_root: Optional[str] = None,

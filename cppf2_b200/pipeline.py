@@ -60,6 +60,7 @@ class PoseResult:
     count_up: float
     count_right: float
     status: int
+    grid_cells: int = 0          # gx*gy*gz of the centre grid (what to grow the grid buffer to on CPPF_STATUS_GRID_OVERFLOW)
 
     @property
     def RT(self) -> np.ndarray:
@@ -233,7 +234,7 @@ class PoseVoter:
         return PoseResult(R=np.array(list(p.R)).reshape(3, 3), t=np.array(list(p.t)), scale=np.array(list(p.scale), np.float32),
                           scale_norm=float(p.scale_norm), loss=float(p.loss), kept=int(p.kept), bin_up=int(p.bin_up),
                           bin_right=int(p.bin_right), count_up=float(p.count_up), count_right=float(p.count_right),
-                          status=int(p.status) | int(extra_status))
+                          status=int(p.status) | int(extra_status), grid_cells=int(p.grid_cells))
 
     def result(self) -> PoseResult:
         """Synchronises the current stream and reads the pose record (152 bytes D2H)."""
@@ -242,7 +243,7 @@ class PoseVoter:
         return PoseResult(R=np.array(list(p.R)).reshape(3, 3), t=np.array(list(p.t)), scale=np.array(list(p.scale), np.float32),
                           scale_norm=float(p.scale_norm), loss=float(p.loss), kept=int(p.kept), bin_up=int(p.bin_up),
                           bin_right=int(p.bin_right), count_up=float(p.count_up), count_right=float(p.count_right),
-                          status=status)
+                          status=status, grid_cells=int(p.grid_cells))
 
     # -- debugging / parity access -------------------------------------------------------------------
     def intermediates(self) -> dict:

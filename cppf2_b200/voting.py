@@ -182,9 +182,10 @@ def vote_center(pc, preds_tr, res, point_idxs, num_rots=36, vis=None):
                                int(num_rots), geom_t.data_ptr(), grid.data_ptr(), grid.numel(), cells, 0, status.data_ptr(), s),
           "cppf_vote_center")
     center_t = struct_tensor(Center, dev)
-    check(lib.cppf_grid_argmax(grid.data_ptr(), geom_t.data_ptr(), float(res), center_t.data_ptr(), s), "cppf_grid_argmax")
+    check(lib.cppf_grid_argmax(grid.data_ptr(), grid.numel(), geom_t.data_ptr(), float(res), status.data_ptr(), center_t.data_ptr(), s),
+          "cppf_grid_argmax")
     grid64 = torch.empty(max(cells, 1), dtype=torch.int64, device=dev)
-    check(lib.cppf_grid_to_i64(grid.data_ptr(), geom_t.data_ptr(), grid64.data_ptr(), s), "cppf_grid_to_i64")
+    check(lib.cppf_grid_to_i64(grid.data_ptr(), grid.numel(), geom_t.data_ptr(), grid64.data_ptr(), s), "cppf_grid_to_i64")
     grid_obj = grid64[:cells].cpu().numpy().reshape(shape)
     center = read_struct(center_t, Center)
     cand_world = np.array(list(center.world), dtype=np.float64)

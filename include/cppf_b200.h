@@ -56,7 +56,8 @@ typedef struct cppf_center {
     int64_t cell[3];
     int64_t linear;         /* flat C-order index of the arg-max cell */
     uint32_t votes;         /* count in that cell */
-    uint32_t pad;
+    uint32_t status;        /* CPPF_STATUS_* of the grid stage: geometry flags, overflow of the caller's grid buffer */
+    int64_t cells;          /* gx*gy*gz of the grid that was (or would have been) voted */
 } cppf_center;
 
 /* Per-instance pose record written by cppf_pose_finalize (eval.py:284-313, :358-363). */
@@ -69,8 +70,9 @@ typedef struct cppf_pose {
     int32_t bin_up, bin_right;
     float count_up, count_right;
     int64_t kept;           /* pairs surviving the back-vote filter */
-    uint32_t status;        /* CPPF_STATUS_* */
-    uint32_t pad;
+    uint32_t status;        /* CPPF_STATUS_* of every stage: extent guard (eval.py:200), grid overflow, no kept pair, refined */
+    uint32_t grid_cells;    /* gx*gy*gz, saturated at 2^32-1: with CPPF_STATUS_GRID_OVERFLOW the grid buffer the caller has to
+                               provide before repeating the call */
 } cppf_pose;
 
 const char *cppf_error_string(int code);
@@ -103,11 +105,17 @@ int cppf_vote_center_ex(const float *pc, int64_t n, const void *idx, int idx_is_
                         uint32_t *status, int mode, int replicas_max, int64_t smem_cells, void *stream);
 int64_t cppf_vote_center_smem_cells(void);
 
-/* First-maximum arg-max of the grid and its world position -> *center (device).  train_dino.py:212-213. */
-int cppf_grid_argmax(const uint32_t *grid, const cppf_grid_geom *geom, double res, cppf_center *center, void *stream);
+/* First-maximum arg-max of the grid and its world position -> *center (device).  train_dino.py:212-213.
+ * grid_capacity = words behind `grid`: a geometry with more cells than that was never voted (CPPF_STATUS_GRID_OVERFLOW)
+ * and is not scanned.  `status` (device, may be NULL) = the word the vote call wrote; it is folded, with the geometry
+ * flags, into center->status so that the pose record carries it. */
+int cppf_grid_argmax(const uint32_t *grid, int64_t grid_capacity, const cppf_grid_geom *geom, double res,
+                     const uint32_t *status, cppf_center *center, void *stream);
 
-/* uint32 -> int64 widening of the grid (the reference returns an int64 numpy grid, train_dino.py:204-206). */
-int cppf_grid_to_i64(const uint32_t *grid, const cppf_grid_geom *geom, int64_t *grid_i64, void *stream);
+/* uint32 -> int64 widening of the first min(geom->cells, grid_capacity) cells (the reference returns an int64 numpy
+ * grid, train_dino.py:204-206). */
+int cppf_grid_to_i64(const uint32_t *grid, int64_t grid_capacity, const cppf_grid_geom *geom, int64_t *grid_i64,
+                     void *stream);
 
 /* ---- decode + vote targets ----------------------------------------------------------------------
  * replaces eval.py:225-235 (softmax, multinomial, pair scale) and generate_target_pairs,
@@ -201,8 +209,9 @@ int cppf_rotation_hist(const float *pc, const void *idx, int idx_is_i64, int64_t
  * cppf_sphere_lut_build returns CPPF_ERR_UNSUPPORTED when some cell needs more than 4 entries (use a finer G). */
 int64_t cppf_sphere_lut_bytes(int G);
 int cppf_sphere_lut_build(const float *sphere_host, int S, float cos_thr, int G, void *lut_host);
-/* Same over the kept items congruent to `part` modulo `n_parts`: in a tuple-sharded run every
- * rank votes its share of the global kept list and the [n_theta,S] bins are summed by one all-reduce. */
+/* Same over the kept TUPLES whose id is congruent to `part` modulo `n_parts` (a partition by tuple id: the order of
+ * kept_list is that of an atomic compaction and differs between runs and ranks); the [n_theta,S] bins of the parts
+ * add up to the whole histogram. */
 int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride, const float *theta,
                             int64_t theta_stride, const int *theta_cols_host, int n_theta, const int32_t *kept_list,
                             const int64_t *kept_count, int64_t M, const int32_t *imp,

@@ -45,6 +45,80 @@ def test_estimator_matches_cpu_pipeline_with_injected_draws():
         assert g.RT.shape == (4, 4) and abs(np.linalg.norm(g.scale) - 1) < 1e-6
 
 
+def test_bf16_heads_with_oracle_draws_match_cpu_pipeline():
+    """The BENCHMARKED configuration (precision=1: bf16 tcgen05 heads) against oracle.pipeline_cpu: the CPU side draws the
+    bins from its float32 logits, the same draws are injected on the GPU, so everything downstream of the draws must be
+    identical -- translation, kept count, sphere bins -- and R within the north-star 0.1 deg.  The bf16 heads then only
+    supply the scale: the median of bf16-computed scale predictions, within 2e-2 relative of the float32 median (measured
+    ~3e-3), and the loss, which divides by ||scale||, within the same bound."""
+    from cppf2_b200.estimator import Instance, PoseEstimator, build_models
+    from cppf2_b200.config import default_category_cfg
+    from oracle.pipeline_cpu import instance_pose_cpu
+    T = 20000
+    cats = ["mug", "can"]
+    models, cfgs = build_models(cats, precision=1, seed=91)
+    assert all(m.precision == 1 for c in cats for m in models[c].values())
+    sds = {c: {br: {k: v.numpy() for k, v in m.state_dict().items()} for br, m in models[c].items()} for c in cats}
+    est = PoseEstimator(models, cfgs, num_pairs=T, max_points=4000)
+    instances, cpu_out, draws = [], [], []
+    for i, cat in enumerate(cats):
+        pc = synth.half_cylinder_cloud(2400 + 200 * i, seed=130 + i, jitter=0.0005)
+        desc = synth.unit_descriptors(pc.shape[0], 1024, seed=140 + i)
+        idx = synth.sample_tuples(pc.shape[0], T, 5, seed=150 + i)
+        out = instance_pose_cpu(pc, idx, default_category_cfg(cat), sds[cat], desc=desc, seed=i,
+                                sym_y_only=cat in ("can", "bottle", "bowl"))
+        cpu_out.append(out)
+        draws.append({br: out[br]["bins"] for br in ("dino", "shot")})
+        instances.append(Instance(pc=pc, category=cat, desc=desc, point_idxs=idx))
+    got = est.estimate(instances, draws=draws)
+    for g, c in zip(got, cpu_out):
+        for br in ("dino", "shot"):
+            r, o = g.results[br], c[br]
+            assert r.status == 0
+            assert np.array_equal(r.t, o["T_est"]), (br, r.t, o["T_est"])
+            assert r.kept == int(o["pairs_mask"].sum())
+            assert r.bin_up == o["bin_up"] and r.bin_right == o["bin_right"]
+            ang = np.degrees(np.arccos(np.clip((np.trace(r.R.T @ o["R_est"]) - 1) / 2, -1, 1)))
+            assert ang < 0.1
+            np.testing.assert_allclose(r.scale, o["pred_scale"], rtol=2e-2)
+            np.testing.assert_allclose(r.loss, o["loss"], rtol=2e-2)
+        cpu_losses = sorted(c[br]["loss"] for br in ("dino", "shot"))
+        if cpu_losses[1] > 1.05 * cpu_losses[0]:          # a clear winner on the CPU side must win here too
+            assert g.branch == c["best"]
+
+
+def test_extent_guard_and_grid_regrowth_through_the_public_call():
+    """eval.py:200: an instance whose extent exceeds 1000 voxels is skipped (None); a cloud whose grid is larger than the
+    voter's buffer (but within the guard) is flagged by the kernels, the buffers are regrown and the instance is repeated --
+    through estimate() with device clouds, i.e. without any host-side hint of the grid size."""
+    from cppf2_b200 import _lib
+    from cppf2_b200.estimator import Instance, PoseEstimator, build_models
+    from cppf2_b200.pipeline import PoseVoter
+    models, cfgs = build_models(["mug"], branches=("shot",), precision=1)
+    est = PoseEstimator(models, cfgs, num_pairs=8192, max_points=4000, seed=2, n_streams=2)
+    for v in est.voters:                                   # small buffers so that an ordinary cloud overflows them
+        v.grid = torch.empty(1 << 12, dtype=torch.int32, device="cuda")
+        v._buffers = None
+    ok = synth.half_cylinder_cloud(1500, seed=5)
+    far = ok.copy()
+    far[0, 2] += 2.5                                       # one stray background point: extent 2.5 m / 2 mm > 1000 voxels
+    cells = PoseVoter.grid_cells_on_host(ok, 0.002)
+    assert cells > (1 << 12)
+    out = est.estimate([Instance(pc=torch.from_numpy(ok).cuda(), category="mug"),
+                        Instance(pc=torch.from_numpy(far).cuda(), category="mug")])
+    assert out[1] is None                                  # guard
+    assert out[0] is not None and np.isfinite(out[0].RT).all()
+    r = out[0].results["shot"]
+    assert r.status & _lib.CPPF_STATUS_GRID_OVERFLOW == 0 and r.grid_cells == cells and r.kept > 0
+    assert all(v.grid.numel() >= cells for v in est.voters)
+    # the regrown estimator gives the same answer as one that had room from the start (same seeds -> same draws)
+    est2 = PoseEstimator(models, cfgs, num_pairs=8192, max_points=4000, seed=2, n_streams=2)
+    idx = synth.sample_tuples(ok.shape[0], 8192, 5, seed=9)
+    a = est.estimate([Instance(pc=ok, category="mug", point_idxs=idx)])[0].results["shot"]
+    b = est2.estimate([Instance(pc=ok, category="mug", point_idxs=idx)])[0].results["shot"]
+    assert np.array_equal(a.t, b.t) and a.kept == b.kept and a.bin_up == b.bin_up
+
+
 def test_estimator_device_rng_and_shot_only():
     """Default path: uniforms from the in-kernel counter-based generator; SHOT-only ensemble (visual_branch only)."""
     from cppf2_b200.estimator import Instance, PoseEstimator, build_models
