@@ -45,6 +45,10 @@ class Pose(C.Structure):
                 ("count_right", C.c_float), ("kept", C.c_int64), ("status", C.c_uint32), ("grid_cells", C.c_uint32)]
 
 
+class ScaleSelect(C.Structure):
+    _fields_ = [("prefix", C.c_uint32 * 3), ("pad", C.c_uint32), ("k", C.c_uint64 * 3)]
+
+
 class VoteParams(C.Structure):
     _fields_ = [("res", C.c_double), ("num_rots", C.c_int), ("num_bins", C.c_int), ("sphere_bins", C.c_int),
                 ("cos_thr", C.c_float), ("band", C.c_int), ("lut_g", C.c_int), ("up_loc", C.c_int), ("right_loc", C.c_int),
@@ -110,6 +114,8 @@ SIGNATURES = {
     "cppf_vote_chain": (I, [P, I64, P, I, I64, I64, P, P, P, I64, P, P, P, P]),
     "cppf_instance_pose": (I, [P, P, P, P]),
     "cppf_pose_workspace_bytes": (I64, [I64]),
+    "cppf_scale_median_hist": (I, [P, P, P, I64, I, P, P, P]),
+    "cppf_scale_median_pick": (I, [P, P, I, P, P, P]),
     "cppf_pose_finalize": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, I64, P]),
     "cppf_pose_finalize_refine": (I, [P, P, I, I64, P, I, P, P, P, P, P, I, P, I, I, I, P, I, F, I64, P, P, I64, P]),
     "cppf_shot_workspace_bytes": (I64, [I64]),

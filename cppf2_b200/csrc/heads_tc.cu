@@ -27,7 +27,7 @@
 
 #ifndef CPPF_TC_EXP
 #define CPPF_TC_EXP 0      // timing experiments only (tools/heads_profile.py): bit 0 no bias loads, 1 issuer sleeps when idle,
-#endif                     // 2 no Final stores, 3 no TMEM loads, 4 no feature spill
+#endif                     // 2 no Final stores, 3 no TMEM loads
 
 namespace cppf {
 namespace tc {
@@ -64,7 +64,7 @@ enum Action : int {
     kActCoordsB = 4,      // DINO chunk B: [coords 30 | pad 2] -> X[0:32)
     kActHiddenT = 5,      // H[h_col : +n) = relu(D + b)      (bf16 -> TMEM)
     kActHiddenS = 6,      // X[dst_col : +n) = relu(D + b)    (bf16 -> shared memory; first layers)
-    kActOut = 7,          // X[dst_col : +n) = D + b (+ X[res_col : +n))   (optionally spilled to the feature scratch)
+    kActOut = 7,          // X[dst_col : +n) = D + b (+ X[res_col : +n))
     kActFinal = 8,        // global output = D + b
     kActOutT = 9,         // Y[dst_col : +n) = D + b          (bf16 -> TMEM, no relu: a layer output that stays in tensor memory)
     kActGatherSum = 10,   // X[0:256) = sum over the tuple's points k of the per-point row block G[idx_k][256 k : 256 k + 256)
@@ -110,7 +110,6 @@ struct Phase {
     int d_col, n;         // accumulator chunk the epilogue reads
     int dst_col;          // X / H / global column the chunk is written to
     int residual, res_col;
-    int store_feat, reload_feat;
     int out_sel;          // Final: 0 = out0 (float32), 1 = out1 (float32), 2 = point features (bf16)
     int out_ld;
 };
@@ -132,7 +131,6 @@ struct Args {
     IdxView idx;
     int arity;
     const unsigned char *weights;       // slab stream of this program
-    __nv_bfloat16 *feat_scratch;        // [rows][256] bf16
     float *out0, *out1;
     __nv_bfloat16 *out_bf16;
     unsigned char *bins;                // non-null: out0 is not written; the logits epilogue draws one bin per (row, coord)
@@ -380,7 +378,6 @@ __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, u
         for (int j = 0; j < NB / 8; ++j) {
             const uint4 packed = pack8(v + 8 * j);
             *reinterpret_cast<uint4 *>(act_chunk(X, row, (ph.dst_col + c) / 8 + j)) = packed;
-            if (!(CPPF_TC_EXP & 16) && ph.store_feat && live) __stcg(reinterpret_cast<uint4 *>(a.feat_scratch + grow * 256 + ph.dst_col + c + 8 * j), packed);
         }
     } else if (NB == 32 && ph.out_sel == 0 && a.bins != nullptr) {
         // kActFinal of the logits with the decode fused in (eval.py:225-229): the 32 columns of this batch are the 32
@@ -740,15 +737,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                             epilogue_batch<8>(ph, a, X, t_slot_lane, row, grow, live, c0);
                         }
                         if (ph.action == kActHiddenT || ph.action == kActOutT) tmem_st_wait();
-                        if (ph.action == kActFinal && ph.reload_feat) {
-                            // X <- the spilled tuple feature (written by this slot's own threads in an earlier phase)
-                            for (int it = sw; it < 16 * 8; it += kSlotWarps) {
-                                const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
-                                const bool ok = row_base + r < a.rows;
-                                cp_async16(x_u32 + c8 * kPlane + r * 16, a.feat_scratch + (ok ? row_base + r : row_base) * 256 + c8 * 8, ok ? 16u : 0u);
-                            }
-                            cp_async_wait_all();
-                        }
                         break;
                     }
                     default: break;
@@ -889,7 +877,6 @@ struct Builder {
     struct OutSpec {
         int action = kActOut;       // kActOut or kActFinal
         int out_col = 0;
-        int store_feat = 0;
         int out_sel = 0, out_ld = 0;
     };
     // in_tmem: the layer input is a bf16 activation in tensor memory (column in_col of the H/Y space, i.e. Y = 128..255),
@@ -928,7 +915,6 @@ struct Builder {
             out.dst_col = os.out_col + ch.first;
             out.residual = !L.has_fc0;
             out.res_col = in_col + ch.first;
-            out.store_feat = os.store_feat;
             out.out_sel = os.out_sel;
             out.out_ld = os.out_ld;
             cur = &out;
@@ -1147,7 +1133,8 @@ static size_t tc_align(size_t x) { return (x + 255) / 256 * 256; }
 extern "C" int64_t cppf_heads_tc_workspace_bytes(const void *state, int64_t T, int64_t n) {
     const State *st = static_cast<const State *>(state);
     if (!st) return 0;
-    return static_cast<int64_t>(tc_align(2 * static_cast<size_t>(st->point_cols) * n) + tc_align(2 * 256 * static_cast<size_t>(T)) + 256);
+    (void)T;      // nothing per tuple lives in the workspace: the tuple feature stays in shared / tensor memory (no spill)
+    return static_cast<int64_t>(tc_align(2 * static_cast<size_t>(st->point_cols) * n) + 256);
 }
 
 extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t n, const void *idx, int idx_is_i64,
@@ -1160,7 +1147,6 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
     if (ws_bytes < cppf_heads_tc_workspace_bytes(state, T, n)) return CPPF_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     __nv_bfloat16 *point_feat = static_cast<__nv_bfloat16 *>(ws);
-    __nv_bfloat16 *feat_scratch = reinterpret_cast<__nv_bfloat16 *>(static_cast<unsigned char *>(ws) + tc_align(2 * static_cast<size_t>(st->point_cols) * n));
     const int sms = device_info().sm_count;
     // Grid: the fewest CTAs that still finish in the minimal number of rounds (a round = one tile in each of a CTA's
     // two slots).  T = 50 000 is 391 tiles = 1.32 rounds of 148 x 2 slots: 148 CTAs would run a full round and then a
@@ -1200,7 +1186,6 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.idx = IdxView{idx, idx_stride, idx_is_i64};
         a.arity = st->model.arity;
         a.weights = st->d_tuple_w;
-        a.feat_scratch = feat_scratch;
         a.out0 = logits;
         a.out1 = scale;
         a.bins = bins;

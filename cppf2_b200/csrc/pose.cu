@@ -140,6 +140,90 @@ __global__ void __launch_bounds__(1024) scale_median_kernel(const float *__restr
     }
 }
 
+// ---- the same lower median when the kept tuples are spread over several GPUs (tuple-sharded runs) -----------
+// torch.median(pred_scales[mask], 0) (eval.py:309) is an exact order statistic per axis, so it is found the way the
+// back-vote percentile is: a most-significant-digit radix selection over the order-preserving uint32 image of the float32
+// values -- here two passes of 16 bits, so that a run costs two histogram exchanges.  Each rank histograms its own kept
+// tuples (cppf_scale_median_hist), the ranks all-reduce the 3 x 65536 counters (integer sum: exact, order-independent), and
+// every rank picks the same digit (cppf_scale_median_pick).  With one rank this is the single-GPU median, bit for bit.
+constexpr int kScaleDigits = 1 << 16;
+
+__global__ void __launch_bounds__(256) scale_hist_kernel(const float *__restrict__ pred_scales,
+                                                         const int32_t *__restrict__ kept_list,
+                                                         const int64_t *__restrict__ kept_count, int pass,
+                                                         const cppf_scale_select *__restrict__ st, uint32_t *__restrict__ hist) {
+    const int64_t M = *kept_count;
+    const uint32_t p0 = st->prefix[0], p1 = st->prefix[1], p2 = st->prefix[2];
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int lane = lane_id();
+    // whole warps iterate together: scale predictions share their leading digits, so lanes with equal digits elect one
+    // leader that adds the group's size (one L2 atomic per distinct digit per warp instead of 32 on the same address)
+    for (int64_t base = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x - lane; base < M; base += stride) {
+        const int64_t i = base + lane;
+        const bool live = i < M;
+        const float *row = pred_scales + 3 * static_cast<int64_t>(live ? kept_list[i] : 0);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const uint32_t key = live ? float_to_key(row[a]) : 0u;
+            const bool on = live && (pass == 0 || (key >> 16) == ((a == 0 ? p0 : (a == 1 ? p1 : p2)) >> 16));
+            const uint32_t digit = pass == 0 ? (key >> 16) : (key & 0xffffu);
+            const uint32_t active = __ballot_sync(0xffffffffu, on);
+            if (on) {
+                const uint32_t peers = __match_any_sync(active, digit);
+                if (lane == __ffs(peers) - 1) atomicAdd(&hist[a * kScaleDigits + digit], static_cast<uint32_t>(__popc(peers)));
+            }
+        }
+    }
+}
+
+// one CTA per axis: the first digit whose cumulative count exceeds the remaining rank
+__global__ void __launch_bounds__(1024) scale_pick_kernel(const uint32_t *__restrict__ hist, const int32_t *__restrict__ kept_total,
+                                                          int pass, cppf_scale_select *__restrict__ st, float *__restrict__ scale_out) {
+    __shared__ unsigned long long s_part[1024];
+    __shared__ int s_owner;
+    const int axis = blockIdx.x, tid = threadIdx.x;
+    const int64_t M = *kept_total;
+    if (M <= 0) {
+        if (tid == 0) {
+            st->prefix[axis] = 0u;
+            st->k[axis] = 0ull;
+            if (pass == 1 && scale_out) scale_out[axis] = 0.0f;
+        }
+        return;
+    }
+    const unsigned long long k = pass == 0 ? static_cast<unsigned long long>((M - 1) / 2) : st->k[axis];   // lower middle element
+    const uint32_t *h = hist + axis * kScaleDigits + tid * 64;
+    unsigned long long mine = 0;
+    for (int j = 0; j < 64; ++j) mine += h[j];
+    s_part[tid] = mine;
+    if (tid == 0) s_owner = 1023;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {            // inclusive scan of the 1024 partial sums
+        const unsigned long long add = tid >= o ? s_part[tid - o] : 0ull;
+        __syncthreads();
+        s_part[tid] += add;
+        __syncthreads();
+    }
+    if (s_part[tid] > k) atomicMin(&s_owner, tid);
+    __syncthreads();
+    if (tid != s_owner) return;
+    unsigned long long cum = tid > 0 ? s_part[tid - 1] : 0ull;
+    int d = 0;
+    for (; d < 63; ++d) {
+        if (cum + h[d] > k) break;
+        cum += h[d];
+    }
+    const uint32_t digit = static_cast<uint32_t>(tid * 64 + d);
+    if (pass == 0) {
+        st->prefix[axis] = digit << 16;
+        st->k[axis] = k - cum;
+    } else {
+        const uint32_t key = (st->prefix[axis] & 0xffff0000u) | digit;
+        st->prefix[axis] = key;
+        if (scale_out) scale_out[axis] = key_to_float(key);
+    }
+}
+
 // ---- online pose refinement (eval.py:319-355, `opt=True`) ---------------------------------------------
 // 100 Adam steps (torch.optim.Adam defaults, lr 1e-2) on the translation (3) and a raw quaternion (x, y, z, w), started at
 // (T_est, identity), minimising mean |((pc - t) @ (Q(q) R_est))[pair] - pred_pairs_scaled| over the kept pairs (the y
@@ -401,6 +485,25 @@ using namespace cppf;
 CPPF_API int64_t cppf_pose_workspace_bytes(int64_t T) {
     // PoseScratch + the refinement's compacted rows (2 per kept pair, at most T pairs)
     return 256 + static_cast<int64_t>(sizeof(RefineRow)) * 2 * (T > 0 ? T : 0);
+}
+
+CPPF_API int cppf_scale_median_hist(const float *pred_scales, const int32_t *kept_list, const int64_t *kept_count, int64_t kept_max,
+                                    int pass, const cppf_scale_select *state, uint32_t *hist, void *stream) {
+    if (!pred_scales || !kept_list || !kept_count || !state || !hist || pass < 0 || pass > 1 || kept_max < 0) return CPPF_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CPPF_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 3 * kScaleDigits, s));
+    if (kept_max == 0) return CPPF_OK;
+    scale_hist_kernel<<<grid_for(kept_max, 256, 4), 256, 0, s>>>(pred_scales, kept_list, kept_count, pass, state, hist);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+CPPF_API int cppf_scale_median_pick(const uint32_t *hist, const int32_t *kept_total, int pass, cppf_scale_select *state,
+                                    float *scale_out, void *stream) {
+    if (!hist || !kept_total || !state || pass < 0 || pass > 1 || (pass == 1 && !scale_out)) return CPPF_ERR_INVALID_ARGUMENT;
+    scale_pick_kernel<<<3, 1024, 0, static_cast<cudaStream_t>(stream)>>>(hist, kept_total, pass, state, scale_out);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
 }
 
 CPPF_API int cppf_pose_finalize(const float *pc, const void *idx, int idx_is_i64, int64_t idx_stride,

@@ -1,39 +1,49 @@
 """Tuple-sharded pose voting: the T tuples of one (instance, branch) split over the ranks of a process group.
 
-SURVEY.md section 8e / BASELINE config 4.  Every tuple's votes are independent given the cloud (the grid
-corners are functions of `pc` only, train_dino.py:172-173), so rank r takes the contiguous block
-[r*T/g, (r+1)*T/g) of `point_idxs_all` with the whole cloud resident, and the path has three exchange steps:
+SURVEY.md section 8e / BASELINE config 4 / the north star's multi-GPU design.  Every tuple's votes are independent given
+the cloud (the grid corners are functions of `pc` only, train_dino.py:172-173), so rank r takes the contiguous block
+[r*T/g, (r+1)*T/g) of `point_idxs_all` (eval.py:207) with the whole cloud resident and runs heads, decode, targets, centre
+votes, back-vote errors, mask, rotation votes and the loss terms on ITS block only.  Nothing per-tuple is replicated and
+nothing but the 4-byte back-vote error crosses the links per tuple.  The exchange steps, one per stage (eval.py:219-313):
 
-  1. centre grid      all_reduce(SUM) of the uint32 counters   -- integer sum, order independent => bit-exact
-  2. back-vote data   all_gather of the per-tuple float32 errors, tuple indices, draws, scales and rotation
-                      targets (54 B/tuple); the exact percentile selection, kept list and importance counts
-                      (eval.py:257-275) are then computed replicated and are identical on every rank
-  3. sphere bins      all_reduce(SUM) of the 2 x 720 float64 rotation bins, every rank having voted the kept
-                      pairs congruent to its rank modulo g
+  E1  centre grid        all_reduce(SUM) of the uint32 counters [cells]          integer sum => bit-exact for any g
+  E2  back-vote errors   all_gather of the float32 errors (4 B/tuple)            every rank then selects the same exact
+                                                                                 order statistic (np.percentile, eval.py:257)
+  E3  importance + scale all_reduce(SUM) of one int32 buffer: per-point occurrence counts [n] (eval.py:260-266), the kept
+                         count, and pass 0 of the scale median's radix histogram [3 x 65536] (eval.py:309)
+  E4  sphere bins        grouped all_reduce(SUM): the 2 x 720 float64 rotation bins (eval.py:277-293; every per-CTA
+                         contribution is a multiple of 2^-32, so the float64 sum is exact below 2^21 per bin and does not
+                         depend on g) and pass 1 of the scale histogram
+  E5  branch loss        all_reduce(SUM) of the sum of the clipped L1 terms (eval.py:358-363; the count follows from the
+                         kept count E3 delivered)
 
-The expensive stages (heads, multinomial decode, targets, the T*R centre votes, the M*R rotation candidates)
-are sharded; selection and pose assembly are cheap and replicated, so all ranks end with the same pose.
+Only E1 is on the critical path of the tuples/s metric; E3-E5 move < 1 MB and are latency-bound.  No host read-back
+happens between a launch and a collective: the grid all-reduce is sized by the cell count the caller knows from the host
+copy of the cloud (`cells_hint`), the rest by T and n.
 
-The orchestration is written against a small stage interface so that the collectives can be exercised on CPU
-(`gloo`, world_size 2) with a test-side implementation of the stages; `CudaStages` is the product
-implementation (libcppf_b200 kernels on the current stream, NCCL collectives) and is the only one this
-package contains -- there is no CPU fallback.
+The orchestration is written against a small stage interface so that the collectives can be exercised on CPU (`gloo`,
+world_size 2) with a test-side implementation of the stages; `CudaStages` is the product implementation (libcppf_b200
+kernels on the current stream, NCCL collectives) and is the only one this package contains -- there is no CPU fallback.
+The online refinement (eval.py:319-355) is not sharded: `opt=True` raises.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import List, Optional
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _lib
-from ._lib import BackvoteSummary, Center, GridGeom, Pose, check
+from ._lib import BackvoteSummary, Center, GridGeom, Pose, ScaleSelect, check
 from .hostmath import percentile_plan
 from .pipeline import PoseResult, PoseVoter, VoteConfig
 from .voting import (angle_tables, cos_threshold, device_index_tensor, idx_args, read_struct, sphere_lut, sphere_points,
-                     stream_ptr, to_device)
+                     stream_ptr, struct_tensor, to_device)
+
+SCALE_DIGITS = 1 << 16
+_SPLITMIX_GAMMA = 0x9E3779B97F4A7C15
 
 
 def shard_bounds(n_items: int, world: int, rank: int):
@@ -44,173 +54,311 @@ def shard_bounds(n_items: int, world: int, rank: int):
     return rank * per, (rank + 1) * per
 
 
+def shard_seed(seed: int, first_tuple: int) -> int:
+    """Seed under which a rank whose block starts at global tuple `first_tuple` draws exactly the uniforms the unsharded
+    call draws for those tuples: the generator is counter-based, u(seed, ctr) = mix(seed + G*(ctr+1)) with ctr = 6*tuple +
+    coordinate (csrc/common.cuh uniform_from_counter), so shifting the counter by 6*first_tuple is a shift of the seed."""
+    return (int(seed) + _SPLITMIX_GAMMA * 6 * int(first_tuple)) & 0xFFFFFFFFFFFFFFFF
+
+
 class ShardedVote:
-    """Backend-agnostic orchestration of one sharded (instance, branch) vote."""
+    """Backend-agnostic orchestration of one sharded (instance, branch) vote: stages + five exchange steps."""
 
     def __init__(self, stages, group=None):
         self.stages = stages
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_collectives = 0           # collectives issued by the last vote()
+        self.timing = None               # optional list: (label, start event, end event) per exchange step (CUDA only)
 
     # -- collectives -----------------------------------------------------------------------------------
-    def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
-        if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-        return t
+    def _exchange(self, label: str, fn):
+        if self.world == 1:
+            return
+        if self.timing is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            self.timing.append((label, a, b))
+        else:
+            fn()
+        self.n_collectives += 1
 
-    def _all_gather(self, local: torch.Tensor) -> torch.Tensor:
+    def _all_reduce(self, label: str, tensors: List[torch.Tensor]):
+        """One exchange step: SUM all-reduce of every tensor of the list, as ONE grouped NCCL launch when the backend
+        coalesces (ncclGroupStart/End under torch.distributed's coalescing manager), else back to back (gloo)."""
+        tensors = [t for t in tensors if t is not None and t.numel() > 0]
+        if not tensors:
+            return
+
+        def run():
+            grouped = len(tensors) > 1 and tensors[0].is_cuda and hasattr(dist, "_coalescing_manager")
+            if grouped:
+                with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=False):
+                    for t in tensors:
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                for t in tensors:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        self._exchange(label, run)
+
+    def _all_gather(self, label: str, local: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.world == 1:
             return local
-        out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        if out is None:
+            out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        self._exchange(label, lambda: dist.all_gather_into_tensor(out, local.contiguous(), group=self.group))
         return out
 
     # -- the chain -------------------------------------------------------------------------------------
-    def vote(self, pc, idx_local, cfg: VoteConfig, pred_scales_local, bins_local, scale_override=None):
-        """`idx_local` [T/g,5], `bins_local` u8 [T/g,6], `pred_scales_local` f32 [T/g,3]: this rank's block.
-        Returns whatever `stages.finalize` returns (a PoseResult for CudaStages)."""
+    def vote(self, pc, idx_local, cfg: VoteConfig, pred_scales_local, bins_local, scale_override=None, cells_hint=None):
+        """`idx_local` [T/g,>=2], `bins_local` u8 [T/g,6], `pred_scales_local` f32 [T/g,3]: this rank's block of one
+        (instance, branch).  `scale_override` (3 floats) reproduces the SHOT branch's reuse of the DINO scale (eval.py:308).
+        Returns whatever `stages.finish` returns (a PoseResult for CudaStages); identical on every rank."""
+        if getattr(cfg, "opt", False):
+            raise NotImplementedError("the online refinement (eval.py:319-355) is not tuple-sharded; run it with opt=False")
         st = self.stages
-        tr_l, rot_l = st.decode_targets(pc, idx_local, bins_local, cfg)
-        grid = st.vote_center(pc, idx_local, tr_l, cfg)                 # this rank's partial grid
-        self._all_reduce(grid)                                          # exchange step 1
-        st.argmax(grid, cfg)
-        errs_l = st.errors(pc, idx_local, tr_l)
-        errs = self._all_gather(errs_l)                                 # exchange step 2
-        idx = self._all_gather(idx_local)
-        bins = self._all_gather(bins_local)
-        scales = self._all_gather(pred_scales_local)
-        rot = self._all_gather(rot_l)
-        st.select_and_mask(errs, idx, pc, cfg)
-        counts = st.rotation_counts(pc, idx, rot, cfg, self.rank, self.world)
-        self._all_reduce(counts)                                        # exchange step 3
-        return st.finalize(pc, idx, bins, scales, counts, cfg, scale_override)
+        self.n_collectives = 0
+        st.begin(pc, idx_local, bins_local, pred_scales_local, cfg, self.world, cells_hint)   # decode, targets, bounds
+        grid = st.vote_center()                                          # this rank's partial grid, flat [cells]
+        self._all_reduce("E1 grid", [grid])
+        st.argmax()                                                      # replicated: same grid everywhere
+        errs_all = self._all_gather("E2 errors", st.errors(), st.errs_all_buffer(self.world))
+        st.select(errs_all)                                              # replicated exact order statistic -> threshold
+        own_scale = scale_override is None
+        x_imp = st.mask_local(own_scale)                                 # int32 [n | kept | scale hist pass 0]
+        self._all_reduce("E3 imp+scale0", [x_imp])
+        st.after_mask(own_scale)                                         # imp_max; scale pick 0, local hist pass 1
+        x_counts = st.rotation_counts()                                  # [counts f64 [2,S]] + [scale hist pass 1]
+        self._all_reduce("E4 bins+scale1", x_counts)
+        x_loss = st.pose_local(scale_override)                           # directions, scale, sum of the local loss terms
+        self._all_reduce("E5 loss", [x_loss])
+        return st.finish()
 
 
 class CudaStages:
-    """The stages as libcppf_b200 kernels; buffers sized for the GLOBAL tuple count, reused across votes."""
+    """The stages as libcppf_b200 kernels on the current stream.  Per-tuple buffers are sized for this rank's BLOCK; only
+    the gathered back-vote errors (4 B/tuple) are sized for the global tuple count."""
 
-    def __init__(self, max_tuples_global: int = 50000, max_points: int = 50000, grid_capacity: int = 1 << 23, device=None):
-        self.v = PoseVoter(max_tuples_global, max_points, grid_capacity, device)
+    def __init__(self, max_tuples_local: int = 50000, max_points: int = 50000, grid_capacity: int = 1 << 23, device=None):
+        self.v = PoseVoter(max_tuples_local, max_points, grid_capacity, device)
         self.lib = self.v.lib
         self.device = self.v.device
+        d = self.device
+        self.sel = struct_tensor(ScaleSelect, d)
+        self.scale_dev = torch.zeros(3, dtype=torch.float32, device=d)
+        self.loss_x = torch.zeros(1, dtype=torch.float64, device=d)
+        self.xbuf = None                 # int32 exchange buffer [n | kept | 3*65536]
+        self.hist1 = torch.zeros(3 * SCALE_DIGITS, dtype=torch.int32, device=d)
+        self.errs_all = None
+        self._cells = {}                 # grid cells per cloud (data_ptr, n, res) when no hint was given: one read-back, cached
 
-    def decode_targets(self, pc, idx_local, bins_local, cfg):
-        v, lib = self.v, self.lib
-        self.pc = to_device(pc, torch.float32, self.device)
-        idx = device_index_tensor(idx_local, self.device)
-        bins = to_device(bins_local, torch.uint8, self.device)
-        T = idx.shape[0]
-        v._ensure(T, self.pc.shape[0], None)
-        ip, i64, istr = idx_args(idx)
-        self.axes = _lib.axes_array(cfg.up, cfg.front, cfg.right)     # call-site order, eval.py:237-240
-        tr, rot = v.targets_tr[:T], v.targets_rot[:T]
-        check(lib.cppf_decode_targets(self.pc.data_ptr(), ip, i64, istr, bins.data_ptr(), T, cfg.num_bins, self.axes,
-                                      tr.data_ptr(), rot.data_ptr(), None, None, stream_ptr()), "cppf_decode_targets")
-        return tr, rot
-
-    def vote_center(self, pc, idx_local, tr_l, cfg):
+    # -- stage 1: decode + targets + centre votes ------------------------------------------------------
+    def begin(self, pc, idx_local, bins_local, scales_local, cfg, world, cells_hint=None):
         v, lib, s = self.v, self.lib, stream_ptr()
-        idx = device_index_tensor(idx_local, self.device)
-        ip, i64, istr = idx_args(idx)
-        N = self.pc.shape[0]
-        ct, st = angle_tables(cfg.num_rots, self.device)
+        if isinstance(pc, np.ndarray) and cells_hint is None:
+            cells_hint = PoseVoter.grid_cells_on_host(pc, cfg.res)
+        self.pc = to_device(pc, torch.float32, self.device)
+        self.idx = device_index_tensor(idx_local, self.device)
+        self.bins = to_device(bins_local, torch.uint8, self.device)
+        self.scales = None if scales_local is None else to_device(scales_local, torch.float32, self.device)
+        self.cfg, self.world = cfg, world
+        T, N = self.idx.shape[0], self.pc.shape[0]
+        self.T_local, self.N = T, N
+        v._ensure(T, N, cells_hint)
+        v._T = T
+        ip, i64, istr = idx_args(self.idx)
+        self.ip = (ip, i64, istr)
+        self.axes = _lib.axes_array(cfg.up, cfg.front, cfg.right)     # call-site order, eval.py:237-240
+        check(lib.cppf_decode_targets(self.pc.data_ptr(), ip, i64, istr, self.bins.data_ptr(), T, cfg.num_bins, self.axes,
+                                      v.targets_tr.data_ptr(), v.targets_rot.data_ptr(), None, None, s), "cppf_decode_targets")
         check(lib.cppf_cloud_bounds(self.pc.data_ptr(), N, float(cfg.res), v.geom.data_ptr(), s), "cppf_cloud_bounds")
-        geom = read_struct(v.geom, GridGeom)          # the all-reduce needs the cell count on the host
-        self.cells = int(geom.cells)
-        if self.cells > v.grid.numel():
-            v.grid = torch.empty(self.cells, dtype=torch.int32, device=self.device)
+        if cells_hint is None:           # device cloud without a hint: one read-back per distinct cloud, then cached
+            key = (self.pc.data_ptr(), N, float(cfg.res))
+            if key not in self._cells:
+                self._cells[key] = int(read_struct(v.geom, GridGeom).cells)
+            cells_hint = self._cells[key]
+            v._ensure(T, N, cells_hint)
+        self.cells = int(cells_hint)
+        need = N + 1 + 3 * SCALE_DIGITS
+        if self.xbuf is None or self.xbuf.numel() < need:
+            self.xbuf = torch.zeros(need, dtype=torch.int32, device=self.device)
+
+    def vote_center(self):
+        v, lib, s = self.v, self.lib, stream_ptr()
+        cfg = self.cfg
+        ip, i64, istr = self.ip
+        ct, st = angle_tables(cfg.num_rots, self.device)
         v.status.zero_()
-        check(lib.cppf_vote_center(self.pc.data_ptr(), N, ip, i64, istr, tr_l.data_ptr(), idx.shape[0], ct.data_ptr(),
+        check(lib.cppf_vote_center(self.pc.data_ptr(), self.N, ip, i64, istr, v.targets_tr.data_ptr(), self.T_local, ct.data_ptr(),
                                    st.data_ptr(), int(cfg.num_rots), v.geom.data_ptr(), v.grid.data_ptr(), v.grid.numel(),
                                    self.cells, 0, v.status.data_ptr(), s), "cppf_vote_center")
         return v.grid[:self.cells]
 
-    def argmax(self, grid, cfg):
+    def argmax(self):
         v = self.v
-        check(self.lib.cppf_grid_argmax(grid.data_ptr(), v.geom.data_ptr(), float(cfg.res), v.center.data_ptr(), stream_ptr()),
-              "cppf_grid_argmax")
+        check(self.lib.cppf_grid_argmax(v.grid.data_ptr(), v.grid.numel(), v.geom.data_ptr(), float(self.cfg.res),
+                                        v.status.data_ptr(), v.center.data_ptr(), stream_ptr()), "cppf_grid_argmax")
 
-    def errors(self, pc, idx_local, tr_l):
+    # -- stage 2: back-vote filter -----------------------------------------------------------------------
+    def errors(self):
         v = self.v
-        idx = device_index_tensor(idx_local, self.device)
-        ip, i64, istr = idx_args(idx)
-        T = idx.shape[0]
-        errs = v.errs[:T]
-        check(self.lib.cppf_backvote_errors(self.pc.data_ptr(), ip, i64, istr, tr_l.data_ptr(), T, v.center.data_ptr(),
-                                            errs.data_ptr(), stream_ptr()), "cppf_backvote_errors")
-        return errs
+        ip, i64, istr = self.ip
+        check(self.lib.cppf_backvote_errors(self.pc.data_ptr(), ip, i64, istr, v.targets_tr.data_ptr(), self.T_local,
+                                            v.center.data_ptr(), v.errs.data_ptr(), stream_ptr()), "cppf_backvote_errors")
+        return v.errs[:self.T_local]
 
-    def select_and_mask(self, errs, idx, pc, cfg):
-        v, lib, s = self.v, self.lib, stream_ptr()
-        T, N = errs.shape[0], self.pc.shape[0]
-        v._ensure(T, N, None)
-        ip, i64, istr = idx_args(idx)
-        rank_lo, gamma = percentile_plan(T, cfg.backproj_ratio)
-        check(lib.cppf_backvote_select(errs.data_ptr(), T, rank_lo, float(gamma), v.summary.data_ptr(),
-                                       v.ws_backvote.data_ptr(), v.ws_backvote.numel(), s), "cppf_backvote_select")
-        check(lib.cppf_backvote_mask(errs.data_ptr(), ip, i64, istr, T, N, v.summary.data_ptr(), v.keep.data_ptr(),
-                                     v.kept_list.data_ptr(), v.imp.data_ptr(), 1, s), "cppf_backvote_mask")
-        check(lib.cppf_backvote_imp_max(v.imp.data_ptr(), N, v.summary.data_ptr(), s), "cppf_backvote_imp_max")
-        self._errs, self._T = errs, T
+    def errs_all_buffer(self, world):
+        T = self.T_local * world
+        if world > 1 and (self.errs_all is None or self.errs_all.numel() != T):
+            self.errs_all = torch.empty(T, dtype=torch.float32, device=self.device)
+        return self.errs_all
 
-    def rotation_counts(self, pc, idx, rot, cfg, part, n_parts):
+    def select(self, errs_all):
+        v, lib = self.v, self.lib
+        T = errs_all.shape[0]
+        rank_lo, gamma = percentile_plan(T, self.cfg.backproj_ratio)
+        check(lib.cppf_backvote_select(errs_all.data_ptr(), T, rank_lo, float(gamma), v.summary.data_ptr(),
+                                       v.ws_backvote.data_ptr(), v.ws_backvote.numel(), stream_ptr()), "cppf_backvote_select")
+        self._errs_all = errs_all
+
+    def _kept_ptr(self):
+        return self.v.summary.data_ptr() + BackvoteSummary.kept.offset
+
+    def mask_local(self, own_scale: bool):
+        """keep / kept_list / occurrence counts of this rank's block; returns the int32 exchange buffer."""
         v, lib, s = self.v, self.lib, stream_ptr()
+        N, T = self.N, self.T_local
+        ip, i64, istr = self.ip
+        x = self.xbuf[:N + 1 + (3 * SCALE_DIGITS if own_scale else 0)]
+        imp = x[:N]
+        # the kernel zeroes imp [n] and the kept counter (zero_outputs = 1)
+        check(lib.cppf_backvote_mask(v.errs.data_ptr(), ip, i64, istr, T, N, v.summary.data_ptr(), v.keep.data_ptr(),
+                                     v.kept_list.data_ptr(), imp.data_ptr(), 1, s), "cppf_backvote_mask")
+        off = BackvoteSummary.kept.offset
+        x[N:N + 1].copy_(v.summary[off:off + 4].view(torch.int32))          # local kept count (< 2^31), little endian low word
+        if own_scale:
+            self.sel.zero_()
+            check(lib.cppf_scale_median_hist(self.scales.data_ptr(), v.kept_list.data_ptr(), self._kept_ptr(), T, 0,
+                                             self.sel.data_ptr(), x[N + 1:].data_ptr(), s), "cppf_scale_median_hist")
+        self._x = x
+        return x
+
+    def after_mask(self, own_scale: bool):
+        v, lib, s = self.v, self.lib, stream_ptr()
+        N, x = self.N, self._x
+        check(lib.cppf_backvote_imp_max(x.data_ptr(), N, v.summary.data_ptr(), s), "cppf_backvote_imp_max")
+        self._hist1 = None
+        if own_scale:
+            check(lib.cppf_scale_median_pick(x[N + 1:].data_ptr(), x[N:].data_ptr(), 0, self.sel.data_ptr(), None, s),
+                  "cppf_scale_median_pick")
+            check(lib.cppf_scale_median_hist(self.scales.data_ptr(), v.kept_list.data_ptr(), self._kept_ptr(), self.T_local, 1,
+                                             self.sel.data_ptr(), self.hist1.data_ptr(), s), "cppf_scale_median_hist")
+            self._hist1 = self.hist1
+
+    # -- stage 3: rotation votes, pose, loss ---------------------------------------------------------------
+    def rotation_counts(self):
+        v, lib, s = self.v, self.lib, stream_ptr()
+        cfg = self.cfg
         S = cfg.num_sphere
         if v.counts.shape != (2, S):
             v.counts = torch.empty((2, S), dtype=torch.float64, device=self.device)
+            v._buffers = None
         v.counts.zero_()
-        ip, i64, istr = idx_args(idx)
+        ip, i64, istr = self.ip
         ct, st = angle_tables(cfg.num_rots, self.device)
         sphere = sphere_points(S, self.device)
         thr = cos_threshold(cfg.angle_tol)
         cols = (C.c_int * 2)(0, 2)
         lut, lut_g = sphere_lut(S, thr, self.device)
-        kept_count_ptr = v.summary.data_ptr() + BackvoteSummary.kept.offset
-        check(lib.cppf_rotation_hist_part(self.pc.data_ptr(), ip, i64, istr, rot.data_ptr(), 3, cols, 2,
-                                          v.kept_list.data_ptr(), kept_count_ptr, idx.shape[0], v.imp.data_ptr(),
-                                          v.summary.data_ptr(), float(cfg.imp_wt_margin), ct.data_ptr(), st.data_ptr(),
-                                          int(cfg.num_rots), sphere.data_ptr(), S, thr, lib.cppf_sphere_band(S, thr),
-                                          None if lut is None else lut.data_ptr(), lut_g, v.counts.data_ptr(), int(part), int(n_parts), s), "cppf_rotation_hist_part")
-        return v.counts
+        # this rank's kept tuples (its own kept_list) with the GLOBAL importance counts of the exchange buffer
+        check(lib.cppf_rotation_hist(self.pc.data_ptr(), ip, i64, istr, v.targets_rot.data_ptr(), 3, cols, 2,
+                                     v.kept_list.data_ptr(), self._kept_ptr(), self.T_local, self._x.data_ptr(),
+                                     v.summary.data_ptr(), float(cfg.imp_wt_margin), ct.data_ptr(), st.data_ptr(),
+                                     int(cfg.num_rots), sphere.data_ptr(), S, thr, lib.cppf_sphere_band(S, thr),
+                                     None if lut is None else lut.data_ptr(), lut_g, v.counts.data_ptr(), s), "cppf_rotation_hist")
+        return [v.counts, self._hist1]
 
-    def finalize(self, pc, idx, bins, scales, counts, cfg, scale_override=None) -> PoseResult:
+    def pose_local(self, scale_override=None):
         v, lib, s = self.v, self.lib, stream_ptr()
+        cfg = self.cfg
         S = cfg.num_sphere
-        ip, i64, istr = idx_args(idx)
-        so = None
-        if scale_override is not None:
+        N, x = self.N, self._x
+        if scale_override is None:
+            check(lib.cppf_scale_median_pick(self.hist1.data_ptr(), x[N:].data_ptr(), 1, self.sel.data_ptr(),
+                                             self.scale_dev.data_ptr(), s), "cppf_scale_median_pick")
+            so = self.scale_dev
+        else:
             so = to_device(np.asarray(scale_override, dtype=np.float32) if not isinstance(scale_override, torch.Tensor)
                            else scale_override, torch.float32, self.device)
+        self._so = so
+        ip, i64, istr = self.ip
         up_loc = int(np.where(np.asarray(cfg.up))[0][0])
         right_loc = int(np.where(np.asarray(cfg.right))[0][0])
         sphere = sphere_points(S, self.device)
-        check(lib.cppf_pose_finalize(self.pc.data_ptr(), ip, i64, istr, bins.data_ptr(), cfg.num_bins, scales.data_ptr(),
-                                     v.kept_list.data_ptr(), v.summary.data_ptr(), counts.data_ptr(), sphere.data_ptr(), S,
-                                     v.center.data_ptr(), up_loc, right_loc, int(cfg.loss_y_only),
-                                     None if so is None else so.data_ptr(), v.pose.data_ptr(), v.ws_pose.data_ptr(),
-                                     v.ws_pose.numel(), s), "cppf_pose_finalize")
-        v._T = idx.shape[0]
-        self._live = (idx, bins, scales, so)
-        return v.result()
+        check(lib.cppf_pose_finalize(self.pc.data_ptr(), ip, i64, istr, self.bins.data_ptr(), cfg.num_bins, None,
+                                     v.kept_list.data_ptr(), v.summary.data_ptr(), v.counts.data_ptr(), sphere.data_ptr(), S,
+                                     v.center.data_ptr(), up_loc, right_loc, int(cfg.loss_y_only), so.data_ptr(),
+                                     v.pose.data_ptr(), v.ws_pose.data_ptr(), v.ws_pose.numel(), s), "cppf_pose_finalize")
+        # this rank's loss terms: the kernel left their float64 sum in the head of its scratch (PoseScratch.loss_sum); the
+        # count of the mean is 2 * kept * (1 | 3) with the global kept count
+        self.loss_x.copy_(v.ws_pose[:8].view(torch.float64))
+        return self.loss_x
+
+    def finish(self) -> PoseResult:
+        """One read-back: the pose record, the global kept count and the all-reduced loss terms."""
+        v = self.v
+        N = self.N
+        tail = torch.cat([self.loss_x, self._x[N:N + 1].to(torch.float64)]).cpu().numpy()
+        r = v.result()
+        kept = int(tail[1])
+        r.kept = kept
+        cnt = 2.0 * kept * (1.0 if self.cfg.loss_y_only else 3.0)
+        r.loss = float(tail[0] / cnt) if cnt > 0 else float("inf")
+        if kept > 0:
+            r.status &= ~_lib.CPPF_STATUS_EMPTY
+        return r
 
     def intermediates(self) -> dict:
-        """Host copies of the replicated intermediates (grid after the all-reduce, kept set, bins)."""
+        """Host copies: the all-reduced grid and importance counts, this rank's block of the kept mask and errors, the
+        all-reduced sphere bins."""
         v = self.v
         geom = read_struct(v.geom, GridGeom)
         shape = tuple(int(g) for g in geom.grid_res)
         summ = read_struct(v.summary, BackvoteSummary)
         center = read_struct(v.center, Center)
-        T = self._T
+        T = self.T_local
         return dict(grid=v.grid[:int(geom.cells)].cpu().numpy().astype(np.int64).reshape(shape),
-                    T_est=np.array(list(center.world)), pairs_mask=v.keep[:T].cpu().numpy().astype(bool),
-                    back_errs=self._errs.cpu().numpy(), imp=v.imp.cpu().numpy(), imp_max=int(summ.imp_max),
-                    counts_up=v.counts[0].cpu().numpy(), counts_right=v.counts[1].cpu().numpy())
+                    T_est=np.array(list(center.world)), pairs_mask_local=v.keep[:T].cpu().numpy().astype(bool),
+                    back_errs_local=v.errs[:T].cpu().numpy(), thr=float(summ.threshold),
+                    imp=self._x[:self.N].cpu().numpy(), imp_max=int(summ.imp_max), kept=int(self._x[self.N].item()),
+                    counts_up=v.counts[0].cpu().numpy(), counts_right=v.counts[1].cpu().numpy(),
+                    scale=self._so.cpu().numpy())
 
 
 class ShardedPoseVoter(ShardedVote):
     """Product form: CUDA stages + the process group's collectives (NCCL on the GPU box)."""
 
-    def __init__(self, max_tuples_global: int = 50000, max_points: int = 50000, grid_capacity: int = 1 << 23, group=None,
+    def __init__(self, max_tuples_local: int = 50000, max_points: int = 50000, grid_capacity: int = 1 << 23, group=None,
                  device=None):
-        super().__init__(CudaStages(max_tuples_global, max_points, grid_capacity, device), group)
+        super().__init__(CudaStages(max_tuples_local, max_points, grid_capacity, device), group)
+
+    def gather_mask(self) -> np.ndarray:
+        """The global kept mask [T] on the host (parity checks only: the path itself never gathers it)."""
+        local = self.stages.v.keep[:self.stages.T_local]
+        return self._all_gather("mask (debug)", local).cpu().numpy().astype(bool)
+
+    def vote_with_heads(self, model, pc, idx_local, cfg: VoteConfig, first_tuple: int, seed: int = 0, desc=None, shot_feat=None,
+                        normal=None, scale_override=None, cells_hint=None):
+        """eval.py:219-313 for this rank's block of tuples, heads included: `model` (BeyondCPPFSHOT with shot_feat / normal,
+        or BeyondCPPFDINO with desc; precision 1) runs on idx_local with the decode fused in, drawing for its tuples the
+        uniforms the unsharded call would draw for them (shard_seed), then the sharded vote."""
+        s = shard_seed(seed, first_tuple)
+        if model.branch == "dino":
+            bins, scales = model.forward_sampled(pc, desc, idx_local, seed=s)
+        else:
+            bins, scales = model.forward_sampled(pc, idx_local, shot_feat, normal, seed=s)
+        self._live = (bins, scales)
+        return self.vote(pc, idx_local, cfg, scales, bins, scale_override=scale_override, cells_hint=cells_hint)

@@ -229,6 +229,22 @@ int cppf_pose_finalize(const float *pc, const void *idx, int idx_is_i64, int64_t
                        const float *scale_override /* 3 floats or NULL: eval.py:308 reuses the DINO scale */,
                        cppf_pose *pose, void *ws, int64_t ws_bytes, void *stream);
 
+/* The scale median when the kept tuples are spread over several GPUs (tuple-sharded runs): torch.median(pred_scales[mask], 0)
+ * (eval.py:309) as a two-pass, 16-bit-digit radix selection per axis.  Per pass every rank calls cppf_scale_median_hist on its
+ * own kept tuples (hist u32 [3][65536], zeroed by the call; kept_count = device count of kept_list entries, kept_max its
+ * host-side bound, sizing the launch), the ranks sum the histograms (integer all-reduce: exact), and every rank calls
+ * cppf_scale_median_pick with the global kept count (device int32).  Pass 1 writes the three medians to scale_out (device),
+ * which then goes to cppf_pose_finalize as scale_override.  With one rank the result equals cppf_pose_finalize's own median. */
+typedef struct cppf_scale_select {
+    uint32_t prefix[3];     /* key bits decided so far, per axis */
+    uint32_t pad;
+    uint64_t k[3];          /* rank still to resolve inside the prefix */
+} cppf_scale_select;
+int cppf_scale_median_hist(const float *pred_scales, const int32_t *kept_list, const int64_t *kept_count, int64_t kept_max,
+                           int pass, const cppf_scale_select *state, uint32_t *hist, void *stream);
+int cppf_scale_median_pick(const uint32_t *hist, const int32_t *kept_total, int pass, cppf_scale_select *state,
+                           float *scale_out, void *stream);
+
 /* Same with the reference's online refinement (eval.py:319-355, `opt=True`, its default) between the pose assembly and
  * the branch loss when refine_iters > 0: refine_iters Adam steps (reference: 100, lr 1e-2) on (t, quaternion) minimising
  * the L1 distance between the canonicalised kept pairs and the scaled predictions, in one single-CTA kernel.  R and t of

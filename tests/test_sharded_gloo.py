@@ -2,8 +2,10 @@
 
 The collectives and the sharding arithmetic are the product's; the stage kernels need a GPU, so this test
 plugs an oracle-backed implementation of the stage interface into `ShardedVote` (test infrastructure only)
-and checks that two ranks, each holding half of the tuples, end with exactly the single-process result:
-bit-identical centre grid, voted centre, kept set and rotation bins' arg-max; float bins within 1e-9.
+and checks that two ranks, each holding half of the tuples and never seeing the other half (only the five exchange
+steps cross: partial grid, 4-byte errors, importance counts + scale histogram, sphere bins + scale histogram, loss sum),
+end with exactly the single-process result: bit-identical centre grid, voted centre, threshold, kept set, importance
+counts, scale median and rotation bins' arg-max; float bins within 1e-9.
 """
 import os
 import socket
@@ -21,70 +23,125 @@ if ROOT not in sys.path:
 
 
 class OracleStages:
-    """The stage interface of cppf2_b200.sharded.ShardedVote on top of the CPU oracle (torch CPU tensors in/out)."""
+    """The stage interface of cppf2_b200.sharded.ShardedVote on top of the CPU oracle (torch CPU tensors cross the
+    collectives).  Every per-tuple stage sees this rank's block only, exactly like CudaStages."""
 
     def __init__(self):
         from oracle import cpu
         self.o = cpu
         self.out = {}
 
-    def decode_targets(self, pc, idx_local, bins_local, cfg):
+    def begin(self, pc, idx_local, bins_local, scales_local, cfg, world, cells_hint=None):
         o = self.o
+        self.cfg = cfg
         self.pc = np.ascontiguousarray(pc, dtype=np.float32)
-        idx = idx_local.numpy()
-        self.pred_l, scaled, _ = o.decode_pairs(self.pc, idx, bins_local.numpy(), cfg.num_bins)
-        tr, rot = o.generate_target_pairs(scaled, cfg.up, cfg.front, cfg.right)
-        return torch.from_numpy(tr), torch.from_numpy(rot)
+        self.idx = idx_local.numpy()
+        self.scales = scales_local.numpy()
+        self.pred_l, scaled, _ = o.decode_pairs(self.pc, self.idx, bins_local.numpy(), cfg.num_bins)
+        self.tr, self.rot = o.generate_target_pairs(scaled, cfg.up, cfg.front, cfg.right)
 
-    def vote_center(self, pc, idx_local, tr_l, cfg):
-        grid, _ = self.o.vote_center(self.pc, tr_l.numpy(), cfg.res, idx_local.numpy()[:, :2], cfg.num_rots)
+    def vote_center(self):
+        grid, _ = self.o.vote_center(self.pc, self.tr, self.cfg.res, self.idx[:, :2], self.cfg.num_rots)
         self.shape = grid.shape
-        return torch.from_numpy(np.ascontiguousarray(grid.reshape(-1)))
+        self.grid = torch.from_numpy(np.ascontiguousarray(grid.reshape(-1)))
+        return self.grid
 
-    def argmax(self, grid, cfg):
+    def argmax(self):
         o = self.o
-        lo, _, gr = o.grid_geometry(self.pc, cfg.res)
+        lo, _, gr = o.grid_geometry(self.pc, self.cfg.res)
         world = np.empty(3, np.float64)
-        g = np.ascontiguousarray(grid.numpy(), dtype=np.int64)
-        o.lib().oracle_grid_argmax(g, gr, lo, float(cfg.res), world)
+        g = np.ascontiguousarray(self.grid.numpy(), dtype=np.int64)
+        o.lib().oracle_grid_argmax(g, gr, lo, float(self.cfg.res), world)
         self.T_est = world
         self.out["grid"] = g.reshape(self.shape).copy()
         self.out["T_est"] = world.copy()
 
-    def errors(self, pc, idx_local, tr_l):
-        o = self.o
-        pairs = self.pc[idx_local.numpy()[:, :2]]
-        tr_back, _ = o.generate_target_pairs(pairs, self._cfg.up, self._cfg.front, self._cfg.right, self.T_est, want_rot=False)
-        return torch.from_numpy(o.backvote_errors(tr_l.numpy(), tr_back))
+    def errors(self):
+        o, cfg = self.o, self.cfg
+        tr_back, _ = o.generate_target_pairs(self.pc[self.idx[:, :2]], cfg.up, cfg.front, cfg.right, self.T_est, want_rot=False)
+        self.errs = o.backvote_errors(self.tr, tr_back)
+        return torch.from_numpy(self.errs)
 
-    def select_and_mask(self, errs, idx, pc, cfg):
-        thr, mask, imp, pair_wt = self.o.backvote_filter(errs.numpy(), idx.numpy(), self.pc.shape[0], cfg.backproj_ratio,
-                                                         cfg.imp_wt_margin)
-        self.mask, self.pair_wt = mask, pair_wt
-        self.out.update(pairs_mask=mask.copy(), imp=imp.copy(), thr=float(thr))
+    def errs_all_buffer(self, world):
+        return None
 
-    def rotation_counts(self, pc, idx, rot, cfg, part, n_parts):
-        o = self.o
-        idx_np, rot_np = idx.numpy(), rot.numpy()
-        kept = np.nonzero(self.mask)[0]
-        mine = np.zeros(idx_np.shape[0], np.uint8)
-        mine[kept[part::n_parts]] = 1
-        wt = np.ones(idx_np.shape[0], np.float64)
-        wt[self.mask] = self.pair_wt
+    def select(self, errs_all):
+        self.thr = np.percentile(errs_all.numpy(), self.cfg.backproj_ratio * 100)      # eval.py:257 on the GLOBAL errors
+        self.out["thr"] = float(self.thr)
+
+    def mask_local(self, own_scale):
+        n = self.pc.shape[0]
+        self.mask = self.errs < self.thr
+        imp = np.bincount(self.idx[self.mask, :2].reshape(-1), minlength=n).astype(np.int32)
+        hist = np.zeros(3 * 65536, np.int32)
+        self.keys = _float_keys(self.scales[self.mask])                                  # [M_local, 3] uint32
+        for a in range(3):
+            np.add.at(hist, a * 65536 + (self.keys[:, a] >> 16), 1)
+        self.x = torch.from_numpy(np.concatenate([imp, np.array([self.mask.sum()], np.int32), hist]))
+        self.out["pairs_mask_local"] = self.mask.copy()
+        return self.x
+
+    def _pick(self, hist, k):
+        cum = np.cumsum(hist.astype(np.int64))
+        d = int(np.searchsorted(cum, k, side="right"))
+        return d, k - (cum[d - 1] if d > 0 else 0)
+
+    def after_mask(self, own_scale):
+        n = self.pc.shape[0]
+        x = self.x.numpy()
+        self.imp, self.kept = x[:n].astype(np.int64), int(x[n])
+        self.out.update(imp=self.imp.copy(), kept=self.kept)
+        self.hi, self.k1 = [], []
+        h1 = np.zeros(3 * 65536, np.int32)
+        for a in range(3):
+            d, k = self._pick(x[n + 1 + a * 65536: n + 1 + (a + 1) * 65536], (self.kept - 1) // 2)
+            self.hi.append(d)
+            self.k1.append(k)
+            sel = (self.keys[:, a] >> 16) == d
+            np.add.at(h1, a * 65536 + (self.keys[sel, a] & 0xffff), 1)
+        self.h1 = torch.from_numpy(h1)
+
+    def rotation_counts(self):
+        o, cfg = self.o, self.cfg
+        imp_wt = self.imp / self.imp.max()
+        wt = np.ones(self.idx.shape[0], np.float64)
+        wt[self.mask] = imp_wt[self.idx[self.mask, :2]].sum(-1) + cfg.imp_wt_margin          # eval.py:274-275, global counts
         sphere = o.fibonacci_sphere(cfg.num_sphere)
-        c_up = o.rotation_counts(self.pc, idx_np, rot_np[:, 0], wt, mine, cfg.num_rots, sphere, cfg.angle_tol)
-        c_right = o.rotation_counts(self.pc, idx_np, rot_np[:, 2], wt, mine, cfg.num_rots, sphere, cfg.angle_tol)
-        return torch.from_numpy(np.stack([c_up, c_right]))
+        keep = self.mask.astype(np.uint8)
+        c_up = o.rotation_counts(self.pc, self.idx, self.rot[:, 0], wt, keep, cfg.num_rots, sphere, cfg.angle_tol)
+        c_right = o.rotation_counts(self.pc, self.idx, self.rot[:, 2], wt, keep, cfg.num_rots, sphere, cfg.angle_tol)
+        self.counts = torch.from_numpy(np.stack([c_up, c_right]))
+        return [self.counts, self.h1]
 
-    def finalize(self, pc, idx, bins, scales, counts, cfg, scale_override=None):
-        o = self.o
-        c = counts.numpy()
+    def pose_local(self, scale_override=None):
+        o, cfg = self.o, self.cfg
+        c = self.counts.numpy()
         sphere = o.fibonacci_sphere(cfg.num_sphere)
         b_up, b_right = int(np.argmax(c[0].astype(np.float32))), int(np.argmax(c[1].astype(np.float32)))
         R = o.assemble_rotation(sphere[b_up], sphere[b_right], cfg.up, cfg.right)
-        scale = o.lower_median(scales.numpy()[self.mask])
+        h1 = self.h1.numpy()
+        keys = [np.uint32((self.hi[a] << 16) | self._pick(h1[a * 65536:(a + 1) * 65536], self.k1[a])[0]) for a in range(3)]
+        scale = _keys_to_float(np.array(keys, np.uint32))
+        canon = (self.pc - self.T_est) @ R / np.linalg.norm(scale)
+        terms = np.clip(np.abs(canon[self.idx[self.mask, :2]] - self.pred_l[self.mask]), 0, 0.1)
+        self.loss_sum = torch.tensor([terms.sum()], dtype=torch.float64)
         self.out.update(counts_up=c[0].copy(), counts_right=c[1].copy(), bin_up=b_up, bin_right=b_right, R_est=R, pred_scale=scale)
+        return self.loss_sum
+
+    def finish(self):
+        self.out["loss"] = float(self.loss_sum[0] / (2 * self.kept * 3))
         return self.out
+
+
+def _float_keys(x):
+    """Order-preserving uint32 image of float32 values (csrc/common.cuh float_to_key)."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.uint32)
+
+
+def _keys_to_float(k):
+    u = np.where(k & 0x80000000, k & 0x7fffffff, ~k).astype(np.uint32)
+    return u.view(np.float32)
 
 
 def _free_port():
@@ -103,10 +160,10 @@ def _worker(rank, world, port, payload, ret):
         cfg = VoteConfig(res=0.002)
         lo, hi = shard_bounds(idx.shape[0], world, rank)
         stages = OracleStages()
-        stages._cfg = cfg
         sv = ShardedVote(stages)
         assert sv.world == world and sv.rank == rank
         out = sv.vote(pc, torch.from_numpy(idx[lo:hi]), cfg, torch.from_numpy(scales[lo:hi]), torch.from_numpy(bins[lo:hi]))
+        assert sv.n_collectives == 5, "one exchange per stage: grid, errors, imp+scale, bins+scale, loss"
         ret[rank] = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in out.items()}
     finally:
         dist.destroy_process_group()
@@ -139,12 +196,15 @@ def test_two_rank_vote_equals_single_process(oracle):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), (pc, idx, bins, scales), ret), nprocs=world, join=True)
     assert set(ret.keys()) == {0, 1}
+    # each rank masked only its own block; together the blocks are the single-process kept set
+    assert np.array_equal(np.concatenate([ret[r]["pairs_mask_local"] for r in range(world)]), ref["pairs_mask"])
     for r in range(world):
         out = ret[r]
         assert np.array_equal(out["grid"], ref["grid"]), "all-reduced grid differs from the single-process grid"
         assert np.array_equal(out["T_est"], ref["T_est"])
-        assert np.array_equal(out["pairs_mask"], ref["pairs_mask"])
+        assert out["thr"] == float(ref["thr"]) and out["kept"] == int(ref["pairs_mask"].sum())
         assert np.array_equal(out["imp"], ref["imp"])
+        np.testing.assert_allclose(out["loss"], ref["loss"], rtol=1e-12)
         np.testing.assert_allclose(out["counts_up"], ref["counts_up"], rtol=1e-9, atol=1e-9)
         np.testing.assert_allclose(out["counts_right"], ref["counts_right"], rtol=1e-9, atol=1e-9)
         assert out["bin_up"] == ref["bin_up"] and out["bin_right"] == ref["bin_right"]
