@@ -11,6 +11,7 @@
 // stream-ordered launches with no host involvement.  It is split into errors / select / mask entry
 // points so that a tuple-sharded run can all-gather the errors (4*T bytes) between them.
 #include "common.cuh"
+#include "frame.cuh"
 
 namespace cppf {
 
@@ -44,13 +45,13 @@ __device__ __forceinline__ void back_targets(const float a[3], const float b[3],
     tr[1] = static_cast<float>(dist);
 }
 
-__global__ void __launch_bounds__(256) backvote_errors_kernel(const float *__restrict__ pc, IdxView idx,
-                                                              const float *__restrict__ targets_tr, int64_t T,
-                                                              const cppf_center *__restrict__ center,
-                                                              float *__restrict__ errs) {
+__device__ __forceinline__ void backvote_errors_body(const float *__restrict__ pc, const IdxView &idx,
+                                                     const float *__restrict__ targets_tr, int64_t T,
+                                                     const cppf_center *__restrict__ center, float *__restrict__ errs,
+                                                     int bid, int nblk) {
     const double ctr[3] = {center->world[0], center->world[1], center->world[2]};
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < T; t += stride) {
+    const int64_t stride = static_cast<int64_t>(nblk) * blockDim.x;
+    for (int64_t t = static_cast<int64_t>(bid) * blockDim.x + threadIdx.x; t < T; t += stride) {
         const int64_t ia = idx.at(t, 0), ib = idx.at(t, 1);
         const float a[3] = {pc[3 * ia], pc[3 * ia + 1], pc[3 * ia + 2]};
         const float b[3] = {pc[3 * ib], pc[3 * ib + 1], pc[3 * ib + 2]};
@@ -60,6 +61,13 @@ __global__ void __launch_bounds__(256) backvote_errors_kernel(const float *__res
         const float d0 = __fsub_rn(tr.x, back[0]), d1 = __fsub_rn(tr.y, back[1]);
         errs[t] = __fsqrt_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));  // np.linalg.norm(axis=-1), eval.py:256
     }
+}
+
+__global__ void __launch_bounds__(256) backvote_errors_kernel(const float *__restrict__ pc, IdxView idx,
+                                                              const float *__restrict__ targets_tr, int64_t T,
+                                                              const cppf_center *__restrict__ center,
+                                                              float *__restrict__ errs) {
+    backvote_errors_body(pc, idx, targets_tr, T, center, errs, blockIdx.x, gridDim.x);
 }
 
 // One radix pass: histogram digit `pass` (most significant first) of the keys that match the prefix
@@ -164,8 +172,8 @@ __global__ void __launch_bounds__(256) select_pass_kernel(const float *__restric
 // launches (two memsets + five passes of ~5 us each, mostly launch latency) become one; results are identical (integer counts).
 constexpr int64_t kSelectSmallMax = 1 << 17;
 
-__global__ void __launch_bounds__(1024) select_small_kernel(const float *__restrict__ errs, int64_t T, int64_t rank_lo, float gamma,
-                                                            cppf_backvote_summary *__restrict__ summary) {
+__device__ __forceinline__ void select_small_body(const float *__restrict__ errs, int64_t T, int64_t rank_lo, float gamma,
+                                                  cppf_backvote_summary *__restrict__ summary) {
     __shared__ uint32_t s_hist[256];
     __shared__ unsigned long long s_cum[256];
     __shared__ uint32_t s_prefix, s_min;
@@ -259,14 +267,23 @@ __global__ void __launch_bounds__(1024) select_small_kernel(const float *__restr
     summary->s_hi = s_hi;
 }
 
-__global__ void __launch_bounds__(256) backvote_mask_kernel(const float *__restrict__ errs, IdxView idx, int64_t T,
-                                                            const cppf_backvote_summary *__restrict__ summary_in,
-                                                            uint8_t *__restrict__ keep, int32_t *__restrict__ kept_list,
-                                                            int32_t *__restrict__ imp,
-                                                            unsigned long long *__restrict__ kept_counter) {
+__global__ void __launch_bounds__(1024) select_small_kernel(const float *__restrict__ errs, int64_t T, int64_t rank_lo, float gamma,
+                                                            cppf_backvote_summary *__restrict__ summary) {
+    select_small_body(errs, T, rank_lo, gamma, summary);
+}
+
+// imp_max != nullptr: the running maximum of the occurrence counts is kept as well (the count a point ends with is the value
+// its last increment returns plus one, so the maximum over all increments is the final maximum; one atomicMax per warp) --
+// the batched path then needs no separate max kernel.
+__device__ __forceinline__ void backvote_mask_body(const float *__restrict__ errs, const IdxView &idx, int64_t T,
+                                                   const cppf_backvote_summary *__restrict__ summary_in,
+                                                   uint8_t *__restrict__ keep, int32_t *__restrict__ kept_list,
+                                                   int32_t *__restrict__ imp, unsigned long long *__restrict__ kept_counter,
+                                                   int32_t *__restrict__ imp_max, int bid, int nblk) {
     const float thr = summary_in->threshold;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t stride = static_cast<int64_t>(nblk) * blockDim.x;
+    const int64_t t0 = static_cast<int64_t>(bid) * blockDim.x + threadIdx.x;
+    int seen_max = 0;
     // whole warps iterate together so that the ballot below is always full-width
     for (int64_t base = t0 - lane_id(); base < T; base += stride) {
         const int64_t t = base + lane_id();
@@ -280,11 +297,25 @@ __global__ void __launch_bounds__(256) backvote_mask_kernel(const float *__restr
         if (k) {
             if (kept_list) kept_list[slot + __popc(m & ((1u << lane_id()) - 1u))] = static_cast<int32_t>(t);
             if (imp) {
-                atomicAdd(&imp[idx.at(t, 0)], 1);  // scatter_add of the flattened endpoints (eval.py:260-266)
-                atomicAdd(&imp[idx.at(t, 1)], 1);
+                const int c0 = atomicAdd(&imp[idx.at(t, 0)], 1);  // scatter_add of the flattened endpoints (eval.py:260-266)
+                const int c1 = atomicAdd(&imp[idx.at(t, 1)], 1);
+                seen_max = max(seen_max, max(c0, c1) + 1);
             }
         }
     }
+    if (imp && imp_max) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) seen_max = max(seen_max, __shfl_xor_sync(0xffffffffu, seen_max, o));
+        if (lane_id() == 0 && seen_max > 0) atomicMax(imp_max, seen_max);
+    }
+}
+
+__global__ void __launch_bounds__(256) backvote_mask_kernel(const float *__restrict__ errs, IdxView idx, int64_t T,
+                                                            const cppf_backvote_summary *__restrict__ summary_in,
+                                                            uint8_t *__restrict__ keep, int32_t *__restrict__ kept_list,
+                                                            int32_t *__restrict__ imp,
+                                                            unsigned long long *__restrict__ kept_counter) {
+    backvote_mask_body(errs, idx, T, summary_in, keep, kept_list, imp, kept_counter, nullptr, blockIdx.x, gridDim.x);
 }
 
 __global__ void __launch_bounds__(1024) imp_max_kernel(const int32_t *__restrict__ imp, int64_t n,
@@ -385,3 +416,47 @@ CPPF_API int cppf_backvote_filter(const float *pc, int64_t n, const void *idx, i
     if (rc) return rc;
     return cppf_backvote_imp_max(imp, n, summary, stream);
 }
+
+// =====================================================================================================================
+// Batched frame path (frame.cuh): the back-vote filter of every job in three launches (errors, exact selection, mask).
+// =====================================================================================================================
+namespace cppf {
+
+__global__ void __launch_bounds__(256) frame_backvote_errors_kernel(const FrameTable *__restrict__ t) {
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.y];
+    const FrameInst &in = t->inst[j.inst];
+    backvote_errors_body(in.pc, in.idx, j.targets_tr, in.T, j.center, j.errs, blockIdx.x, gridDim.x);
+}
+
+__global__ void __launch_bounds__(1024) frame_select_kernel(const FrameTable *__restrict__ t) {
+    if (static_cast<int>(blockIdx.x) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.x];
+    const FrameInst &in = t->inst[j.inst];
+    if (in.T <= 0) return;
+    select_small_body(j.errs, in.T, j.rank_lo, j.gamma, j.summary);
+}
+
+__global__ void __launch_bounds__(256) frame_backvote_mask_kernel(const FrameTable *__restrict__ t) {
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.y];
+    const FrameInst &in = t->inst[j.inst];
+    // imp [n], the kept counter and imp_max were zeroed by frame_prep_kernel
+    backvote_mask_body(j.errs, in.idx, in.T, j.summary, j.keep, j.kept_list, j.imp,
+                       reinterpret_cast<unsigned long long *>(&j.summary->kept), &j.summary->imp_max, blockIdx.x, gridDim.x);
+}
+
+int frame_launch_backvote(const FrameTable *t, int nj, int64_t T_cap, cudaStream_t s) {
+    if (nj <= 0) return CPPF_OK;
+    if (T_cap > kSelectSmallMax) return CPPF_ERR_UNSUPPORTED;      // the single-CTA selection; larger T: the per-job path
+    const int per_job = std::max(1, std::min<int>(div_up(T_cap, 256), (device_info().sm_count * 8 + nj - 1) / nj));
+    frame_backvote_errors_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_select_kernel<<<nj, 1024, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_backvote_mask_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+}  // namespace cppf

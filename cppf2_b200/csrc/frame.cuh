@@ -111,7 +111,6 @@ struct FrameShared {                    // identical for every job of a frame; p
     float cos_thr;
     const uint2 *lut_cells;
     const float *cos_tab, *sin_tab, *sphere;
-    long long smem_cells;               // shared-memory budget of the privatised centre vote, in cells
 };
 
 // Launchers of the batched stages, each in the file that owns the single-job kernels.  `t` is the DEVICE table; `ni` / `nj`
@@ -120,9 +119,9 @@ struct FrameShared {                    // identical for every job of a frame; p
 int frame_launch_sample_tuples(const FrameTable *t, int ni, int64_t T_cap, cudaStream_t s);                       // targets.cu
 int frame_launch_shot(const FrameTable *t, int ni, int64_t n_cap, cudaStream_t s);                                // shot.cu
 int frame_launch_heads(const FrameTable *t, const FrameTable *host, const void *const *tc_states, cudaStream_t s);   // heads_tc.cu
-int frame_launch_prep(const FrameTable *t, int nj, const FrameShared &sh, cudaStream_t s);                        // vote_center.cu
-int frame_launch_decode_zero(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s);  // targets.cu
-int frame_launch_vote_center(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s);  // vote_center.cu
+
+
+int frame_launch_center(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s);        // vote_center.cu
 int frame_launch_backvote(const FrameTable *t, int nj, int64_t T_cap, cudaStream_t s);                            // backvote.cu
 int frame_launch_rotation(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s);     // rotation.cu
 int frame_launch_pose(const FrameTable *t, int nj, int64_t T_cap, int any_refine, const FrameShared &sh, cudaStream_t s);  // pose.cu

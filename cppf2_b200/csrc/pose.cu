@@ -2,6 +2,7 @@
 // cross product, lower-median scale of the kept tuples) and eval.py:358-363 (branch selection loss).
 // Three tiny stream-ordered kernels; nothing returns to the host until the caller reads cppf_pose.
 #include "common.cuh"
+#include "frame.cuh"
 
 namespace cppf {
 
@@ -13,14 +14,13 @@ struct PoseScratch {  // head of the workspace, zeroed by the host wrapper
 };
 
 // ---- directions + rotation matrix -------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pose_directions_kernel(const double *__restrict__ counts,
-                                                              const float *__restrict__ sphere, int S,
-                                                              const cppf_center *__restrict__ center,
-                                                              const cppf_backvote_summary *__restrict__ summary,
-                                                              int up_loc, int right_loc, cppf_pose *__restrict__ pose) {
+__device__ __forceinline__ void pose_directions_body(const double *__restrict__ counts, const float *__restrict__ sphere, int S,
+                                                     const cppf_center *__restrict__ center,
+                                                     const cppf_backvote_summary *__restrict__ summary, int up_loc,
+                                                     int right_loc, cppf_pose *__restrict__ pose) {
     // first arg-max of float32(counts) per angle column: the reference accumulates in float32 (eval.py:39)
-    __shared__ float s_val[2][8];
-    __shared__ int s_idx[2][8];
+    __shared__ float s_val[2][32];
+    __shared__ int s_idx[2][32];
     __shared__ int s_best[2];
     __shared__ float s_bestv[2];
     for (int c = 0; c < 2; ++c) {
@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(256) pose_directions_kernel(const double *__re
         const int c = threadIdx.x;
         float bv = s_val[c][0];
         int bi = s_idx[c][0];
-        for (int w = 1; w < 8; ++w)
+        const int n_w = static_cast<int>(blockDim.x >> 5);
+        for (int w = 1; w < n_w; ++w)
             if (s_val[c][w] > bv || (s_val[c][w] == bv && s_idx[c][w] < bi)) {
                 bv = s_val[c][w];
                 bi = s_idx[c][w];
@@ -94,16 +95,22 @@ __global__ void __launch_bounds__(256) pose_directions_kernel(const double *__re
     pose->grid_cells = center->cells > 0xffffffffll ? 0xffffffffu : static_cast<uint32_t>(center->cells);
 }
 
+__global__ void __launch_bounds__(256) pose_directions_kernel(const double *__restrict__ counts,
+                                                              const float *__restrict__ sphere, int S,
+                                                              const cppf_center *__restrict__ center,
+                                                              const cppf_backvote_summary *__restrict__ summary,
+                                                              int up_loc, int right_loc, cppf_pose *__restrict__ pose) {
+    pose_directions_body(counts, sphere, S, center, summary, up_loc, right_loc, pose);
+}
+
 // ---- lower median of the kept scale predictions, one CTA per axis ------------------------------------
-__global__ void __launch_bounds__(1024) scale_median_kernel(const float *__restrict__ pred_scales,
-                                                            const int32_t *__restrict__ kept_list,
-                                                            const cppf_backvote_summary *__restrict__ summary,
-                                                            const float *__restrict__ scale_override,
-                                                            cppf_pose *__restrict__ pose) {
+__device__ __forceinline__ void scale_median_body(const float *__restrict__ pred_scales, const int32_t *__restrict__ kept_list,
+                                                  const cppf_backvote_summary *__restrict__ summary,
+                                                  const float *__restrict__ scale_override, cppf_pose *__restrict__ pose,
+                                                  int axis) {
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_prefix;
     __shared__ unsigned long long s_k;
-    const int axis = blockIdx.x;
     const int64_t M = summary->kept;
     if (scale_override || M <= 0) {
         if (threadIdx.x == 0) pose->scale[axis] = scale_override ? scale_override[axis] : 0.0f;
@@ -138,6 +145,14 @@ __global__ void __launch_bounds__(1024) scale_median_kernel(const float *__restr
         }
         if (threadIdx.x == 0) pose->scale[axis] = key_to_float(s_prefix);
     }
+}
+
+__global__ void __launch_bounds__(1024) scale_median_kernel(const float *__restrict__ pred_scales,
+                                                            const int32_t *__restrict__ kept_list,
+                                                            const cppf_backvote_summary *__restrict__ summary,
+                                                            const float *__restrict__ scale_override,
+                                                            cppf_pose *__restrict__ pose) {
+    scale_median_body(pred_scales, kept_list, summary, scale_override, pose, blockIdx.x);
 }
 
 // ---- the same lower median when the kept tuples are spread over several GPUs (tuple-sharded runs) -----------
@@ -240,12 +255,11 @@ struct __align__(8) RefineRow {
     float y[3];
 };
 
-__global__ void __launch_bounds__(512, 1) pose_refine_kernel(const float *__restrict__ pc, IdxView idx,
-                                                              const uint8_t *__restrict__ bins, int num_bins,
-                                                              const int32_t *__restrict__ kept_list,
-                                                              const cppf_backvote_summary *__restrict__ summary,
-                                                              int loss_y_only, int iters, float lr,
-                                                              RefineRow *__restrict__ rows, cppf_pose *__restrict__ pose) {
+__device__ __forceinline__ void pose_refine_body(const float *__restrict__ pc, const IdxView &idx,
+                                                 const uint8_t *__restrict__ bins, int num_bins,
+                                                 const int32_t *__restrict__ kept_list,
+                                                 const cppf_backvote_summary *__restrict__ summary, int loss_y_only, int iters,
+                                                 float lr, RefineRow *__restrict__ rows, cppf_pose *__restrict__ pose) {
     __shared__ double s_part[16][12];
     __shared__ double s_tot[12];
     __shared__ float s_pose[12];                                // rot (9) and t (3) of the current step
@@ -421,13 +435,21 @@ __global__ void __launch_bounds__(512, 1) pose_refine_kernel(const float *__rest
     }
 }
 
+__global__ void __launch_bounds__(512, 1) pose_refine_kernel(const float *__restrict__ pc, IdxView idx,
+                                                              const uint8_t *__restrict__ bins, int num_bins,
+                                                              const int32_t *__restrict__ kept_list,
+                                                              const cppf_backvote_summary *__restrict__ summary,
+                                                              int loss_y_only, int iters, float lr,
+                                                              RefineRow *__restrict__ rows, cppf_pose *__restrict__ pose) {
+    pose_refine_body(pc, idx, bins, num_bins, kept_list, summary, loss_y_only, iters, lr, rows, pose);
+}
+
 // ---- branch loss: mean clip(|canon(pc[pair]) - pred_pairs|, 0, 0.1) over kept pairs (eval.py:358-363) -
-__global__ void __launch_bounds__(256) pose_loss_kernel(const float *__restrict__ pc, IdxView idx,
-                                                        const uint8_t *__restrict__ bins, int num_bins,
-                                                        const int32_t *__restrict__ kept_list,
-                                                        const cppf_backvote_summary *__restrict__ summary,
-                                                        int loss_y_only, cppf_pose *__restrict__ pose,
-                                                        PoseScratch *__restrict__ scratch) {
+__device__ __forceinline__ void pose_loss_body(const float *__restrict__ pc, const IdxView &idx,
+                                               const uint8_t *__restrict__ bins, int num_bins,
+                                               const int32_t *__restrict__ kept_list,
+                                               const cppf_backvote_summary *__restrict__ summary, int loss_y_only,
+                                               cppf_pose *__restrict__ pose, PoseScratch *__restrict__ scratch, int bid, int nblk) {
     __shared__ double s_sum[8];
     __shared__ bool s_last;
     const int64_t M = summary->kept;
@@ -442,8 +464,8 @@ __global__ void __launch_bounds__(256) pose_loss_kernel(const float *__restrict_
     for (int i = 0; i < 3; ++i) t[i] = pose->t[i];
     const float denom = static_cast<float>(num_bins - 1);
     double acc = 0.0;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < 2 * M; i += stride) {
+    const int64_t stride = static_cast<int64_t>(nblk) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(bid) * blockDim.x + threadIdx.x; i < 2 * M; i += stride) {
         const int64_t m = kept_list[i >> 1];
         const int end = static_cast<int>(i & 1);
         const int64_t ip = idx.at(m, end);
@@ -466,7 +488,7 @@ __global__ void __launch_bounds__(256) pose_loss_kernel(const float *__restrict_
         for (int w = 1; w < 8; ++w) acc += s_sum[w];
         atomicAdd(&scratch->loss_sum, acc);
         __threadfence();
-        s_last = (atomicAdd(&scratch->ticket, 1u) == gridDim.x - 1);
+        s_last = (atomicAdd(&scratch->ticket, 1u) == static_cast<unsigned int>(nblk) - 1u);
     }
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
@@ -476,6 +498,65 @@ __global__ void __launch_bounds__(256) pose_loss_kernel(const float *__restrict_
         pose->loss = M > 0 ? total / cnt : INFINITY;
         pose->scale_norm = sn;
     }
+}
+
+__global__ void __launch_bounds__(256) pose_loss_kernel(const float *__restrict__ pc, IdxView idx,
+                                                        const uint8_t *__restrict__ bins, int num_bins,
+                                                        const int32_t *__restrict__ kept_list,
+                                                        const cppf_backvote_summary *__restrict__ summary,
+                                                        int loss_y_only, cppf_pose *__restrict__ pose,
+                                                        PoseScratch *__restrict__ scratch) {
+    pose_loss_body(pc, idx, bins, num_bins, kept_list, summary, loss_y_only, pose, scratch, blockIdx.x, gridDim.x);
+}
+
+// =====================================================================================================================
+// Batched frame path (frame.cuh): pose assembly of every job in two launches (three with the refinement).
+// =====================================================================================================================
+// blockIdx.x = 0: top-1 directions + rotation matrix of the job; 1..3: lower median of the kept scale predictions, one axis
+// each.  The SHOT branch of an instance takes the median over the DINO branch's kept tuples (scale_from; eval.py:308-310
+// reuses the DINO scale) -- recomputed here rather than read from the other job's record, so that the jobs of one launch
+// stay independent.
+__global__ void __launch_bounds__(1024) frame_pose_dirs_scale_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.y];
+    if (blockIdx.x == 0) {
+        pose_directions_body(j.counts, sh.sphere, sh.S, j.center, j.summary, j.up_loc, j.right_loc, j.pose);
+    } else {
+        const FrameJob &src = t->job[j.scale_from];
+        scale_median_body(src.scales, src.kept_list, src.summary, nullptr, j.pose, static_cast<int>(blockIdx.x) - 1);
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) frame_pose_refine_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    if (static_cast<int>(blockIdx.x) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.x];
+    if (j.refine_iters <= 0) return;
+    const FrameInst &in = t->inst[j.inst];
+    RefineRow *rows = reinterpret_cast<RefineRow *>(static_cast<unsigned char *>(j.ws_pose) + 256);
+    pose_refine_body(in.pc, in.idx, j.bins, sh.num_bins, j.kept_list, j.summary, j.loss_y_only, j.refine_iters, j.refine_lr, rows, j.pose);
+}
+
+__global__ void __launch_bounds__(256) frame_pose_loss_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.y];
+    const FrameInst &in = t->inst[j.inst];
+    pose_loss_body(in.pc, in.idx, j.bins, sh.num_bins, j.kept_list, j.summary, j.loss_y_only, j.pose,
+                   static_cast<PoseScratch *>(j.ws_pose), blockIdx.x, gridDim.x);
+}
+
+int frame_launch_pose(const FrameTable *t, int nj, int64_t T_cap, int any_refine, const FrameShared &sh, cudaStream_t s) {
+    (void)T_cap;
+    if (nj <= 0) return CPPF_OK;
+    frame_pose_dirs_scale_kernel<<<dim3(4, nj), 1024, 0, s>>>(t, sh);
+    CPPF_LAUNCH_CHECK();
+    if (any_refine) {
+        frame_pose_refine_kernel<<<nj, 512, 0, s>>>(t, sh);
+        CPPF_LAUNCH_CHECK();
+    }
+    const int per_job = std::max(4, device_info().sm_count * 2 / nj);
+    frame_pose_loss_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t, sh);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
 }
 
 }  // namespace cppf

@@ -11,6 +11,7 @@
 // 1/weight in float64.  Bins are float64 in shared memory (720 x 8 B per angle column), flushed with
 // one global atomicAdd(double) per non-zero bin per CTA.
 #include "common.cuh"
+#include "frame.cuh"
 
 namespace cppf {
 
@@ -163,12 +164,13 @@ struct ThetaCols {
     int n;
 };
 
-__global__ void __launch_bounds__(256) rotation_hist_kernel(
-    const float *__restrict__ pc, IdxView idx, const float *__restrict__ theta, int64_t theta_stride, ThetaCols cols,
+__device__ __forceinline__ void rotation_hist_body(
+    const float *__restrict__ pc, const IdxView &idx, const float *__restrict__ theta, int64_t theta_stride, const ThetaCols &cols,
     const int32_t *__restrict__ kept_list, const int64_t *__restrict__ kept_count, int64_t M,
     const int32_t *__restrict__ imp, const cppf_backvote_summary *__restrict__ summary, double margin,
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R, const float *__restrict__ sphere, int S,
-    float cos_thr, int band, const uint2 *__restrict__ lut_cells, int lut_g, double *__restrict__ counts, int part, int n_parts) {
+    float cos_thr, int band, const uint2 *__restrict__ lut_cells, int lut_g, double *__restrict__ counts, int part, int n_parts,
+    int bid, int nblk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *s_bins = reinterpret_cast<unsigned long long *>(smem_raw);     // [n_theta][S], 32.32 fixed point
     float *s_sphere = reinterpret_cast<float *>(s_bins + cols.n * S);        // [S][3]
@@ -185,8 +187,8 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
     const double imp_max = (imp && summary) ? static_cast<double>(summary->imp_max) : 1.0;
     const float half_sm1 = 0.5f * static_cast<float>(S - 1);
     const int lane = lane_id();
-    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int64_t warp = (static_cast<int64_t>(bid) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(nblk) * blockDim.x) >> 5;
     // a partitioned run (cppf_rotation_hist_part) votes the TUPLES congruent to `part` modulo `n_parts`: the partition is by
     // tuple id, not by position in kept_list, whose order (atomic compaction) differs from run to run and rank to rank
     for (int64_t it = warp; it < n_items; it += n_warps) {
@@ -220,6 +222,53 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
     __syncthreads();
     for (int i = threadIdx.x; i < cols.n * S; i += blockDim.x)
         if (s_bins[i] != 0ull) atomicAdd(&counts[i], static_cast<double>(s_bins[i]) * (1.0 / 4294967296.0));
+}
+
+__global__ void __launch_bounds__(256) rotation_hist_kernel(
+    const float *__restrict__ pc, IdxView idx, const float *__restrict__ theta, int64_t theta_stride, ThetaCols cols,
+    const int32_t *__restrict__ kept_list, const int64_t *__restrict__ kept_count, int64_t M,
+    const int32_t *__restrict__ imp, const cppf_backvote_summary *__restrict__ summary, double margin,
+    const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R, const float *__restrict__ sphere, int S,
+    float cos_thr, int band, const uint2 *__restrict__ lut_cells, int lut_g, double *__restrict__ counts, int part, int n_parts) {
+    rotation_hist_body(pc, idx, theta, theta_stride, cols, kept_list, kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere,
+                       S, cos_thr, band, lut_cells, lut_g, counts, part, n_parts, blockIdx.x, gridDim.x);
+}
+
+// Batched frame path (frame.cuh): the rotation votes of every job (angle columns 0 and 2: `up` and `right`, eval.py:277-293)
+// in one launch; blockIdx.y = job.
+__global__ void __launch_bounds__(256) frame_rotation_hist_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.y];
+    const FrameInst &in = t->inst[j.inst];
+    ThetaCols cols;
+    cols.n = 2;
+    cols.col[0] = 0;
+    cols.col[1] = 2;
+    cols.col[2] = 0;
+    // CTAs beyond what the kept count can use leave at once (they would only zero and flush empty bins)
+    const int64_t kept = j.summary->kept;
+    const int64_t useful = (kept + 7) / 8 + 1;            // 8 warps per CTA, at least one kept tuple per warp
+    const int nblk = static_cast<int>(useful < static_cast<int64_t>(gridDim.x) ? useful : gridDim.x);
+    if (static_cast<int>(blockIdx.x) >= nblk) return;
+    rotation_hist_body(in.pc, in.idx, j.targets_rot, 3, cols, j.kept_list, &j.summary->kept, in.T, j.imp, j.summary, j.imp_margin,
+                       sh.cos_tab, sh.sin_tab, sh.R, sh.sphere, sh.S, sh.cos_thr, sh.band, sh.lut_cells, sh.lut_g, j.counts, 0, 1,
+                       blockIdx.x, nblk);
+}
+
+int frame_launch_rotation(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s) {
+    if (nj <= 0) return CPPF_OK;
+    const size_t smem = 2 * static_cast<size_t>(sh.S) * sizeof(double) + 3 * static_cast<size_t>(sh.S) * sizeof(float) +
+                        2 * static_cast<size_t>(sh.R) * sizeof(float);
+    if (smem > static_cast<size_t>(device_info().max_smem_optin)) return CPPF_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        CPPF_CUDA_TRY(cudaFuncSetAttribute(frame_rotation_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // per job as many CTAs as the single-job launch (kept ~ T/10, one warp per kept tuple at a time), the whole launch a few
+    // CTAs per SM
+    const int64_t guess = T_cap / 8 + 1;
+    const int per_job = std::max(1, std::min<int>(div_up(guess * 32, 256), std::max(8, device_info().sm_count * 4 / nj)));
+    frame_rotation_hist_kernel<<<dim3(per_job, nj), 256, smem, s>>>(t, sh);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
 }
 
 }  // namespace cppf

@@ -31,8 +31,8 @@ __device__ __forceinline__ int replica_count(int64_t cells, int64_t capacity, in
 // ---------------------------------------------------------------------------------------------------
 // bounds: single CTA, coalesced sweep, shared-memory tree reduction.  N <= 50 000 by eval.py:195.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) cloud_bounds_kernel(const float *__restrict__ pc, int64_t n, float res,
-                                                            cppf_grid_geom *__restrict__ geom) {
+__device__ __forceinline__ void cloud_bounds_body(const float *__restrict__ pc, int64_t n, float res,
+                                                  cppf_grid_geom *__restrict__ geom) {
     __shared__ float s_lo[3][32], s_hi[3][32];
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     // flat float index i = 3*p + k: consecutive threads read consecutive floats; k = i % 3
@@ -99,25 +99,36 @@ __global__ void __launch_bounds__(1024) cloud_bounds_kernel(const float *__restr
     }
 }
 
+__global__ void __launch_bounds__(1024) cloud_bounds_kernel(const float *__restrict__ pc, int64_t n, float res,
+                                                            cppf_grid_geom *__restrict__ geom) {
+    cloud_bounds_body(pc, n, res, geom);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // zero the live part of the grid (size known only on the device)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ grid, int64_t capacity,
-                                                        const cppf_grid_geom *__restrict__ geom,
-                                                        uint32_t *__restrict__ status, int replicas_max) {
+__device__ __forceinline__ void grid_zero_body(uint32_t *__restrict__ grid, int64_t capacity,
+                                               const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ status,
+                                               int replicas_max, int bid, int nblk) {
     int64_t cells = geom->cells;
     if (cells <= capacity) cells *= replica_count(cells, capacity, replicas_max);
     if (cells > capacity) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && status) atomicOr(status, CPPF_STATUS_GRID_OVERFLOW);
+        if (bid == 0 && threadIdx.x == 0 && status) atomicOr(status, CPPF_STATUS_GRID_OVERFLOW);
         cells = capacity;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && status && geom->flags) atomicOr(status, geom->flags);
+    if (bid == 0 && threadIdx.x == 0 && status && geom->flags) atomicOr(status, geom->flags);
     int64_t vec = cells >> 2;
     uint4 *g4 = reinterpret_cast<uint4 *>(grid);
-    int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int64_t stride = static_cast<int64_t>(nblk) * blockDim.x;
+    int64_t tid = static_cast<int64_t>(bid) * blockDim.x + threadIdx.x;
     for (int64_t i = tid; i < vec; i += stride) g4[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int64_t i = (vec << 2) + tid; i < cells; i += stride) grid[i] = 0u;
+}
+
+__global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ grid, int64_t capacity,
+                                                        const cppf_grid_geom *__restrict__ geom,
+                                                        uint32_t *__restrict__ status, int replicas_max) {
+    grid_zero_body(grid, capacity, geom, status, replicas_max, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -143,12 +154,12 @@ constexpr int kMaxRotsSmem = 1024;
 // MODE 0: RED straight to the L2-resident grid; `replicas` copies of the grid (copy = block % replicas)
 //         spread the hot cache lines of the vote peak over several L2 slices.
 // MODE 1: the whole grid lives in this CTA's shared memory (cells*4 B <= ~220 KB), flushed at the end.
-template <int CHUNK, int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS) vote_center_kernel(
-    const float *__restrict__ pc, IdxView idx, const float *__restrict__ preds_tr, int64_t T,
+template <int CHUNK, int MODE>
+__device__ __forceinline__ void vote_center_body(
+    const float *__restrict__ pc, const IdxView &idx, const float *__restrict__ preds_tr, int64_t T,
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R,
     const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ grid, int64_t capacity, int replicas_max,
-    int64_t smem_cells, uint32_t *__restrict__ status) {
+    int64_t smem_cells, uint32_t *__restrict__ status, int bid, int nblk) {
     __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
     extern __shared__ __align__(16) uint32_t s_grid[];
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(THREADS) vote_center_kernel(
     const int64_t cells = geom->cells;
     if (MODE == 1) {
         if (cells > smem_cells) {  // the caller's bound on the grid size was wrong: flag, never corrupt
-            if (blockIdx.x == 0 && threadIdx.x == 0 && status) atomicOr(status, CPPF_STATUS_GRID_OVERFLOW);
+            if (bid == 0 && threadIdx.x == 0 && status) atomicOr(status, CPPF_STATUS_GRID_OVERFLOW);
             return;
         }
         for (int64_t i = threadIdx.x; i < cells; i += blockDim.x) s_grid[i] = 0u;
@@ -166,7 +177,7 @@ __global__ void __launch_bounds__(THREADS) vote_center_kernel(
     __syncthreads();
 
     if (cells > capacity) return;  // flagged by grid_zero_kernel
-    if (MODE == 0) grid += (blockIdx.x % replica_count(cells, capacity, replicas_max)) * cells;
+    if (MODE == 0) grid += (bid % replica_count(cells, capacity, replicas_max)) * cells;
     const float res = geom->res;
     const float inv_res = __frcp_rn(res);      // correctly rounded reciprocal of the launch-wide divisor (see div_by)
     const float lo0 = geom->lo[0], lo1 = geom->lo[1], lo2 = geom->lo[2];
@@ -174,8 +185,8 @@ __global__ void __launch_bounds__(THREADS) vote_center_kernel(
               g2 = static_cast<int>(geom->grid_res[2]);
 
     const int lane = lane_id();
-    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int64_t warp = (static_cast<int64_t>(bid) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(nblk) * blockDim.x) >> 5;
 
     for (int64_t base = warp * CHUNK; base < T; base += n_warps * CHUNK) {
         // ---- per-tuple frame, one tuple per lane (train_dino.py:176-192) -------------------------
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(THREADS) vote_center_kernel(
     if (MODE == 1) {
         __syncthreads();
         // staggered flush: CTA b starts at its own offset so that the CTAs do not sweep the lines in lock step
-        const int64_t start = (cells / gridDim.x) * blockIdx.x;
+        const int64_t start = (cells / nblk) * bid;
         for (int64_t i = threadIdx.x; i < cells; i += blockDim.x) {
             int64_t j = i + start;
             j = j >= cells ? j - cells : j;
@@ -243,6 +254,16 @@ __global__ void __launch_bounds__(THREADS) vote_center_kernel(
             if (v) atomicAdd(grid + j, v);
         }
     }
+}
+
+template <int CHUNK, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) vote_center_kernel(
+    const float *__restrict__ pc, IdxView idx, const float *__restrict__ preds_tr, int64_t T,
+    const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R,
+    const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ grid, int64_t capacity, int replicas_max,
+    int64_t smem_cells, uint32_t *__restrict__ status) {
+    vote_center_body<CHUNK, MODE>(pc, idx, preds_tr, T, cos_tab, sin_tab, R, geom, grid, capacity, replicas_max, smem_cells, status,
+                                  blockIdx.x, gridDim.x);
 }
 
 // sums replicas 1..K-1 into replica 0
@@ -444,3 +465,141 @@ CPPF_API int cppf_grid_to_i64(const uint32_t *grid, int64_t grid_capacity, const
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }
+
+// =====================================================================================================================
+// Batched frame path (frame.cuh): the centre-vote stage of EVERY (instance, branch) job of a frame in four launches.
+// blockIdx.y selects the job; all sizes come from the device-resident table, so the launch dimensions do not depend on the
+// frame's content.  Arithmetic = the bodies above, so grids are bit-identical to the single-job calls.
+// =====================================================================================================================
+#include "frame.cuh"
+#include "targets.cuh"
+
+namespace cppf {
+
+// prep: bounds of the job's cloud -> geom, and every small accumulator of the chain zeroed (centre record incl. its key /
+// ticket words, back-vote summary incl. kept and imp_max, status, sphere bins, importance counts, pose scratch)
+__global__ void __launch_bounds__(1024) frame_prep_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    if (static_cast<int>(blockIdx.x) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.x];
+    const FrameInst &in = t->inst[j.inst];
+    cloud_bounds_body(in.pc, in.n, j.res, j.geom);
+    const int tid = threadIdx.x;
+    uint32_t *c = reinterpret_cast<uint32_t *>(j.center);
+    for (int i = tid; i < static_cast<int>(sizeof(cppf_center) / 4); i += 1024) c[i] = 0u;
+    uint32_t *sm = reinterpret_cast<uint32_t *>(j.summary);
+    for (int i = tid; i < static_cast<int>(sizeof(cppf_backvote_summary) / 4); i += 1024) sm[i] = 0u;
+    if (tid == 0) *j.status = 0u;
+    uint32_t *ws = reinterpret_cast<uint32_t *>(j.ws_pose);
+    for (int i = tid; i < 64; i += 1024) ws[i] = 0u;                       // PoseScratch (first 256 bytes of ws_pose)
+    for (int i = tid; i < 2 * sh.S; i += 1024) j.counts[i] = 0.0;
+    for (int i = tid; i < in.n; i += 1024) j.imp[i] = 0;
+}
+
+// decode + targets of the job's tuples (eval.py:230-240), and the live part of its grid zeroed
+__global__ void __launch_bounds__(256) frame_decode_zero_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.y];
+    const FrameInst &in = t->inst[j.inst];
+    grid_zero_body(j.grid, j.grid_capacity, j.geom, j.status, sh.replicas_max, blockIdx.x, gridDim.x);
+    Axes ax;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ax.v[i] = j.axes[i];
+    decode_targets_body(in.pc, in.idx, j.bins, in.T, sh.num_bins, ax, j.targets_tr, j.targets_rot, nullptr, nullptr, blockIdx.x,
+                        gridDim.x);
+}
+
+// Every job votes with RED into its L2-resident grid copies (the mode the per-job path picks for all but the smallest
+// grids; at the frame's T <= 2^17 it is also the faster one for those: ncu 37 us against 48 us per job, and a launch whose
+// CTAs each reserve a whole SM's shared memory would serialise the jobs).
+__global__ void __launch_bounds__(kVoteThreads) frame_vote_center_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.y];
+    const FrameInst &in = t->inst[j.inst];
+    // as many CTAs as the single-job launch would use for this T (the grid is sized for the capacity)
+    const int64_t warps = (in.T + 7) / 8;
+    int64_t nblk = (warps + kVoteThreads / 32 - 1) / (kVoteThreads / 32);
+    if (nblk > static_cast<int64_t>(gridDim.x)) nblk = gridDim.x;
+    if (static_cast<int64_t>(blockIdx.x) >= nblk) return;
+    vote_center_body<8, 0>(in.pc, in.idx, j.targets_tr, in.T, sh.cos_tab, sh.sin_tab, sh.R, j.geom, j.grid, j.grid_capacity,
+                           sh.replicas_max, 0, j.status, blockIdx.x, static_cast<int>(nblk));
+}
+
+// replicas folded into copy 0 and the first-maximum arg-max in ONE pass (the fold kernel's sum feeds the key directly);
+// the last CTA of a job converts to world space (train_dino.py:212-213) exactly like grid_argmax_kernel
+__global__ void __launch_bounds__(256) frame_fold_argmax_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.y];
+    const cppf_grid_geom *geom = j.geom;
+    const bool overflow = geom->cells > j.grid_capacity;
+    const int64_t cells = overflow ? 0 : geom->cells;
+    const int replicas = replica_count(cells, j.grid_capacity, sh.replicas_max);
+    uint32_t *grid = j.grid;
+    unsigned long long best = 0ull;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < cells; i += stride) {
+        uint32_t acc = grid[i];
+        if (replicas > 1) {
+            for (int k = 1; k < replicas; ++k) acc += grid[k * cells + i];
+            grid[i] = acc;
+        }
+        const unsigned long long k = (static_cast<unsigned long long>(acc) << 32) |
+                                     static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(i));
+        best = k > best ? k : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    __shared__ unsigned long long s_best[8];
+    __shared__ bool s_last;
+    cppf_center *out = j.center;
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(&out->linear);     // zeroed by frame_prep_kernel
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(&out->status);
+    if (lane_id() == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) best = s_best[w] > best ? s_best[w] : best;
+        atomicMax(key, best);
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(key);
+        int64_t lin = static_cast<int64_t>(0xffffffffu - static_cast<uint32_t>(k & 0xffffffffull));
+        if (cells <= 0) lin = 0;
+        const int64_t g1 = geom->grid_res[1], g2 = geom->grid_res[2];
+        const int64_t cell[3] = {lin / (g1 * g2), (lin / g2) % g1, lin % g2};
+        for (int a = 0; a < 3; ++a) {
+            out->cell[a] = cell[a];
+            out->world[a] = __dadd_rn(static_cast<double>(geom->lo[a]), __dmul_rn(static_cast<double>(cell[a]), j.res64));
+        }
+        out->linear = lin;
+        out->votes = static_cast<uint32_t>(k >> 32);
+        out->cells = geom->cells;
+        out->status = geom->flags | (overflow ? CPPF_STATUS_GRID_OVERFLOW : 0u) | *j.status;
+    }
+}
+
+int frame_launch_center(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s) {
+    const DeviceInfo &dev = device_info();
+    if (nj <= 0) return CPPF_OK;
+    frame_prep_kernel<<<nj, 1024, 0, s>>>(t, sh);
+    CPPF_LAUNCH_CHECK();
+    const int per_job = std::max(1, std::min<int>(div_up(T_cap, 256), (dev.sm_count * 8 + nj - 1) / nj));
+    frame_decode_zero_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t, sh);
+    CPPF_LAUNCH_CHECK();
+    {
+        const int64_t warps = (T_cap + 7) / 8;
+        const int blocks = static_cast<int>(std::min<int64_t>((warps + 7) / 8, static_cast<int64_t>(dev.sm_count) * 8));
+        frame_vote_center_kernel<<<dim3(blocks, nj), kVoteThreads, 0, s>>>(t, sh);
+        CPPF_LAUNCH_CHECK();
+    }
+    frame_fold_argmax_kernel<<<dim3(std::max(1, dev.sm_count * 4 / std::max(1, nj / 2)), nj), 256, 0, s>>>(t, sh);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+}  // namespace cppf

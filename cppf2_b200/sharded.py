@@ -11,9 +11,10 @@ nothing but the 4-byte back-vote error crosses the links per tuple.  The exchang
                                                                                  order statistic (np.percentile, eval.py:257)
   E3  importance + scale all_reduce(SUM) of one int32 buffer: per-point occurrence counts [n] (eval.py:260-266), the kept
                          count, and pass 0 of the scale median's radix histogram [3 x 65536] (eval.py:309)
-  E4  sphere bins        grouped all_reduce(SUM): the 2 x 720 float64 rotation bins (eval.py:277-293; every per-CTA
-                         contribution is a multiple of 2^-32, so the float64 sum is exact below 2^21 per bin and does not
-                         depend on g) and pass 1 of the scale histogram
+  E4  sphere bins        the 2 x 720 float64 rotation bins (eval.py:277-293) and pass 1 of the int32 scale histogram: two dtypes,
+                         so their byte images cross in ONE all_gather (0.8 MB per rank) and every rank adds them in rank order
+                         (every per-CTA bin contribution is a multiple of 2^-32, so the float64 sums are exact below 2^21 per
+                         bin and do not depend on g)
   E5  branch loss        all_reduce(SUM) of the sum of the clipped L1 terms (eval.py:358-363; the count follows from the
                          kept count E3 delivered)
 
@@ -87,22 +88,35 @@ class ShardedVote:
         self.n_collectives += 1
 
     def _all_reduce(self, label: str, tensors: List[torch.Tensor]):
-        """One exchange step: SUM all-reduce of every tensor of the list, as ONE grouped NCCL launch when the backend
-        coalesces (ncclGroupStart/End under torch.distributed's coalescing manager), else back to back (gloo)."""
+        """One exchange step: the SUM over the ranks of every tensor of the list, in place.  One dtype: one all_reduce (a
+        single flat buffer is what the stages hand over).  Mixed dtypes (E4: float64 sphere bins + int32 histogram): NCCL
+        reduces one dtype per call, so the byte images travel in ONE all_gather instead and every rank adds the g images
+        in rank order -- a fixed summation order, so the float64 bins are identical on every rank by construction."""
         tensors = [t for t in tensors if t is not None and t.numel() > 0]
-        if not tensors:
+        if not tensors or self.world == 1:
             return
-
-        def run():
-            grouped = len(tensors) > 1 and tensors[0].is_cuda and hasattr(dist, "_coalescing_manager")
-            if grouped:
-                with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=False):
-                    for t in tensors:
-                        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-            else:
+        if len({t.dtype for t in tensors}) == 1:
+            def run():
                 for t in tensors:
                     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-        self._exchange(label, run)
+            if len(tensors) > 1:
+                raise ValueError("same-dtype payloads of one exchange step must share one flat buffer")
+            self._exchange(label, run)
+            return
+        segs, off = [], 0
+        for t in tensors:
+            nb = t.numel() * t.element_size()
+            segs.append((off, nb))
+            off += (nb + 15) // 16 * 16
+        flat = torch.zeros(off, dtype=torch.uint8, device=tensors[0].device)
+        for t, (o, nb) in zip(tensors, segs):
+            flat[o:o + nb].copy_(t.contiguous().reshape(-1).view(torch.uint8))
+        gathered = torch.empty(self.world * off, dtype=torch.uint8, device=flat.device)
+        self._exchange(label, lambda: dist.all_gather_into_tensor(gathered, flat, group=self.group))
+        out = gathered.view(self.world, off)
+        for t, (o, nb) in zip(tensors, segs):
+            parts = out[:, o:o + nb].contiguous().view(t.dtype).reshape((self.world,) + tuple(t.shape))
+            t.copy_(parts.sum(0, dtype=t.dtype))
 
     def _all_gather(self, label: str, local: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.world == 1:

@@ -370,10 +370,52 @@ typedef struct cppf_instance_io {
     uint64_t seed_dino, seed_shot;
     int64_t cells_hint;
     cppf_pose *pose_dino, *pose_shot;
+    int32_t *idx_draw;          /* cppf_frame_pose only: with idx == NULL the tuple indices are drawn on the device (eval.py:207,
+                                   cppf_sample_tuples semantics, seed_idx) into this int32 [T,5] buffer */
+    uint64_t seed_idx;
 } cppf_instance_io;
 
 int cppf_instance_pose(const cppf_instance_io *io, const cppf_vote_params *params, const cppf_vote_buffers *buffers,
                        void *stream);
+
+/* ---- one FRAME in one call -------------------------------------------------------------------------
+ * The instance loop of eval.py:153-372 over every detection of a frame, batched: each stage (tuple sampling, SHOT, the
+ * heads of both branches, decode, centre votes, back-vote filter, rotation votes, pose) is launched ONCE for all instances /
+ * (instance, branch) jobs -- about 25 launches per frame whose grids carry a job dimension, instead of ~50 per instance.
+ * Results are identical to cppf_instance_pose per instance (same kernels' arithmetic, same seeds).  Everything that changes
+ * from frame to frame travels in one table (table_host -> table_dev, one small copy); launch dimensions depend on the
+ * capacities only, so with mode = CPPF_FRAME_ENQUEUE_ONLY the call can be captured in a CUDA graph once and replayed after
+ * refreshing the table with mode = CPPF_FRAME_FILL_ONLY (which touches table_host only and launches nothing).
+ * Requirements: bf16 tensor-core heads (cppf_heads_has_tc), T <= 2^17 per instance, 5-point tuples; ws_heads of an instance
+ * holds the per-point tables of BOTH branches (cppf_frame_heads_workspace_bytes).  Job 2i is the DINO branch of instance i,
+ * job 2i+1 its SHOT branch. */
+#define CPPF_FRAME_MAX_INSTANCES 16
+#define CPPF_FRAME_ALL 0
+#define CPPF_FRAME_FILL_ONLY 1
+#define CPPF_FRAME_ENQUEUE_ONLY 2
+
+typedef struct cppf_frame {
+    int n_instances;                    /* 0 .. CPPF_FRAME_MAX_INSTANCES (ignored by CPPF_FRAME_ENQUEUE_ONLY) */
+    int mode;                           /* CPPF_FRAME_* */
+    const cppf_instance_io *io;         /* [n_instances], host */
+    const cppf_vote_params *params;     /* [n_instances], host: the category configuration of each instance; the members that
+                                           size kernels (num_rots, num_bins, sphere_bins, tables, lut) are taken from params[0] and
+                                           from `shared` below and must agree across instances */
+    const cppf_vote_buffers *buffers;   /* [2 * n_instances], host */
+    const cppf_vote_params *shared;     /* the frame-wide members (tables, lattice, lut, thresholds); also used by ENQUEUE_ONLY */
+    const struct cppf_heads *heads_dino_any, *heads_shot_any;   /* any model of each branch (the architecture sizes the heads
+                                           launches); NULL: that branch is never run */
+    void *table_host;                   /* pinned host scratch of cppf_frame_table_bytes() */
+    void *table_dev;                    /* device scratch of the same size */
+    int capacity_instances;             /* grids are sized for this many instances, ... */
+    int replicas_max;                   /* centre-vote grid copies for L2-voted grids (0: default) */
+    int64_t capacity_tuples;            /* ... this many tuples per instance ... */
+    int64_t capacity_points;            /* ... and this many points per instance */
+} cppf_frame;
+
+int64_t cppf_frame_table_bytes(void);
+int64_t cppf_frame_heads_workspace_bytes(const struct cppf_heads *heads_dino, const struct cppf_heads *heads_shot, int64_t n);
+int cppf_frame_pose(const cppf_frame *frame, void *stream);
 
 /* ---- SHOT descriptor ----------------------------------------------------------------------------
  * replaces shot.compute / shot.estimate_normal, src_shot/shot.cpp:12-42, :45-100 (PCL NormalEstimation +

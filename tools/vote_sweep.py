@@ -117,6 +117,7 @@ def run_sharded(T: int, cloud: str, dev, rank: int, world: int, reps: int = 5, w
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(coll_ms, op=dist.ReduceOp.MAX)
     mid = sv.stages.intermediates()
+    n_coll = sv.n_collectives
     parity = None
     if check:
         mask_all = sv.gather_mask()                      # collective: every rank takes part
@@ -156,7 +157,7 @@ def run_sharded(T: int, cloud: str, dev, rank: int, world: int, reps: int = 5, w
                "n_gpus": world, "heads": "SHOT branch, bf16 tcgen05, decode fused" if with_heads else None,
                "ms": t, "tuples_per_sec": T / (t * 1e-3), "collective_ms": float(coll_ms.item()),
                "collective_share": float(coll_ms.item()) / t, "collectives": {k: round(v, 4) for k, v in coll.items()},
-               "n_collectives": sv.n_collectives, "kept": int(res_s.kept), "parity": parity}
+               "n_collectives": n_coll, "kept": int(res_s.kept), "parity": parity}
     del sv
     torch.cuda.empty_cache()
     return out
