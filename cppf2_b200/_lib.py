@@ -71,7 +71,19 @@ class InstanceIO(C.Structure):
                 ("heads_shot", C.c_void_p), ("normal_r", C.c_float), ("shot_r", C.c_float), ("shot_desc", C.c_void_p),
                 ("normals", C.c_void_p), ("ws_shot", C.c_void_p), ("ws_shot_bytes", C.c_int64), ("bins", C.c_void_p),
                 ("scales", C.c_void_p), ("ws_heads", C.c_void_p), ("ws_heads_bytes", C.c_int64), ("seed_dino", C.c_uint64),
-                ("seed_shot", C.c_uint64), ("cells_hint", C.c_int64), ("pose_dino", C.c_void_p), ("pose_shot", C.c_void_p)]
+                ("seed_shot", C.c_uint64), ("cells_hint", C.c_int64), ("pose_dino", C.c_void_p), ("pose_shot", C.c_void_p),
+                ("idx_draw", C.c_void_p), ("seed_idx", C.c_uint64)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("n_instances", C.c_int), ("mode", C.c_int), ("io", C.c_void_p), ("params", C.c_void_p), ("buffers", C.c_void_p),
+                ("shared", C.c_void_p), ("heads_dino_any", C.c_void_p), ("heads_shot_any", C.c_void_p), ("table_host", C.c_void_p),
+                ("table_dev", C.c_void_p), ("capacity_instances", C.c_int), ("replicas_max", C.c_int),
+                ("capacity_tuples", C.c_int64), ("capacity_points", C.c_int64)]
+
+
+FRAME_FILL, FRAME_COPY, FRAME_LAUNCH, FRAME_ALL = 1, 2, 4, 7
+FRAME_MAX_INSTANCES = 16
 
 
 P, I, I64, F, D, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
@@ -113,6 +125,9 @@ SIGNATURES = {
     "cppf_interpolate_features": (I, [P, I, I, I, I64, I64, I64, P, I64, F, I, P, P]),
     "cppf_vote_chain": (I, [P, I64, P, I, I64, I64, P, P, P, I64, P, P, P, P]),
     "cppf_instance_pose": (I, [P, P, P, P]),
+    "cppf_frame_table_bytes": (I64, []),
+    "cppf_frame_heads_workspace_bytes": (I64, [P, P, I64]),
+    "cppf_frame_pose": (I, [P, P]),
     "cppf_pose_workspace_bytes": (I64, [I64]),
     "cppf_scale_median_hist": (I, [P, P, P, I64, I, P, P, P]),
     "cppf_scale_median_pick": (I, [P, P, I, P, P, P]),

@@ -118,7 +118,7 @@ struct FrameShared {                    // identical for every job of a frame; p
 // exit at once); T_cap / n_cap bound the per-job tuple and point counts.
 int frame_launch_sample_tuples(const FrameTable *t, int ni, int64_t T_cap, cudaStream_t s);                       // targets.cu
 int frame_launch_shot(const FrameTable *t, int ni, int64_t n_cap, cudaStream_t s);                                // shot.cu
-int frame_launch_heads(const FrameTable *t, const FrameTable *host, const void *const *tc_states, cudaStream_t s);   // heads_tc.cu
+int frame_launch_heads(const FrameTable *t, const void *const *tc_states, int ni, int64_t n_cap, int64_t T_cap, cudaStream_t s);   // heads_tc.cu
 
 
 int frame_launch_center(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s);        // vote_center.cu

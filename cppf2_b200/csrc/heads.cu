@@ -437,6 +437,10 @@ CPPF_API int cppf_heads_destroy(cppf_heads *h) {
 
 CPPF_API int cppf_heads_has_tc(const cppf_heads *h) { return (h && h->tc) ? 1 : 0; }
 
+// internal (frame.cu): the tensor-core state and branch of a model
+extern "C" const void *cppf_heads_tc_state(const cppf_heads *h) { return h ? h->tc : nullptr; }
+extern "C" int cppf_heads_branch(const cppf_heads *h) { return h ? h->model.branch : -1; }
+
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 CPPF_API int64_t cppf_heads_workspace_bytes(const cppf_heads *h, int64_t T, int64_t n, int precision) {

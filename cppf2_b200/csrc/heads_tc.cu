@@ -19,6 +19,7 @@
 // The issue order is static (phase-major, slot-minor), so producer and issuer agree without communication.
 // HBM sees only the program's inputs (points, normals, per-point features, tuple indices) and its outputs.
 #include "heads_common.cuh"
+#include "frame.cuh"
 
 #include <cuda_bf16.h>
 #include <cstdlib>
@@ -120,23 +121,6 @@ struct Program {
     int gather_cols;
     Phase phase[kMaxPhases];
     Slab slab[kMaxSlabs];
-};
-
-struct Args {
-    int64_t rows;                       // tuples or points
-    const float *x;                     // LoadRows source [rows][x_ld]
-    int x_ld;
-    const float *pc, *normal;           // tuple encoders
-    const __nv_bfloat16 *point_feat;    // [n][gather_cols] bf16 (per-point program output)
-    IdxView idx;
-    int arity;
-    const unsigned char *weights;       // slab stream of this program
-    float *out0, *out1;
-    __nv_bfloat16 *out_bf16;
-    unsigned char *bins;                // non-null: out0 is not written; the logits epilogue draws one bin per (row, coord)
-    const float *u01;                   // [rows][6] injected uniforms or nullptr (counter-based generator keyed by seed)
-    unsigned long long seed;
-    long long *prof;                    // optional [gridDim.x][64] cycle counters (cppf_debug_heads_tc_profile)
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------
@@ -330,10 +314,44 @@ __device__ __forceinline__ void tuple_geometry_chunks(const float *__restrict__ 
     }
 }
 
-// Static tile assignment: round r gives slot s of CTA b the tile (r*kSlots + s)*gridDim.x + b, so that a
-// partial last round leaves whole second slots idle instead of half of the CTAs.
-__device__ __forceinline__ int64_t tile_of(int round, int slot) {
-    return (static_cast<int64_t>(round) * kSlots + slot) * gridDim.x + blockIdx.x;
+// Work assignment.  The unit is a PAIR of 128-row tiles of one job (both slots of a CTA share every weight slab of the
+// round, so they must run the same job's weights); round r gives CTA b the pair r * gridDim.x + b of the concatenation of
+// all jobs' pairs.  A launch carries one job (`one`, kernel-parameter space) or the jobs of a frame (`multi`, device
+// memory: same program, different rows / weights / outputs).  Every role evaluates this identically.
+//
+// The CTAs share the pairs in full rounds: with P pairs and G CTAs launched, ceil(P / G) rounds are unavoidable, so only
+// G' = ceil(P / rounds) CTAs take part (391 tiles = 196 pairs on 148 SMs: 98 CTAs x 2 rounds, not 148 + 48; a frame's
+// 1176 pairs: 147 CTAs x 8 rounds) and the rest leave their SMs to whatever else is queued.  G' is computed here, on the
+// device, from the table: the host may launch for a capacity (CUDA-graph replay) without unbalancing the last round.
+__device__ __forceinline__ int cta_share(const MultiArgs *__restrict__ multi, const Args &one) {
+    const int n_jobs = multi ? multi->n_jobs : 1;
+    int64_t total = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const int64_t rows = multi ? multi->job[j].rows : one.rows;
+        total += ((rows + kRows - 1) / kRows + 1) >> 1;
+    }
+    if (total <= 0) return 1;
+    const int64_t g = gridDim.x;
+    const int64_t rounds = (total + g - 1) / g;
+    return static_cast<int>((total + rounds - 1) / rounds);
+}
+
+__device__ __forceinline__ bool pair_of(const MultiArgs *__restrict__ multi, const Args &one, int64_t q, int &job, int64_t &tile0,
+                                        int64_t &n_tiles) {
+    const int n_jobs = multi ? multi->n_jobs : 1;
+    for (int j = 0; j < n_jobs; ++j) {
+        const int64_t rows = multi ? multi->job[j].rows : one.rows;
+        const int64_t tiles = (rows + kRows - 1) / kRows;
+        const int64_t pairs = (tiles + 1) >> 1;
+        if (q < pairs) {
+            job = j;
+            tile0 = 2 * q;
+            n_tiles = tiles;
+            return true;
+        }
+        q -= pairs;
+    }
+    return false;
 }
 
 // One batch of NB accumulator columns of this thread's row: v = D + bias, then the action's sink.
@@ -432,7 +450,8 @@ __device__ __forceinline__ long long prof_clock() {
 }
 
 template <bool kProf>
-__global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_constant__ Program prog, const __grid_constant__ Args a) {
+__global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_constant__ Program prog, const __grid_constant__ Args one,
+                                                               const MultiArgs *__restrict__ multi) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t s_tmem_base;
     const uint32_t ring0 = smem_u32(smem + kSmemRing);
@@ -465,8 +484,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
     if (tmem != 0) __trap();     // one CTA per SM owning all 512 columns: the allocation starts at lane 0, column 0
-    const int64_t n_tiles = (a.rows + kRows - 1) / kRows;
-    const int n_rounds = static_cast<int>((n_tiles + static_cast<int64_t>(kSlots) * gridDim.x - 1) / (static_cast<int64_t>(kSlots) * gridDim.x));
+    const int n_ctas = cta_share(multi, one);                       // CTAs that take part (see pair_of)
+    const int64_t q0 = static_cast<int>(blockIdx.x) < n_ctas ? static_cast<int64_t>(blockIdx.x) : (1ll << 60);   // others: no pair
 
     if (warp == kEpiWarps) {
         // =============================== weight producer ===============================================
@@ -476,9 +495,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         uint32_t seq = 0;
         long long t_wait = 0;
         const long long t_begin = prof_clock<kProf>();
-        for (int round = 0; round < n_rounds; ++round) {
-            if (tile_of(round, 0) >= n_tiles) break;
-            const unsigned char *src = a.weights;
+        for (int round = 0;; ++round) {
+            int job;
+            int64_t tile0, n_tiles;
+            if (!pair_of(multi, one, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
+            const unsigned char *src = multi ? multi->job[job].weights : one.weights;
             for (int i = 0; i < prog.n_slabs; ++i, ++seq) {
                 const uint32_t bytes = prog.slab[i].bytes();
                 const uint32_t stage = seq % kStages, turn = seq / kStages;
@@ -493,9 +514,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                 src += bytes;
             }
         }
-        if (kProf && a.prof && leader) {
-            a.prof[blockIdx.x * 64 + 4] = prof_clock<kProf>() - t_begin;
-            a.prof[blockIdx.x * 64 + 5] = t_wait;
+        if (kProf && one.prof && leader) {
+            one.prof[blockIdx.x * 64 + 4] = prof_clock<kProf>() - t_begin;
+            one.prof[blockIdx.x * 64 + 5] = t_wait;
         }
     } else if (warp > kEpiWarps) {
         // =============================== MMA issuers (one warp per slot) ================================
@@ -514,10 +535,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         const uint32_t ring_lo = ring0 >> 4;
         const uint32_t t_slot = static_cast<uint32_t>(s * kSlotTmem);     // TMEM base is 0: the CTA owns all 512 columns (checked above)
         uint32_t stage = 0, turn = 0, act_par = 0;
-        for (int round = 0; round < n_rounds; ++round) {
-            if (tile_of(round, s) >= n_tiles) break;
+        for (int round = 0;; ++round) {
+            int job;
+            int64_t tile0, n_tiles;
+            if (!pair_of(multi, one, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
+            if (tile0 + s >= n_tiles) continue;     // a job with an odd tile count: its last pair has no second tile
             // slot 1 never runs a round that slot 0 skips; slot 0 releases the slabs alone in rounds slot 1 skips
-            const bool other_active = s == 1 || tile_of(round, 1) < n_tiles;
+            const bool other_active = s == 1 || tile0 + 1 < n_tiles;
             for (int i = 0; i < prog.n_slabs; ++i) {
                 const uint4 w = *reinterpret_cast<const uint4 *>(&prog.slab[i]);      // a_lo, idesc, nd, misc
                 const uint32_t flags = w.w >> 24;
@@ -576,8 +600,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                 ++n_steps;
             }
         }
-        if (kProf && a.prof && leader) {
-            long long *o = a.prof + blockIdx.x * 64 + 40 + 8 * s;
+        if (kProf && one.prof && leader) {
+            long long *o = one.prof + blockIdx.x * 64 + 40 + 8 * s;
             o[0] = prof_clock<kProf>() - t_begin;
             o[1] = t_act;
             o[2] = t_full;
@@ -598,9 +622,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         uint32_t done_seq = 0;
         long long t_done = 0, t_actn[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_arrive = 0;
         const long long t_begin = prof_clock<kProf>();
-        for (int round = 0; round < n_rounds; ++round) {
-            const int64_t tile = tile_of(round, slot);
-            if (tile >= n_tiles) break;
+        for (int round = 0;; ++round) {
+            int job;
+            int64_t tile0, n_tiles;
+            if (!pair_of(multi, one, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
+            const int64_t tile = tile0 + slot;
+            if (tile >= n_tiles) continue;
+            const Args &a = multi ? multi->job[job] : one;
             const int64_t row_base = tile * kRows;
             const int64_t grow = row_base + row;
             const bool live = grow < a.rows;
@@ -752,8 +780,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                 t_arrive += prof_clock<kProf>() - t0;
             }
         }
-        if (kProf && a.prof && sw == 0 && lane == 0) {
-            long long *o = a.prof + blockIdx.x * 64 + 8 + 16 * slot;
+        if (kProf && one.prof && sw == 0 && lane == 0) {
+            long long *o = one.prof + blockIdx.x * 64 + 8 + 16 * slot;
             o[0] = prof_clock<kProf>() - t_begin;
             o[1] = t_done;
             for (int k = 0; k < 10; ++k) o[2 + k] = t_actn[k];
@@ -1137,6 +1165,15 @@ extern "C" int64_t cppf_heads_tc_workspace_bytes(const void *state, int64_t T, i
     return static_cast<int64_t>(tc_align(2 * static_cast<size_t>(st->point_cols) * n) + 256);
 }
 
+static int64_t pairs_of(int64_t rows) { return ((rows + kRows - 1) / kRows + 1) / 2; }
+
+// At most one CTA per SM; how many of them take part is decided on the device (cta_share): the fewest that still finish
+// in the minimal number of rounds.  CPPF_TC_GRID=full is gone with the host-side balancing it switched off.
+static int blocks_for_pairs(int64_t pairs) {
+    const int sms = device_info().sm_count;
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(pairs, sms)));
+}
+
 extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t n, const void *idx, int idx_is_i64,
                                      int64_t idx_stride, int64_t T, const float *feat, const float *normal, float *logits,
                                      float *scale, unsigned char *bins, const float *u01, unsigned long long seed, void *ws,
@@ -1147,23 +1184,6 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
     if (ws_bytes < cppf_heads_tc_workspace_bytes(state, T, n)) return CPPF_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     __nv_bfloat16 *point_feat = static_cast<__nv_bfloat16 *>(ws);
-    const int sms = device_info().sm_count;
-    // Grid: the fewest CTAs that still finish in the minimal number of rounds (a round = one tile in each of a CTA's
-    // two slots).  T = 50 000 is 391 tiles = 1.32 rounds of 148 x 2 slots: 148 CTAs would run a full round and then a
-    // round with 95 half-empty CTAs (one slot idle, no MMA/epilogue overlap); 98 CTAs run two full rounds and leave
-    // 50 SMs to the kernels of the other instances' streams.  CPPF_TC_GRID=full restores one CTA per SM.
-    static const char grid_mode = [] {
-        const char *e = getenv("CPPF_TC_GRID");
-        return e ? e[0] : 'b';
-    }();
-    const bool grid_full = grid_mode == 'f';
-    auto blocks_for = [&](int64_t rows) {
-        const int64_t tiles = (rows + kRows - 1) / kRows;
-        if (grid_full || tiles <= sms) return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, sms)));   // small: latency first
-        const int64_t rounds = std::max<int64_t>(1, (tiles + static_cast<int64_t>(kSlots) * sms - 1) / (static_cast<int64_t>(kSlots) * sms));
-        const int64_t per_cta = rounds * kSlots;
-        return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((tiles + per_cta - 1) / per_cta, sms)));
-    };
     {
         Args a{};
         a.rows = n;
@@ -1173,7 +1193,7 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.weights = st->d_point_w;
         a.out_bf16 = point_feat;
         a.prof = nullptr;
-        chain_tc_kernel<false><<<blocks_for(n), kThreads, kSmemTotal, s>>>(st->point_prog, a);
+        chain_tc_kernel<false><<<blocks_for_pairs(pairs_of(n)), kThreads, kSmemTotal, s>>>(st->point_prog, a, nullptr);
         CPPF_LAUNCH_CHECK();
     }
     if (T == 0) return CPPF_OK;
@@ -1192,9 +1212,67 @@ extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t
         a.u01 = u01;
         a.seed = seed;
         a.prof = g_tc_prof;
-        if (a.prof) chain_tc_kernel<true><<<blocks_for(T), kThreads, kSmemTotal, s>>>(st->tuple_prog, a);
-        else chain_tc_kernel<false><<<blocks_for(T), kThreads, kSmemTotal, s>>>(st->tuple_prog, a);
+        if (a.prof) chain_tc_kernel<true><<<blocks_for_pairs(pairs_of(T)), kThreads, kSmemTotal, s>>>(st->tuple_prog, a, nullptr);
+        else chain_tc_kernel<false><<<blocks_for_pairs(pairs_of(T)), kThreads, kSmemTotal, s>>>(st->tuple_prog, a, nullptr);
         CPPF_LAUNCH_CHECK();
     }
     return CPPF_OK;
 }
+
+// ---- batched frame path (frame.cuh) ------------------------------------------------------------------------------------
+// All instances' per-point programs of a branch in one launch, all their per-tuple programs in another: the program (layer
+// inventory, slab list) is the branch's architecture and identical for every category; rows, inputs, outputs and the weight
+// stream come from the frame table.  126 point tiles fill the GPU where six 33-CTA launches ran at a tenth of its rate, and
+// the tuple tiles of all jobs form full rounds (6 x 391 tiles = 1176 pairs = 8 rounds of 147 CTAs).
+extern "C" int cppf_heads_tc_fill_job(const void *state, int kind, const float *pc, int64_t n, const void *idx, int idx_is_i64,
+                                      int64_t idx_stride, int64_t T, const float *feat, const float *normal, void *point_feat,
+                                      float *scale, unsigned char *bins, unsigned long long seed, void *args_out) {
+    const State *st = static_cast<const State *>(state);
+    if (!st || !args_out) return CPPF_ERR_INVALID_ARGUMENT;
+    Args a{};
+    a.arity = st->model.arity;
+    if (kind == 0) {
+        a.rows = n;
+        a.x = feat;
+        a.x_ld = st->model.branch == 0 ? CPPF_SHOT_DIM : 1024;
+        a.weights = st->d_point_w;
+        a.out_bf16 = static_cast<__nv_bfloat16 *>(point_feat);
+    } else {
+        a.rows = T;
+        a.pc = pc;
+        a.normal = normal;
+        a.point_feat = static_cast<const __nv_bfloat16 *>(point_feat);
+        a.idx = IdxView{idx, idx_stride, idx_is_i64};
+        a.weights = st->d_tuple_w;
+        a.out1 = scale;
+        a.bins = bins;
+        a.seed = seed;
+    }
+    *static_cast<Args *>(args_out) = a;
+    return CPPF_OK;
+}
+
+extern "C" int64_t cppf_heads_tc_point_bytes(const void *state, int64_t n) {
+    const State *st = static_cast<const State *>(state);
+    return st ? static_cast<int64_t>(tc_align(2 * static_cast<size_t>(st->point_cols) * n)) : 0;
+}
+
+namespace cppf {
+
+// tc_states[branch] = any model of the branch (its two programs); rows_cap[kind] bounds the rows of a job, ni the jobs
+int frame_launch_heads(const FrameTable *t, const void *const *tc_states, int ni, int64_t n_cap, int64_t T_cap, cudaStream_t s) {
+    if (ni <= 0) return CPPF_OK;
+    for (int kind = 0; kind < 2; ++kind)
+        for (int branch = 1; branch >= 0; --branch) {        // DINO first: it does not wait for the SHOT descriptors
+            const State *st = static_cast<const State *>(tc_states[branch]);
+            if (!st) continue;
+            const int64_t pairs = pairs_of(kind == 0 ? n_cap : T_cap) * ni;
+            Args none{};
+            chain_tc_kernel<false><<<blocks_for_pairs(pairs), kThreads, kSmemTotal, s>>>(kind == 0 ? st->point_prog : st->tuple_prog, none,
+                                                                                       &t->heads[kind][branch]);
+            CPPF_LAUNCH_CHECK();
+        }
+    return CPPF_OK;
+}
+
+}  // namespace cppf

@@ -15,6 +15,7 @@
 // votes.  Histogram: every neighbour's quadrilinear contributions go to a per-warp 352-float histogram in
 // shared memory (float atomics), then L2-normalised and written as one coalesced 1408-byte row.
 #include "common.cuh"
+#include "frame.cuh"
 
 #include <math_constants.h>
 
@@ -24,20 +25,13 @@ constexpr int kShotWarps = 8;                    // key-points in flight per CTA
 constexpr int kShotMaxCells = 1 << 21;           // cell table capacity (coarsened beyond that)
 constexpr int kShotListCap = 768;                // cached neighbours per key-point (more: the cells are swept again)
 
-struct ShotGrid {        // device-resident search grid header
-    float lo[3];
-    float inv;           // 1 / cell edge
-    int dim[3];
-    int cells;
-};
-
 __device__ __forceinline__ int shot_coord(float v, float lo, float inv, int dim) {
     int c = static_cast<int>((v - lo) * inv);
     return min(max(c, 0), dim - 1);
 }
 
-__global__ void shot_grid_setup_kernel(const cppf_grid_geom *__restrict__ bounds, float radius, ShotGrid *__restrict__ g) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one thread
+__device__ __forceinline__ void shot_grid_setup(const cppf_grid_geom *__restrict__ bounds, float radius, ShotGrid *__restrict__ g) {
     float inv = 1.0f / radius;
     int dim[3];
     long long cells;
@@ -59,11 +53,13 @@ __global__ void shot_grid_setup_kernel(const cppf_grid_geom *__restrict__ bounds
     g->cells = static_cast<int>(cells);
 }
 
-__global__ void __launch_bounds__(256) shot_cell_count_kernel(const float *__restrict__ pc, int n,
-                                                              const ShotGrid *__restrict__ g, int *__restrict__ cell_of,
-                                                              int *__restrict__ cell_count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void shot_grid_setup_kernel(const cppf_grid_geom *__restrict__ bounds, float radius, ShotGrid *__restrict__ g) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    shot_grid_setup(bounds, radius, g);
+}
+
+__device__ __forceinline__ void shot_cell_count_one(const float *__restrict__ pc, int i, const ShotGrid *__restrict__ g,
+                                                    int *__restrict__ cell_of, int *__restrict__ cell_count) {
     const float x = pc[3 * i], y = pc[3 * i + 1], z = pc[3 * i + 2];
     int cell = -1;
     if (isfinite(x) && isfinite(y) && isfinite(z)) {
@@ -74,9 +70,17 @@ __global__ void __launch_bounds__(256) shot_cell_count_kernel(const float *__res
     cell_of[i] = cell;
 }
 
+__global__ void __launch_bounds__(256) shot_cell_count_kernel(const float *__restrict__ pc, int n,
+                                                              const ShotGrid *__restrict__ g, int *__restrict__ cell_of,
+                                                              int *__restrict__ cell_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    shot_cell_count_one(pc, i, g, cell_of, cell_count);
+}
+
 // exclusive scan of cell_count[0..cells) into cell_start[0..cells], single CTA
-__global__ void __launch_bounds__(1024) shot_cell_scan_kernel(const ShotGrid *__restrict__ g, const int *__restrict__ cell_count,
-                                                              int *__restrict__ cell_start, int *__restrict__ cell_fill) {
+__device__ __forceinline__ void shot_cell_scan_body(const ShotGrid *__restrict__ g, const int *__restrict__ cell_count,
+                                                    int *__restrict__ cell_start, int *__restrict__ cell_fill) {
     __shared__ int s_part[1024];
     const int cells = g->cells;
     const int per = (cells + 1023) / 1024;
@@ -100,27 +104,37 @@ __global__ void __launch_bounds__(1024) shot_cell_scan_kernel(const ShotGrid *__
     if (threadIdx.x == 1023) cell_start[cells] = s_part[1023];
 }
 
-__global__ void __launch_bounds__(256) shot_scatter_kernel(const float *__restrict__ pc, int n, const int *__restrict__ cell_of,
-                                                           int *__restrict__ cell_fill, float4 *__restrict__ sorted) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void __launch_bounds__(1024) shot_cell_scan_kernel(const ShotGrid *__restrict__ g, const int *__restrict__ cell_count,
+                                                              int *__restrict__ cell_start, int *__restrict__ cell_fill) {
+    shot_cell_scan_body(g, cell_count, cell_start, cell_fill);
+}
+
+__device__ __forceinline__ void shot_scatter_one(const float *__restrict__ pc, int i, const int *__restrict__ cell_of,
+                                                 int *__restrict__ cell_fill, float4 *__restrict__ sorted) {
     const int cell = cell_of[i];
     if (cell < 0) return;
     const int pos = atomicAdd(&cell_fill[cell], 1);
     sorted[pos] = make_float4(pc[3 * i], pc[3 * i + 1], pc[3 * i + 2], __int_as_float(i));
 }
 
+__global__ void __launch_bounds__(256) shot_scatter_kernel(const float *__restrict__ pc, int n, const int *__restrict__ cell_of,
+                                                           int *__restrict__ cell_fill, float4 *__restrict__ sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    shot_scatter_one(pc, i, cell_of, cell_fill, sorted);
+}
+
 // The atomic scatter leaves each cell's points in arrival order, which changes from run to run.  Rank every
 // point of a cell by its original index (one warp per cell, counting sort by comparison: segments hold
 // ~100 points when the cloud is voxel-sampled at radius/10 as the reference does) so that the sorted copy,
 // and with it every floating-point accumulation order downstream, is deterministic.
-__global__ void __launch_bounds__(256) shot_cell_order_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
-                                                              const float4 *__restrict__ scattered,
-                                                              float4 *__restrict__ sorted) {
+__device__ __forceinline__ void shot_cell_order_body(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
+                                                     const float4 *__restrict__ scattered, float4 *__restrict__ sorted,
+                                                     int bid, int nblk) {
     const int cells = gp->cells;
     const int lane = lane_id();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (bid * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (nblk * blockDim.x) >> 5;
     for (int c = warp; c < cells; c += n_warps) {
         const int b = cell_start[c], e = cell_start[c + 1];
         for (int t = b + lane; t < e; t += 32) {
@@ -131,6 +145,12 @@ __global__ void __launch_bounds__(256) shot_cell_order_kernel(const ShotGrid *__
             sorted[b + rank] = mine;
         }
     }
+}
+
+__global__ void __launch_bounds__(256) shot_cell_order_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
+                                                              const float4 *__restrict__ scattered,
+                                                              float4 *__restrict__ sorted) {
+    shot_cell_order_body(gp, cell_start, scattered, sorted, blockIdx.x, gridDim.x);
 }
 
 // Points with non-finite coordinates never enter the grid: their outputs are NaN (PCL: isFinite checks).
@@ -247,17 +267,15 @@ __device__ void eigen33_smallest(const float mat[9], float evec[3]) {
 }
 
 // ---- normals: NormalEstimation::computePointNormal + flipNormalTowardsViewpoint(origin) ----------------
-__global__ void __launch_bounds__(kShotWarps * 32) shot_normals_kernel(const ShotGrid *__restrict__ gp,
-                                                                      const int *__restrict__ cell_start,
-                                                                      const float4 *__restrict__ sorted, int n_sorted_max,
-                                                                      float radius_sq, float *__restrict__ normals,
-                                                                      float4 *__restrict__ normals_sorted) {
+__device__ __forceinline__ void shot_normals_body(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
+                                                  const float4 *__restrict__ sorted, float radius_sq,
+                                                  float *__restrict__ normals, float4 *__restrict__ normals_sorted, int bid,
+                                                  int nblk) {
     const ShotGrid g = *gp;
     const int n_sorted = cell_start[g.cells];
     const int lane = lane_id();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    (void)n_sorted_max;
+    const int warp = (bid * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (nblk * blockDim.x) >> 5;
     for (int s = warp; s < n_sorted; s += n_warps) {
         const float4 pq = sorted[s];
         const float p[3] = {pq.x, pq.y, pq.z};
@@ -311,6 +329,15 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_normals_kernel(const Sho
             if (normals_sorted) normals_sorted[s] = make_float4(nrm[0], nrm[1], nrm[2], 0.0f);
         }
     }
+}
+
+__global__ void __launch_bounds__(kShotWarps * 32) shot_normals_kernel(const ShotGrid *__restrict__ gp,
+                                                                      const int *__restrict__ cell_start,
+                                                                      const float4 *__restrict__ sorted, int n_sorted_max,
+                                                                      float radius_sq, float *__restrict__ normals,
+                                                                      float4 *__restrict__ normals_sorted) {
+    (void)n_sorted_max;
+    shot_normals_body(gp, cell_start, sorted, radius_sq, normals, normals_sorted, blockIdx.x, gridDim.x);
 }
 
 // ---- cyclic Jacobi, symmetric 3x3, double (stands in for Eigen::SelfAdjointEigenSolver<Matrix3d>) ------
@@ -376,10 +403,10 @@ __device__ void jacobi_eigen3(const double Ain[6] /* xx xy xz yy yz zz */, doubl
 // weights in float (SHOT's quadrilinear interpolation is continuous across every bin boundary, so the
 // descriptor moves by ~1e-7).
 template <typename REAL>
-__global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
+__device__ __forceinline__ void shot_descriptor_body(
     const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
     const float4 *__restrict__ normals_sorted, float radius_f, double radius, float *__restrict__ desc,
-    float *__restrict__ rf_out) {
+    float *__restrict__ rf_out, int bid, int nblk) {
     // The histogram accumulates in 32-bit fixed point: shared-memory float atomicAdd is a compare-and-swap loop (60 % of this
     // kernel's stall samples, ncu; so is the 64-bit integer add), the 32-bit integer add is one native ATOMS.ADD.  A neighbour
     // adds at most 5 over all bins, so with `total` neighbours a scale of 2^k, k = 32 - bits(5 total + 1) (<= 24), cannot
@@ -395,8 +422,8 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
     const float radius_sq = static_cast<float>(radius * radius);
     const int lane = lane_id();
     const int wib = threadIdx.x >> 5;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (bid * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (nblk * blockDim.x) >> 5;
     unsigned int *hist = s_hist[wib];
     float hist_scale = 1.0f;
     auto hist_add = [&](int bin_index, float v) { atomicAdd(&hist[bin_index], __float2uint_rn(v * hist_scale)); };
@@ -633,6 +660,14 @@ __global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
     }
 }
 
+template <typename REAL>
+__global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
+    const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
+    const float4 *__restrict__ normals_sorted, float radius_f, double radius, float *__restrict__ desc,
+    float *__restrict__ rf_out) {
+    shot_descriptor_body<REAL>(gp, cell_start, sorted, normals_sorted, radius_f, radius, desc, rf_out, blockIdx.x, gridDim.x);
+}
+
 // normals_sorted[s] = normals_in[orig(s)]: used when the caller supplies the normals
 __global__ void __launch_bounds__(256) shot_gather_normals_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
                                                                   const float4 *__restrict__ sorted,
@@ -645,16 +680,9 @@ __global__ void __launch_bounds__(256) shot_gather_normals_kernel(const ShotGrid
     normals_sorted[s] = make_float4(normals_in[3 * orig], normals_in[3 * orig + 1], normals_in[3 * orig + 2], 0.0f);
 }
 
-struct ShotWorkspace {
-    cppf_grid_geom *bounds;
-    ShotGrid *grid;
-    int *cell_of, *cell_count, *cell_start, *cell_fill;
-    float4 *sorted, *normals_sorted;
-};
-
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
-static size_t shot_carve(void *ws, int64_t n, ShotWorkspace *out) {
+size_t shot_carve(void *ws, int64_t n, ShotWorkspace *out) {
     unsigned char *base = static_cast<unsigned char *>(ws);
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -690,6 +718,103 @@ static int shot_build_grid(const float *pc, int64_t n, float radius, const ShotW
     shot_scatter_kernel<<<nb, 256, 0, s>>>(pc, static_cast<int>(n), w.cell_of, w.cell_fill, w.normals_sorted);
     CPPF_LAUNCH_CHECK();
     shot_cell_order_kernel<<<grid_for(n * 8, 256, 8), 256, 0, s>>>(w.grid, w.cell_start, w.normals_sorted, w.sorted);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
+// =====================================================================================================================
+// Batched frame path (frame.cuh): SHOT-352 + normals of every instance of a frame in seven launches; blockIdx.y = instance.
+// Same bodies as the single-cloud kernels, so descriptors are identical to cppf_shot_compute_ex(fast_math = 1).
+// =====================================================================================================================
+__device__ __forceinline__ bool frame_shot_instance(const FrameTable *t, const FrameInst *&in) {
+    if (static_cast<int>(blockIdx.y) >= t->n_inst) return false;
+    in = &t->inst[blockIdx.y];
+    return in->shot_desc != nullptr && in->n > 0;
+}
+
+// bounds -> search grid header -> its cell counters zeroed (one CTA per instance)
+__global__ void __launch_bounds__(1024) frame_shot_setup_kernel(const FrameTable *__restrict__ t) {
+    const FrameInst *in;
+    if (!frame_shot_instance(t, in)) return;
+    const float cell_r = fmaxf(in->normal_r, in->shot_r);      // one grid serves both searches
+    cloud_bounds_shared(in->pc, in->n, cell_r, in->sw.bounds);
+    __syncthreads();
+    if (threadIdx.x == 0) shot_grid_setup(in->sw.bounds, cell_r, in->sw.grid);
+    __syncthreads();
+    const int cells = in->sw.grid->cells;
+    for (int i = threadIdx.x; i <= cells; i += blockDim.x) in->sw.cell_count[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) frame_shot_count_kernel(const FrameTable *__restrict__ t) {
+    const FrameInst *in;
+    if (!frame_shot_instance(t, in)) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < in->n; i += gridDim.x * blockDim.x)
+        shot_cell_count_one(in->pc, i, in->sw.grid, in->sw.cell_of, in->sw.cell_count);
+}
+
+__global__ void __launch_bounds__(1024) frame_shot_scan_kernel(const FrameTable *__restrict__ t) {
+    const FrameInst *in;
+    if (!frame_shot_instance(t, in)) return;
+    shot_cell_scan_body(in->sw.grid, in->sw.cell_count, in->sw.cell_start, in->sw.cell_fill);
+}
+
+__global__ void __launch_bounds__(256) frame_shot_scatter_kernel(const FrameTable *__restrict__ t) {
+    const FrameInst *in;
+    if (!frame_shot_instance(t, in)) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < in->n; i += gridDim.x * blockDim.x)
+        shot_scatter_one(in->pc, i, in->sw.cell_of, in->sw.cell_fill, in->sw.normals_sorted);   // staging: ordered next
+}
+
+__global__ void __launch_bounds__(256) frame_shot_order_kernel(const FrameTable *__restrict__ t) {
+    const FrameInst *in;
+    if (!frame_shot_instance(t, in)) return;
+    shot_cell_order_body(in->sw.grid, in->sw.cell_start, in->sw.normals_sorted, in->sw.sorted, blockIdx.x, gridDim.x);
+}
+
+// normals; points with non-finite coordinates (never in the grid) get their NaN rows here
+__global__ void __launch_bounds__(kShotWarps * 32) frame_shot_normals_kernel(const FrameTable *__restrict__ t) {
+    const FrameInst *in;
+    if (!frame_shot_instance(t, in)) return;
+    const float nanv = CUDART_NAN_F;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < in->n; i += (gridDim.x * blockDim.x) >> 5) {
+        if (in->sw.cell_of[i] >= 0) continue;
+        const int lane = lane_id();
+        if (lane < 3) in->normals[3 * i + lane] = nanv;
+        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) in->shot_desc[static_cast<size_t>(i) * CPPF_SHOT_DIM + j] = nanv;
+    }
+    const float nr2 = static_cast<float>(static_cast<double>(in->normal_r) * static_cast<double>(in->normal_r));
+    shot_normals_body(in->sw.grid, in->sw.cell_start, in->sw.sorted, nr2, in->normals, in->sw.normals_sorted, blockIdx.x, gridDim.x);
+}
+
+__global__ void __launch_bounds__(kShotWarps * 32) frame_shot_descriptor_kernel(const FrameTable *__restrict__ t) {
+    const FrameInst *in;
+    if (!frame_shot_instance(t, in)) return;
+    shot_descriptor_body<float>(in->sw.grid, in->sw.cell_start, in->sw.sorted, in->sw.normals_sorted, in->shot_r,
+                                static_cast<double>(in->shot_r), in->shot_desc, nullptr, blockIdx.x, gridDim.x);
+}
+
+int frame_launch_shot(const FrameTable *t, int ni, int64_t n_cap, cudaStream_t s) {
+    if (ni <= 0 || n_cap <= 0) return CPPF_OK;
+    const int sms = device_info().sm_count;
+    // per instance: enough CTAs for the capacity, the whole launch a few waves of the GPU
+    auto per_inst = [&](int64_t items, int threads, int per_sm) {
+        const int64_t need = (items + threads - 1) / threads;
+        const int64_t cap = std::max<int64_t>(1, (static_cast<int64_t>(sms) * per_sm + ni - 1) / ni);
+        return static_cast<int>(std::max<int64_t>(1, std::min(need, cap)));
+    };
+    frame_shot_setup_kernel<<<dim3(1, ni), 1024, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_shot_count_kernel<<<dim3(per_inst(n_cap, 256, 8), ni), 256, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_shot_scan_kernel<<<dim3(1, ni), 1024, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_shot_scatter_kernel<<<dim3(per_inst(n_cap, 256, 8), ni), 256, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_shot_order_kernel<<<dim3(per_inst(n_cap * 8, 256, 8), ni), 256, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_shot_normals_kernel<<<dim3(per_inst(n_cap * 32, kShotWarps * 32, 8), ni), kShotWarps * 32, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_shot_descriptor_kernel<<<dim3(per_inst(n_cap * 32, kShotWarps * 32, 4), ni), kShotWarps * 32, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }

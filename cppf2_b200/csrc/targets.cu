@@ -90,6 +90,31 @@ __global__ void __launch_bounds__(256) sample_tuples_kernel(int64_t n, int64_t c
     }
 }
 
+// Batched frame path (frame.cuh): the tuple indices of every instance that brought none (eval.py:207), one launch.  Same
+// generator and counters as sample_tuples_kernel with the instance's seed, so cppf_sample_tuples reproduces them.
+__global__ void __launch_bounds__(256) frame_sample_tuples_kernel(const FrameTable *__restrict__ t) {
+    if (static_cast<int>(blockIdx.y) >= t->n_inst) return;
+    const FrameInst &in = t->inst[blockIdx.y];
+    if (in.idx_draw == nullptr) return;
+    const int64_t count = static_cast<int64_t>(in.T) * 5;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+        uint64_t z = in.seed_idx + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(i) + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        in.idx_draw[i] = static_cast<int32_t>(__umul64hi(z, static_cast<uint64_t>(in.n)));
+    }
+}
+
+int frame_launch_sample_tuples(const FrameTable *t, int ni, int64_t T_cap, cudaStream_t s) {
+    if (ni <= 0 || T_cap <= 0) return CPPF_OK;
+    const int per_inst = std::max(1, std::min<int>(div_up(T_cap * 5, 256), (device_info().sm_count * 8 + ni - 1) / ni));
+    frame_sample_tuples_kernel<<<dim3(per_inst, ni), 256, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    return CPPF_OK;
+}
+
 }  // namespace cppf
 
 using namespace cppf;

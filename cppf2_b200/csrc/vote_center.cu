@@ -31,77 +31,9 @@ __device__ __forceinline__ int replica_count(int64_t cells, int64_t capacity, in
 // ---------------------------------------------------------------------------------------------------
 // bounds: single CTA, coalesced sweep, shared-memory tree reduction.  N <= 50 000 by eval.py:195.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cloud_bounds_body(const float *__restrict__ pc, int64_t n, float res,
-                                                  cppf_grid_geom *__restrict__ geom) {
-    __shared__ float s_lo[3][32], s_hi[3][32];
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    // flat float index i = 3*p + k: consecutive threads read consecutive floats; k = i % 3
-    for (int64_t i = threadIdx.x; i < 3 * n; i += 3 * 1024) {
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            int64_t j = i + static_cast<int64_t>(u) * 1024;
-            if (j < 3 * n) {
-                float v = pc[j];
-                int k = static_cast<int>(j % 3);
-                // k is thread-dependent; keep the three accumulators in registers with selects
-                lo[0] = (k == 0 && v < lo[0]) ? v : lo[0];
-                lo[1] = (k == 1 && v < lo[1]) ? v : lo[1];
-                lo[2] = (k == 2 && v < lo[2]) ? v : lo[2];
-                hi[0] = (k == 0 && v > hi[0]) ? v : hi[0];
-                hi[1] = (k == 1 && v > hi[1]) ? v : hi[1];
-                hi[2] = (k == 2 && v > hi[2]) ? v : hi[2];
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
-            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
-        }
-        if (lane_id() == 0) {
-            s_lo[k][threadIdx.x >> 5] = lo[k];
-            s_hi[k][threadIdx.x >> 5] = hi[k];
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float l = s_lo[k][threadIdx.x], h = s_hi[k][threadIdx.x];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
-                h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
-            }
-            lo[k] = l;
-            hi[k] = h;
-        }
-        if (threadIdx.x == 0) {
-            uint32_t flags = (n <= 0) ? CPPF_STATUS_EMPTY : 0u;
-            float ext_max = 0.0f;
-            int64_t cells = 1;
-            for (int k = 0; k < 3; ++k) {
-                geom->lo[k] = lo[k];
-                geom->hi[k] = hi[k];
-                float ext = __fsub_rn(hi[k], lo[k]);
-                ext_max = fmaxf(ext_max, ext);
-                int64_t g = (n > 0) ? static_cast<int64_t>(__fdiv_rn(ext, res)) + 1 : 1;  // trunc toward zero
-                geom->grid_res[k] = g;
-                cells *= g;
-            }
-            if (__fdiv_rn(ext_max, res) > 1000.0f) flags |= CPPF_STATUS_GRID_GUARD;  // eval.py:200
-            geom->res = res;
-            geom->cells = cells;
-            geom->flags = flags;
-        }
-    }
-}
-
 __global__ void __launch_bounds__(1024) cloud_bounds_kernel(const float *__restrict__ pc, int64_t n, float res,
                                                             cppf_grid_geom *__restrict__ geom) {
-    cloud_bounds_body(pc, n, res, geom);
+    cloud_bounds_shared(pc, n, res, geom);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -482,7 +414,7 @@ __global__ void __launch_bounds__(1024) frame_prep_kernel(const FrameTable *__re
     if (static_cast<int>(blockIdx.x) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.x];
     const FrameInst &in = t->inst[j.inst];
-    cloud_bounds_body(in.pc, in.n, j.res, j.geom);
+    cloud_bounds_shared(in.pc, in.n, j.res, j.geom);
     const int tid = threadIdx.x;
     uint32_t *c = reinterpret_cast<uint32_t *>(j.center);
     for (int i = tid; i < static_cast<int>(sizeof(cppf_center) / 4); i += 1024) c[i] = 0u;

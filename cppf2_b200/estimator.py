@@ -88,7 +88,8 @@ class PoseEstimator:
 
     def __init__(self, models: Dict[str, Dict[str, object]], cfgs: Dict[str, dict], num_pairs: int = 50000,
                  num_rots: int = 180, angle_tol: float = 1.0, backproj_ratio: float = 0.1, imp_wt_margin: float = 0.01,
-                 seed: int = 0, max_points: int = 50000, device=None, n_streams: Optional[int] = None, opt: bool = False):
+                 seed: int = 0, max_points: int = 50000, device=None, n_streams: Optional[int] = None, opt: bool = False,
+                 grid_capacity: int = 1 << 23):
         self.models, self.cfgs = models, cfgs
         self.num_pairs, self.num_rots = int(num_pairs), int(num_rots)
         self.angle_tol, self.backproj_ratio, self.imp_wt_margin = angle_tol, backproj_ratio, imp_wt_margin
@@ -99,7 +100,9 @@ class PoseEstimator:
         # Instances are independent (eval.py:153): instance i runs on lane i % n_streams, each lane a CUDA stream with its
         # own voter buffers, so the small latency-bound kernels of one instance fill the SMs another leaves idle.
         self.n_streams = max(1, int(n_streams if n_streams is not None else os.environ.get("CPPF_STREAMS", "6")))
-        self.voters = [PoseVoter(self.num_pairs, max_points, device=self.device) for _ in range(self.n_streams)]
+        # centre-grid words per voter; a grid that does not fit is flagged by the kernels and the buffers are regrown (PendingFrame)
+        self.grid_capacity = int(grid_capacity)
+        self.voters = [PoseVoter(self.num_pairs, max_points, self.grid_capacity, device=self.device) for _ in range(self.n_streams)]
         self.voter = self.voters[0]
         self.lanes = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)] if self.n_streams > 1 else []
         self.pose_bytes = C.sizeof(Pose)
@@ -107,6 +110,16 @@ class PoseEstimator:
         self.launches = 0
         self._lane_bufs: Dict[int, dict] = {}
         self.one_call = os.environ.get("CPPF_ONE_CALL", "1") != "0"      # cppf_instance_pose per instance (bf16 heads, no injected draws)
+        # cppf_frame_pose: every stage launched once for all instances of the frame (~25 launches per frame instead of ~50 per
+        # instance); same conditions as the one-call path.  CPPF_FRAME_CALL=0 falls back to one call per instance on the lanes.
+        self.frame_call = os.environ.get("CPPF_FRAME_CALL", "1") != "0"
+        self.use_graph = os.environ.get("CPPF_FRAME_GRAPH", "0") != "0"  # replay the frame's kernel sequence from a CUDA graph
+        self.replicas_max = int(os.environ.get("CPPF_FRAME_REPLICAS", "0"))
+        self._job_voters: List[PoseVoter] = []
+        self._slot_bufs: Dict[int, dict] = {}
+        self._tables = None            # (ring of pinned host tables, device table, cursor)
+        self._graphs: Dict[tuple, object] = {}
+        self.max_points = int(max_points)
         self._pose_ring: Dict[int, List[torch.Tensor]] = {}      # free pinned pose buffers by row count
         self.host_threads = max(1, int(os.environ.get("CPPF_HOST_THREADS", "1")))
         self._pool = None
@@ -173,6 +186,9 @@ class PoseEstimator:
         `draws[i][branch]` may inject the multinomial draws (uint8 [T,6]) of an (instance, branch) for parity runs.
         Inputs may already be device tensors (device-resident benchmarking) or host arrays (`staged` = self.stage(...)
         uploads them on the copy stream; without it they are copied here, in stream order)."""
+        if self._frame_path_ok(instances, draws):
+            self._frames += 1
+            return self._enqueue_frame(instances, pose_buf, staged)
         plan = []
         launches = 0
         self._frames += 1
@@ -207,6 +223,171 @@ class PoseEstimator:
             main.wait_event(ev)
         self.launches = launches
         return plan
+
+    # -- the whole frame in one call ------------------------------------------------------------------------------------
+    def _frame_path_ok(self, instances, draws) -> bool:
+        if not (self.frame_call and draws is None and self.timing_hook is None and 0 < len(instances) <= _lib.FRAME_MAX_INSTANCES):
+            return False
+        for inst in instances:
+            heads = self.models.get(inst.category)
+            if not heads or not all(getattr(m, "precision", 0) == 1 for m in heads.values()):
+                return False
+            T = self.num_pairs if inst.point_idxs is None else inst.point_idxs.shape[0]
+            if T > (1 << 17) or (inst.point_idxs is not None and inst.point_idxs.shape[1] < 5):
+                return False
+        return True
+
+    def _slot_buffers(self, slot: int, n: int, T: int, heads: dict) -> dict:
+        """Device buffers of instance slot `slot` of a frame (SHOT outputs and scratch, draws and scales of both branches,
+        the per-point tables of both heads, drawn tuple indices), grown on demand and reused across frames."""
+        lib = _lib.load()
+        buf = self._slot_bufs.get(slot)
+        hd, hs = heads.get("dino"), heads.get("shot")
+        if buf is None or buf["cap"] < n or buf["cap_T"] < T:
+            cap = max(n, 4096 if buf is None else buf["cap"])
+            cap_T = max(T, self.num_pairs if buf is None else buf["cap_T"])
+            d = self.device
+            buf = dict(cap=cap, cap_T=cap_T, shot_desc=torch.empty((cap, 352), dtype=torch.float32, device=d),
+                       normals=torch.empty((cap, 3), dtype=torch.float32, device=d),
+                       ws_shot=torch.empty(int(lib.cppf_shot_workspace_bytes(cap)), dtype=torch.uint8, device=d),
+                       bins=torch.empty((2, cap_T, 6), dtype=torch.uint8, device=d),
+                       scales=torch.empty((2, cap_T, 3), dtype=torch.float32, device=d),
+                       idx=torch.empty((cap_T, 5), dtype=torch.int32, device=d), ws_heads=None)
+            self._slot_bufs[slot] = buf
+        need = int(lib.cppf_frame_heads_workspace_bytes(None if hd is None else hd._handle, None if hs is None else hs._handle, buf["cap"]))
+        if buf["ws_heads"] is None or buf["ws_heads"].numel() < need:
+            buf["ws_heads"] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return buf
+
+    def _frame_tables(self):
+        """Ring of pinned host tables (a table must stay untouched until its copy has executed: one per frame in flight) and
+        the device table the kernels read."""
+        if self._tables is None:
+            nbytes = int(_lib.load().cppf_frame_table_bytes())
+            ring = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(8)]
+            self._tables = [ring, torch.empty(nbytes, dtype=torch.uint8, device=self.device), 0, [None] * 8]
+        ring, dev, cur, events = self._tables
+        k = cur % len(ring)
+        if events[k] is not None:
+            events[k].synchronize()          # the frame that used this table 8 frames ago has long copied it
+        self._tables[2] = cur + 1
+        return ring[k], dev, k
+
+    def _enqueue_frame(self, instances: Sequence[Instance], pose_buf: torch.Tensor, staged) -> List[dict]:
+        """cppf_frame_pose: every stage of the instance loop launched once for all instances (csrc/frame.cu)."""
+        lib = _lib.load()
+        n_i = len(instances)
+        main = torch.cuda.current_stream(self.device)
+        while len(self._job_voters) < 2 * n_i:
+            self._job_voters.append(PoseVoter(self.num_pairs, self.max_points, self.grid_capacity, device=self.device))
+        io = (_lib.InstanceIO * n_i)()
+        par = (_lib.VoteParams * n_i)()
+        bufs = (_lib.VoteBuffers * (2 * n_i))()
+        plan, keep = [], []
+        any_dino = any_shot = None
+        max_n = max_T = 0
+        for i, inst in enumerate(instances):
+            vc = self.vote_config(inst.category)
+            st = None if staged is None else staged[i]
+            if st is not None:
+                main.wait_event(st["ready"])
+                pc, cells_hint, idx, desc_dev = st["pc"], st["cells_hint"], st["idx"], st["desc"]
+            else:
+                on_host = isinstance(inst.pc, np.ndarray)
+                cells_hint = PoseVoter.grid_cells_on_host(inst.pc, vc.res) if on_host else getattr(inst, "cells_hint", None)
+                pc = to_device(inst.pc, torch.float32, self.device)
+                idx = inst.point_idxs
+                if idx is not None and not isinstance(idx, torch.Tensor):
+                    idx = to_device(idx, torch.int32 if idx.dtype == np.int32 else torch.int64, self.device)
+                desc_dev = None if inst.desc is None else to_device(inst.desc, torch.float32, self.device)
+            heads = self.models[inst.category]
+            dino = heads.get("dino") if desc_dev is not None else None
+            sh = heads.get("shot")
+            for m in (dino, sh):
+                if m is not None:
+                    m._ensure(self.device)
+            any_dino = any_dino or dino
+            any_shot = any_shot or sh
+            n = pc.shape[0]
+            T = self.num_pairs if idx is None else idx.shape[0]
+            max_n, max_T = max(max_n, n), max(max_T, T)
+            buf = self._slot_buffers(i, n, T, {k: m for k, m in (("dino", dino), ("shot", sh)) if m is not None})
+            par[i] = self._job_voters[2 * i]._vote_params(vc, T)
+            for b in range(2):
+                v = self._job_voters[2 * i + b]
+                v._ensure(T, n, cells_hint)
+                v._T = T
+                v._live = (pc, idx, desc_dev)
+                bufs[2 * i + b] = v._vote_buffers(vc.num_sphere)
+            if idx is not None:
+                ip, i64, istr = idx_args(idx)
+            else:
+                ip, i64, istr = None, 0, 5
+            o = io[i]
+            o.pc, o.n, o.idx, o.idx_is_i64, o.idx_stride, o.T = pc.data_ptr(), n, ip, i64, istr, T
+            o.dino_desc = None if dino is None else desc_dev.data_ptr()
+            o.heads_dino = None if dino is None else dino._handle
+            o.heads_shot = None if sh is None else sh._handle
+            o.normal_r = o.shot_r = float(vc.res * 10)                                      # eval.py:210
+            o.shot_desc, o.normals = buf["shot_desc"].data_ptr(), buf["normals"].data_ptr()
+            o.ws_shot, o.ws_shot_bytes = buf["ws_shot"].data_ptr(), buf["ws_shot"].numel()
+            o.bins, o.scales = buf["bins"].data_ptr(), buf["scales"].data_ptr()
+            o.ws_heads, o.ws_heads_bytes = buf["ws_heads"].data_ptr(), buf["ws_heads"].numel()
+            o.seed_dino, o.seed_shot = self.seed + 7919 * (2 * i), self.seed + 7919 * (2 * i + 1)
+            o.cells_hint = int(cells_hint or 0)
+            o.pose_dino, o.pose_shot = pose_buf[2 * i].data_ptr(), pose_buf[2 * i + 1].data_ptr()
+            o.idx_draw = buf["idx"].data_ptr() if idx is None else None
+            o.seed_idx = (self.seed << 40) + (self._frames << 8) + i
+            keep.append((pc, idx, desc_dev))
+            slots = {}
+            if dino is not None:
+                slots["dino"] = 2 * i
+            if sh is not None:
+                slots["shot"] = 2 * i + 1
+            plan.append(dict(slots=slots, category=inst.category))
+        table_host, table_dev, k = self._frame_tables()
+        frame = _lib.Frame(n_instances=n_i, mode=_lib.FRAME_ALL, io=C.addressof(io), params=C.addressof(par), buffers=C.addressof(bufs),
+                           shared=C.addressof(par), heads_dino_any=None if any_dino is None else any_dino._handle,
+                           heads_shot_any=None if any_shot is None else any_shot._handle, table_host=table_host.data_ptr(),
+                           table_dev=table_dev.data_ptr(), capacity_instances=0, replicas_max=self.replicas_max,
+                           capacity_tuples=0, capacity_points=0)
+        if self.use_graph:
+            self._replay_frame(frame, n_i, max_T, max_n)
+        else:
+            check(lib.cppf_frame_pose(C.byref(frame), stream_ptr()), "cppf_frame_pose")
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._tables[3][k] = ev
+        self._frame_live = keep
+        n_jobs = sum(len(p["slots"]) for p in plan)
+        # sample (1) + SHOT (7) + heads (2 per branch run) + centre (4) + back-vote (3) + rotation (1) + pose (2 or 3), + the table copy
+        self.launches = 1 + (7 if any_shot is not None else 0) + 2 * ((any_dino is not None) + (any_shot is not None)) + 4 + 3 + 1 + \
+            (3 if self.opt else 2) + 1 if n_jobs else 0
+        return plan
+
+    def _replay_frame(self, frame, n_i: int, max_T: int, max_n: int):
+        """The frame's kernel sequence from a CUDA graph: launch dimensions depend on capacities only (csrc/frame.cu), so one
+        captured graph serves every frame that fits them; per frame only the table is refilled and copied (eagerly, from a
+        rotating pinned buffer) before the replay."""
+        lib = _lib.load()
+        cap_i = 8 if n_i <= 8 else _lib.FRAME_MAX_INSTANCES
+        cap_T = self.num_pairs if max_T <= self.num_pairs else (1 << 17)
+        cap_n = 8192 if max_n <= 8192 else 50000
+        key = (cap_i, cap_T, cap_n, frame.heads_dino_any is not None, frame.heads_shot_any is not None, self.opt)
+        frame.capacity_instances, frame.capacity_tuples, frame.capacity_points = cap_i, cap_T, cap_n
+        frame.mode = _lib.FRAME_FILL | _lib.FRAME_COPY
+        check(lib.cppf_frame_pose(C.byref(frame), stream_ptr()), "cppf_frame_pose (table)")
+        g = self._graphs.get(key)
+        if g is None:
+            frame.mode = _lib.FRAME_LAUNCH
+            check(lib.cppf_frame_pose(C.byref(frame), stream_ptr()), "cppf_frame_pose (warm-up)")     # one-time attribute opt-ins
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.Stream(device=self.device)):
+                check(lib.cppf_frame_pose(C.byref(frame), stream_ptr()), "cppf_frame_pose (capture)")
+            self._graphs[key] = g
+            return        # the warm-up call above already ran this frame
+        g.replay()
 
     def _lane_buffers(self, lane: int, n: int, T: int, heads: dict) -> dict:
         """Per-lane device buffers of the one-call instance path, grown on demand (points AND tuples: an Instance may bring
@@ -355,7 +536,8 @@ class PoseEstimator:
         return need
 
     def _grow_grids(self, cells: int):
-        for v in self.voters:
+        self.grid_capacity = max(self.grid_capacity, int(cells))
+        for v in list(self.voters) + list(self._job_voters):
             if v.grid.numel() < cells:
                 v.grid = torch.empty(int(cells), dtype=torch.int32, device=self.device)
                 v._buffers = None

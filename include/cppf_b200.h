@@ -384,30 +384,32 @@ int cppf_instance_pose(const cppf_instance_io *io, const cppf_vote_params *param
  * (instance, branch) jobs -- about 25 launches per frame whose grids carry a job dimension, instead of ~50 per instance.
  * Results are identical to cppf_instance_pose per instance (same kernels' arithmetic, same seeds).  Everything that changes
  * from frame to frame travels in one table (table_host -> table_dev, one small copy); launch dimensions depend on the
- * capacities only, so with mode = CPPF_FRAME_ENQUEUE_ONLY the call can be captured in a CUDA graph once and replayed after
- * refreshing the table with mode = CPPF_FRAME_FILL_ONLY (which touches table_host only and launches nothing).
+ * capacities only, so the kernel sequence (mode = CPPF_FRAME_LAUNCH) can be captured in a CUDA graph once and replayed
+ * after refreshing the table (mode = CPPF_FRAME_FILL | CPPF_FRAME_COPY: fills table_host and queues its copy, no kernel).
+ * table_host must stay untouched until its copy has executed: callers with several frames in flight rotate pinned buffers.
  * Requirements: bf16 tensor-core heads (cppf_heads_has_tc), T <= 2^17 per instance, 5-point tuples; ws_heads of an instance
  * holds the per-point tables of BOTH branches (cppf_frame_heads_workspace_bytes).  Job 2i is the DINO branch of instance i,
  * job 2i+1 its SHOT branch. */
 #define CPPF_FRAME_MAX_INSTANCES 16
-#define CPPF_FRAME_ALL 0
-#define CPPF_FRAME_FILL_ONLY 1
-#define CPPF_FRAME_ENQUEUE_ONLY 2
+#define CPPF_FRAME_FILL 1        /* build the frame's table in table_host (host work only) */
+#define CPPF_FRAME_COPY 2        /* queue the copy table_host -> table_dev */
+#define CPPF_FRAME_LAUNCH 4      /* queue the kernels; reads the table on the device only */
+#define CPPF_FRAME_ALL 7
 
 typedef struct cppf_frame {
-    int n_instances;                    /* 0 .. CPPF_FRAME_MAX_INSTANCES (ignored by CPPF_FRAME_ENQUEUE_ONLY) */
-    int mode;                           /* CPPF_FRAME_* */
+    int n_instances;                    /* 0 .. CPPF_FRAME_MAX_INSTANCES (used by CPPF_FRAME_FILL) */
+    int mode;                           /* bit set of CPPF_FRAME_FILL / COPY / LAUNCH */
     const cppf_instance_io *io;         /* [n_instances], host */
     const cppf_vote_params *params;     /* [n_instances], host: the category configuration of each instance; the members that
                                            size kernels (num_rots, num_bins, sphere_bins, tables, lut) are taken from params[0] and
                                            from `shared` below and must agree across instances */
     const cppf_vote_buffers *buffers;   /* [2 * n_instances], host */
-    const cppf_vote_params *shared;     /* the frame-wide members (tables, lattice, lut, thresholds); also used by ENQUEUE_ONLY */
+    const cppf_vote_params *shared;     /* the frame-wide members (tables, lattice, lut, thresholds, refine_iters > 0) */
     const struct cppf_heads *heads_dino_any, *heads_shot_any;   /* any model of each branch (the architecture sizes the heads
                                            launches); NULL: that branch is never run */
     void *table_host;                   /* pinned host scratch of cppf_frame_table_bytes() */
     void *table_dev;                    /* device scratch of the same size */
-    int capacity_instances;             /* grids are sized for this many instances, ... */
+    int capacity_instances;             /* grids are sized for this many instances (0 with CPPF_FRAME_FILL: this frame's counts), ... */
     int replicas_max;                   /* centre-vote grid copies for L2-voted grids (0: default) */
     int64_t capacity_tuples;            /* ... this many tuples per instance ... */
     int64_t capacity_points;            /* ... and this many points per instance */

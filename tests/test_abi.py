@@ -48,12 +48,13 @@ def test_struct_layouts_match_header_sizes(tmp_path):
     src.write_text('#include "cppf_b200.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu\\n", '
                    'sizeof(cppf_grid_geom), sizeof(cppf_center), sizeof(cppf_backvote_summary), sizeof(cppf_pose));'
                    'printf("%zu %zu\\n", sizeof(cppf_vote_params), sizeof(cppf_vote_buffers));'
-                   'printf("%zu\\n", sizeof(cppf_instance_io));return 0;}\n')
+                   'printf("%zu %zu %zu\\n", sizeof(cppf_instance_io), sizeof(cppf_frame), sizeof(cppf_scale_select));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     assert sizes == [ctypes.sizeof(_lib.GridGeom), ctypes.sizeof(_lib.Center), ctypes.sizeof(_lib.BackvoteSummary),
-                     ctypes.sizeof(_lib.Pose), ctypes.sizeof(_lib.VoteParams), ctypes.sizeof(_lib.VoteBuffers), ctypes.sizeof(_lib.InstanceIO)]
+                     ctypes.sizeof(_lib.Pose), ctypes.sizeof(_lib.VoteParams), ctypes.sizeof(_lib.VoteBuffers), ctypes.sizeof(_lib.InstanceIO),
+                     ctypes.sizeof(_lib.Frame), ctypes.sizeof(_lib.ScaleSelect)]
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -95,10 +95,8 @@ def test_extent_guard_and_grid_regrowth_through_the_public_call():
     from cppf2_b200.estimator import Instance, PoseEstimator, build_models
     from cppf2_b200.pipeline import PoseVoter
     models, cfgs = build_models(["mug"], branches=("shot",), precision=1)
-    est = PoseEstimator(models, cfgs, num_pairs=8192, max_points=4000, seed=2, n_streams=2)
-    for v in est.voters:                                   # small buffers so that an ordinary cloud overflows them
-        v.grid = torch.empty(1 << 12, dtype=torch.int32, device="cuda")
-        v._buffers = None
+    # small grid buffers so that an ordinary cloud overflows them
+    est = PoseEstimator(models, cfgs, num_pairs=8192, max_points=4000, seed=2, n_streams=2, grid_capacity=1 << 12)
     ok = synth.half_cylinder_cloud(1500, seed=5)
     far = ok.copy()
     far[0, 2] += 2.5                                       # one stray background point: extent 2.5 m / 2 mm > 1000 voxels
@@ -110,7 +108,7 @@ def test_extent_guard_and_grid_regrowth_through_the_public_call():
     assert out[0] is not None and np.isfinite(out[0].RT).all()
     r = out[0].results["shot"]
     assert r.status & _lib.CPPF_STATUS_GRID_OVERFLOW == 0 and r.grid_cells == cells and r.kept > 0
-    assert all(v.grid.numel() >= cells for v in est.voters)
+    assert all(v.grid.numel() >= cells for v in list(est.voters) + list(est._job_voters))
     # the regrown estimator gives the same answer as one that had room from the start (same seeds -> same draws)
     est2 = PoseEstimator(models, cfgs, num_pairs=8192, max_points=4000, seed=2, n_streams=2)
     idx = synth.sample_tuples(ok.shape[0], 8192, 5, seed=9)
@@ -156,31 +154,72 @@ def test_estimate_frame_from_depth_and_masks():
         assert z.min() - 0.6 < p.RT[2, 3] < z.max() + 0.6
 
 
-def test_one_call_instance_path_equals_python_sequence():
-    """cppf_instance_pose (one host call per instance) queues the same kernels with the same seeds as the Python sequence
-    of shot.compute / forward_sampled / vote: identical translations, kept counts, bins and scales; rotations equal up to the
-    float64 summation order of the sphere bins."""
+def test_frame_call_and_one_call_paths_equal_python_sequence():
+    """cppf_frame_pose (every stage launched once for the whole frame), cppf_instance_pose (one host call per instance) and the
+    Python sequence of shot.compute / forward_sampled / vote queue the same arithmetic with the same seeds: identical
+    translations, kept counts, bins and scales; rotations equal up to the float64 summation order of the sphere bins."""
     from cppf2_b200.estimator import Instance, PoseEstimator, build_models
-    cats = ["mug", "laptop"]
+    cats = ["mug", "laptop", "bowl"]
     models, cfgs = build_models(cats, precision=1, seed=5)
     est = PoseEstimator(models, cfgs, num_pairs=20000, max_points=4000, seed=11)
     instances = []
     for i, cat in enumerate(cats):
         pc = synth.half_cylinder_cloud(2200 + 500 * i, seed=60 + i, jitter=0.0005)
-        instances.append(Instance(pc=pc, category=cat, desc=synth.unit_descriptors(pc.shape[0], 1024, seed=70 + i),
-                                  point_idxs=synth.sample_tuples(pc.shape[0], 20000, 5, seed=80 + i)))
-    assert est.one_call
-    a = est.estimate(instances)
+        desc = synth.unit_descriptors(pc.shape[0], 1024, seed=70 + i) if i != 2 else None      # third instance: SHOT branch only
+        instances.append(Instance(pc=pc, category=cat, desc=desc, point_idxs=synth.sample_tuples(pc.shape[0], 20000, 5, seed=80 + i)))
+    assert est.frame_call and est.one_call
+    a = est.estimate(instances)                       # the whole frame in one call
+    assert est.launches < 40
+    est.frame_call = False
+    b = est.estimate(instances)                       # one call per instance, instances on the lanes
     est.one_call = False
-    b = est.estimate(instances)
-    for x, y in zip(a, b):
-        assert x.branch == y.branch
-        for br in ("dino", "shot"):
-            r, o = x.results[br], y.results[br]
-            assert np.array_equal(r.t, o.t) and r.kept == o.kept and r.bin_up == o.bin_up and r.bin_right == o.bin_right
-            assert np.array_equal(r.scale, o.scale)
-            np.testing.assert_allclose(r.R, o.R, atol=1e-9)
-            np.testing.assert_allclose(r.loss, o.loss, rtol=1e-9)
+    c = est.estimate(instances)                       # the Python sequence
+    for x, y, z in zip(a, b, c):
+        assert x.branch == y.branch == z.branch
+        assert set(x.results) == set(z.results)
+        for br in x.results:
+            for r, o in ((x.results[br], z.results[br]), (y.results[br], z.results[br])):
+                assert r.status == 0
+                assert np.array_equal(r.t, o.t) and r.kept == o.kept and r.bin_up == o.bin_up and r.bin_right == o.bin_right
+                assert np.array_equal(r.scale, o.scale)
+                np.testing.assert_allclose(r.R, o.R, atol=1e-9)
+                np.testing.assert_allclose(r.loss, o.loss, rtol=1e-9)
+    # the SHOT-only instance takes its scale from its own head (no DINO branch to reuse)
+    assert set(a[2].results) == {"shot"} and np.isfinite(a[2].scale).all()
+
+
+def test_frame_call_with_device_drawn_tuples_and_graph_replay():
+    """The default public call: tuple indices drawn on the device inside the frame call; then the same frames through the
+    CUDA-graph replay of the frame's kernel sequence -- identical poses, frame after frame (the table is the only thing
+    that changes between replays)."""
+    from cppf2_b200.estimator import Instance, PoseEstimator, build_models
+    cats = ["can", "camera"]
+    models, cfgs = build_models(cats, precision=1, seed=9)
+    frames = []
+    for f in range(3):
+        insts = []
+        for i, cat in enumerate(cats[: 2 - (f == 2)]):           # the third frame has one instance only
+            pc = synth.half_cylinder_cloud(1800 + 400 * i + 100 * f, seed=90 + 10 * f + i, jitter=0.0005)
+            insts.append(Instance(pc=pc, category=cat, desc=synth.unit_descriptors(pc.shape[0], 1024, seed=95 + 10 * f + i)))
+        frames.append(insts)
+    outs = []
+    for use_graph in (False, True):
+        est = PoseEstimator(models, cfgs, num_pairs=16384, max_points=4000, seed=21)
+        est.use_graph = use_graph
+        outs.append([est.estimate(fr) for fr in frames])
+        assert est.frame_call
+        if use_graph:
+            assert len(est._graphs) == 1               # one captured sequence served all three frames
+    for fa, fb in zip(*outs):
+        assert len(fa) == len(fb)
+        for x, y in zip(fa, fb):
+            assert x.branch == y.branch
+            for br in x.results:
+                r, o = x.results[br], y.results[br]
+                assert r.status == 0 and r.kept > 0
+                assert np.array_equal(r.t, o.t) and r.kept == o.kept and r.bin_up == o.bin_up and r.bin_right == o.bin_right
+                assert np.array_equal(r.scale, o.scale)
+                np.testing.assert_allclose(r.R, o.R, atol=1e-9)
 
 
 def test_result_pickles_through_the_frame_loop(tmp_path):
