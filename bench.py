@@ -14,8 +14,9 @@ metric / value : tuples voted per second, inputs resident in HBM when the timed 
 e2e            : same metric through the public call (PoseEstimator.submit()/result(), one frame in flight ahead) with
                  HOST buffers: per step the clouds and descriptors are copied from pinned host memory, the tuple indices
                  are drawn on the device and the pose records are read back; median of three K-step passes.
-roofline       : the heads kernel (tensor-bound): executed flops / CUDA-event time of the heads stages in a second,
-                 single-stream pass; per-stage medians.  clocks: in-process NVML, attached before the warm-up.
+roofline       : the heads kernel (tensor-bound): executed flops / CUDA-event time of the frame's heads stage (4 launches:
+                 per-point and per-tuple programs of both branches over all instances), events recorded by the call at the
+                 stage boundaries; per-stage medians.  clocks: in-process NVML, attached before the warm-up.
 --opt          : with the reference's online refinement (eval.py:319-355) in every (instance, branch).
 N > 1          : one process per GPU (torchrun), frames sharded across ranks, no data-path collective (weak
                  scaling); time is the max over ranks.
@@ -231,7 +232,7 @@ def workload_config(instances_per_step: int = N_INSTANCES):
                         "seeded unit-norm DINO descriptors), 50000 tuples x 180 rotations per (instance, branch)",
             "instances_per_step": instances_per_step, "tuples_per_step": 2 * NUM_PAIRS * instances_per_step,
             "num_pairs": NUM_PAIRS, "num_rots": NUM_ROTS, "sphere_bins": 720,
-            "l2": "256 MB buffer written between timed steps (L2 flush; in the e2e leg on the upload stream ahead of each step's copies)", "parallelism": "frames sharded across ranks, no collective; instances of a frame on concurrent CUDA streams"}
+            "l2": "256 MB buffer written between timed steps (L2 flush; in the e2e leg on the upload stream ahead of each step's copies)", "parallelism": "frames sharded across ranks, no collective; every stage of a frame launched once for all its instances (cppf_frame_pose)"}
 
 
 def main():
@@ -331,36 +332,54 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in step_events]
     total_ms = float(sum(step_ms))
 
-    # per-kernel durations for the roofline: the same steps on ONE stream (no overlap between instances), CUDA events
-    # around each stage on the launching stream
-    est1 = PoseEstimator(models, cfgs, num_pairs=NUM_PAIRS, num_rots=NUM_ROTS, seed=rank, n_streams=1, opt=args.opt)
-    stage_events = {}
+    # per-stage durations for the roofline: the same steps, same estimator, same single stream, with CUDA events recorded by
+    # cppf_frame_pose itself at the stage boundaries of the launching stream (the frame is ~25 batched launches in order:
+    # tuple sampling, SHOT, heads, centre vote, back-vote filter, rotation vote, pose)
+    stage_ms, serial_ms = {}, float(np.median(step_ms))
+    if est.frame_call:
+        per_step = []
+        for _ in range(args.steps):
+            flush.zero_()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+            est.stage_events = evs
+            est.enqueue(dev_instances, pose_buf)
+            per_step.append(evs)
+        est.stage_events = None
+        torch.cuda.synchronize()
+        for k, name in enumerate(_lib.FRAME_STAGES):
+            stage_ms[name] = float(np.median([evs[k].elapsed_time(evs[k + 1]) for evs in per_step]))
+        serial_ms = float(np.median([evs[0].elapsed_time(evs[7]) for evs in per_step]))
+        stage_ms["heads_shot"], stage_ms["heads_dino"] = stage_ms["heads"], 0.0
+        stage_ms["vote_shot"] = stage_ms["center"] + stage_ms["backvote"] + stage_ms["rotation"] + stage_ms["pose"]
+        stage_ms["vote_dino"] = 0.0
+    else:
+        est1 = PoseEstimator(models, cfgs, num_pairs=NUM_PAIRS, num_rots=NUM_ROTS, seed=rank, n_streams=1, opt=args.opt)
+        stage_events = {}
 
-    def hook(stage, begin):
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record()
-        stage_events.setdefault(stage, []).append(ev)
-    for _ in range(3):
-        est1.enqueue(dev_instances, pose_buf)
-    torch.cuda.synchronize()
-    est1.timing_hook = hook
-    serial_events = []
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        est1.enqueue(dev_instances, pose_buf)
-        b.record()
-        serial_events.append((a, b))
-    torch.cuda.synchronize()
-    est1.timing_hook = None
-    # per step: the stage's intervals summed; over the steps: the MEDIAN (one disturbed step does not move the roofline)
-    serial_ms = float(np.median([a.elapsed_time(b) for a, b in serial_events]))
-    stage_ms = {}
-    for stage, evs in stage_events.items():
-        per = len(evs) // (2 * args.steps)                 # (begin, end) pairs of this stage per step
-        iv = [evs[i].elapsed_time(evs[i + 1]) for i in range(0, len(evs) - 1, 2)]
-        stage_ms[stage] = float(np.median([sum(iv[k * per:(k + 1) * per]) for k in range(args.steps)])) if per else 0.0
+        def hook(stage, begin):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            stage_events.setdefault(stage, []).append(ev)
+        for _ in range(3):
+            est1.enqueue(dev_instances, pose_buf)
+        torch.cuda.synchronize()
+        est1.timing_hook = hook
+        serial_events = []
+        for _ in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            est1.enqueue(dev_instances, pose_buf)
+            b.record()
+            serial_events.append((a, b))
+        torch.cuda.synchronize()
+        est1.timing_hook = None
+        serial_ms = float(np.median([a.elapsed_time(b) for a, b in serial_events]))
+        for stage, evs in stage_events.items():
+            per = len(evs) // (2 * args.steps)                 # (begin, end) pairs of this stage per step
+            iv = [evs[i].elapsed_time(evs[i + 1]) for i in range(0, len(evs) - 1, 2)]
+            stage_ms[stage] = float(np.median([sum(iv[k * per:(k + 1) * per]) for k in range(args.steps)])) if per else 0.0
+        del est1
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -441,7 +460,6 @@ def main():
     # cross NVLink (cppf2_b200/sharded.py), and rank 0 re-runs the whole T unsharded for the parity flags.
     sharded = None
     if args.sharded_log2:
-        del est1
         torch.cuda.empty_cache()
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         from vote_sweep import run_sharded
@@ -482,7 +500,8 @@ def main():
     shot_bytes = n_pts * 1432
     kernels = {
         "heads": {"ms": heads_ms, "share": heads_ms / serial_ms, "achieved_tflops": flops / (heads_ms * 1e-3) / 1e12 if heads_ms else None},
-        "vote_chain": {"ms": vote_ms, "share": vote_ms / serial_ms, "alg_GBps": vote_bytes / (vote_ms * 1e-3) / 1e9 if vote_ms else None},
+        "vote_chain": {"ms": vote_ms, "share": vote_ms / serial_ms, "alg_GBps": vote_bytes / (vote_ms * 1e-3) / 1e9 if vote_ms else None,
+                       "stages_ms": {k: stage_ms[k] for k in ("center", "backvote", "rotation", "pose") if k in stage_ms}},
         "shot": {"ms": shot_ms, "share": shot_ms / serial_ms, "alg_GBps": shot_bytes / (shot_ms * 1e-3) / 1e9 if shot_ms else None},
     }
     if heads_ms >= max(vote_ms, shot_ms):
@@ -530,8 +549,11 @@ def main():
             "dtype": {0: "f32", 1: "bf16", 2: "bf16 (SHOT head, tcgen05) + f32 (DINO head)"}[precision], "data": "synthetic", "config": workload_config(),
             "frames_per_sec": world * 1e3 / ms_per_step, "instances": n_inst, "points": n_pts, "refinement": bool(args.opt),
             "roofline": roofline, "kernels": kernels, "sharded": sharded,
-            "kernel_timing": {"how": "same steps on one stream (instances serialised), CUDA events per stage on the launching stream",
-                              "ms_per_step_serial": serial_ms, "streams_in_timed_run": est.n_streams}, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "kernel_timing": {"how": ("the timed configuration itself (cppf_frame_pose: every stage launched once for all instances, one stream), "
+                                      "CUDA events recorded by the call at the stage boundaries, median over the steps") if est.frame_call else
+                                     "same steps on one stream (instances serialised), CUDA events per stage on the launching stream",
+                              "ms_per_step_staged": serial_ms, "frame_call": bool(est.frame_call), "cuda_graph": bool(est.use_graph)},
+            "cpu_baseline": cpu_baseline, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "frames_per_sec": world * 1e3 / (e2e_ms / args.steps),
                     "passes_ms_per_step": [t / args.steps for t in e2e_passes], "clocks": e2e_clocks,

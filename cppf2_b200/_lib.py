@@ -79,11 +79,12 @@ class Frame(C.Structure):
     _fields_ = [("n_instances", C.c_int), ("mode", C.c_int), ("io", C.c_void_p), ("params", C.c_void_p), ("buffers", C.c_void_p),
                 ("shared", C.c_void_p), ("heads_dino_any", C.c_void_p), ("heads_shot_any", C.c_void_p), ("table_host", C.c_void_p),
                 ("table_dev", C.c_void_p), ("capacity_instances", C.c_int), ("replicas_max", C.c_int),
-                ("capacity_tuples", C.c_int64), ("capacity_points", C.c_int64)]
+                ("capacity_tuples", C.c_int64), ("capacity_points", C.c_int64), ("stage_events", C.c_void_p)]
 
 
 FRAME_FILL, FRAME_COPY, FRAME_LAUNCH, FRAME_ALL = 1, 2, 4, 7
 FRAME_MAX_INSTANCES = 16
+FRAME_STAGES = ("sample", "shot", "heads", "center", "backvote", "rotation", "pose")      # between the 8 stage events
 
 
 P, I, I64, F, D, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64

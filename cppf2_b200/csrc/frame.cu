@@ -8,6 +8,7 @@
 //   (1)] -> loss (1)
 #include "frame.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 using namespace cppf;
@@ -188,12 +189,33 @@ CPPF_API int cppf_frame_pose(const cppf_frame *f, void *stream) {
     const FrameTable *t = static_cast<const FrameTable *>(f->table_dev);
     const FrameShared sh = shared_of(p, f->replicas_max);
     const void *tc_states[2] = {cppf_heads_tc_state(f->heads_shot_any), cppf_heads_tc_state(f->heads_dino_any)};
-    int rc;
-    if ((rc = frame_launch_sample_tuples(t, ni, T_cap, s))) return rc;
-    if (tc_states[0] && (rc = frame_launch_shot(t, ni, n_cap, s))) return rc;
-    if ((rc = frame_launch_heads(t, tc_states, ni, n_cap, T_cap, s))) return rc;
-    if ((rc = frame_launch_center(t, nj, T_cap, sh, s))) return rc;
-    if ((rc = frame_launch_backvote(t, nj, T_cap, s))) return rc;
-    if ((rc = frame_launch_rotation(t, nj, T_cap, sh, s))) return rc;
-    return frame_launch_pose(t, nj, T_cap, any_refine ? 1 : 0, sh, s);
+    int rc, stage = 0;
+    // CPPF_FRAME_SYNC=1 (debugging): synchronise after every stage and name the one whose kernels failed
+    static const int sync_stages = [] {
+        const char *e = getenv("CPPF_FRAME_SYNC");
+        return e ? atoi(e) : 0;             // 1: synchronise per stage; 2: also report every completed stage
+    }();
+    static const char *const stage_name[] = {"begin", "tuple sampling", "SHOT", "heads", "centre vote", "back-vote", "rotation", "pose"};
+    auto mark = [&]() -> int {
+        if (sync_stages) {
+            const cudaError_t e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) {
+                fprintf(stderr, "[cppf_b200] cppf_frame_pose: stage '%s' failed: %s\n", stage_name[stage < 8 ? stage : 7], cudaGetErrorString(e));
+                return CPPF_ERR_CUDA;
+            }
+            if (sync_stages > 1) fprintf(stderr, "[cppf_b200] cppf_frame_pose: stage '%s' done\n", stage_name[stage < 8 ? stage : 7]);
+        }
+        if (f->stage_events && f->stage_events[stage]) CPPF_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(f->stage_events[stage]), s));
+        ++stage;
+        return CPPF_OK;
+    };
+    if ((rc = mark())) return rc;
+    if ((rc = frame_launch_sample_tuples(t, ni, T_cap, s)) || (rc = mark())) return rc;
+    if ((tc_states[0] && (rc = frame_launch_shot(t, ni, n_cap, s))) || (rc = mark())) return rc;
+    if ((rc = frame_launch_heads(t, tc_states, ni, n_cap, T_cap, s)) || (rc = mark())) return rc;
+    if ((rc = frame_launch_center(t, nj, T_cap, sh, s)) || (rc = mark())) return rc;
+    if ((rc = frame_launch_backvote(t, nj, T_cap, s)) || (rc = mark())) return rc;
+    if ((rc = frame_launch_rotation(t, nj, T_cap, sh, s)) || (rc = mark())) return rc;
+    if ((rc = frame_launch_pose(t, nj, T_cap, any_refine ? 1 : 0, sh, s))) return rc;
+    return mark();
 }

@@ -155,7 +155,7 @@ __device__ __forceinline__ bool elect_one() {   // one lane of the (converged) w
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
-        if (spin > (1u << 26)) __trap();
+        if (spin > (1u << 22)) __trap();      // >> any legitimate wait (a whole launch is < 1 ms): a deadlock surfaces within seconds
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -323,38 +323,43 @@ __device__ __forceinline__ void tuple_geometry_chunks(const float *__restrict__ 
 // G' = ceil(P / rounds) CTAs take part (391 tiles = 196 pairs on 148 SMs: 98 CTAs x 2 rounds, not 148 + 48; a frame's
 // 1176 pairs: 147 CTAs x 8 rounds) and the rest leave their SMs to whatever else is queued.  G' is computed here, on the
 // device, from the table: the host may launch for a capacity (CUDA-graph replay) without unbalancing the last round.
-__device__ __forceinline__ int cta_share(const MultiArgs *__restrict__ multi, const Args &one) {
+__device__ __forceinline__ int cta_share(const MultiArgs *__restrict__ multi, const Args &one, bool &single) {
     const int n_jobs = multi ? multi->n_jobs : 1;
-    int64_t total = 0;
+    int64_t pairs = 0, tiles = 0;
     for (int j = 0; j < n_jobs; ++j) {
         const int64_t rows = multi ? multi->job[j].rows : one.rows;
-        total += ((rows + kRows - 1) / kRows + 1) >> 1;
+        const int64_t t = (rows + kRows - 1) / kRows;
+        tiles += t;
+        pairs += (t + 1) >> 1;
     }
-    if (total <= 0) return 1;
     const int64_t g = gridDim.x;
+    // few tiles (the per-point programs: ~20 tiles per cloud): one tile per CTA on as many SMs as there are tiles finishes
+    // in one tile time; pairing them would halve the SMs in use and serialise two tiles per CTA
+    single = tiles <= g;
+    const int64_t total = single ? tiles : pairs;
+    if (total <= 0) return 1;
     const int64_t rounds = (total + g - 1) / g;
     return static_cast<int>((total + rounds - 1) / rounds);
 }
 
-__device__ __forceinline__ bool pair_of(const MultiArgs *__restrict__ multi, const Args &one, int64_t q, int &job, int64_t &tile0,
-                                        int64_t &n_tiles) {
+__device__ __forceinline__ bool pair_of(const MultiArgs *__restrict__ multi, const Args &one, bool single, int64_t q, int &job,
+                                        int64_t &tile0, int64_t &n_tiles) {
     const int n_jobs = multi ? multi->n_jobs : 1;
     for (int j = 0; j < n_jobs; ++j) {
         const int64_t rows = multi ? multi->job[j].rows : one.rows;
         const int64_t tiles = (rows + kRows - 1) / kRows;
-        const int64_t pairs = (tiles + 1) >> 1;
-        if (q < pairs) {
+        const int64_t units = single ? tiles : (tiles + 1) >> 1;
+        if (q < units) {
             job = j;
-            tile0 = 2 * q;
-            n_tiles = tiles;
+            tile0 = single ? q : 2 * q;
+            n_tiles = single ? q + 1 : tiles;      // single-tile units: the second slot never has a tile
             return true;
         }
-        q -= pairs;
+        q -= units;
     }
     return false;
 }
 
-// One batch of NB accumulator columns of this thread's row: v = D + bias, then the action's sink.
 template <int NB>
 __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, unsigned char *X, uint32_t t_slot_lane, int row,
                                                int64_t grow, bool live, int c /* column inside the chunk */) {
@@ -484,7 +489,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
     if (tmem != 0) __trap();     // one CTA per SM owning all 512 columns: the allocation starts at lane 0, column 0
-    const int n_ctas = cta_share(multi, one);                       // CTAs that take part (see pair_of)
+    bool single;
+    const int n_ctas = cta_share(multi, one, single);               // CTAs that take part (see pair_of)
     const int64_t q0 = static_cast<int>(blockIdx.x) < n_ctas ? static_cast<int64_t>(blockIdx.x) : (1ll << 60);   // others: no pair
 
     if (warp == kEpiWarps) {
@@ -498,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         for (int round = 0;; ++round) {
             int job;
             int64_t tile0, n_tiles;
-            if (!pair_of(multi, one, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
+            if (!pair_of(multi, one, single, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
             const unsigned char *src = multi ? multi->job[job].weights : one.weights;
             for (int i = 0; i < prog.n_slabs; ++i, ++seq) {
                 const uint32_t bytes = prog.slab[i].bytes();
@@ -538,10 +544,23 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         for (int round = 0;; ++round) {
             int job;
             int64_t tile0, n_tiles;
-            if (!pair_of(multi, one, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
-            if (tile0 + s >= n_tiles) continue;     // a job with an odd tile count: its last pair has no second tile
-            // slot 1 never runs a round that slot 0 skips; slot 0 releases the slabs alone in rounds slot 1 skips
-            const bool other_active = s == 1 || tile0 + 1 < n_tiles;
+            if (!pair_of(multi, one, single, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
+            if (tile0 + s >= n_tiles) {
+                // No tile for this slot in this round (a job's odd last tile, or single-tile units).  The slot still walks
+                // the weight ring slab by slab -- wait for the fill, release it -- so that it stays within one ring turn of
+                // the producer: mbarrier waits are by phase PARITY, and a warp that skipped a whole round (~30 turns) would
+                // pass or block on the wrong phases in its next round.
+                for (int i = 0; i < prog.n_slabs; ++i) {
+                    mbar_wait(bar_full + 8 * stage, turn);
+                    if (leader) mbar_arrive(bar_empty + 8 * stage);
+                    __syncwarp();
+                    if (++stage == kStages) {
+                        stage = 0;
+                        turn ^= 1u;
+                    }
+                }
+                continue;
+            }
             for (int i = 0; i < prog.n_slabs; ++i) {
                 const uint4 w = *reinterpret_cast<const uint4 *>(&prog.slab[i]);      // a_lo, idesc, nd, misc
                 const uint32_t flags = w.w >> 24;
@@ -586,7 +605,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                         }
                     }
                     umma_commit(bar_empty + 8 * stage);                 // this slot is done with the slab once these MMAs retire
-                    if (!other_active) mbar_arrive(bar_empty + 8 * stage);
                     if (flags & kSlabLast) umma_commit(bar_done + 8 * s);
                 }
                 __syncwarp();
@@ -625,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         for (int round = 0;; ++round) {
             int job;
             int64_t tile0, n_tiles;
-            if (!pair_of(multi, one, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
+            if (!pair_of(multi, one, single, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
             const int64_t tile = tile0 + slot;
             if (tile >= n_tiles) continue;
             const Args &a = multi ? multi->job[job] : one;
@@ -1171,7 +1189,7 @@ static int64_t pairs_of(int64_t rows) { return ((rows + kRows - 1) / kRows + 1) 
 // in the minimal number of rounds.  CPPF_TC_GRID=full is gone with the host-side balancing it switched off.
 static int blocks_for_pairs(int64_t pairs) {
     const int sms = device_info().sm_count;
-    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(pairs, sms)));
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(2 * pairs, sms)));      // up to one CTA per tile when tiles are few
 }
 
 extern "C" int cppf_heads_tc_forward(const void *state, const float *pc, int64_t n, const void *idx, int idx_is_i64,

@@ -115,6 +115,7 @@ class PoseEstimator:
         self.frame_call = os.environ.get("CPPF_FRAME_CALL", "1") != "0"
         self.use_graph = os.environ.get("CPPF_FRAME_GRAPH", "0") != "0"  # replay the frame's kernel sequence from a CUDA graph
         self.replicas_max = int(os.environ.get("CPPF_FRAME_REPLICAS", "0"))
+        self.stage_events = None        # optional list of 8 torch.cuda.Event(enable_timing=True), recorded at the stage boundaries
         self._job_voters: List[PoseVoter] = []
         self._slot_bufs: Dict[int, dict] = {}
         self._tables = None            # (ring of pinned host tables, device table, cursor)
@@ -351,7 +352,12 @@ class PoseEstimator:
                            heads_shot_any=None if any_shot is None else any_shot._handle, table_host=table_host.data_ptr(),
                            table_dev=table_dev.data_ptr(), capacity_instances=0, replicas_max=self.replicas_max,
                            capacity_tuples=0, capacity_points=0)
-        if self.use_graph:
+        if self.stage_events is not None:          # per-stage timing on the launching stream (bench.py): 8 torch events
+            for e in self.stage_events:
+                e.record(main)                     # creates the underlying cudaEvent_t (torch events are lazy)
+            handles = (C.c_void_p * len(self.stage_events))(*[e.cuda_event for e in self.stage_events])
+            frame.stage_events = C.addressof(handles)
+        if self.use_graph and self.stage_events is None:
             self._replay_frame(frame, n_i, max_T, max_n)
         else:
             check(lib.cppf_frame_pose(C.byref(frame), stream_ptr()), "cppf_frame_pose")

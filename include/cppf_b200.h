@@ -413,7 +413,11 @@ typedef struct cppf_frame {
     int replicas_max;                   /* centre-vote grid copies for L2-voted grids (0: default) */
     int64_t capacity_tuples;            /* ... this many tuples per instance ... */
     int64_t capacity_points;            /* ... and this many points per instance */
+    void *const *stage_events;          /* optional (CPPF_FRAME_LAUNCH): CPPF_FRAME_STAGE_EVENTS cudaEvent_t handles recorded on the
+                                           stream at the stage boundaries -- begin, after tuple sampling, SHOT, heads, centre vote,
+                                           back-vote filter, rotation vote, pose -- for per-stage timing on the launching stream */
 } cppf_frame;
+#define CPPF_FRAME_STAGE_EVENTS 8
 
 int64_t cppf_frame_table_bytes(void);
 int64_t cppf_frame_heads_workspace_bytes(const struct cppf_heads *heads_dino, const struct cppf_heads *heads_shot, int64_t n);

