@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             mbar_init(bar_empty + 8 * s, kSlots);     // a slab is shared: both slots' MMAs must retire before it is refilled
         }
         for (int s = 0; s < kSlots; ++s) {
-            mbar_init(bar_act + 8 * s, kSlotWarps);
+            mbar_init(bar_act + 8 * s, kEpiWarps);      // every epilogue warp arrives for whichever slot it has just served
             mbar_init(bar_done + 8 * s, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -627,179 +627,194 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             o[4] = n_steps;
         }
     } else {
-        // =============================== prologue / epilogue warps of one slot ===========================
-        const int slot = warp / kSlotWarps, sw = warp % kSlotWarps, stid = tid - slot * kSlotWarps * 32;
-        const int row = (sw & 3) * 32 + lane;          // TMEM lane == tile row  (warp % 4 selects the lane quadrant)
-        const int half = sw >> 2;                      // which half of the chunk's columns this thread handles
-        unsigned char *X = smem + kSmemX + slot * kXBytes;
-        const uint32_t x_u32 = smem_u32(X);
-        int *idx_s = reinterpret_cast<int *>(smem + kSmemIdx) + slot * kRows * kIdxStride;
-        const uint32_t t_slot_lane = tmem + static_cast<uint32_t>(slot * kSlotTmem) + (static_cast<uint32_t>((sw & 3) * 32) << 16);
+        // =============================== prologue / epilogue warps (all 16 serve both slots) ==============
+        // The 16 warps work on ONE slot at a time, alternating: action(slot 0, phase p), action(slot 1, phase p), action(slot 0,
+        // p + 1) ...  While they convert slot 1's accumulator the tensor pipe runs the MMAs slot 0's arrive just released, and
+        // vice versa (ping-pong).  With 8 dedicated warps per slot each slot's epilogue took about as long as both slots' MMAs
+        // together and its warps then idled for the MMAs; with 16 warps on the ready slot an action takes half as long and no
+        // epilogue warp ever waits while the other slot has work.  TMEM lane access fixes the row ownership: warp w reads lanes
+        // 32 (w % 4) .. +31, so the four warps of a lane quadrant split a chunk's columns four ways (two ways for the narrow
+        // chunks of the scale head).
+        const int ew = warp, etid = tid;                 // 0..15, 0..511
+        const int row = (ew & 3) * 32 + lane;            // TMEM lane == tile row
+        const int quarter = ew >> 2;                     // which share of the chunk's columns this thread handles
         // (8 rows x 4 chunks) per warp pass for the row movers: conflict-free 16-byte shared stores, whole 32 B sectors
         const int mv_r = lane & 7, mv_c = lane >> 3;
-        uint32_t done_seq = 0;
+        uint32_t done_seq[kSlots] = {0, 0};
         long long t_done = 0, t_actn[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_arrive = 0;
         const long long t_begin = prof_clock<kProf>();
         for (int round = 0;; ++round) {
             int job;
             int64_t tile0, n_tiles;
             if (!pair_of(multi, one, single, static_cast<int64_t>(round) * n_ctas + q0, job, tile0, n_tiles)) break;
-            const int64_t tile = tile0 + slot;
-            if (tile >= n_tiles) continue;
             const Args &a = multi ? multi->job[job] : one;
-            const int64_t row_base = tile * kRows;
-            const int64_t grow = row_base + row;
-            const bool live = grow < a.rows;
+            const int n_active = tile0 + 1 < n_tiles ? 2 : 1;
             if (a.idx.ptr != nullptr) {
-                // the tile's tuple indices, once: every gather below reads them from shared memory
-                for (int e = stid; e < kRows * a.arity; e += kSlotWarps * 32) {
-                    const int r = e / a.arity, k = e - r * a.arity;
-                    idx_s[r * kIdxStride + k] = row_base + r < a.rows ? static_cast<int>(a.idx.at(row_base + r, k)) : 0;
+                // the tiles' tuple indices, once: every gather below reads them from shared memory
+                for (int sl = 0; sl < n_active; ++sl) {
+                    int *idx_sl = reinterpret_cast<int *>(smem + kSmemIdx) + sl * kRows * kIdxStride;
+                    const int64_t rb = (tile0 + sl) * kRows;
+                    for (int e = etid; e < kRows * a.arity; e += kEpiWarps * 32) {
+                        const int r = e / a.arity, k = e - r * a.arity;
+                        idx_sl[r * kIdxStride + k] = rb + r < a.rows ? static_cast<int>(a.idx.at(rb + r, k)) : 0;
+                    }
                 }
-                named_bar(1 + slot, kSlotWarps * 32);
+                named_bar(1, kEpiWarps * 32);
             }
             for (int p = 0; p < prog.n_phases; ++p) {
                 const Phase &ph = prog.phase[p];
-                long long t0 = prof_clock<kProf>();
-                if (ph.wait_done) {
-                    mbar_wait(bar_done + 8 * slot, done_seq & 1u);
-                    ++done_seq;
-                    tc_fence_after();
-                }
-                long long t1 = prof_clock<kProf>();
-                t_done += t1 - t0;
-                switch (ph.action) {
-                    case kActLoadRows: {
-                        const int cb_n = ph.width >> 5;                  // blocks of 4 chunks
-                        for (int it0 = sw; it0 < 16 * cb_n; it0 += 4 * kSlotWarps) {
-                            float4 lo[4], hi[4];
+                for (int slot = 0; slot < n_active; ++slot) {
+                    unsigned char *X = smem + kSmemX + slot * kXBytes;
+                    const uint32_t x_u32 = smem_u32(X);
+                    const int *idx_s = reinterpret_cast<const int *>(smem + kSmemIdx) + slot * kRows * kIdxStride;
+                    const uint32_t t_slot_lane = tmem + static_cast<uint32_t>(slot * kSlotTmem) + (static_cast<uint32_t>((ew & 3) * 32) << 16);
+                    const int64_t row_base = (tile0 + slot) * kRows;
+                    const int64_t grow = row_base + row;
+                    const bool live = grow < a.rows;
+                    long long t0 = prof_clock<kProf>();
+                    if (ph.wait_done) {
+                        mbar_wait(bar_done + 8 * slot, done_seq[slot] & 1u);
+                        ++done_seq[slot];
+                        tc_fence_after();
+                    }
+                    long long t1 = prof_clock<kProf>();
+                    t_done += t1 - t0;
+                    switch (ph.action) {
+                        case kActLoadRows: {
+                            const int cb_n = ph.width >> 5;                  // blocks of 4 chunks
+                            for (int it0 = ew; it0 < 16 * cb_n; it0 += 4 * kEpiWarps) {
+                                float4 lo[4], hi[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {               // four independent row segments in flight
-                                const int it = it0 + u * kSlotWarps;
-                                const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
-                                const int64_t gr = row_base + r;
-                                lo[u] = hi[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                                if (it < 16 * cb_n && gr < a.rows && c8 * 8 < ph.cols) {      // cols is a multiple of 8
-                                    const float4 *src = reinterpret_cast<const float4 *>(a.x + gr * a.x_ld + ph.src_col + c8 * 8);
-                                    lo[u] = __ldg(src);
-                                    hi[u] = __ldg(src + 1);
+                                for (int u = 0; u < 4; ++u) {               // four independent row segments in flight
+                                    const int it = it0 + u * kEpiWarps;
+                                    const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
+                                    const int64_t gr = row_base + r;
+                                    lo[u] = hi[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                    if (it < 16 * cb_n && gr < a.rows && c8 * 8 < ph.cols) {      // cols is a multiple of 8
+                                        const float4 *src = reinterpret_cast<const float4 *>(a.x + gr * a.x_ld + ph.src_col + c8 * 8);
+                                        lo[u] = __ldg(src);
+                                        hi[u] = __ldg(src + 1);
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int it = it0 + u * kEpiWarps;
+                                    if (it >= 16 * cb_n) break;
+                                    const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
+                                    float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] = (v[j] == v[j]) ? v[j] : 0.0f;   // NaN rows of invalid SHOT points count as zeros (eval.py:215)
+                                    *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = pack8(v);
                                 }
                             }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int it = it0 + u * kSlotWarps;
-                                if (it >= 16 * cb_n) break;
-                                const int r = (it & 15) * 8 + mv_r, c8 = (it >> 4) * 4 + mv_c;
-                                float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = (v[j] == v[j]) ? v[j] : 0.0f;   // NaN rows of invalid SHOT points count as zeros (eval.py:215)
-                                *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = pack8(v);
+                            break;
+                        }
+                        case kActEncodeShotA: {
+                            // features (64 bf16 = one 128-byte line per point) of tuple slots 0..3 -> X[0:256): a warp pass copies the
+                            // whole lines of 4 rows (see kActGatherSum for why not 8 half lines); asynchronous 16-byte copies
+                            // straight into the operand layout, all in flight at once
+                            for (int it = ew; it < 32 * 4; it += kEpiWarps) {
+                                const int r = (it & 31) * 4 + (lane >> 3), k = it >> 5, c8 = k * 8 + (lane & 7);
+                                const bool ok = row_base + r < a.rows;
+                                cp_async16(x_u32 + c8 * kPlane + r * 16, a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + k]) * 64 + (lane & 7) * 8,
+                                           ok ? 16u : 0u);
                             }
+                            cp_async_wait_all();
+                            break;
                         }
-                        break;
-                    }
-                    case kActEncodeShotA: {
-                        // features (64 bf16 = one 128-byte line per point) of tuple slots 0..3 -> X[0:256): a warp pass copies the
-                        // whole lines of 4 rows (see kActGatherSum for why not 8 half lines); asynchronous 16-byte copies
-                        // straight into the operand layout, all in flight at once
-                        for (int it = sw; it < 32 * 4; it += kSlotWarps) {
-                            const int r = (it & 31) * 4 + (lane >> 3), k = it >> 5, c8 = k * 8 + (lane & 7);
-                            const bool ok = row_base + r < a.rows;
-                            cp_async16(x_u32 + c8 * kPlane + r * 16, a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + k]) * 64 + (lane & 7) * 8,
-                                       ok ? 16u : 0u);
+                        case kActGather: {
+                            // one 256-wide per-point row (tuple slot src_col) -> X[0:256)
+                            for (int it = ew; it < 32 * 4; it += kEpiWarps) {
+                                const int r = (it & 31) * 4 + (lane >> 3), c8 = (it >> 5) * 8 + (lane & 7);
+                                const bool ok = row_base + r < a.rows;
+                                cp_async16(x_u32 + c8 * kPlane + r * 16,
+                                           a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + ph.src_col]) * prog.gather_cols + c8 * 8, ok ? 16u : 0u);
+                            }
+                            cp_async_wait_all();
+                            break;
                         }
-                        cp_async_wait_all();
-                        break;
-                    }
-                    case kActGather: {
-                        // one 256-wide per-point row (tuple slot src_col) -> X[0:256)
-                        for (int it = sw; it < 32 * 4; it += kSlotWarps) {
-                            const int r = (it & 31) * 4 + (lane >> 3), c8 = (it >> 5) * 8 + (lane & 7);
-                            const bool ok = row_base + r < a.rows;
-                            cp_async16(x_u32 + c8 * kPlane + r * 16,
-                                       a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + ph.src_col]) * prog.gather_cols + c8 * 8, ok ? 16u : 0u);
+                        case kActEncodeShotB: {
+                            for (int it = ew; it < 32; it += kEpiWarps) {   // features of tuple slot 4 -> columns 0..63, whole lines
+                                const int r = it * 4 + (lane >> 3), c8 = lane & 7;
+                                const bool ok = row_base + r < a.rows;
+                                cp_async16(x_u32 + c8 * kPlane + r * 16, a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + 4]) * 64 + c8 * 8, ok ? 16u : 0u);
+                            }
+                            if (etid < 2 * kRows) {   // geometry of row etid % 128 (two threads per row): coords -> columns 64..93, normals -> 94..103, zeros -> 104..111
+                                const int r = etid & (kRows - 1);
+                                tuple_geometry_chunks(a.pc, a.normal, idx_s + r * kIdxStride, row_base + r < a.rows, true, etid >> 7, X, r, 8);
+                            }
+                            cp_async_wait_all();
+                            break;
                         }
-                        cp_async_wait_all();
-                        break;
-                    }
-                    case kActEncodeShotB: {
-                        for (int it = sw; it < 32; it += kSlotWarps) {   // features of tuple slot 4 -> columns 0..63, whole lines
-                            const int r = it * 4 + (lane >> 3), c8 = lane & 7;
-                            const bool ok = row_base + r < a.rows;
-                            cp_async16(x_u32 + c8 * kPlane + r * 16, a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + 4]) * 64 + c8 * 8, ok ? 16u : 0u);
-                        }
-                        {   // geometry of row stid % 128: coords -> columns 64..93, normals -> 94..103, zeros -> 104..111
-                            const int r = stid & (kRows - 1);
-                            tuple_geometry_chunks(a.pc, a.normal, idx_s + r * kIdxStride, row_base + r < a.rows, true, stid >> 7, X, r, 8);
-                        }
-                        cp_async_wait_all();
-                        break;
-                    }
-                    case kActGatherSum: {
-                        // desc_pair_transform by linearity (train_dino.py:95-96): W [256, 5*256] applied to the concatenation of
-                        // the 5 transformed descriptors = sum_k W_k f(desc[idx_k]); the per-point program has stored
-                        // G[n][256 k : 256 k + 256) = W_k f(desc_n) (+ bias in block 0) as bf16, so a tuple costs five 512-byte row
-                        // gathers and no tensor work.  Sum in float32, one rounding to bf16 into the operand layout.
-                        const int64_t ld = prog.gather_cols;
+                        case kActGatherSum: {
+                            // desc_pair_transform by linearity (train_dino.py:95-96): W [256, 5*256] applied to the concatenation of
+                            // the 5 transformed descriptors = sum_k W_k f(desc[idx_k]); the per-point program has stored
+                            // G[n][256 k : 256 k + 256) = W_k f(desc_n) (+ bias in block 0) as bf16, so a tuple costs five 512-byte row
+                            // gathers and no tensor work.  Sum in float32, one rounding to bf16 into the operand layout.
+                            const int64_t ld = prog.gather_cols;
 #pragma unroll 1
-                        for (int it = sw; it < 32 * 4; it += kSlotWarps) {
-                            // a warp pass = 4 rows x 128 contiguous bytes: whole 128-byte lines per L2 request (a 64-byte
-                            // half-line mapping moves the same sectors with twice the requests); the shared-memory stores
-                            // then land 2-way conflicted, which is the cheaper side
-                            const int r = (it & 31) * 4 + (lane >> 3), c8 = (it >> 5) * 8 + (lane & 7);
-                            uint4 g[5];
+                            for (int it = ew; it < 32 * 4; it += kEpiWarps) {
+                                // a warp pass = 4 rows x 128 contiguous bytes: whole 128-byte lines per L2 request (a 64-byte
+                                // half-line mapping moves the same sectors with twice the requests); the shared-memory stores
+                                // then land 2-way conflicted, which is the cheaper side
+                                const int r = (it & 31) * 4 + (lane >> 3), c8 = (it >> 5) * 8 + (lane & 7);
+                                uint4 g[5];
 #pragma unroll
-                            for (int k = 0; k < 5; ++k)          // five independent 16-byte loads in flight per lane
-                                g[k] = __ldg(reinterpret_cast<const uint4 *>(a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + k]) * ld + k * 256 + c8 * 8));
-                            float acc[8], v[8];
-                            unpack8(g[0], acc);
+                                for (int k = 0; k < 5; ++k)          // five independent 16-byte loads in flight per lane
+                                    g[k] = __ldg(reinterpret_cast<const uint4 *>(a.point_feat + static_cast<int64_t>(idx_s[r * kIdxStride + k]) * ld + k * 256 + c8 * 8));
+                                float acc[8], v[8];
+                                unpack8(g[0], acc);
 #pragma unroll
-                            for (int k = 1; k < 5; ++k) {
-                                unpack8(g[k], v);
+                                for (int k = 1; k < 5; ++k) {
+                                    unpack8(g[k], v);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                                    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                                }
+                                *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = row_base + r < a.rows ? pack8(acc) : make_uint4(0, 0, 0, 0);
                             }
-                            *reinterpret_cast<uint4 *>(act_chunk(X, r, c8)) = row_base + r < a.rows ? pack8(acc) : make_uint4(0, 0, 0, 0);
+                            break;
                         }
-                        break;
-                    }
-                    case kActCoordsB: {
-                        {   // coords -> columns 0..29, zeros -> 30..31
-                            const int r = stid & (kRows - 1);
-                            tuple_geometry_chunks(a.pc, a.normal, idx_s + r * kIdxStride, row_base + r < a.rows, false, stid >> 7, X, r, 0);
+                        case kActCoordsB: {
+                            if (etid < 2 * kRows) {   // coords -> columns 0..29, zeros -> 30..31
+                                const int r = etid & (kRows - 1);
+                                tuple_geometry_chunks(a.pc, a.normal, idx_s + r * kIdxStride, row_base + r < a.rows, false, etid >> 7, X, r, 0);
+                            }
+                            break;
                         }
-                        break;
-                    }
-                    case kActHiddenT:
-                    case kActOutT:
-                    case kActHiddenS:
-                    case kActOut:
-                    case kActFinal: {
-                        const int per = ph.n >> 1;               // columns of the chunk per thread: 8, 32, 64 or 128
-                        const int c0 = half * per;
-                        if (per >= 32) {
-                            for (int c = c0; c < c0 + per; c += 32) epilogue_batch<32>(ph, a, X, t_slot_lane, row, grow, live, c);
-                        } else {
-                            epilogue_batch<8>(ph, a, X, t_slot_lane, row, grow, live, c0);
+                        case kActHiddenT:
+                        case kActOutT:
+                        case kActHiddenS:
+                        case kActOut:
+                        case kActFinal: {
+                            // wide chunks (128 / 256 columns): four threads per row, 32 / 64 columns each; narrow chunks (16 / 64): the
+                            // first two warps of the quadrant, 8 / 32 columns each
+                            if (ph.n >= 128) {
+                                const int per = ph.n >> 2;
+                                for (int c = quarter * per; c < (quarter + 1) * per; c += 32) epilogue_batch<32>(ph, a, X, t_slot_lane, row, grow, live, c);
+                            } else if (quarter < 2) {
+                                const int per = ph.n >> 1;
+                                if (per >= 32) epilogue_batch<32>(ph, a, X, t_slot_lane, row, grow, live, quarter * per);
+                                else epilogue_batch<8>(ph, a, X, t_slot_lane, row, grow, live, quarter * per);
+                            }
+                            if (ph.action == kActHiddenT || ph.action == kActOutT) tmem_st_wait();
+                            break;
                         }
-                        if (ph.action == kActHiddenT || ph.action == kActOutT) tmem_st_wait();
-                        break;
+                        default: break;
                     }
-                    default: break;
+                    t0 = prof_clock<kProf>();
+                    if (kProf) t_actn[ph.action] += t0 - t1;
+                    if (ph.n_parts) {
+                        if (ph.action != kActHiddenT && ph.action != kActOutT) fence_async_smem();   // generic-proxy writes to X -> visible to the tensor core's async proxy
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_act + 8 * slot);
+                    }
+                    t_arrive += prof_clock<kProf>() - t0;
                 }
-                t0 = prof_clock<kProf>();
-                if (kProf) t_actn[ph.action] += t0 - t1;
-                if (ph.n_parts) {
-                    if (ph.action != kActHiddenT && ph.action != kActOutT) fence_async_smem();   // generic-proxy writes to X -> visible to the tensor core's async proxy
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_act + 8 * slot);
-                }
-                t_arrive += prof_clock<kProf>() - t0;
             }
         }
-        if (kProf && one.prof && sw == 0 && lane == 0) {
-            long long *o = one.prof + blockIdx.x * 64 + 8 + 16 * slot;
+        if (kProf && one.prof && ew == 0 && lane == 0) {
+            long long *o = one.prof + blockIdx.x * 64 + 8;
             o[0] = prof_clock<kProf>() - t_begin;
             o[1] = t_done;
             for (int k = 0; k < 10; ++k) o[2 + k] = t_actn[k];
