@@ -86,19 +86,15 @@ __global__ void __launch_bounds__(256) select_pass_kernel(const float *__restric
     const uint32_t decided = pass == 0 ? 0u : (pass >= 4 ? 0xffffffffu : ~((1u << (shift + 8)) - 1u));
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     uint32_t local_min = 0xffffffffu;
-    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < T; t += stride) {
-        const uint32_t key = float_to_key(errs[t]);
+    // whole warps iterate together (warp_hist_add is a full-warp operation)
+    for (int64_t base = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x - lane_id(); base < T; base += stride) {
+        const int64_t t = base + lane_id();
+        const bool valid = t < T;
+        const uint32_t key = valid ? float_to_key(errs[t]) : 0u;
         if (pass < 4) {
-            // back-vote errors share their leading digits (same exponent), so a plain shared-memory atomic per key
-            // serialises on a handful of bins: lanes with equal digits elect one leader that adds the group's size
-            const bool in_prefix = (key & decided) == (prefix & decided);
-            const uint32_t active = __ballot_sync(__activemask(), in_prefix);
-            if (in_prefix) {
-                const uint32_t digit = (key >> shift) & 0xffu;
-                const uint32_t peers = __match_any_sync(active, digit);
-                if (lane_id() == __ffs(peers) - 1) atomicAdd(&s_hist[digit], static_cast<uint32_t>(__popc(peers)));
-            }
-        } else if (key > prefix) {
+            // back-vote errors share their leading digits (same exponent): one leader adds for the warp when all lanes agree
+            warp_hist_add(s_hist, (key >> shift) & 0xffu, valid && (key & decided) == (prefix & decided));
+        } else if (valid && key > prefix) {
             local_min = key < local_min ? key : local_min;
         }
     }
@@ -172,6 +168,12 @@ __global__ void __launch_bounds__(256) select_pass_kernel(const float *__restric
 // launches (two memsets + five passes of ~5 us each, mostly launch latency) become one; results are identical (integer counts).
 constexpr int64_t kSelectSmallMax = 1 << 17;
 
+// kCached: the CTA first copies the keys into its shared memory (T * 4 bytes: 200 KB at T = 50 000, B200 has 227 KB per CTA),
+// so the errors are read from L2 once instead of five times -- a single CTA sweeping 200 KB is bound by L2 latency, and the
+// sweeps were 60 of the kernel's 75 us at T = 50 000.
+constexpr int64_t kSelectCachedMax = 55 * 1024;            // keys the shared-memory cache holds (220 KB)
+
+template <bool kCached>
 __device__ __forceinline__ void select_small_body(const float *__restrict__ errs, int64_t T, int64_t rank_lo, float gamma,
                                                   cppf_backvote_summary *__restrict__ summary) {
     __shared__ uint32_t s_hist[256];
@@ -187,6 +189,19 @@ __device__ __forceinline__ void select_small_body(const float *__restrict__ errs
         s_equal = 0ull;
         s_min = 0xffffffffu;
     }
+    // thread tid owns the tuples u * blockDim.x + tid: coalesced, and every warp iterates the same u (full-width ballots)
+    extern __shared__ __align__(16) uint32_t s_keys[];
+    const int per = static_cast<int>((T + blockDim.x - 1) / blockDim.x);
+    if (kCached) {
+        for (int64_t t = tid; t < T; t += blockDim.x) s_keys[t] = float_to_key(__ldg(errs + t));     // all loads in flight at once
+        __syncthreads();
+    }
+    auto key_at = [&](int u, bool &in) -> uint32_t {
+        const int64_t t = static_cast<int64_t>(u) * blockDim.x + tid;
+        in = t < T;
+        if (!in) return 0u;
+        return kCached ? s_keys[t] : float_to_key(__ldg(errs + t));
+    };
     for (int pass = 0; pass < 4; ++pass) {
         if (tid < 256) s_hist[tid] = 0u;
         if (tid == 0) s_digit = 256;
@@ -194,28 +209,13 @@ __device__ __forceinline__ void select_small_body(const float *__restrict__ errs
         const uint32_t prefix = s_prefix;
         const int shift = 24 - 8 * pass;
         const uint32_t decided = pass == 0 ? 0u : ~((1u << (shift + 8)) - 1u);
-        // whole warps iterate together (full-width ballot); four independent loads in flight per thread: one CTA sweeping
-        // 200 KB is bound by L2 latency, not bandwidth
-        for (int64_t base = tid - lane; base < T; base += 4 * blockDim.x) {
-            uint32_t key[4];
-            bool in[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t t = base + u * blockDim.x + lane;
-                in[u] = t < T;
-                key[u] = in[u] ? float_to_key(__ldg(errs + t)) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const bool in_prefix = in[u] && (key[u] & decided) == (prefix & decided);
-                const uint32_t active = __ballot_sync(0xffffffffu, in_prefix);
-                if (in_prefix) {      // lanes with equal digits elect one leader that adds the group's size (see select_pass_kernel)
-                    const uint32_t digit = (key[u] >> shift) & 0xffu;
-                    const uint32_t peers = __match_any_sync(active, digit);
-                    if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], static_cast<uint32_t>(__popc(peers)));
-                }
-            }
-        }
+        auto count = [&](int u) {
+            bool in;
+            const uint32_t key = key_at(u, in);
+            const bool in_prefix = in && (key & decided) == (prefix & decided);
+            warp_hist_add(s_hist, (key >> shift) & 0xffu, in_prefix);
+        };
+        for (int u = 0; u < per; ++u) count(u);
         __syncthreads();
         if (tid < 256) s_cum[tid] = s_hist[tid];
         __syncthreads();
@@ -241,10 +241,10 @@ __device__ __forceinline__ void select_small_body(const float *__restrict__ errs
     }
     const uint32_t prefix = s_prefix;
     uint32_t local_min = 0xffffffffu;
-#pragma unroll 4
-    for (int64_t t = tid; t < T; t += blockDim.x) {
-        const uint32_t key = float_to_key(__ldg(errs + t));
-        if (key > prefix && key < local_min) local_min = key;
+    for (int u = 0; u < per; ++u) {
+        bool in;
+        const uint32_t key = key_at(u, in);
+        if (in && key > prefix && key < local_min) local_min = key;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -268,9 +268,13 @@ __device__ __forceinline__ void select_small_body(const float *__restrict__ errs
 }
 
 __global__ void __launch_bounds__(1024) select_small_kernel(const float *__restrict__ errs, int64_t T, int64_t rank_lo, float gamma,
-                                                            cppf_backvote_summary *__restrict__ summary) {
-    select_small_body(errs, T, rank_lo, gamma, summary);
+                                                            cppf_backvote_summary *__restrict__ summary, int cached) {
+    if (cached) select_small_body<true>(errs, T, rank_lo, gamma, summary);
+    else select_small_body<false>(errs, T, rank_lo, gamma, summary);
 }
+
+// dynamic shared memory of the cached form for up to T keys (0: the keys do not fit, sweep L2)
+static size_t select_cache_bytes(int64_t T) { return T <= kSelectCachedMax ? static_cast<size_t>(T) * sizeof(uint32_t) : 0; }
 
 // imp_max != nullptr: the running maximum of the occurrence counts is kept as well (the count a point ends with is the value
 // its last increment returns plus one, so the maximum over all increments is the final maximum; one atomicMax per warp) --
@@ -363,7 +367,11 @@ CPPF_API int cppf_backvote_select(const float *errs, int64_t T, int64_t rank_lo,
     if (ws_bytes < cppf_backvote_workspace_bytes(T, 0)) return CPPF_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (T <= kSelectSmallMax) {
-        select_small_kernel<<<1, 1024, 0, s>>>(errs, T, rank_lo, gamma, summary);
+        const size_t cache = select_cache_bytes(T);
+        if (cache > 48 * 1024)
+            CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(select_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          static_cast<int>(kSelectCachedMax * sizeof(uint32_t))));
+        select_small_kernel<<<1, 1024, cache, s>>>(errs, T, rank_lo, gamma, summary, cache ? 1 : 0);
         CPPF_LAUNCH_CHECK();
         return CPPF_OK;
     }
@@ -429,12 +437,13 @@ __global__ void __launch_bounds__(256) frame_backvote_errors_kernel(const FrameT
     backvote_errors_body(in.pc, in.idx, j.targets_tr, in.T, j.center, j.errs, blockIdx.x, gridDim.x);
 }
 
-__global__ void __launch_bounds__(1024) frame_select_kernel(const FrameTable *__restrict__ t) {
+__global__ void __launch_bounds__(1024) frame_select_kernel(const FrameTable *__restrict__ t, int cached) {
     if (static_cast<int>(blockIdx.x) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.x];
     const FrameInst &in = t->inst[j.inst];
     if (in.T <= 0) return;
-    select_small_body(j.errs, in.T, j.rank_lo, j.gamma, j.summary);
+    if (cached) select_small_body<true>(j.errs, in.T, j.rank_lo, j.gamma, j.summary);
+    else select_small_body<false>(j.errs, in.T, j.rank_lo, j.gamma, j.summary);
 }
 
 __global__ void __launch_bounds__(256) frame_backvote_mask_kernel(const FrameTable *__restrict__ t) {
@@ -452,7 +461,11 @@ int frame_launch_backvote(const FrameTable *t, int nj, int64_t T_cap, cudaStream
     const int per_job = std::max(1, std::min<int>(div_up(T_cap, 256), (device_info().sm_count * 8 + nj - 1) / nj));
     frame_backvote_errors_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
-    frame_select_kernel<<<nj, 1024, 0, s>>>(t);
+    const size_t cache = select_cache_bytes(T_cap);
+    if (cache > 48 * 1024)
+        CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(frame_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      static_cast<int>(kSelectCachedMax * sizeof(uint32_t))));
+    frame_select_kernel<<<nj, 1024, cache, s>>>(t, cache ? 1 : 0);
     CPPF_LAUNCH_CHECK();
     frame_backvote_mask_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();

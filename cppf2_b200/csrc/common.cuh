@@ -136,6 +136,24 @@ __device__ __forceinline__ float uniform_from_counter(uint64_t seed, uint64_t ct
     return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// Histogram add of a whole (converged) warp: lanes with `on` add 1 to h[digit].  Keys of one selection pass usually share
+// their leading digits, so the common case is "every lane hits the same bin": one leader adds the group's size (a plain
+// per-lane atomicAdd would serialise 32-deep on one shared-memory address).  Mixed digits fall back to per-lane adds, which
+// then spread over the bins.  (__match_any_sync would aggregate every group, but costs ~100 cycles per call on this part:
+// it made a 50 000-key selection by one CTA take 75 us.)
+__device__ __forceinline__ void warp_hist_add(uint32_t *h, uint32_t digit, bool on) {
+    const uint32_t active = __ballot_sync(0xffffffffu, on);
+    if (active == 0u) return;
+    const int leader = __ffs(active) - 1;
+    const uint32_t d0 = __shfl_sync(0xffffffffu, digit, leader);
+    const uint32_t same = __ballot_sync(0xffffffffu, on && digit == d0);
+    if (same == active) {
+        if ((threadIdx.x & 31) == leader) atomicAdd(&h[d0], static_cast<uint32_t>(__popc(active)));
+    } else if (on) {
+        atomicAdd(&h[digit], 1u);
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -101,6 +101,8 @@ struct FrameJob {                       // one (instance, branch)
 struct FrameTable {
     int n_inst, n_jobs;
     int any_refine, pad;
+    int shot_base[kFrameMaxInst + 1];   // prefix sums of the point counts of the instances that run SHOT: the per-point SHOT
+                                        // kernels spread one flat list of points over the grid
     FrameInst inst[kFrameMaxInst];
     FrameJob job[kFrameMaxJobs];
     tc::MultiArgs heads[2][2];          // [kind: 0 per-point program, 1 per-tuple program][branch]

@@ -125,9 +125,14 @@ __device__ __forceinline__ void scale_median_body(const float *__restrict__ pred
             const int shift = 24 - 8 * pass;
             const uint32_t decided = pass == 0 ? 0u : ~((1u << (shift + 8)) - 1u);
             const uint32_t prefix = s_prefix;
-            for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
-                const uint32_t key = float_to_key(pred_scales[3 * static_cast<int64_t>(kept_list[i]) + axis]);
-                if ((key & decided) == (prefix & decided)) atomicAdd(&s_hist[(key >> shift) & 0xffu], 1u);
+            // whole warps iterate together; scale predictions share their leading digits, so lanes with equal digits elect one
+            // leader that adds the group's size instead of serialising on one shared-memory address
+            for (int64_t base = threadIdx.x - lane_id(); base < M; base += blockDim.x) {
+                const int64_t i = base + lane_id();
+                const bool live = i < M;
+                const uint32_t key = live ? float_to_key(pred_scales[3 * static_cast<int64_t>(kept_list[i]) + axis]) : 0u;
+                const bool on = live && (key & decided) == (prefix & decided);
+                warp_hist_add(s_hist, (key >> shift) & 0xffu, on);
             }
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -182,11 +187,7 @@ __global__ void __launch_bounds__(256) scale_hist_kernel(const float *__restrict
             const uint32_t key = live ? float_to_key(row[a]) : 0u;
             const bool on = live && (pass == 0 || (key >> 16) == ((a == 0 ? p0 : (a == 1 ? p1 : p2)) >> 16));
             const uint32_t digit = pass == 0 ? (key >> 16) : (key & 0xffffu);
-            const uint32_t active = __ballot_sync(0xffffffffu, on);
-            if (on) {
-                const uint32_t peers = __match_any_sync(active, digit);
-                if (lane == __ffs(peers) - 1) atomicAdd(&hist[a * kScaleDigits + digit], static_cast<uint32_t>(__popc(peers)));
-            }
+            warp_hist_add(hist + a * kScaleDigits, digit, on);
         }
     }
 }

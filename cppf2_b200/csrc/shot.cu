@@ -267,6 +267,63 @@ __device__ void eigen33_smallest(const float mat[9], float evec[3]) {
 }
 
 // ---- normals: NormalEstimation::computePointNormal + flipNormalTowardsViewpoint(origin) ----------------
+// normal of the point at sorted position s (one warp): NormalEstimation::computePointNormal + flipNormalTowardsViewpoint
+__device__ __forceinline__ void shot_normal_point(const ShotGrid &g, const int *__restrict__ cell_start,
+                                                  const float4 *__restrict__ sorted, float radius_sq,
+                                                  float *__restrict__ normals, float4 *__restrict__ normals_sorted, int s, int lane) {
+    const float4 pq = sorted[s];
+    const float p[3] = {pq.x, pq.y, pq.z};
+    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for_each_candidate(g, cell_start, sorted, p, lane, [&](int, const float4 &q) {
+        if (flann_dist2(p, q) < radius_sq) {
+            acc[0] += q.x * q.x;
+            acc[1] += q.x * q.y;
+            acc[2] += q.x * q.z;
+            acc[3] += q.y * q.y;
+            acc[4] += q.y * q.z;
+            acc[5] += q.z * q.z;
+            acc[6] += q.x;
+            acc[7] += q.y;
+            acc[8] += q.z;
+            ++cnt;
+        }
+    });
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[i] = warp_sum(acc[i]);
+    cnt = warp_sum(cnt);
+    float nrm[3] = {CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F};
+    if (cnt >= 3) {
+        const float c = static_cast<float>(cnt);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] /= c;
+        float cov[9];
+        cov[0] = acc[0] - acc[6] * acc[6];
+        cov[1] = acc[1] - acc[6] * acc[7];
+        cov[2] = acc[2] - acc[6] * acc[8];
+        cov[4] = acc[3] - acc[7] * acc[7];
+        cov[5] = acc[4] - acc[7] * acc[8];
+        cov[8] = acc[5] - acc[8] * acc[8];
+        cov[3] = cov[1];
+        cov[6] = cov[2];
+        cov[7] = cov[5];
+        eigen33_smallest(cov, nrm);
+        const float cos_theta = (-p[0]) * nrm[0] + (-p[1]) * nrm[1] + (-p[2]) * nrm[2];
+        if (cos_theta < 0.0f) {
+            nrm[0] = -nrm[0];
+            nrm[1] = -nrm[1];
+            nrm[2] = -nrm[2];
+        }
+    }
+    if (lane == 0) {
+        const int orig = __float_as_int(pq.w);
+        normals[3 * orig] = nrm[0];
+        normals[3 * orig + 1] = nrm[1];
+        normals[3 * orig + 2] = nrm[2];
+        if (normals_sorted) normals_sorted[s] = make_float4(nrm[0], nrm[1], nrm[2], 0.0f);
+    }
+}
+
 __device__ __forceinline__ void shot_normals_body(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
                                                   const float4 *__restrict__ sorted, float radius_sq,
                                                   float *__restrict__ normals, float4 *__restrict__ normals_sorted, int bid,
@@ -276,59 +333,7 @@ __device__ __forceinline__ void shot_normals_body(const ShotGrid *__restrict__ g
     const int lane = lane_id();
     const int warp = (bid * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (nblk * blockDim.x) >> 5;
-    for (int s = warp; s < n_sorted; s += n_warps) {
-        const float4 pq = sorted[s];
-        const float p[3] = {pq.x, pq.y, pq.z};
-        float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        int cnt = 0;
-        for_each_candidate(g, cell_start, sorted, p, lane, [&](int, const float4 &q) {
-            if (flann_dist2(p, q) < radius_sq) {
-                acc[0] += q.x * q.x;
-                acc[1] += q.x * q.y;
-                acc[2] += q.x * q.z;
-                acc[3] += q.y * q.y;
-                acc[4] += q.y * q.z;
-                acc[5] += q.z * q.z;
-                acc[6] += q.x;
-                acc[7] += q.y;
-                acc[8] += q.z;
-                ++cnt;
-            }
-        });
-#pragma unroll
-        for (int i = 0; i < 9; ++i) acc[i] = warp_sum(acc[i]);
-        cnt = warp_sum(cnt);
-        float nrm[3] = {CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F};
-        if (cnt >= 3) {
-            const float c = static_cast<float>(cnt);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) acc[i] /= c;
-            float cov[9];
-            cov[0] = acc[0] - acc[6] * acc[6];
-            cov[1] = acc[1] - acc[6] * acc[7];
-            cov[2] = acc[2] - acc[6] * acc[8];
-            cov[4] = acc[3] - acc[7] * acc[7];
-            cov[5] = acc[4] - acc[7] * acc[8];
-            cov[8] = acc[5] - acc[8] * acc[8];
-            cov[3] = cov[1];
-            cov[6] = cov[2];
-            cov[7] = cov[5];
-            eigen33_smallest(cov, nrm);
-            const float cos_theta = (-p[0]) * nrm[0] + (-p[1]) * nrm[1] + (-p[2]) * nrm[2];
-            if (cos_theta < 0.0f) {
-                nrm[0] = -nrm[0];
-                nrm[1] = -nrm[1];
-                nrm[2] = -nrm[2];
-            }
-        }
-        if (lane == 0) {
-            const int orig = __float_as_int(pq.w);
-            normals[3 * orig] = nrm[0];
-            normals[3 * orig + 1] = nrm[1];
-            normals[3 * orig + 2] = nrm[2];
-            if (normals_sorted) normals_sorted[s] = make_float4(nrm[0], nrm[1], nrm[2], 0.0f);
-        }
-    }
+    for (int s = warp; s < n_sorted; s += n_warps) shot_normal_point(g, cell_start, sorted, radius_sq, normals, normals_sorted, s, lane);
 }
 
 __global__ void __launch_bounds__(kShotWarps * 32) shot_normals_kernel(const ShotGrid *__restrict__ gp,
@@ -402,6 +407,246 @@ __device__ void jacobi_eigen3(const double Ain[6] /* xx xy xz yy yz zz */, doubl
 // REAL = double reproduces PCL's double interpolation weights; REAL = float evaluates acos/atan2 and the
 // weights in float (SHOT's quadrilinear interpolation is continuous across every bin boundary, so the
 // descriptor moves by ~1e-7).
+// SHOT-352 row of the point at sorted position s (one warp): LRF (shot_lrf.hpp::getLocalRF) + histogram (shot.hpp).
+// hist [352] and list [kShotListCap] are this warp's shared-memory scratch.
+template <typename REAL>
+__device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const int *__restrict__ cell_start,
+                                                      const float4 *__restrict__ sorted, const float4 *__restrict__ normals_sorted,
+                                                      float radius_f, double radius, float *__restrict__ desc,
+                                                      float *__restrict__ rf_out, unsigned int *hist, int *list, int s, int lane) {
+    const float radius_sq = static_cast<float>(radius * radius);
+    float hist_scale = 1.0f;
+    auto hist_add = [&](int bin_index, float v) { atomicAdd(&hist[bin_index], __float2uint_rn(v * hist_scale)); };
+    (void)radius_f;
+    const REAL r12 = static_cast<REAL>(radius / 2), r14 = static_cast<REAL>(radius / 4), r34 = static_cast<REAL>((radius * 3) / 4);
+    const REAL RAD_45 = static_cast<REAL>(0.78539816339744830961566084581988);
+    const REAL RAD_90 = static_cast<REAL>(1.5707963267948966192313216916398);
+    const REAL RAD_135 = static_cast<REAL>(2.3561944901923449288469825374596);
+    const REAL RAD_7_8 = static_cast<REAL>(2.7488935718910690836548129603691);
+
+    const float4 pq = sorted[s];
+    const float p[3] = {pq.x, pq.y, pq.z};
+    const int orig = __float_as_int(pq.w);
+    float *out = desc + static_cast<size_t>(orig) * CPPF_SHOT_DIM;
+
+    // pass A: weighted scatter matrix in double (shot_lrf.hpp::getLocalRF)
+    double cov[6] = {0, 0, 0, 0, 0, 0}, wsum = 0.0;
+    int valid = 0, total = 0;
+    int n_list = 0;                                  // warp-uniform
+    {
+        const int cx = shot_coord(p[0], g.lo[0], g.inv, g.dim[0]);
+        const int cy = shot_coord(p[1], g.lo[1], g.inv, g.dim[1]);
+        const int cz = shot_coord(p[2], g.lo[2], g.inv, g.dim[2]);
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+        for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+                const int row = (x * g.dim[1] + y) * g.dim[2];
+                const int b = cell_start[row + z0], e = cell_start[row + z1 + 1];  // z-neighbours are contiguous
+                for (int j0 = b; j0 < e; j0 += 32) {     // same visiting order as for_each_candidate, whole warp converged
+                    const int j = j0 + lane;
+                    bool hit = false;
+                    if (j < e) {
+                        const float4 q = sorted[j];
+                        const float d2 = flann_dist2(p, q);
+                        if (d2 < radius_sq) {
+                            hit = true;
+                            ++total;
+                            if (!(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
+                                const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
+                                             vz = static_cast<double>(__fsub_rn(q.z, p[2]));
+                                const double w = radius - sqrt(static_cast<double>(d2));
+                                cov[0] += w * (vx * vx);
+                                cov[1] += w * (vx * vy);
+                                cov[2] += w * (vx * vz);
+                                cov[3] += w * (vy * vy);
+                                cov[4] += w * (vy * vz);
+                                cov[5] += w * (vz * vz);
+                                wsum += w;
+                                ++valid;
+                            }
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m) {
+                        const int pos = n_list + __popc(m & ((1u << lane) - 1u));
+                        if (hit && pos < kShotListCap) list[pos] = j;
+                        n_list += __popc(m);
+                    }
+                }
+            }
+    }
+    __syncwarp();
+    const bool listed = n_list <= kShotListCap;
+    // passes B and C: the cached neighbours when they fit, else the cells again
+    auto for_each_neighbour = [&](auto &&f) {
+        if (listed) {
+            for (int k = lane; k < n_list; k += 32) {
+                const int j = list[k];
+                f(j, sorted[j]);
+            }
+        } else {
+            for_each_candidate(g, cell_start, sorted, p, lane, f);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < 6; ++i) cov[i] = warp_sum(cov[i]);
+    wsum = warp_sum(wsum);
+    valid = warp_sum(valid);
+    total = warp_sum(total);
+
+    bool ok = valid >= 5 && total >= 5;
+    float fx[3], fy[3], fz[3];
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cov[i] /= wsum;
+        double w[3], V[9];
+        jacobi_eigen3(cov, w, V);
+        ok = isfinite(w[0]) && isfinite(w[1]) && isfinite(w[2]);
+        double v1[3] = {V[2], V[5], V[8]};  // largest eigenvalue  -> x
+        double v3[3] = {V[0], V[3], V[6]};  // smallest eigenvalue -> z
+        // pass B: sign disambiguation votes
+        int plus_t = 0, plus_n = 0;
+        for_each_neighbour([&](int, const float4 &q) {
+            if (flann_dist2(p, q) < radius_sq && !(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
+                const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
+                             vz = static_cast<double>(__fsub_rn(q.z, p[2]));
+                if (vx * v1[0] + vy * v1[1] + vz * v1[2] >= 0.0) ++plus_t;
+                if (vx * v3[0] + vy * v3[1] + vz * v3[2] >= 0.0) ++plus_n;
+            }
+        });
+        plus_t = 2 * warp_sum(plus_t) - valid;
+        plus_n = 2 * warp_sum(plus_n) - valid;
+        // exact ties fall back to PCL's search-order dependent rule (5 neighbours around the median
+        // of the kd-tree order); without that order the axis is left as the solver produced it.
+        if (plus_t < 0) { v1[0] = -v1[0]; v1[1] = -v1[1]; v1[2] = -v1[2]; }
+        if (plus_n < 0) { v3[0] = -v3[0]; v3[1] = -v3[1]; v3[2] = -v3[2]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            fx[k] = static_cast<float>(v1[k]);
+            fz[k] = static_cast<float>(v3[k]);
+        }
+        cross3f(fz, fx, fy);
+    }
+    if (rf_out && lane < 9) {
+        const float v = !ok ? CUDART_NAN_F : (lane < 3 ? fx[lane] : (lane < 6 ? fy[lane - 3] : fz[lane - 6]));
+        rf_out[static_cast<size_t>(orig) * 9 + lane] = v;
+    }
+    if (!ok) {  // invalid LRF or fewer than 5 neighbours: NaN row (shot.hpp::computeFeature / computePointSHOT)
+        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) out[j] = CUDART_NAN_F;
+        return;
+    }
+
+    // pass C: histogram (shot.hpp::createBinDistanceShape + interpolateSingleChannel)
+    for (int j = lane; j < CPPF_SHOT_DIM; j += 32) hist[j] = 0u;
+    {
+        const unsigned m = 5u * static_cast<unsigned>(total) + 1u;          // total < 2^29 points
+        const int k = min(24, __clz(m));                                    // 32 - bits(m)
+        hist_scale = static_cast<float>(1u << k);
+    }
+    __syncwarp();
+    for_each_neighbour([&](int j, const float4 &q) {
+        const float d2 = flann_dist2(p, q);
+        if (!(d2 < radius_sq)) return;
+        const float4 nq = normals_sorted[j];
+        if (!(isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z))) return;
+        REAL cosine = static_cast<REAL>(nq.x * fz[0] + nq.y * fz[1] + nq.z * fz[2]);
+        cosine = cosine > REAL(1) ? REAL(1) : (cosine < REAL(-1) ? REAL(-1) : cosine);
+        REAL bin = ((REAL(1) + cosine) * REAL(10)) / REAL(2);
+        const float dl[3] = {__fsub_rn(q.x, p[0]), __fsub_rn(q.y, p[1]), __fsub_rn(q.z, p[2])};
+        const REAL distance = static_cast<REAL>(sqrt(static_cast<double>(d2)));
+        if (fabs(static_cast<double>(distance)) < 1e-15) return;
+        REAL xr = static_cast<REAL>(dl[0] * fx[0] + dl[1] * fx[1] + dl[2] * fx[2]);
+        REAL yr = static_cast<REAL>(dl[0] * fy[0] + dl[1] * fy[1] + dl[2] * fy[2]);
+        REAL zr = static_cast<REAL>(dl[0] * fz[0] + dl[1] * fz[1] + dl[2] * fz[2]);
+        if (fabs(static_cast<double>(yr)) < 1e-30) yr = 0;
+        if (fabs(static_cast<double>(xr)) < 1e-30) xr = 0;
+        if (fabs(static_cast<double>(zr)) < 1e-30) zr = 0;
+        const int bit4 = ((yr > 0) || ((yr == 0) && (xr < 0))) ? 1 : 0;
+        const int bit3 = ((xr > 0) || ((xr == 0) && (yr > 0))) ? (1 - bit4) : bit4;
+        int di = ((bit4 << 3) + (bit3 << 2)) << 1;
+        const REAL ax = xr < 0 ? -xr : xr, ay = yr < 0 ? -yr : yr;
+        if ((xr * yr > 0) || (xr == 0))
+            di += (ax >= ay) ? 0 : 4;
+        else
+            di += (ax > ay) ? 4 : 0;
+        di += zr > 0 ? 1 : 0;
+        di += (distance > r12) ? 2 : 0;
+        const int step = static_cast<int>(floor(static_cast<double>(bin) + 0.5));
+        const int vol = di * 11;
+        bin -= static_cast<REAL>(step);
+        REAL wgt = REAL(1) - (bin < 0 ? -bin : bin);
+        if (bin > 0)
+            hist_add(vol + ((step + 1) % 10), static_cast<float>(bin));
+        else
+            hist_add(vol + ((step - 1 + 10) % 10), -static_cast<float>(bin));
+        if (distance > r12) {
+            const REAL rd = (distance - r34) / r12;
+            if (distance > r34)
+                wgt += REAL(1) - rd;
+            else {
+                wgt += REAL(1) + rd;
+                hist_add((di - 2) * 11 + step, -static_cast<float>(rd));
+            }
+        } else {
+            const REAL rd = (distance - r14) / r12;
+            if (distance < r14)
+                wgt += REAL(1) + rd;
+            else {
+                wgt += REAL(1) - rd;
+                hist_add((di + 2) * 11 + step, static_cast<float>(rd));
+            }
+        }
+        REAL ic = zr / distance;
+        ic = ic < REAL(-1) ? REAL(-1) : (ic > REAL(1) ? REAL(1) : ic);
+        const REAL incl = acos(ic);
+        if (incl > RAD_90 || (fabs(static_cast<double>(incl - RAD_90)) < 1e-30 && zr <= 0)) {
+            const REAL id = (incl - RAD_135) / RAD_90;
+            if (incl > RAD_135)
+                wgt += REAL(1) - id;
+            else {
+                wgt += REAL(1) + id;
+                hist_add((di + 1) * 11 + step, -static_cast<float>(id));
+            }
+        } else {
+            const REAL id = (incl - RAD_45) / RAD_90;
+            if (incl < RAD_45)
+                wgt += REAL(1) + id;
+            else {
+                wgt += REAL(1) - id;
+                hist_add((di - 1) * 11 + step, static_cast<float>(id));
+            }
+        }
+        if (yr != 0 || xr != 0) {
+            const REAL az = atan2(yr, xr);
+            const int sel = di >> 2;
+            REAL ad = (az - (-RAD_7_8 + RAD_45 * static_cast<REAL>(sel))) / RAD_45;
+            ad = ad < REAL(-0.5) ? REAL(-0.5) : (ad > REAL(0.5) ? REAL(0.5) : ad);
+            if (ad > 0) {
+                wgt += REAL(1) - ad;
+                hist_add(((di + 4) % 32) * 11 + step, static_cast<float>(ad));
+            } else {
+                wgt += REAL(1) + ad;
+                hist_add(((di - 4 + 32) % 32) * 11 + step, -static_cast<float>(ad));
+            }
+        }
+        hist_add(vol + step, static_cast<float>(wgt));
+    });
+    __syncwarp();
+    // normalizeHistogram: float squares accumulated in double, divide by float(norm)
+    double acc = 0.0;
+    float hv[CPPF_SHOT_DIM / 32];
+#pragma unroll
+    for (int u = 0; u < CPPF_SHOT_DIM / 32; ++u) {
+        hv[u] = static_cast<float>(static_cast<double>(hist[lane + 32 * u]) / static_cast<double>(hist_scale));
+        acc += static_cast<double>(hv[u] * hv[u]);
+    }
+    acc = warp_sum(acc);
+    const float nrm = static_cast<float>(sqrt(acc));
+#pragma unroll
+    for (int u = 0; u < CPPF_SHOT_DIM / 32; ++u) out[lane + 32 * u] = hv[u] / nrm;
+    __syncwarp();
+}
+
 template <typename REAL>
 __device__ __forceinline__ void shot_descriptor_body(
     const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
@@ -419,245 +664,12 @@ __device__ __forceinline__ void shot_descriptor_body(
     __shared__ int s_list[kShotWarps][kShotListCap];
     const ShotGrid g = *gp;
     const int n_sorted = cell_start[g.cells];
-    const float radius_sq = static_cast<float>(radius * radius);
     const int lane = lane_id();
     const int wib = threadIdx.x >> 5;
     const int warp = (bid * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (nblk * blockDim.x) >> 5;
-    unsigned int *hist = s_hist[wib];
-    float hist_scale = 1.0f;
-    auto hist_add = [&](int bin_index, float v) { atomicAdd(&hist[bin_index], __float2uint_rn(v * hist_scale)); };
-    int *list = s_list[wib];
-    (void)radius_f;
-    const REAL r12 = static_cast<REAL>(radius / 2), r14 = static_cast<REAL>(radius / 4), r34 = static_cast<REAL>((radius * 3) / 4);
-    const REAL RAD_45 = static_cast<REAL>(0.78539816339744830961566084581988);
-    const REAL RAD_90 = static_cast<REAL>(1.5707963267948966192313216916398);
-    const REAL RAD_135 = static_cast<REAL>(2.3561944901923449288469825374596);
-    const REAL RAD_7_8 = static_cast<REAL>(2.7488935718910690836548129603691);
-
-    for (int s = warp; s < n_sorted; s += n_warps) {
-        const float4 pq = sorted[s];
-        const float p[3] = {pq.x, pq.y, pq.z};
-        const int orig = __float_as_int(pq.w);
-        float *out = desc + static_cast<size_t>(orig) * CPPF_SHOT_DIM;
-
-        // pass A: weighted scatter matrix in double (shot_lrf.hpp::getLocalRF)
-        double cov[6] = {0, 0, 0, 0, 0, 0}, wsum = 0.0;
-        int valid = 0, total = 0;
-        int n_list = 0;                                  // warp-uniform
-        {
-            const int cx = shot_coord(p[0], g.lo[0], g.inv, g.dim[0]);
-            const int cy = shot_coord(p[1], g.lo[1], g.inv, g.dim[1]);
-            const int cz = shot_coord(p[2], g.lo[2], g.inv, g.dim[2]);
-            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
-            for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x)
-                for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
-                    const int row = (x * g.dim[1] + y) * g.dim[2];
-                    const int b = cell_start[row + z0], e = cell_start[row + z1 + 1];  // z-neighbours are contiguous
-                    for (int j0 = b; j0 < e; j0 += 32) {     // same visiting order as for_each_candidate, whole warp converged
-                        const int j = j0 + lane;
-                        bool hit = false;
-                        if (j < e) {
-                            const float4 q = sorted[j];
-                            const float d2 = flann_dist2(p, q);
-                            if (d2 < radius_sq) {
-                                hit = true;
-                                ++total;
-                                if (!(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
-                                    const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
-                                                 vz = static_cast<double>(__fsub_rn(q.z, p[2]));
-                                    const double w = radius - sqrt(static_cast<double>(d2));
-                                    cov[0] += w * (vx * vx);
-                                    cov[1] += w * (vx * vy);
-                                    cov[2] += w * (vx * vz);
-                                    cov[3] += w * (vy * vy);
-                                    cov[4] += w * (vy * vz);
-                                    cov[5] += w * (vz * vz);
-                                    wsum += w;
-                                    ++valid;
-                                }
-                            }
-                        }
-                        const unsigned m = __ballot_sync(0xffffffffu, hit);
-                        if (m) {
-                            const int pos = n_list + __popc(m & ((1u << lane) - 1u));
-                            if (hit && pos < kShotListCap) list[pos] = j;
-                            n_list += __popc(m);
-                        }
-                    }
-                }
-        }
-        __syncwarp();
-        const bool listed = n_list <= kShotListCap;
-        // passes B and C: the cached neighbours when they fit, else the cells again
-        auto for_each_neighbour = [&](auto &&f) {
-            if (listed) {
-                for (int k = lane; k < n_list; k += 32) {
-                    const int j = list[k];
-                    f(j, sorted[j]);
-                }
-            } else {
-                for_each_candidate(g, cell_start, sorted, p, lane, f);
-            }
-        };
-#pragma unroll
-        for (int i = 0; i < 6; ++i) cov[i] = warp_sum(cov[i]);
-        wsum = warp_sum(wsum);
-        valid = warp_sum(valid);
-        total = warp_sum(total);
-
-        bool ok = valid >= 5 && total >= 5;
-        float fx[3], fy[3], fz[3];
-        if (ok) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) cov[i] /= wsum;
-            double w[3], V[9];
-            jacobi_eigen3(cov, w, V);
-            ok = isfinite(w[0]) && isfinite(w[1]) && isfinite(w[2]);
-            double v1[3] = {V[2], V[5], V[8]};  // largest eigenvalue  -> x
-            double v3[3] = {V[0], V[3], V[6]};  // smallest eigenvalue -> z
-            // pass B: sign disambiguation votes
-            int plus_t = 0, plus_n = 0;
-            for_each_neighbour([&](int, const float4 &q) {
-                if (flann_dist2(p, q) < radius_sq && !(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
-                    const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
-                                 vz = static_cast<double>(__fsub_rn(q.z, p[2]));
-                    if (vx * v1[0] + vy * v1[1] + vz * v1[2] >= 0.0) ++plus_t;
-                    if (vx * v3[0] + vy * v3[1] + vz * v3[2] >= 0.0) ++plus_n;
-                }
-            });
-            plus_t = 2 * warp_sum(plus_t) - valid;
-            plus_n = 2 * warp_sum(plus_n) - valid;
-            // exact ties fall back to PCL's search-order dependent rule (5 neighbours around the median
-            // of the kd-tree order); without that order the axis is left as the solver produced it.
-            if (plus_t < 0) { v1[0] = -v1[0]; v1[1] = -v1[1]; v1[2] = -v1[2]; }
-            if (plus_n < 0) { v3[0] = -v3[0]; v3[1] = -v3[1]; v3[2] = -v3[2]; }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                fx[k] = static_cast<float>(v1[k]);
-                fz[k] = static_cast<float>(v3[k]);
-            }
-            cross3f(fz, fx, fy);
-        }
-        if (rf_out && lane < 9) {
-            const float v = !ok ? CUDART_NAN_F : (lane < 3 ? fx[lane] : (lane < 6 ? fy[lane - 3] : fz[lane - 6]));
-            rf_out[static_cast<size_t>(orig) * 9 + lane] = v;
-        }
-        if (!ok) {  // invalid LRF or fewer than 5 neighbours: NaN row (shot.hpp::computeFeature / computePointSHOT)
-            for (int j = lane; j < CPPF_SHOT_DIM; j += 32) out[j] = CUDART_NAN_F;
-            continue;
-        }
-
-        // pass C: histogram (shot.hpp::createBinDistanceShape + interpolateSingleChannel)
-        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) hist[j] = 0u;
-        {
-            const unsigned m = 5u * static_cast<unsigned>(total) + 1u;          // total < 2^29 points
-            const int k = min(24, __clz(m));                                    // 32 - bits(m)
-            hist_scale = static_cast<float>(1u << k);
-        }
-        __syncwarp();
-        for_each_neighbour([&](int j, const float4 &q) {
-            const float d2 = flann_dist2(p, q);
-            if (!(d2 < radius_sq)) return;
-            const float4 nq = normals_sorted[j];
-            if (!(isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z))) return;
-            REAL cosine = static_cast<REAL>(nq.x * fz[0] + nq.y * fz[1] + nq.z * fz[2]);
-            cosine = cosine > REAL(1) ? REAL(1) : (cosine < REAL(-1) ? REAL(-1) : cosine);
-            REAL bin = ((REAL(1) + cosine) * REAL(10)) / REAL(2);
-            const float dl[3] = {__fsub_rn(q.x, p[0]), __fsub_rn(q.y, p[1]), __fsub_rn(q.z, p[2])};
-            const REAL distance = static_cast<REAL>(sqrt(static_cast<double>(d2)));
-            if (fabs(static_cast<double>(distance)) < 1e-15) return;
-            REAL xr = static_cast<REAL>(dl[0] * fx[0] + dl[1] * fx[1] + dl[2] * fx[2]);
-            REAL yr = static_cast<REAL>(dl[0] * fy[0] + dl[1] * fy[1] + dl[2] * fy[2]);
-            REAL zr = static_cast<REAL>(dl[0] * fz[0] + dl[1] * fz[1] + dl[2] * fz[2]);
-            if (fabs(static_cast<double>(yr)) < 1e-30) yr = 0;
-            if (fabs(static_cast<double>(xr)) < 1e-30) xr = 0;
-            if (fabs(static_cast<double>(zr)) < 1e-30) zr = 0;
-            const int bit4 = ((yr > 0) || ((yr == 0) && (xr < 0))) ? 1 : 0;
-            const int bit3 = ((xr > 0) || ((xr == 0) && (yr > 0))) ? (1 - bit4) : bit4;
-            int di = ((bit4 << 3) + (bit3 << 2)) << 1;
-            const REAL ax = xr < 0 ? -xr : xr, ay = yr < 0 ? -yr : yr;
-            if ((xr * yr > 0) || (xr == 0))
-                di += (ax >= ay) ? 0 : 4;
-            else
-                di += (ax > ay) ? 4 : 0;
-            di += zr > 0 ? 1 : 0;
-            di += (distance > r12) ? 2 : 0;
-            const int step = static_cast<int>(floor(static_cast<double>(bin) + 0.5));
-            const int vol = di * 11;
-            bin -= static_cast<REAL>(step);
-            REAL wgt = REAL(1) - (bin < 0 ? -bin : bin);
-            if (bin > 0)
-                hist_add(vol + ((step + 1) % 10), static_cast<float>(bin));
-            else
-                hist_add(vol + ((step - 1 + 10) % 10), -static_cast<float>(bin));
-            if (distance > r12) {
-                const REAL rd = (distance - r34) / r12;
-                if (distance > r34)
-                    wgt += REAL(1) - rd;
-                else {
-                    wgt += REAL(1) + rd;
-                    hist_add((di - 2) * 11 + step, -static_cast<float>(rd));
-                }
-            } else {
-                const REAL rd = (distance - r14) / r12;
-                if (distance < r14)
-                    wgt += REAL(1) + rd;
-                else {
-                    wgt += REAL(1) - rd;
-                    hist_add((di + 2) * 11 + step, static_cast<float>(rd));
-                }
-            }
-            REAL ic = zr / distance;
-            ic = ic < REAL(-1) ? REAL(-1) : (ic > REAL(1) ? REAL(1) : ic);
-            const REAL incl = acos(ic);
-            if (incl > RAD_90 || (fabs(static_cast<double>(incl - RAD_90)) < 1e-30 && zr <= 0)) {
-                const REAL id = (incl - RAD_135) / RAD_90;
-                if (incl > RAD_135)
-                    wgt += REAL(1) - id;
-                else {
-                    wgt += REAL(1) + id;
-                    hist_add((di + 1) * 11 + step, -static_cast<float>(id));
-                }
-            } else {
-                const REAL id = (incl - RAD_45) / RAD_90;
-                if (incl < RAD_45)
-                    wgt += REAL(1) + id;
-                else {
-                    wgt += REAL(1) - id;
-                    hist_add((di - 1) * 11 + step, static_cast<float>(id));
-                }
-            }
-            if (yr != 0 || xr != 0) {
-                const REAL az = atan2(yr, xr);
-                const int sel = di >> 2;
-                REAL ad = (az - (-RAD_7_8 + RAD_45 * static_cast<REAL>(sel))) / RAD_45;
-                ad = ad < REAL(-0.5) ? REAL(-0.5) : (ad > REAL(0.5) ? REAL(0.5) : ad);
-                if (ad > 0) {
-                    wgt += REAL(1) - ad;
-                    hist_add(((di + 4) % 32) * 11 + step, static_cast<float>(ad));
-                } else {
-                    wgt += REAL(1) + ad;
-                    hist_add(((di - 4 + 32) % 32) * 11 + step, -static_cast<float>(ad));
-                }
-            }
-            hist_add(vol + step, static_cast<float>(wgt));
-        });
-        __syncwarp();
-        // normalizeHistogram: float squares accumulated in double, divide by float(norm)
-        double acc = 0.0;
-        float hv[CPPF_SHOT_DIM / 32];
-#pragma unroll
-        for (int u = 0; u < CPPF_SHOT_DIM / 32; ++u) {
-            hv[u] = static_cast<float>(static_cast<double>(hist[lane + 32 * u]) / static_cast<double>(hist_scale));
-            acc += static_cast<double>(hv[u] * hv[u]);
-        }
-        acc = warp_sum(acc);
-        const float nrm = static_cast<float>(sqrt(acc));
-#pragma unroll
-        for (int u = 0; u < CPPF_SHOT_DIM / 32; ++u) out[lane + 32 * u] = hv[u] / nrm;
-        __syncwarp();
-    }
+    for (int s = warp; s < n_sorted; s += n_warps)
+        shot_descriptor_point<REAL>(g, cell_start, sorted, normals_sorted, radius_f, radius, desc, rf_out, s_hist[wib], s_list[wib], s, lane);
 }
 
 template <typename REAL>
@@ -771,26 +783,50 @@ __global__ void __launch_bounds__(256) frame_shot_order_kernel(const FrameTable 
     shot_cell_order_body(in->sw.grid, in->sw.cell_start, in->sw.normals_sorted, in->sw.sorted, blockIdx.x, gridDim.x);
 }
 
-// normals; points with non-finite coordinates (never in the grid) get their NaN rows here
-__global__ void __launch_bounds__(kShotWarps * 32) frame_shot_normals_kernel(const FrameTable *__restrict__ t) {
-    const FrameInst *in;
-    if (!frame_shot_instance(t, in)) return;
-    const float nanv = CUDART_NAN_F;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < in->n; i += (gridDim.x * blockDim.x) >> 5) {
-        if (in->sw.cell_of[i] >= 0) continue;
-        const int lane = lane_id();
-        if (lane < 3) in->normals[3 * i + lane] = nanv;
-        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) in->shot_desc[static_cast<size_t>(i) * CPPF_SHOT_DIM + j] = nanv;
-    }
-    const float nr2 = static_cast<float>(static_cast<double>(in->normal_r) * static_cast<double>(in->normal_r));
-    shot_normals_body(in->sw.grid, in->sw.cell_start, in->sw.sorted, nr2, in->normals, in->sw.normals_sorted, blockIdx.x, gridDim.x);
+// The two per-point kernels take ONE flat list of all instances' points (shot_base = prefix sums of the clouds' sizes): warp w
+// of the grid owns the flat positions w, w + n_warps, ...  A frame's clouds differ in size by 2-3x; with one grid row per
+// instance the largest cloud set the time of the launch.
+__device__ __forceinline__ int frame_shot_locate(const FrameTable *__restrict__ t, int g, int &s) {
+    int i = 0;
+    while (i + 1 < t->n_inst && g >= t->shot_base[i + 1]) ++i;
+    s = g - t->shot_base[i];
+    return i;
 }
 
-__global__ void __launch_bounds__(kShotWarps * 32) frame_shot_descriptor_kernel(const FrameTable *__restrict__ t) {
-    const FrameInst *in;
-    if (!frame_shot_instance(t, in)) return;
-    shot_descriptor_body<float>(in->sw.grid, in->sw.cell_start, in->sw.sorted, in->sw.normals_sorted, in->shot_r,
-                                static_cast<double>(in->shot_r), in->shot_desc, nullptr, blockIdx.x, gridDim.x);
+// normals; points with non-finite coordinates (never in the grid) get their NaN rows here
+__global__ void __launch_bounds__(kShotWarps * 32) frame_shot_normals_kernel(const FrameTable *__restrict__ t) {
+    const int total = t->shot_base[t->n_inst];
+    const int lane = lane_id();
+    const float nanv = CUDART_NAN_F;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total; g += (gridDim.x * blockDim.x) >> 5) {
+        int s;
+        const FrameInst &in = t->inst[frame_shot_locate(t, g, s)];
+        // position s serves twice: as an ORIGINAL index for the NaN rows of points outside the grid ...
+        if (in.sw.cell_of[s] < 0) {
+            if (lane < 3) in.normals[3 * s + lane] = nanv;
+            for (int j = lane; j < CPPF_SHOT_DIM; j += 32) in.shot_desc[static_cast<size_t>(s) * CPPF_SHOT_DIM + j] = nanv;
+        }
+        // ... and as a SORTED position for the normal of the point stored there
+        const ShotGrid gr = *in.sw.grid;
+        if (s >= in.sw.cell_start[gr.cells]) continue;
+        const float nr2 = static_cast<float>(static_cast<double>(in.normal_r) * static_cast<double>(in.normal_r));
+        shot_normal_point(gr, in.sw.cell_start, in.sw.sorted, nr2, in.normals, in.sw.normals_sorted, s, lane);
+    }
+}
+
+__global__ void __launch_bounds__(kShotWarps * 32, 3) frame_shot_descriptor_kernel(const FrameTable *__restrict__ t) {
+    __shared__ unsigned int s_hist[kShotWarps][CPPF_SHOT_DIM];
+    __shared__ int s_list[kShotWarps][kShotListCap];
+    const int total = t->shot_base[t->n_inst];
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total; g += (gridDim.x * blockDim.x) >> 5) {
+        int s;
+        const FrameInst &in = t->inst[frame_shot_locate(t, g, s)];
+        const ShotGrid gr = *in.sw.grid;
+        if (s >= in.sw.cell_start[gr.cells]) continue;
+        shot_descriptor_point<float>(gr, in.sw.cell_start, in.sw.sorted, in.sw.normals_sorted, in.shot_r, static_cast<double>(in.shot_r),
+                                     in.shot_desc, nullptr, s_hist[wib], s_list[wib], s, lane);
+    }
 }
 
 int frame_launch_shot(const FrameTable *t, int ni, int64_t n_cap, cudaStream_t s) {
@@ -812,9 +848,11 @@ int frame_launch_shot(const FrameTable *t, int ni, int64_t n_cap, cudaStream_t s
     CPPF_LAUNCH_CHECK();
     frame_shot_order_kernel<<<dim3(per_inst(n_cap * 8, 256, 8), ni), 256, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
-    frame_shot_normals_kernel<<<dim3(per_inst(n_cap * 32, kShotWarps * 32, 8), ni), kShotWarps * 32, 0, s>>>(t);
+    // flat over all instances' points: a whole number of waves, capped by the work the capacity allows
+    const int64_t warps_cap = n_cap * ni;
+    frame_shot_normals_kernel<<<grid_for(warps_cap * 32, kShotWarps * 32, 8), kShotWarps * 32, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
-    frame_shot_descriptor_kernel<<<dim3(per_inst(n_cap * 32, kShotWarps * 32, 4), ni), kShotWarps * 32, 0, s>>>(t);
+    frame_shot_descriptor_kernel<<<grid_for(warps_cap * 32, kShotWarps * 32, 3), kShotWarps * 32, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }

@@ -44,9 +44,9 @@ __device__ __forceinline__ void grid_zero_body(uint32_t *__restrict__ grid, int6
                                                int replicas_max, int bid, int nblk) {
     int64_t cells = geom->cells;
     if (cells <= capacity) cells *= replica_count(cells, capacity, replicas_max);
-    if (cells > capacity) {
+    if (cells > capacity || geom->cells > 0x7fffffffll) {     // beyond the caller's buffer, or beyond the 32-bit cell index of the vote
         if (bid == 0 && threadIdx.x == 0 && status) atomicOr(status, CPPF_STATUS_GRID_OVERFLOW);
-        cells = capacity;
+        cells = cells > capacity ? capacity : cells;
     }
     if (bid == 0 && threadIdx.x == 0 && status && geom->flags) atomicOr(status, geom->flags);
     int64_t vec = cells >> 2;
@@ -108,7 +108,7 @@ __device__ __forceinline__ void vote_center_body(
     }
     __syncthreads();
 
-    if (cells > capacity) return;  // flagged by grid_zero_kernel
+    if (cells > capacity || cells > 0x7fffffffll) return;  // flagged by grid_zero_kernel
     if (MODE == 0) grid += (bid % replica_count(cells, capacity, replicas_max)) * cells;
     const float res = geom->res;
     const float inv_res = __frcp_rn(res);      // correctly rounded reciprocal of the launch-wide divisor (see div_by)
@@ -168,9 +168,11 @@ __device__ __forceinline__ void vote_center_body(
                 const int i2 = __float2int_rz(__fadd_rn(q2, 0.5f));
                 // strictly inside (cell 0 never receives votes, :200)
                 if (i0 > 0 && i1 > 0 && i2 > 0 && i0 < g0 && i1 < g1 && i2 < g2) {
-                    const int64_t lin = (static_cast<int64_t>(i0) * g1 + i1) * g2 + i2;
+                    // 32-bit cell index (grids beyond 2^31 cells are never voted, see above): the 64-bit form was 13 of the
+                    // ~64 instructions of a vote, and this loop is issue-bound (ncu: 75 % issue slots busy)
+                    const int lin = (i0 * g1 + i1) * g2 + i2;
                     if (MODE == 1) atomicAdd(s_grid + lin, 1u);   // ATOMS
-                    else atomicAdd(grid + lin, 1u);               // result unused -> RED.E.ADD
+                    else atomicAdd(grid + lin, 1u);               // result unused: a reduction at L2
                 }
             }
         }
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(256) grid_argmax_kernel(const uint32_t *__rest
                                                           unsigned int *__restrict__ ticket) {
     // a grid larger than the caller's buffer was never voted (grid_zero_kernel raised CPPF_STATUS_GRID_OVERFLOW): nothing to
     // scan, and nothing may be read past the buffer
-    const bool overflow = geom->cells > capacity;
+    const bool overflow = geom->cells > capacity || geom->cells > 0x7fffffffll;
     const int64_t cells = overflow ? 0 : geom->cells;
     unsigned long long best = 0ull;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(256) frame_fold_argmax_kernel(const FrameTable
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
     const cppf_grid_geom *geom = j.geom;
-    const bool overflow = geom->cells > j.grid_capacity;
+    const bool overflow = geom->cells > j.grid_capacity || geom->cells > 0x7fffffffll;
     const int64_t cells = overflow ? 0 : geom->cells;
     const int replicas = replica_count(cells, j.grid_capacity, sh.replicas_max);
     uint32_t *grid = j.grid;
