@@ -115,6 +115,7 @@ class PoseEstimator:
         self.frame_call = os.environ.get("CPPF_FRAME_CALL", "1") != "0"
         self.use_graph = os.environ.get("CPPF_FRAME_GRAPH", "0") != "0"  # replay the frame's kernel sequence from a CUDA graph
         self.replicas_max = int(os.environ.get("CPPF_FRAME_REPLICAS", "0"))
+        self._prep_stream = None        # cloud preparation of submit_frame (overlaps the previous frame's kernels)
         self.stage_events = None        # optional list of 8 torch.cuda.Event(enable_timing=True), recorded at the stage boundaries
         self._job_voters: List[PoseVoter] = []
         self._slot_bufs: Dict[int, dict] = {}
@@ -556,27 +557,41 @@ class PoseEstimator:
         loop.  `desc_fn(i, pix)` returns the [N,1024] key-point descriptors of instance i at the kept pixels `pix`
         (row*W + col, CUDA int32) -- the DINOv2 backbone is not part of this path; None runs the SHOT branch only.
         Instances with fewer than 50 valid pixels or an extent above 1000 voxels are skipped like the reference does."""
+        return self.submit_frame(depth, masks, categories, intrinsics, desc_fn, depth_div, frame_seed).result()
+
+    def submit_frame(self, depth, masks, categories: Sequence[str], intrinsics, desc_fn=None, depth_div: float = 1000.0,
+                     frame_seed: int = 0) -> "PendingRawFrame":
+        """Asynchronous form of `estimate_frame`.  The cloud preparation (uploads, back-projection, voxel down-sampling, two
+        small read-backs of point counts) runs on its own stream, so that it -- and the host work around it -- overlaps the
+        kernels of the previous frame; the instance loop is then queued on the caller's stream and `.result()` waits for
+        this frame only."""
         from . import cloud
         dev = self.device
-        d = depth if isinstance(depth, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(depth))
-        d = d.to(dev, non_blocking=True)
-        m = [(x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))).to(dev, non_blocking=True) for x in masks]
-        res = [self.vote_config(c).res for c in categories]
-        clouds = cloud.prepare_instance_clouds(d, m, intrinsics, res, depth_div=depth_div, seed=self.seed * 8191 + frame_seed)
-        instances, where = [], []
-        for i, item in enumerate(clouds):
-            if item is None:
-                continue
-            pc, pix = item
-            desc = None if desc_fn is None else desc_fn(i, pix)
-            instances.append(Instance(pc=pc, category=categories[i], desc=desc, point_idxs=None))
-            where.append(i)
-        out: List[Optional[InstancePose]] = [None] * len(masks)
-        if not instances:
-            return out
-        for i, p in zip(where, self.estimate(instances)):      # extent guard and grid regrowth: collect() / PendingFrame
-            out[i] = p
-        return out
+        main = torch.cuda.current_stream(dev)
+        if self._prep_stream is None:
+            self._prep_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._prep_stream):
+            d = depth if isinstance(depth, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(depth))
+            d = d.to(dev, non_blocking=True)
+            m = [(x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))).to(dev, non_blocking=True) for x in masks]
+            res = [self.vote_config(c).res for c in categories]
+            clouds = cloud.prepare_instance_clouds(d, m, intrinsics, res, depth_div=depth_div, seed=self.seed * 8191 + frame_seed)
+            instances, where = [], []
+            for i, item in enumerate(clouds):
+                if item is None:
+                    continue
+                pc, pix = item
+                desc = None if desc_fn is None else desc_fn(i, pix)
+                for t in (pc, pix, desc):
+                    if isinstance(t, torch.Tensor) and t.is_cuda:
+                        t.record_stream(main)
+                instances.append(Instance(pc=pc, category=categories[i], desc=desc, point_idxs=None))
+                where.append(i)
+            ready = torch.cuda.Event()
+            ready.record(self._prep_stream)
+        main.wait_event(ready)
+        pending = self.submit(instances) if instances else None      # extent guard and grid regrowth: collect() / PendingFrame
+        return PendingRawFrame(pending, where, len(masks))
 
     def submit(self, instances: Sequence[Instance], draws: Optional[List[dict]] = None) -> "PendingFrame":
         """Asynchronous form of `estimate`: starts the uploads, queues the kernels and the pose read-back (into pinned host
@@ -640,6 +655,20 @@ class PendingFrame:
                 out[i] = p
         self._instances = self._draws = None
         self._out = out
+        return out
+
+
+class PendingRawFrame:
+    """A raw frame queued by PoseEstimator.submit_frame(): result() maps the posed instances back to the detections."""
+
+    def __init__(self, pending: Optional[PendingFrame], where: List[int], n_detections: int):
+        self._pending, self._where, self._n = pending, where, n_detections
+
+    def result(self) -> List[Optional[InstancePose]]:
+        out: List[Optional[InstancePose]] = [None] * self._n
+        if self._pending is not None:
+            for i, p in zip(self._where, self._pending.result()):
+                out[i] = p
         return out
 
 

@@ -4,7 +4,8 @@ from (depth, masks) in pinned host memory to (RT, scale) per instance, frames/s 
     python tools/batched_eval.py [--frames 256] [--gpus N]          (N > 1: launch under torchrun, one rank per GPU)
 
 Every rank owns frames rank, rank+world, ...; no data-path collective (frames are independent, eval.py:132); the final
-gather of the pose records is one all_gather_object.  DINO descriptors are seeded unit-norm stand-ins taken from a
+gather of the pose records is one all_gather_object.  The public asynchronous call keeps one frame in flight ahead
+(PoseEstimator.submit_frame / .result).  DINO descriptors are seeded unit-norm stand-ins taken from a
 device-resident pool (the DINOv2 backbone is out of scope), heads are random-init (no checkpoints in the mount).
 """
 import argparse
@@ -54,16 +55,24 @@ def main():
     def desc_fn(i, pix):
         return pool[: pix.shape[0]]
 
-    def run(fr, k):
-        return est.estimate_frame(fr["depth"], fr["masks"], fr["cats"], synth.REAL275_K, desc_fn=desc_fn, frame_seed=k)
+    def submit(fr, k):
+        return est.submit_frame(fr["depth"], fr["masks"], fr["cats"], synth.REAL275_K, desc_fn=desc_fn, frame_seed=k)
 
     for k in range(min(3, len(frames))):
-        run(frames[k], k)
+        submit(frames[k], k).result()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    # one frame in flight ahead: frame k + 1 is uploaded and its clouds prepared (own stream) while frame k's kernels run
     t0 = time.perf_counter()
-    poses = [run(fr, k) for k, fr in enumerate(frames)]
+    poses, pending = [], None
+    for k, fr in enumerate(frames):
+        nxt = submit(fr, k)
+        if pending is not None:
+            poses.append(pending.result())
+        pending = nxt
+    if pending is not None:
+        poses.append(pending.result())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     n_inst = sum(1 for p in poses for q in p if q is not None)
