@@ -322,15 +322,19 @@ class CudaStages:
         return self.loss_x
 
     def finish(self) -> PoseResult:
-        """One read-back: the pose record, the global kept count and the all-reduced loss terms."""
+        """ONE read-back: the pose record, the status word, the all-reduced loss sum and the global kept count."""
         v = self.v
         N = self.N
-        tail = torch.cat([self.loss_x, self._x[N:N + 1].to(torch.float64)]).cpu().numpy()
-        r = v.result()
-        kept = int(tail[1])
+        nb = v.pose.numel()
+        pack = torch.cat([v.pose, v.status.view(torch.uint8), self.loss_x.view(torch.uint8),
+                          self._x[N:N + 1].view(torch.uint8)]).cpu().numpy()
+        status = int(pack[nb:nb + 4].view(np.int32)[0])
+        loss_sum = float(pack[nb + 4:nb + 12].view(np.float64)[0])
+        kept = int(pack[nb + 12:nb + 16].view(np.int32)[0])
+        r = PoseVoter.parse(pack[:nb].tobytes(), extra_status=status)
         r.kept = kept
         cnt = 2.0 * kept * (1.0 if self.cfg.loss_y_only else 3.0)
-        r.loss = float(tail[0] / cnt) if cnt > 0 else float("inf")
+        r.loss = loss_sum / cnt if cnt > 0 else float("inf")
         if kept > 0:
             r.status &= ~_lib.CPPF_STATUS_EMPTY
         return r
