@@ -55,13 +55,17 @@ def load_peaks():
 
 
 def heads_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per tuple-program launch of the heads kernel, from the committed
-    `ncu --set full` capture (profiles/r01_heads_v5_ncu_full.json); None when the summary is absent."""
-    path = os.path.join(ROOT, "profiles", "r01_heads_v5_ncu_full.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum of the heads stage of one frame = its four launches (per-point and per-tuple
+    programs of both branches over all instances), from the committed `ncu --set full` capture of this command
+    (profiles/r02_frame_ncu_full.json, tools/ncu_summary.py); None when the summary is absent."""
+    path = os.path.join(ROOT, "profiles", "r02_frame_ncu_full.json")
     try:
-        return json.load(open(path))["traffic_bytes_per_tuple_launch_mean"]
+        for k in json.load(open(path))["kernels"]:
+            if "chain_tc_kernel" in k["kernel"]:
+                return int(round((k["dram_read_MB"] + k["dram_write_MB"]) * 1e6 * k["launches"]))
     except Exception:
-        return None
+        pass
+    return None
 
 
 def build_frame(frame_id: int):
@@ -509,7 +513,8 @@ def main():
         ach = kernels["heads"]["achieved_tflops"]
         roofline = {"kernel": "heads (ResLayer chains, %s)" % {0: "fp32 CUDA cores", 1: "bf16 tcgen05", 2: "SHOT bf16 tcgen05 + DINO fp32 CUDA cores"}[precision], "bound": "tensor",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": heads_traffic(),
-                    "traffic_note": "DRAM bytes per tuple-program launch (ncu --set full, profiles/r01_heads_v5_ncu_full.md)",
+                    "traffic_note": "DRAM bytes of the heads stage of one frame (4 launches; ncu --set full, profiles/r02_frame_ncu_full.md); "
+                                    "algorithmic: descriptors 88 MB + tuple indices 12 MB + draws/scales 11 MB + weights 8 MB per frame",
                     "peak_source": peaks["source"] + ", sustained"}
     elif vote_ms >= shot_ms:
         ach = kernels["vote_chain"]["alg_GBps"]

@@ -37,9 +37,12 @@ __device__ __forceinline__ void rotation_candidate(const RotFrame &f, float cr, 
     }
     float nv = norm3_torch(v[0], v[1], v[2]);
     nv = nv < 1e-7f ? 1e-7f : nv;
-    up[0] = __fdiv_rn(v[0], nv);
-    up[1] = __fdiv_rn(v[1], nv);
-    up[2] = __fdiv_rn(v[2], nv);
+    // three correctly rounded quotients by one divisor: one reciprocal + FMA corrections (div_by) instead of three IEEE
+    // division sequences; |v[k]| <= nv, so every quotient is a normal number in [-1, 1] (or zero)
+    const float inv = __frcp_rn(nv);
+    up[0] = div_by(v[0], nv, inv);
+    up[1] = div_by(v[1], nv, inv);
+    up[2] = div_by(v[2], nv, inv);
 }
 
 // Tests direction p against the lattice band and adds w to every bin it hits.

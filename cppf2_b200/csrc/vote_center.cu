@@ -66,20 +66,6 @@ __global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ g
 // ---------------------------------------------------------------------------------------------------
 // the vote kernel
 // ---------------------------------------------------------------------------------------------------
-// a / b with the correctly rounded quotient of IEEE division (what torch computes, train_dino.py:199) for a divisor that is
-// the same for the whole launch: q = a * RN(1/b) followed by two residual corrections in FMA arithmetic -- the sequence the
-// hardware division's fast path runs after its reciprocal refinement, minus the per-call reciprocal and range check (5
-// instructions instead of ~11; three divisions are a quarter of a vote's instructions and the shared-memory mode is issue-bound).
-// The operands here are finite and far from the denormal range (grid coordinates in metres over a voxel size); a NaN stays a
-// NaN.  Bit-exactness of the grids against the torch-CPU golden vectors and the oracle is what the tests check.
-__device__ __forceinline__ float div_by(float a, float b, float inv_b) {
-    float q = __fmul_rn(a, inv_b);
-    float r = __fmaf_rn(-b, q, a);
-    q = __fmaf_rn(r, inv_b, q);
-    r = __fmaf_rn(-b, q, a);
-    return __fmaf_rn(r, inv_b, q);
-}
-
 constexpr int kVoteThreads = 256;
 constexpr int kMaxRotsSmem = 1024;
 
