@@ -47,6 +47,14 @@ SCALE_DIGITS = 1 << 16
 _SPLITMIX_GAMMA = 0x9E3779B97F4A7C15
 
 
+class Packed:
+    """Payloads of different dtypes that live side by side in ONE byte buffer (`parts` are typed views into `buffer`, each
+    starting at a 16-byte boundary): an exchange step moves the buffer as it is, without staging copies."""
+
+    def __init__(self, buffer: torch.Tensor, parts):
+        self.buffer, self.parts = buffer, list(parts)
+
+
 def shard_bounds(n_items: int, world: int, rank: int):
     """Contiguous block of rank `rank`; requires equal blocks (T = 50 000 divides by 1, 2, 4, 8)."""
     if n_items % world != 0:
@@ -72,6 +80,14 @@ class ShardedVote:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_collectives = 0           # collectives issued by the last vote()
         self.timing = None               # optional list: (label, start event, end event) per exchange step (CUDA only)
+        self.stage_marks = None          # optional list: (label, event) at the stage boundaries of vote() (CUDA only)
+
+    def _mark(self, label: str):
+        """Optional per-stage timing (CUDA only): `stage_marks` = list that receives (label, event) at the stage boundaries."""
+        if self.stage_marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.stage_marks.append((label, e))
 
     # -- collectives -----------------------------------------------------------------------------------
     def _exchange(self, label: str, fn):
@@ -92,7 +108,8 @@ class ShardedVote:
         single flat buffer is what the stages hand over).  Mixed dtypes (E4: float64 sphere bins + int32 histogram): NCCL
         reduces one dtype per call, so the byte images travel in ONE all_gather instead and every rank adds the g images
         in rank order -- a fixed summation order, so the float64 bins are identical on every rank by construction."""
-        tensors = [t for t in tensors if t is not None and t.numel() > 0]
+        packed = tensors if isinstance(tensors, Packed) else None
+        tensors = [t for t in (packed.parts if packed is not None else tensors) if t is not None and t.numel() > 0]
         if not tensors or self.world == 1:
             return
         if len({t.dtype for t in tensors}) == 1:
@@ -108,15 +125,19 @@ class ShardedVote:
             nb = t.numel() * t.element_size()
             segs.append((off, nb))
             off += (nb + 15) // 16 * 16
-        flat = torch.zeros(off, dtype=torch.uint8, device=tensors[0].device)
-        for t, (o, nb) in zip(tensors, segs):
-            flat[o:o + nb].copy_(t.contiguous().reshape(-1).view(torch.uint8))
+        if packed is not None and packed.buffer.numel() == off:
+            flat = packed.buffer                                  # the payloads already sit in one byte buffer
+        else:
+            flat = torch.zeros(off, dtype=torch.uint8, device=tensors[0].device)
+            for t, (o, nb) in zip(tensors, segs):
+                flat[o:o + nb].copy_(t.contiguous().reshape(-1).view(torch.uint8))
         gathered = torch.empty(self.world * off, dtype=torch.uint8, device=flat.device)
         self._exchange(label, lambda: dist.all_gather_into_tensor(gathered, flat, group=self.group))
         out = gathered.view(self.world, off)
         for t, (o, nb) in zip(tensors, segs):
-            parts = out[:, o:o + nb].contiguous().view(t.dtype).reshape((self.world,) + tuple(t.shape))
-            t.copy_(parts.sum(0, dtype=t.dtype))
+            # rows of `out` start at multiples of 16 bytes: the typed view needs no copy; sum over the ranks in rank order
+            parts = out[:, o:o + nb].view(t.dtype).reshape((self.world,) + tuple(t.shape))
+            torch.sum(parts, 0, dtype=t.dtype, out=t)
 
     def _all_gather(self, label: str, local: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.world == 1:
@@ -127,29 +148,40 @@ class ShardedVote:
         return out
 
     # -- the chain -------------------------------------------------------------------------------------
-    def vote(self, pc, idx_local, cfg: VoteConfig, pred_scales_local, bins_local, scale_override=None, cells_hint=None):
+    def vote(self, pc, idx_local, cfg: VoteConfig, pred_scales_local, bins_local, scale_override=None, cells_hint=None,
+             lazy: bool = False):
         """`idx_local` [T/g,>=2], `bins_local` u8 [T/g,6], `pred_scales_local` f32 [T/g,3]: this rank's block of one
         (instance, branch).  `scale_override` (3 floats) reproduces the SHOT branch's reuse of the DINO scale (eval.py:308).
-        Returns whatever `stages.finish` returns (a PoseResult for CudaStages); identical on every rank."""
+        Returns the pose (identical on every rank); with `lazy` the un-synchronised handle of `stages.finish`, whose
+        `.result()` reads it back -- a caller that streams votes resolves the handles later and the GPU never idles between
+        two votes."""
         if getattr(cfg, "opt", False):
             raise NotImplementedError("the online refinement (eval.py:319-355) is not tuple-sharded; run it with opt=False")
         st = self.stages
         self.n_collectives = 0
+        mark = self._mark
+        mark("start")
         st.begin(pc, idx_local, bins_local, pred_scales_local, cfg, self.world, cells_hint)   # decode, targets, bounds
         grid = st.vote_center()                                          # this rank's partial grid, flat [cells]
+        mark("decode+centre vote")
         self._all_reduce("E1 grid", [grid])
         st.argmax()                                                      # replicated: same grid everywhere
         errs_all = self._all_gather("E2 errors", st.errors(), st.errs_all_buffer(self.world))
+        mark("E1+argmax+errors+E2")
         st.select(errs_all)                                              # replicated exact order statistic -> threshold
         own_scale = scale_override is None
         x_imp = st.mask_local(own_scale)                                 # int32 [n | kept | scale hist pass 0]
+        mark("select+mask")
         self._all_reduce("E3 imp+scale0", [x_imp])
         st.after_mask(own_scale)                                         # imp_max; scale pick 0, local hist pass 1
         x_counts = st.rotation_counts()                                  # [counts f64 [2,S]] + [scale hist pass 1]
+        mark("E3+rotation vote")
         self._all_reduce("E4 bins+scale1", x_counts)
         x_loss = st.pose_local(scale_override)                           # directions, scale, sum of the local loss terms
         self._all_reduce("E5 loss", [x_loss])
-        return st.finish()
+        mark("E4+pose+E5")
+        out = st.finish()
+        return out if lazy or not hasattr(out, "result") else out.result()
 
 
 class CudaStages:
@@ -165,7 +197,8 @@ class CudaStages:
         self.scale_dev = torch.zeros(3, dtype=torch.float32, device=d)
         self.loss_x = torch.zeros(1, dtype=torch.float64, device=d)
         self.xbuf = None                 # int32 exchange buffer [n | kept | 3*65536]
-        self.hist1 = torch.zeros(3 * SCALE_DIGITS, dtype=torch.int32, device=d)
+        self.x4 = None                   # byte buffer of exchange E4: [sphere bins f64 [2,S] | scale histogram pass 1 i32 [3*65536]]
+        self.hist1 = None
         self.errs_all = None
         self._cells = {}                 # grid cells per cloud (data_ptr, n, res) when no hint was given: one read-back, cached
 
@@ -266,6 +299,7 @@ class CudaStages:
         check(lib.cppf_backvote_imp_max(x.data_ptr(), N, v.summary.data_ptr(), s), "cppf_backvote_imp_max")
         self._hist1 = None
         if own_scale:
+            self._e4_buffers(self.cfg.num_sphere)
             check(lib.cppf_scale_median_pick(x[N + 1:].data_ptr(), x[N:].data_ptr(), 0, self.sel.data_ptr(), None, s),
                   "cppf_scale_median_pick")
             check(lib.cppf_scale_median_hist(self.scales.data_ptr(), v.kept_list.data_ptr(), self._kept_ptr(), self.T_local, 1,
@@ -273,13 +307,21 @@ class CudaStages:
             self._hist1 = self.hist1
 
     # -- stage 3: rotation votes, pose, loss ---------------------------------------------------------------
+    def _e4_buffers(self, S: int):
+        """Sphere bins and the pass-1 scale histogram as typed views of one byte buffer (exchange E4 moves it as it is)."""
+        cb = 2 * S * 8
+        cb_pad = (cb + 15) // 16 * 16
+        if self.x4 is None or self.x4.numel() != cb_pad + 3 * SCALE_DIGITS * 4:
+            self.x4 = torch.zeros(cb_pad + 3 * SCALE_DIGITS * 4, dtype=torch.uint8, device=self.device)
+            self.v.counts = self.x4[:cb].view(torch.float64).view(2, S)
+            self.v._buffers = None
+            self.hist1 = self.x4[cb_pad:].view(torch.int32)
+
     def rotation_counts(self):
         v, lib, s = self.v, self.lib, stream_ptr()
         cfg = self.cfg
         S = cfg.num_sphere
-        if v.counts.shape != (2, S):
-            v.counts = torch.empty((2, S), dtype=torch.float64, device=self.device)
-            v._buffers = None
+        self._e4_buffers(S)
         v.counts.zero_()
         ip, i64, istr = self.ip
         ct, st = angle_tables(cfg.num_rots, self.device)
@@ -293,7 +335,9 @@ class CudaStages:
                                      v.summary.data_ptr(), float(cfg.imp_wt_margin), ct.data_ptr(), st.data_ptr(),
                                      int(cfg.num_rots), sphere.data_ptr(), S, thr, lib.cppf_sphere_band(S, thr),
                                      None if lut is None else lut.data_ptr(), lut_g, v.counts.data_ptr(), s), "cppf_rotation_hist")
-        return [v.counts, self._hist1]
+        if self._hist1 is None:
+            return [v.counts]
+        return Packed(self.x4, [v.counts, self._hist1])
 
     def pose_local(self, scale_override=None):
         v, lib, s = self.v, self.lib, stream_ptr()
@@ -321,23 +365,14 @@ class CudaStages:
         self.loss_x.copy_(v.ws_pose[:8].view(torch.float64))
         return self.loss_x
 
-    def finish(self) -> PoseResult:
-        """ONE read-back: the pose record, the status word, the all-reduced loss sum and the global kept count."""
+    def finish(self) -> "PendingShardedPose":
+        """Packs the pose record, the status word, the all-reduced loss sum and the global kept count into ONE fresh device
+        tensor; `.result()` reads it back (the only host synchronisation of a vote).  A caller that streams votes keeps
+        the handle and resolves it later: the next vote's kernels are queued without waiting for this one."""
         v = self.v
         N = self.N
-        nb = v.pose.numel()
-        pack = torch.cat([v.pose, v.status.view(torch.uint8), self.loss_x.view(torch.uint8),
-                          self._x[N:N + 1].view(torch.uint8)]).cpu().numpy()
-        status = int(pack[nb:nb + 4].view(np.int32)[0])
-        loss_sum = float(pack[nb + 4:nb + 12].view(np.float64)[0])
-        kept = int(pack[nb + 12:nb + 16].view(np.int32)[0])
-        r = PoseVoter.parse(pack[:nb].tobytes(), extra_status=status)
-        r.kept = kept
-        cnt = 2.0 * kept * (1.0 if self.cfg.loss_y_only else 3.0)
-        r.loss = loss_sum / cnt if cnt > 0 else float("inf")
-        if kept > 0:
-            r.status &= ~_lib.CPPF_STATUS_EMPTY
-        return r
+        pack = torch.cat([v.pose, v.status.view(torch.uint8), self.loss_x.view(torch.uint8), self._x[N:N + 1].view(torch.uint8)])
+        return PendingShardedPose(pack, v.pose.numel(), bool(self.cfg.loss_y_only))
 
     def intermediates(self) -> dict:
         """Host copies: the all-reduced grid and importance counts, this rank's block of the kept mask and errors, the
@@ -356,6 +391,29 @@ class CudaStages:
                     scale=self._so.cpu().numpy())
 
 
+class PendingShardedPose:
+    """Result handle of one sharded vote (CudaStages.finish)."""
+
+    def __init__(self, pack: torch.Tensor, pose_bytes: int, loss_y_only: bool):
+        self._pack, self._nb, self._y = pack, pose_bytes, loss_y_only
+        self._out = None
+
+    def result(self) -> PoseResult:
+        if self._out is None:
+            pack, nb = self._pack.cpu().numpy(), self._nb
+            status = int(pack[nb:nb + 4].view(np.int32)[0])
+            loss_sum = float(pack[nb + 4:nb + 12].view(np.float64)[0])
+            kept = int(pack[nb + 12:nb + 16].view(np.int32)[0])
+            r = PoseVoter.parse(pack[:nb].tobytes(), extra_status=status)
+            r.kept = kept
+            cnt = 2.0 * kept * (1.0 if self._y else 3.0)
+            r.loss = loss_sum / cnt if cnt > 0 else float("inf")
+            if kept > 0:
+                r.status &= ~_lib.CPPF_STATUS_EMPTY
+            self._out, self._pack = r, None
+        return self._out
+
+
 class ShardedPoseVoter(ShardedVote):
     """Product form: CUDA stages + the process group's collectives (NCCL on the GPU box)."""
 
@@ -369,14 +427,15 @@ class ShardedPoseVoter(ShardedVote):
         return self._all_gather("mask (debug)", local).cpu().numpy().astype(bool)
 
     def vote_with_heads(self, model, pc, idx_local, cfg: VoteConfig, first_tuple: int, seed: int = 0, desc=None, shot_feat=None,
-                        normal=None, scale_override=None, cells_hint=None):
+                        normal=None, scale_override=None, cells_hint=None, lazy: bool = False):
         """eval.py:219-313 for this rank's block of tuples, heads included: `model` (BeyondCPPFSHOT with shot_feat / normal,
         or BeyondCPPFDINO with desc; precision 1) runs on idx_local with the decode fused in, drawing for its tuples the
         uniforms the unsharded call would draw for them (shard_seed), then the sharded vote."""
         s = shard_seed(seed, first_tuple)
+        self._mark("heads begin")
         if model.branch == "dino":
             bins, scales = model.forward_sampled(pc, desc, idx_local, seed=s)
         else:
             bins, scales = model.forward_sampled(pc, idx_local, shot_feat, normal, seed=s)
         self._live = (bins, scales)
-        return self.vote(pc, idx_local, cfg, scales, bins, scale_override=scale_override, cells_hint=cells_hint)
+        return self.vote(pc, idx_local, cfg, scales, bins, scale_override=scale_override, cells_hint=cells_hint, lazy=lazy)

@@ -92,7 +92,8 @@ def test_rotation_parts_sum_to_whole():
     st.select(st.errors())
     st.mask_local(True)
     st.after_mask(True)
-    whole = st.rotation_counts()[0].clone()
+    out = st.rotation_counts()              # the sphere bins (and, packed next to them, the scale histogram of exchange E4)
+    whole = (out.parts[0] if hasattr(out, "parts") else out[0]).clone()
     v, lib = st.v, st.lib
     S = cfg.num_sphere
     thr = cos_threshold(cfg.angle_tol)

@@ -87,11 +87,11 @@ def run_sharded(T: int, cloud: str, dev, rank: int, world: int, reps: int = 5, w
         bins_l, scales_l = torch.from_numpy(b).to(dev), torch.from_numpy(s).to(dev)
     sv = ShardedPoseVoter(hi - lo, n, grid_capacity=max(1 << 22, 32 * cells), device=dev)
 
-    def one():
+    def one(lazy=False):
         if with_heads:
             return sv.vote_with_heads(model, pc_d, idx_l, cfg, first_tuple=lo, seed=seed, shot_feat=desc, normal=normals,
-                                      cells_hint=cells)
-        return sv.vote(pc_d, idx_l, cfg, scales_l, bins_l, cells_hint=cells)
+                                      cells_hint=cells, lazy=lazy)
+        return sv.vote(pc_d, idx_l, cfg, scales_l, bins_l, cells_hint=cells, lazy=lazy)
 
     res_s = None
     for _ in range(warm):
@@ -102,12 +102,24 @@ def run_sharded(T: int, cloud: str, dev, rank: int, world: int, reps: int = 5, w
         torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     sv.timing = []
+    sv.stage_marks = []
     ev[0].record()
-    for _ in range(reps):
-        res_s = one()
+    # streamed votes: each returns its un-synchronised handle, so the next vote is queued while this one runs; the poses are
+    # read back after the timed region (the last one is the one checked)
+    handles = [one(lazy=True) for _ in range(reps)]
     ev[1].record()
     torch.cuda.synchronize()
+    res_s = [h.result() for h in handles][-1]
     ms = torch.tensor([ev[0].elapsed_time(ev[1]) / reps], device=dev, dtype=torch.float64)
+    # per-stage breakdown of this rank (mean over the reps): interval from each mark to the next
+    stages = {}
+    marks = sv.stage_marks
+    sv.stage_marks = None
+    for (la, ea), (lb, eb) in zip(marks[:-1], marks[1:]):
+        name = "heads" if la == "heads begin" else (lb if lb != "heads begin" else "finish+next")
+        if lb == "heads begin" or name == "finish+next":
+            continue
+        stages[name] = stages.get(name, 0.0) + ea.elapsed_time(eb) / reps
     coll = {}
     for label, a, b in sv.timing:
         coll[label] = coll.get(label, 0.0) + a.elapsed_time(b) / reps
@@ -157,6 +169,7 @@ def run_sharded(T: int, cloud: str, dev, rank: int, world: int, reps: int = 5, w
                "n_gpus": world, "heads": "SHOT branch, bf16 tcgen05, decode fused" if with_heads else None,
                "ms": t, "tuples_per_sec": T / (t * 1e-3), "collective_ms": float(coll_ms.item()),
                "collective_share": float(coll_ms.item()) / t, "collectives": {k: round(v, 4) for k, v in coll.items()},
+               "stages_ms_rank0": {k: round(v, 4) for k, v in stages.items()},
                "n_collectives": n_coll, "kept": int(res_s.kept), "parity": parity}
     del sv
     torch.cuda.empty_cache()
