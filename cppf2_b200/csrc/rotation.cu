@@ -209,9 +209,16 @@ __device__ __forceinline__ void rotation_hist_body(
         // the pair weight 1 / (imp_i + imp_j + margin) lies in (0, 1 / margin]: rounded once to 2^-32 (relative 5e-10 at
         // the smallest weight the reference can produce, 1 / 2.01); weights beyond 2^31 saturate
         const unsigned long long wv = __double2ull_rn(fmin(w, 2147483648.0) * 4294967296.0);
+        // the pair frame (ab, x, y) is the same for every angle column; the float64 tangents of the columns are evaluated side
+        // by side, lane c taking column c (the warp runs the tan() sequence once instead of once per column)
+        RotFrame f;
+        if (!pair_frame(a, b, true, f.ab, f.x)) continue;                     // warp-uniform (train_dino.py:222 mask)
+        cross_torch(f.x, f.ab, f.y);
+        const int my_col = (lane == 1 && cols.n > 1) ? cols.col[1] : ((lane == 2 && cols.n > 2) ? cols.col[2] : cols.col[0]);
+        const float tn_lane = static_cast<float>(tan(static_cast<double>(theta[m * theta_stride + my_col])));
         for (int c = 0; c < cols.n; ++c) {
-            RotFrame f;
-            if (!rotation_frame(a, b, theta[m * theta_stride + cols.col[c]], f)) break;  // warp-uniform
+            f.tn = __shfl_sync(0xffffffffu, tn_lane, c);
+            f.sg = f.tn > 0.0f ? 1.0f : -1.0f;  // torch.where(tan > 0, 1., -1.)
             unsigned long long *bins = s_bins + c * S;
             auto add = [&](int i) { fixed_add(&bins[i], wv); };
             for (int r = lane; r < R; r += 32) {

@@ -80,7 +80,8 @@ def test_refinement_lowers_the_unclipped_objective():
 
 
 def test_estimator_opt_flag_runs_both_paths_alike():
-    """opt=True through the public call: the one-call instance path and the step-by-step Python sequence agree."""
+    """opt=True through the public call: the whole-frame call (batched refinement kernel), the one-call instance path and the
+    step-by-step Python sequence agree."""
     import os
     from cppf2_b200 import synth
     from cppf2_b200.estimator import Instance, PoseEstimator, build_models
@@ -89,22 +90,24 @@ def test_estimator_opt_flag_runs_both_paths_alike():
     idx = synth.sample_tuples(pc.shape[0], 4096, 5, seed=3)
     models, cfgs = build_models(["mug"], precision=1)
     outs = []
-    for one_call in ("1", "0"):
-        os.environ["CPPF_ONE_CALL"] = one_call
+    for frame_call, one_call in (("1", "1"), ("0", "1"), ("0", "0")):
+        os.environ["CPPF_FRAME_CALL"], os.environ["CPPF_ONE_CALL"] = frame_call, one_call
         try:
             est = PoseEstimator(models, cfgs, num_pairs=4096, max_points=pc.shape[0], opt=True, seed=7)
+            assert est.frame_call == (frame_call == "1")
             outs.append(est.estimate([Instance(pc=pc, category="mug", desc=desc, point_idxs=idx)])[0])
         finally:
             os.environ.pop("CPPF_ONE_CALL", None)
-    a, b = outs
-    assert a is not None and b is not None
-    for br in a.results:
-        ra, rb = a.results[br], b.results[br]
-        assert ra.status & 8 and rb.status & 8 and ra.kept == rb.kept                 # CPPF_STATUS_REFINED on both paths
-        for r in (ra, rb):
-            assert np.isfinite(r.R).all() and np.isfinite(r.t).all() and np.isfinite(r.loss)
-            assert np.allclose(r.R @ r.R.T, np.eye(3), atol=1e-5)                      # Q(q) R_est stays a rotation
-        # Same kernels and inputs on both paths.  The kept list leaves the atomic compaction in a different order from launch to
-        # launch; the float64 row sums make a step independent of that order except for a last-bit rounding, and 100 Adam steps
-        # on the predictions of RANDOM-INIT heads (an ill-conditioned objective) can amplify such a bit: reported, not asserted.
-        print(f"{br}: one-call vs step-by-step after refinement: max |dR| {np.abs(ra.R - rb.R).max():.2e}, max |dt| {np.abs(ra.t - rb.t).max():.2e}")
+            os.environ.pop("CPPF_FRAME_CALL", None)
+    assert all(o is not None for o in outs)
+    for a, b in ((outs[0], outs[2]), (outs[1], outs[2])):
+        for br in a.results:
+            ra, rb = a.results[br], b.results[br]
+            assert ra.status & 8 and rb.status & 8 and ra.kept == rb.kept                 # CPPF_STATUS_REFINED on both paths
+            for r in (ra, rb):
+                assert np.isfinite(r.R).all() and np.isfinite(r.t).all() and np.isfinite(r.loss)
+                assert np.allclose(r.R @ r.R.T, np.eye(3), atol=1e-5)                      # Q(q) R_est stays a rotation
+            # Same kernels and inputs on both paths.  The kept list leaves the atomic compaction in a different order from launch to
+            # launch; the float64 row sums make a step independent of that order except for a last-bit rounding, and 100 Adam steps
+            # on the predictions of RANDOM-INIT heads (an ill-conditioned objective) can amplify such a bit: reported, not asserted.
+            print(f"{br}: one-call vs step-by-step after refinement: max |dR| {np.abs(ra.R - rb.R).max():.2e}, max |dt| {np.abs(ra.t - rb.t).max():.2e}")
