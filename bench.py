@@ -5,7 +5,9 @@
 
 Workload (BASELINE.json configs[1]): one synthetic REAL275-shaped 640x480 depth frame with 6 instances,
 SHOT + DINO ensemble (random-init heads, seeded unit-norm stand-ins for the DINOv2 descriptors), T = 50 000
-tuples x 180 rotations per (instance, branch).  A step is one pass of the hot path over that frame: SHOT-352
+tuples x 180 rotations per (instance, branch).  The frames of a stream cycle through a pool of 7 such frames (13-19 k
+points each) and are dealt round-robin to the ranks: step k of rank r is frame (k * N + r) % 7, so every rank and every N
+sees the same mix.  A step is one pass of the hot path over one frame: SHOT-352
 + normals, tuple sampling, both heads, multinomial decode, centre vote, back-vote filter, rotation votes,
 pose + ensemble selection -- 12 (instance, branch) votes = 600 000 tuples.  Depth back-projection and voxel
 down-sampling are "next" rows of the scope table and run once, untimed.
@@ -42,6 +44,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NUM_PAIRS, NUM_ROTS, N_INSTANCES = 50000, 180, 6
+FRAME_POOL = 7      # distinct synthetic frames; step k of rank r runs frame (k * world + r) % FRAME_POOL (7 is coprime with 2, 4, 8:
+                    # every rank cycles through the whole pool, so the ranks' work is balanced and every N times the same mix)
 METRIC, UNIT = "tuples_voted_per_sec", "tuples/s"
 
 
@@ -236,6 +240,7 @@ def workload_config(instances_per_step: int = N_INSTANCES):
                         "seeded unit-norm DINO descriptors), 50000 tuples x 180 rotations per (instance, branch)",
             "instances_per_step": instances_per_step, "tuples_per_step": 2 * NUM_PAIRS * instances_per_step,
             "num_pairs": NUM_PAIRS, "num_rots": NUM_ROTS, "sphere_bins": 720,
+            "frame_pool": FRAME_POOL,
             "l2": "256 MB buffer written between timed steps (L2 flush; in the e2e leg on the upload stream ahead of each step's copies)", "parallelism": "frames sharded across ranks, no collective; every stage of a frame launched once for all its instances (cppf_frame_pose)"}
 
 
@@ -280,8 +285,14 @@ def main():
     _lib.load()
     peaks = load_peaks()
 
-    raw = build_frame(rank)            # frame sharding: rank r owns frame r
-    cats = sorted({i["category"] for i in raw})
+    # frame sharding: the frames of the stream are dealt round-robin to the ranks; step k of rank r is frame k * world + r of a
+    # stream that cycles through FRAME_POOL synthetic frames
+    pool = [build_frame(f) for f in range(FRAME_POOL)]
+    raw = pool[0]
+
+    def frame_of(k):
+        return (k * world + rank) % FRAME_POOL
+    cats = sorted({i["category"] for fr in pool for i in fr})
     models, cfgs = build_models(cats, precision=0)
     # heads precision per model: bf16 tcgen05 where the library carries the packed tensor-core weights for that
     # branch, else the float32 path (--precision 0 forces float32 everywhere)
@@ -294,19 +305,23 @@ def main():
             used.add((m.branch, m.precision))
     precision = 1 if all(p == 1 for _, p in used) else (0 if all(p == 0 for _, p in used) else 2)
     est = PoseEstimator(models, cfgs, num_pairs=NUM_PAIRS, num_rots=NUM_ROTS, seed=rank, opt=args.opt)
-    n_inst = len(raw)
-    tuples_per_step = 2 * NUM_PAIRS * n_inst
+    n_inst_of = [len(fr) for fr in pool]
+    n_pts_of = [sum(i["pc"].shape[0] for i in fr) for fr in pool]
+    n_inst = n_inst_of[0]
 
     # ---- device-resident inputs for the kernel-side number --------------------------------------------------
     rng = np.random.default_rng(100 + rank)
-    dev_instances = []
-    for inst in raw:
-        idx = torch.from_numpy(rng.integers(0, inst["pc"].shape[0], (NUM_PAIRS, 5), dtype=np.int32)).to(dev)
-        di = Instance(pc=torch.from_numpy(inst["pc"]).to(dev), category=inst["category"], desc=torch.from_numpy(inst["desc"]).to(dev),
-                      point_idxs=idx)
-        di.cells_hint = est.voter.grid_cells_on_host(inst["pc"], inst["cfg"]["res"])
-        dev_instances.append(di)
-    pose_buf = torch.zeros((n_inst * 2, est.pose_bytes), dtype=torch.uint8, device=dev)
+    dev_frames = []
+    for fr in pool:
+        dev_instances = []
+        for inst in fr:
+            idx = torch.from_numpy(rng.integers(0, inst["pc"].shape[0], (NUM_PAIRS, 5), dtype=np.int32)).to(dev)
+            di = Instance(pc=torch.from_numpy(inst["pc"]).to(dev), category=inst["category"], desc=torch.from_numpy(inst["desc"]).to(dev),
+                          point_idxs=idx)
+            di.cells_hint = est.voter.grid_cells_on_host(inst["pc"], inst["cfg"]["res"])
+            dev_instances.append(di)
+        dev_frames.append(dev_instances)
+    pose_buf = torch.zeros((max(n_inst_of) * 2, est.pose_bytes), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -315,8 +330,8 @@ def main():
         torch.cuda.synchronize()
 
     ClockSampler.attach(local)         # NVML initialised here, ahead of the warm-up: nothing driver-side starts inside a timed region
-    for _ in range(max(args.warmup, 3)):
-        est.enqueue(dev_instances, pose_buf)
+    for k in range(max(args.warmup, 3, FRAME_POOL)):      # every frame of the pool once: all buffers reach their final size
+        est.enqueue(dev_frames[k % FRAME_POOL], pose_buf)
     torch.cuda.synchronize()
     launches = est.launches
 
@@ -324,17 +339,18 @@ def main():
     sampler.start()
     barrier()
     step_events = []
-    for _ in range(args.steps):
+    for k in range(args.steps):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        est.enqueue(dev_instances, pose_buf)      # instances fan out over the estimator's lanes and join before b
+        est.enqueue(dev_frames[frame_of(k)], pose_buf)      # cppf_frame_pose: every stage once for all instances of the frame
         b.record()
         step_events.append((a, b))
     barrier()
     clocks = sampler.summary()
     step_ms = [a.elapsed_time(b) for a, b in step_events]
     total_ms = float(sum(step_ms))
+    tuples_mine = float(sum(2 * NUM_PAIRS * n_inst_of[frame_of(k)] for k in range(args.steps)))
 
     # per-stage durations for the roofline: the same steps, same estimator, same single stream, with CUDA events recorded by
     # cppf_frame_pose itself at the stage boundaries of the launching stream (the frame is ~25 batched launches in order:
@@ -342,17 +358,17 @@ def main():
     stage_ms, serial_ms = {}, float(np.median(step_ms))
     if est.frame_call:
         per_step = []
-        for _ in range(args.steps):
+        for k in range(args.steps):
             flush.zero_()
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
             est.stage_events = evs
-            est.enqueue(dev_instances, pose_buf)
+            est.enqueue(dev_frames[frame_of(k)], pose_buf)
             per_step.append(evs)
         est.stage_events = None
         torch.cuda.synchronize()
-        for k, name in enumerate(_lib.FRAME_STAGES):
-            stage_ms[name] = float(np.median([evs[k].elapsed_time(evs[k + 1]) for evs in per_step]))
-        serial_ms = float(np.median([evs[0].elapsed_time(evs[7]) for evs in per_step]))
+        for k, name in enumerate(_lib.FRAME_STAGES):          # mean over the steps (the frames of the pool differ in size)
+            stage_ms[name] = float(np.mean([evs[k].elapsed_time(evs[k + 1]) for evs in per_step]))
+        serial_ms = float(np.mean([evs[0].elapsed_time(evs[7]) for evs in per_step]))
         stage_ms["heads_shot"], stage_ms["heads_dino"] = stage_ms["heads"], 0.0
         stage_ms["vote_shot"] = stage_ms["center"] + stage_ms["backvote"] + stage_ms["rotation"] + stage_ms["pose"]
         stage_ms["vote_dino"] = 0.0
@@ -364,16 +380,16 @@ def main():
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             stage_events.setdefault(stage, []).append(ev)
-        for _ in range(3):
-            est1.enqueue(dev_instances, pose_buf)
+        for k in range(FRAME_POOL):
+            est1.enqueue(dev_frames[k], pose_buf)
         torch.cuda.synchronize()
         est1.timing_hook = hook
         serial_events = []
-        for _ in range(args.steps):
+        for k in range(args.steps):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            est1.enqueue(dev_instances, pose_buf)
+            est1.enqueue(dev_frames[frame_of(k)], pose_buf)
             b.record()
             serial_events.append((a, b))
         torch.cuda.synchronize()
@@ -388,42 +404,41 @@ def main():
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-        cnt = torch.tensor([tuples_per_step], device=dev, dtype=torch.float64)
+        cnt = torch.tensor([tuples_mine], device=dev, dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        tuples_all = float(cnt.item())
+        tuples_all = float(cnt.item())                # tuples of all ranks over the K steps
     else:
-        tuples_all = float(tuples_per_step)
+        tuples_all = tuples_mine
     ms_per_step = total_ms / args.steps
-    value = tuples_all / (ms_per_step * 1e-3)
+    value = tuples_all / (total_ms * 1e-3)
 
     # ---- end to end through the public call with host buffers -------------------------------------------------
-    host_instances = []
-    h2d = 0
-    for inst in raw:
-        pc_p, desc_p = torch.from_numpy(inst["pc"]).pin_memory(), torch.from_numpy(inst["desc"]).pin_memory()
-        host_instances.append((pc_p, desc_p, inst))
-        h2d += pc_p.numel() * 4 + desc_p.numel() * 4
+    host_frames, h2d_of = [], []
+    for f, fr in enumerate(pool):
+        items, nbytes = [], 0
+        for inst in fr:
+            pc_p, desc_p = torch.from_numpy(inst["pc"]).pin_memory(), torch.from_numpy(inst["desc"]).pin_memory()
+            items.append((pc_p, desc_p, inst))
+            nbytes += pc_p.numel() * 4 + desc_p.numel() * 4
+        host_frames.append(items)
+        h2d_of.append(nbytes)
+    h2d = int(round(np.mean([h2d_of[frame_of(k)] for k in range(args.steps)])))
 
-    def e2e_step():
-        # the public call: pinned host clouds + descriptors in, poses out; tuple indices (eval.py:207) are drawn on the
-        # device by the estimator (point_idxs=None), uploads run on its copy stream ahead of the kernels
+    def e2e_instances(f):
+        # the public call's inputs: pinned host clouds + descriptors; tuple indices (eval.py:207) are drawn on the device by
+        # the estimator (point_idxs=None), uploads run on its copy stream ahead of the kernels
         insts = []
-        for k, (pc_p, desc_p, inst) in enumerate(host_instances):
+        for j, (pc_p, desc_p, inst) in enumerate(host_frames[f]):
             it = Instance(pc=pc_p, category=inst["category"], desc=desc_p, point_idxs=None)
-            it.cells_hint = dev_instances[k].cells_hint
+            it.cells_hint = dev_frames[f][j].cells_hint
             insts.append(it)
-        return est.estimate(insts)
+        return insts
 
-    def e2e_submit():
-        insts = []
-        for k, (pc_p, desc_p, inst) in enumerate(host_instances):
-            it = Instance(pc=pc_p, category=inst["category"], desc=desc_p, point_idxs=None)
-            it.cells_hint = dev_instances[k].cells_hint
-            insts.append(it)
-        return est.submit(insts)
+    def e2e_submit(k):
+        return est.submit(e2e_instances(frame_of(k)))
 
-    for _ in range(5):
-        poses = e2e_step()
+    for k in range(2 * FRAME_POOL):                           # twice through the pool: the caching allocator has seen every size
+        poses = est.estimate(e2e_instances(k % FRAME_POOL))
     import gc
     gc.collect()
     gc.disable()          # no collector pause inside the timed host loop
@@ -438,10 +453,10 @@ def main():
         barrier()
         t0 = time.perf_counter()
         pending = None
-        for _ in range(args.steps):
+        for k in range(args.steps):
             with torch.cuda.stream(est.copy_stream):      # L2 flush ahead of this step's uploads, off the compute streams
                 flush.zero_()
-            nxt = e2e_submit()
+            nxt = e2e_submit(k)
             if pending is not None:
                 poses = pending.result()
             pending = nxt
@@ -455,8 +470,8 @@ def main():
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e_value = tuples_all / (e2e_ms / args.steps * 1e-3)
-    d2h = n_inst * 2 * est.pose_bytes
+    e2e_value = tuples_all / (e2e_ms * 1e-3)                  # tuples of all ranks over the K steps / the pass
+    d2h = int(round(np.mean([n_inst_of[frame_of(k)] for k in range(args.steps)]) * 2 * est.pose_bytes))
 
     # ---- tuple-sharded leg (the north star's multi-GPU design; BASELINE configs[3]) -----------------------------------
     # ONE (instance, branch) whose T tuples are split over the N ranks, heads included (eval.py:219-313): every rank runs
@@ -490,7 +505,8 @@ def main():
         return
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------
-    n_pts = sum(i["pc"].shape[0] for i in raw)
+    n_pts = float(np.mean([n_pts_of[frame_of(k)] for k in range(args.steps)]))          # per step, over this rank's frames
+    n_inst = float(np.mean([n_inst_of[frame_of(k)] for k in range(args.steps)]))
     heads_ms = stage_ms.get("heads_shot", 0.0) + stage_ms.get("heads_dino", 0.0)
     vote_ms = stage_ms.get("vote_shot", 0.0) + stage_ms.get("vote_dino", 0.0)
     shot_ms = stage_ms.get("shot", 0.0)
@@ -539,20 +555,22 @@ def main():
         timings = {}
         t0 = time.perf_counter()
         n_done = 0
-        for inst in raw:
+        for inst in raw:                                   # frame 0 of the pool
             run_cpu_instance(inst, sds, crng, timings, opt=args.opt)
             n_done += 1
             if time.perf_counter() - t0 > 30.0:
                 break
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": 2 * NUM_PAIRS * n_done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                        "sample": f"{n_done} of {n_inst} instances of the same frame, both branches, {dt:.1f} s; stage seconds "
+                        "sample": f"{n_done} of {len(raw)} instances of frame 0 of the pool, both branches, {dt:.1f} s; stage seconds "
                                   + ", ".join(f"{k} {v:.2f}" for k, v in timings.items())}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {0: "f32", 1: "bf16", 2: "bf16 (SHOT head, tcgen05) + f32 (DINO head)"}[precision], "data": "synthetic", "config": workload_config(),
             "frames_per_sec": world * 1e3 / ms_per_step, "instances": n_inst, "points": n_pts, "refinement": bool(args.opt),
+            "frame_pool": {"frames": FRAME_POOL, "points_per_frame": n_pts_of, "instances_per_frame": n_inst_of,
+                           "schedule": "step k of rank r runs frame (k * n_gpus + r) % frames"},
             "roofline": roofline, "kernels": kernels, "sharded": sharded,
             "kernel_timing": {"how": ("the timed configuration itself (cppf_frame_pose: every stage launched once for all instances, one stream), "
                                       "CUDA events recorded by the call at the stage boundaries, median over the steps") if est.frame_call else
