@@ -401,7 +401,10 @@ CPPF_API int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_i
     // lookup table a tuple is cheap and the per-CTA bin flush dominates: two CTAs per SM, several tuples per warp.
     const int64_t guess = (kept_list ? (M / 8 + 1) : M) + 1;
     const uint2 *cells = lut ? reinterpret_cast<const uint2 *>(static_cast<const unsigned char *>(lut) + 16) : nullptr;
-    rotation_hist_kernel<<<grid_for(guess * 32, 256, lut ? 2 : 4), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    // few kept tuples (one frame's T = 50 000 -> ~6 000): the per-CTA bin flush dominates, two CTAs per SM; many (the tuple
+    // sweep's 10^5 .. 10^6): the kernel is issue-bound and wants all the warps the registers allow (four CTAs per SM)
+    const int per_sm = (lut && guess < 32768) ? 2 : 4;
+    rotation_hist_kernel<<<grid_for(guess * 32, 256, per_sm), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         pc, iv, theta, theta_stride, cols, kept_list, kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere, S,
         cos_thr, band, cells, lut_g, counts, part, n_parts);
     CPPF_LAUNCH_CHECK();

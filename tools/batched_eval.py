@@ -58,7 +58,7 @@ def main():
     def submit(fr, k):
         return est.submit_frame(fr["depth"], fr["masks"], fr["cats"], synth.REAL275_K, desc_fn=desc_fn, frame_seed=k)
 
-    for k in range(min(3, len(frames))):
+    for k in range(min(8, len(frames))):          # warm-up: allocator, lazily created buffers, every stream
         submit(frames[k], k).result()
     torch.cuda.synchronize()
     if world > 1:
