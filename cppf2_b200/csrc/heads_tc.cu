@@ -110,7 +110,7 @@ struct Phase {
     int width;            // LoadRows: columns written (zero padded), multiple of 32
     int d_col, n;         // accumulator chunk the epilogue reads
     int dst_col;          // X / H / global column the chunk is written to
-    int residual, res_col;
+    int residual, res_col;     // residual: 0 none, 1 = X[res_col : +n) in shared memory, 2 = bf16 in tensor memory (H/Y column res_col)
     int out_sel;          // Final: 0 = out0 (float32), 1 = out1 (float32), 2 = point features (bf16)
     int out_ld;
 };
@@ -214,6 +214,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 8 consecutive 32-bit columns (16 packed bf16) of this thread's lane; no wait (tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, uint32_t r[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
@@ -226,6 +232,11 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t r[4]) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
@@ -369,6 +380,20 @@ __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, u
         for (int j = 0; j < NB; ++j) v[j] = static_cast<float>(row + j);
     } else if (NB == 32) tmem_ld32(t_slot_lane + static_cast<uint32_t>(ph.d_col + c), v);
     else tmem_ld8(t_slot_lane + static_cast<uint32_t>(ph.d_col + c), v);
+    if (NB == 32 && ph.residual == 2) {
+        // the layer input lives in tensor memory (bf16 pairs, H/Y column space): identity residual read back from there
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {      // two loads of 8 columns: 8 fewer live registers than one of 16 (no spills)
+            uint32_t y[8];
+            tmem_ld8_raw(t_slot_lane + kHTmem + static_cast<uint32_t>((ph.res_col + c) >> 1) + 8u * h, y);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[16 * h + 2 * j] += __uint_as_float(y[j] << 16);
+                v[16 * h + 2 * j + 1] += __uint_as_float(y[j] & 0xffff0000u);
+            }
+        }
+    }
     if (ph.action == kActHiddenT || ph.action == kActOutT) {
         uint32_t p[NB / 2];
         if (ph.action == kActHiddenT) {
@@ -388,7 +413,7 @@ __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, u
                 make_uint4(pack2_relu(v[8 * j], v[8 * j + 1]), pack2_relu(v[8 * j + 2], v[8 * j + 3]), pack2_relu(v[8 * j + 4], v[8 * j + 5]),
                            pack2_relu(v[8 * j + 6], v[8 * j + 7]));
     } else if (ph.action == kActOut) {
-        if (ph.residual) {
+        if (ph.residual == 1) {
 #pragma unroll
             for (int j = 0; j < NB / 8; ++j) {
                 float x[8];
@@ -409,10 +434,14 @@ __device__ __forceinline__ void epilogue_batch(const Phase &ph, const Args &a, u
             float m = v[0];
 #pragma unroll
             for (int j = 1; j < NB; ++j) m = fmaxf(m, v[j]);
+            // exp(v - m) = 2^(v log2e - m log2e): one FFMA (the product is exact inside it; the rounding of m log2e is common to
+            // the 32 bins and cancels in the CDF) and one MUFU.EX2 per bin instead of expf's nine instructions
+            constexpr float kLog2e = 1.4426950408889634f;
+            const float shift = -m * kLog2e;
             float run = 0.0f;
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
-                run += expf(v[j] - m);
+                run += ex2_approx(fmaf(v[j], kLog2e, shift));
                 v[j] = run;
             }
             const int64_t r6 = grow * 6 + ((ph.dst_col + c) >> 5);
@@ -974,7 +1003,7 @@ struct Builder {
             out.n = n_pad;
             out.cols = ch.second;
             out.dst_col = os.out_col + ch.first;
-            out.residual = !L.has_fc0;
+            out.residual = L.has_fc0 ? 0 : (in_tmem ? 2 : 1);
             out.res_col = in_col + ch.first;
             out.out_sel = os.out_sel;
             out.out_ld = os.out_ld;
@@ -986,27 +1015,31 @@ struct Builder {
     // First ResLayer of a stack whose input is wider than 256 columns (always din != dout, dout = 128): the input
     // arrives as two K-chunks through X[0:...).  `first` is the phase whose action produced chunk A (256 columns,
     // source columns cols_a of the layer input); chunk B (cols_b, padded to kb) is produced by `action_b`.
+    // out_tmem: the layer output goes to tensor memory (Y = H/Y columns 128..255 = TMEM columns 192..255) as the A operand of
+    // the next layer.  The accumulators then swap sides -- fc1 in D[128:256), the output sum in D[0:128) -- so that the
+    // output epilogue never writes columns another warp is still reading.
     Phase *wide_first_layer(const ResLayerDesc &L, Phase *first, const std::vector<int> &cols_a, int action_b,
-                            const std::vector<int> &cols_b, int kb, int out_col, Phase **phase_b) {
+                            const std::vector<int> &cols_b, int kb, int out_col, Phase **phase_b, bool out_tmem = false) {
         const int n = 128;   // dout
-        add_part(*first, 0, 0, 256, 0, n, 1, push_weight(w + L.w1, L.din, 0, L.dout, n, cols_a, 256));
-        add_part(*first, 0, 0, 256, 128, n, 1, push_weight(w + L.w0, L.din, 0, L.dout, n, cols_a, 256));
+        const int d_hid = out_tmem ? 128 : 0, d_out = out_tmem ? 0 : 128;
+        add_part(*first, 0, 0, 256, d_hid, n, 1, push_weight(w + L.w1, L.din, 0, L.dout, n, cols_a, 256));
+        add_part(*first, 0, 0, 256, d_out, n, 1, push_weight(w + L.w0, L.din, 0, L.dout, n, cols_a, 256));
         Phase &pb = add(action_b, 1);
-        add_part(pb, 0, 0, kb, 0, n, 0, push_weight(w + L.w1, L.din, 0, L.dout, n, cols_b, kb));
-        add_part(pb, 0, 0, kb, 128, n, 0, push_weight(w + L.w0, L.din, 0, L.dout, n, cols_b, kb));
-        add_bias(pb, 0, w + L.b1, nullptr, 0, L.dout, n);
+        add_part(pb, 0, 0, kb, d_hid, n, 0, push_weight(w + L.w1, L.din, 0, L.dout, n, cols_b, kb));
+        add_part(pb, 0, 0, kb, d_out, n, 0, push_weight(w + L.w0, L.din, 0, L.dout, n, cols_b, kb));
+        add_bias(pb, d_hid, w + L.b1, nullptr, 0, L.dout, n);
         if (phase_b) *phase_b = &pb;
         Phase &hid = add(kActHiddenS, 1);     // H -> X[0:128) (chunk B has been consumed)
-        hid.d_col = 0;
+        hid.d_col = d_hid;
         hid.n = n;
         hid.dst_col = 0;
-        add_part(hid, 0, 0, n, 128, n, 0, push_weight(w + L.w2, L.dout, 0, L.dout, n, iota(L.dout), n));
-        add_bias(hid, 128, w + L.b2, w + L.b0, 0, L.dout, n);
-        Phase &out = add(kActOut, 1);
-        out.d_col = 128;
+        add_part(hid, 0, 0, n, d_out, n, 0, push_weight(w + L.w2, L.dout, 0, L.dout, n, iota(L.dout), n));
+        add_bias(hid, d_out, w + L.b2, w + L.b0, 0, L.dout, n);
+        Phase &out = add(out_tmem ? kActOutT : kActOut, 1);
+        out.d_col = d_out;
         out.n = n;
         out.cols = L.dout;
-        out.dst_col = out_col;
+        out.dst_col = out_tmem ? 128 : out_col;
         return &out;
     }
 };
@@ -1034,7 +1067,21 @@ using namespace cppf::tc;
 // Appends a stack whose layers all take <= 256 input columns.  The layer outputs alternate so that a layer that
 // widens 128 -> 256 finds its input in X[128:256) and can write its first output chunk to X[0:128) while the
 // second GEMM still reads the input.
-static Phase *append_stack(Builder &b, const StackDesc &s, int first_layer, Phase *cur, int in_col, const Builder::OutSpec &last) {
+//
+// tmem_chain: a 128-wide layer output that feeds a layer whose hidden activation is at most 128 wide stays in tensor memory
+// (Y, next to H) as bf16 -- the next fc1 takes it as its A operand from there and the identity residual is read back from
+// there -- so that a run of 128 -> 128 ResLayers never stores to shared memory: no generic-proxy stores competing with the
+// MMAs' operand reads, no fence.proxy.async before the hand-off.  Same roundings (bf16 once per layer output) either way.
+static bool tmem_chain_enabled() {
+    const char *e = getenv("CPPF_TC_TMEM_CHAIN");
+    return !(e && e[0] == '0');
+}
+static bool next_takes_tmem(const ResLayerDesc &L, const ResLayerDesc &nx) {
+    return tmem_chain_enabled() && L.dout == 128 && nx.din == 128 && nx.dout <= 128;
+}
+
+static Phase *append_stack(Builder &b, const StackDesc &s, int first_layer, Phase *cur, int in_col, const Builder::OutSpec &last,
+                           int in_tmem = 0) {
     for (int l = first_layer; l < s.n_layers; ++l) {
         const ResLayerDesc &L = s.layer[l];
         Builder::OutSpec os;
@@ -1042,23 +1089,26 @@ static Phase *append_stack(Builder &b, const StackDesc &s, int first_layer, Phas
             os = last;
         } else {
             const ResLayerDesc &nx = s.layer[l + 1];
-            // the next layer widens beyond its input and has a projection: park this output in the upper half
-            os.out_col = (nx.has_fc0 && nx.dout > 128 && L.dout <= 128) ? 128 : 0;
+            if (next_takes_tmem(L, nx)) {
+                os.action = kActOutT;
+                os.out_col = 128;          // Y
+            } else {
+                // the next layer widens beyond its input and has a projection: park this output in the upper half
+                os.out_col = (nx.has_fc0 && nx.dout > 128 && L.dout <= 128) ? 128 : 0;
+            }
         }
-        cur = b.res_layer(L, cur, in_col, os);
+        cur = b.res_layer(L, cur, in_col, os, in_tmem);
         in_col = os.out_col;
+        in_tmem = os.action == kActOutT ? 1 : 0;
     }
     return cur;
 }
 
-extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, void **state) {
-    *state = nullptr;
-    const HeadsModel &m = *model;
+// Host only: the two programs and their weight streams (no CUDA call).
+static int build_programs(const HeadsModel &m, const float *w, Builder &pb, Builder &tb, int *point_cols) {
     if (m.arity != 5) return CPPF_ERR_UNSUPPORTED;   // the tile layouts below assume 5-point tuples (10 pairs)
-    State *st = new State{};
-    st->model = m;
+    struct { int point_cols; } stv{0}, *st = &stv;
     // ---- per-point program -------------------------------------------------------------------------------
-    Builder pb;
     pb.w = w;
     if (m.branch == 0) {   // shot_encoder: [n,352] -> [n,64] bf16; first layer 352 = 256 + 96
         Phase *cur = &pb.add(kActLoadRows, 0);
@@ -1066,7 +1116,8 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         cur->cols = 256;
         cur->width = 256;
         Phase *pbb = nullptr;
-        cur = pb.wide_first_layer(m.shot_encoder.layer[0], cur, Builder::iota(256), kActLoadRows, Builder::iota(96, 256), 96, 0, &pbb);
+        const bool pt_tmem = next_takes_tmem(m.shot_encoder.layer[0], m.shot_encoder.layer[1]);
+        cur = pb.wide_first_layer(m.shot_encoder.layer[0], cur, Builder::iota(256), kActLoadRows, Builder::iota(96, 256), 96, 0, &pbb, pt_tmem);
         pbb->src_col = 256;
         pbb->cols = 96;
         pbb->width = 96;
@@ -1074,7 +1125,7 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         last.action = kActFinal;
         last.out_sel = 2;
         last.out_ld = 64;
-        cur = append_stack(pb, m.shot_encoder, 1, cur, 0, last);
+        cur = append_stack(pb, m.shot_encoder, 1, cur, pt_tmem ? 128 : 0, last, pt_tmem ? 1 : 0);
         st->point_cols = 64;
     } else {
         // desc_transform (train_dino.py:80,95) hoisted per point: Linear 1024 -> 256 as four K-chunks, output f kept in X as
@@ -1110,22 +1161,22 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         st->point_cols = 256 * m.arity;
     }
     // ---- per-tuple program -------------------------------------------------------------------------------
-    Builder tb;
     tb.w = w;
     Phase *cur;
     const ResLayerDesc &T0 = m.tuple_encoder.layer[0];
+    const bool t0_tmem = next_takes_tmem(T0, m.tuple_encoder.layer[1]);
     if (m.branch == 0) {
         // tuple_encoder.0 input (train_shot.py:75-83) = [coords 30 | normals 10 | feats 5x64]; chunk A = feats of
         // slots 0..3 (source columns 40..295), chunk B = [feats of slot 4 (296..359) | coords+normals (0..39) | pad 8]
         cur = &tb.add(kActEncodeShotA, 0);
         std::vector<int> cols_b = Builder::iota(64, 296);
         for (int k = 0; k < 40; ++k) cols_b.push_back(k);
-        cur = tb.wide_first_layer(T0, cur, Builder::iota(256, 40), kActEncodeShotB, cols_b, 112, 0, nullptr);
+        cur = tb.wide_first_layer(T0, cur, Builder::iota(256, 40), kActEncodeShotB, cols_b, 112, 0, nullptr, t0_tmem);
     } else {
         // desc_pair_transform of the 5 gathered descriptors = sum of 5 per-point row blocks (kActGatherSum, see the
         // per-point program); its output is chunk A of tuple_encoder.0 ([coords 30 | pair 256])
         Phase &pair = tb.add(kActGatherSum, 0);
-        cur = tb.wide_first_layer(T0, &pair, Builder::iota(256, 30), kActCoordsB, Builder::iota(30), 32, 0, nullptr);
+        cur = tb.wide_first_layer(T0, &pair, Builder::iota(256, 30), kActCoordsB, Builder::iota(30), 32, 0, nullptr, t0_tmem);
     }
     {
         // tuple_encoder output = the feature both heads read, left in X[0:256).  The scale head runs FIRST and keeps its
@@ -1133,15 +1184,12 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         // logit head starts: no spill of the feature to global memory, no reload.
         Builder::OutSpec feat;
         // layers 1..4 are 128 -> 128; layer 5 widens to 256: append_stack parks layer 4's output in X[128:256)
-        cur = append_stack(tb, m.tuple_encoder, 1, cur, 0, feat);
+        cur = append_stack(tb, m.tuple_encoder, 1, cur, t0_tmem ? 128 : 0, feat, t0_tmem ? 1 : 0);
         const StackDesc &S = m.scale_encoder;
         bool scale_in_tmem = S.n_layers >= 2;
         for (int l = 1; l < S.n_layers; ++l) scale_in_tmem = scale_in_tmem && S.layer[l].has_fc0 && S.layer[l].din % 16 == 0 && S.layer[l].din <= 128;
         scale_in_tmem = scale_in_tmem && S.layer[0].has_fc0 && S.layer[0].dout <= 128;
-        if (!scale_in_tmem) {
-            delete st;
-            return CPPF_ERR_UNSUPPORTED;
-        }
+        if (!scale_in_tmem) return CPPF_ERR_UNSUPPORTED;
         for (int l = 0; l < S.n_layers; ++l) {
             Builder::OutSpec os;
             if (l == S.n_layers - 1) {
@@ -1160,12 +1208,23 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
         logits.out_ld = 192;
         cur = append_stack(tb, m.logit_encoder, 0, cur, 0, logits);
     }
-    if (pb.prog.n_phases > kMaxPhases || tb.prog.n_phases > kMaxPhases || !pb.finalize() || !tb.finalize()) {
-        delete st;
-        return CPPF_ERR_UNSUPPORTED;
-    }
+    if (pb.prog.n_phases > kMaxPhases || tb.prog.n_phases > kMaxPhases || !pb.finalize() || !tb.finalize()) return CPPF_ERR_UNSUPPORTED;
     pb.prog.gather_cols = tb.prog.gather_cols = st->point_cols;
-    int rc = upload(pb, &st->point_prog, &st->d_point_w);
+    *point_cols = st->point_cols;
+    return CPPF_OK;
+}
+
+extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, void **state) {
+    *state = nullptr;
+    const HeadsModel &m = *model;
+    Builder pb, tb;
+    int point_cols = 0;
+    int rc = build_programs(m, w, pb, tb, &point_cols);
+    if (rc != CPPF_OK) return rc;
+    State *st = new State{};
+    st->model = m;
+    st->point_cols = point_cols;
+    rc = upload(pb, &st->point_prog, &st->d_point_w);
     if (rc == CPPF_OK) rc = upload(tb, &st->tuple_prog, &st->d_tuple_w);
     if (rc != CPPF_OK) {
         delete st;
@@ -1174,6 +1233,35 @@ extern "C" int cppf_heads_tc_create(const HeadsModel *model, const float *w, voi
     CPPF_CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     CPPF_CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     *state = st;
+    return CPPF_OK;
+}
+
+
+// Debug hook (host only, no CUDA): prints the phases and MMA parts of the branch's two programs -- the data flow a change to
+// the builder must keep consistent (which accumulator / activation region every phase reads and writes).
+CPPF_API int cppf_debug_heads_tc_dump(int branch, int num_more) {
+    const HeadsModel m = describe_heads(branch, num_more);
+    std::vector<float> w(static_cast<size_t>(m.n_floats), 0.0f);
+    Builder pb, tb;
+    int point_cols = 0;
+    const int rc = build_programs(m, w.data(), pb, tb, &point_cols);
+    if (rc != CPPF_OK) return rc;
+    static const char *names[] = {"LoadRows", "EncShotA", "EncShotB", "Gather", "CoordsB", "HiddenT", "HiddenS", "Out", "Final", "OutT", "GatherSum"};
+    const Builder *bs[2] = {&pb, &tb};
+    for (int k = 0; k < 2; ++k) {
+        const Builder &b = *bs[k];
+        printf("== %s program: %d phases, %d slabs, %zu weight bytes\n", k == 0 ? "point" : "tuple", b.prog.n_phases, b.prog.n_slabs,
+               b.stream.size() * 2);
+        for (int p = 0; p < b.prog.n_phases; ++p) {
+            const Phase &ph = b.prog.phase[p];
+            printf("  %2d %-9s wait=%d d_col=%3d n=%3d dst=%3d res=%d@%3d out_sel=%d |", p, names[ph.action], ph.wait_done, ph.d_col, ph.n,
+                   ph.dst_col, ph.residual, ph.res_col, ph.out_sel);
+            for (const Part &pt : b.parts[p])
+                printf(" [A=%s%d K=%d -> D%d n=%d %s]", pt.a_tmem == 1 ? "T" : (pt.a_tmem == 2 ? "1" : "X"), pt.a_col, pt.k_cols, pt.d_col, pt.n,
+                       pt.init ? "init" : "acc");
+            printf("\n");
+        }
+    }
     return CPPF_OK;
 }
 

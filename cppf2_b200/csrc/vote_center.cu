@@ -72,17 +72,21 @@ constexpr int kMaxRotsSmem = 1024;
 // MODE 0: RED straight to the L2-resident grid; `replicas` copies of the grid (copy = block % replicas)
 //         spread the hot cache lines of the vote peak over several L2 slices.
 // MODE 1: the whole grid lives in this CTA's shared memory (cells*4 B <= ~220 KB), flushed at the end.
-template <int CHUNK, int MODE>
+// NITER > 0: the rotation loop is unrolled for exactly NITER warp passes (R = 180 -> 6; no trip-count arithmetic between the
+// passes); 0: any R.
+template <int CHUNK, int MODE, int NITER = 0>
 __device__ __forceinline__ void vote_center_body(
     const float *__restrict__ pc, const IdxView &idx, const float *__restrict__ preds_tr, int64_t T,
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R,
     const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ grid, int64_t capacity, int replicas_max,
-    int64_t smem_cells, uint32_t *__restrict__ status, int bid, int nblk) {
-    __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
+    int64_t smem_cells, uint32_t *__restrict__ status, int bid, int nblk, float *__restrict__ s_cos, float *__restrict__ s_sin) {
     extern __shared__ __align__(16) uint32_t s_grid[];
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        s_cos[r] = cos_tab[r];
-        s_sin[r] = sin_tab[r];
+    // the tables are padded to whole warps with NaN: a padding lane's quotient is NaN, its cell converts to 0, and cell 0 never
+    // receives votes -- no `r < R` predicate (and no branch around the loads) in the vote loop
+    const int R_pad = (R + 31) & ~31;
+    for (int r = threadIdx.x; r < R_pad; r += blockDim.x) {
+        s_cos[r] = r < R ? cos_tab[r] : __int_as_float(0x7fc00000);
+        s_sin[r] = r < R ? sin_tab[r] : __int_as_float(0x7fc00000);
     }
     const int64_t cells = geom->cells;
     if (MODE == 1) {
@@ -96,6 +100,8 @@ __device__ __forceinline__ void vote_center_body(
 
     if (cells > capacity || cells > 0x7fffffffll) return;  // flagged by grid_zero_kernel
     if (MODE == 0) grid += (bid % replica_count(cells, capacity, replicas_max)) * cells;
+    uint32_t *vote_base = MODE == 1 ? s_grid : grid;
+    if (MODE == 0) asm volatile("" : "+l"(vote_base));      // one 64-bit base register: the vote's address is a single IMAD.WIDE
     const float res = geom->res;
     const float inv_res = __frcp_rn(res);      // correctly rounded reciprocal of the launch-wide divisor (see div_by)
     const float lo0 = geom->lo[0], lo1 = geom->lo[1], lo2 = geom->lo[2];
@@ -103,6 +109,8 @@ __device__ __forceinline__ void vote_center_body(
               g2 = static_cast<int>(geom->grid_res[2]);
 
     const int lane = lane_id();
+    const float *cos_l = s_cos + lane, *sin_l = s_sin + lane;
+    const uint32_t right_of_lane = ~((2u << lane) - 1u);       // the lanes to the right of this one
     const int64_t warp = (static_cast<int64_t>(bid) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (static_cast<int64_t>(nblk) * blockDim.x) >> 5;
 
@@ -139,11 +147,8 @@ __device__ __forceinline__ void vote_center_body(
                         x2 = __shfl_sync(0xffffffffu, x[2], j);
             const float y0 = __shfl_sync(0xffffffffu, y[0], j), y1 = __shfl_sync(0xffffffffu, y[1], j),
                         y2 = __shfl_sync(0xffffffffu, y[2], j);
-#pragma unroll 2
-            for (int r0 = 0; r0 < R; r0 += 32) {          // warp-uniform: the run detection below is a full-warp operation
-                const int r = r0 + lane;
-                const bool in = r < R;
-                const float cr = in ? s_cos[r] : 0.0f, sr = in ? s_sin[r] : 0.0f;
+            auto vote32 = [&](int r0) {                   // warp-uniform: the run detection below is a full-warp operation
+                const float cr = cos_l[r0], sr = sin_l[r0];
                 // offset = cos*x + sin*y (mul, mul, add); g = ((c + offset) - lo) / res; cell = trunc(g + 0.5)
                 const float o0 = __fadd_rn(__fmul_rn(cr, x0), __fmul_rn(sr, y0));
                 const float o1 = __fadd_rn(__fmul_rn(cr, x1), __fmul_rn(sr, y1));
@@ -154,8 +159,8 @@ __device__ __forceinline__ void vote_center_body(
                 const int i0 = __float2int_rz(__fadd_rn(q0, 0.5f));
                 const int i1 = __float2int_rz(__fadd_rn(q1, 0.5f));
                 const int i2 = __float2int_rz(__fadd_rn(q2, 0.5f));
-                // strictly inside (cell 0 never receives votes, :200)
-                const bool valid = in && i0 > 0 && i1 > 0 && i2 > 0 && i0 < g0 && i1 < g1 && i2 < g2;
+                // strictly inside (cell 0 never receives votes, :200); a padding lane's NaN converts to 0
+                const bool valid = i0 > 0 && i1 > 0 && i2 > 0 && i0 < g0 && i1 < g1 && i2 < g2;
                 // 32-bit cell index (grids beyond 2^31 cells are never voted, see above): the 64-bit form was 13 of the
                 // ~64 instructions of a vote
                 const int lin = valid ? (i0 * g1 + i1) * g2 + i2 : -1 - lane;
@@ -167,12 +172,18 @@ __device__ __forceinline__ void vote_center_body(
                 const int left = __shfl_up_sync(0xffffffffu, lin, 1);
                 const bool head = lane == 0 || lin != left;
                 const uint32_t heads = __ballot_sync(0xffffffffu, head);
-                if (valid && head) {
-                    const uint32_t above = heads & ~((2u << lane) - 1u);           // run heads to the right of this lane
-                    const uint32_t run = static_cast<uint32_t>((above ? __ffs(above) - 1 : 32) - lane);
-                    if (MODE == 1) atomicAdd(s_grid + lin, run);   // ATOMS
-                    else atomicAdd(grid + lin, run);               // result unused: a reduction at L2
-                }
+                // distance to the next run head on the right = trailing zeros of the heads to the right, popc(~h & (h - 1)); with
+                // no head there the formula gives 32, i.e. the run reaches the end of the warp
+                const uint32_t hr = heads & right_of_lane;
+                const uint32_t run = static_cast<uint32_t>(__popc(~hr & (hr - 1u)) - lane);
+                if (valid && head) atomicAdd(vote_base + lin, run);      // ATOMS (MODE 1) / a reduction at L2 (result unused)
+            };
+            if (NITER > 0) {
+#pragma unroll
+                for (int k = 0; k < NITER; ++k) vote32(32 * k);
+            } else {
+#pragma unroll 2
+                for (int r0 = 0; r0 < R_pad; r0 += 32) vote32(r0);
             }
         }
     }
@@ -189,14 +200,15 @@ __device__ __forceinline__ void vote_center_body(
     }
 }
 
-template <int CHUNK, int MODE, int THREADS>
+template <int CHUNK, int MODE, int THREADS, int NITER>
 __global__ void __launch_bounds__(THREADS) vote_center_kernel(
     const float *__restrict__ pc, IdxView idx, const float *__restrict__ preds_tr, int64_t T,
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R,
     const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ grid, int64_t capacity, int replicas_max,
     int64_t smem_cells, uint32_t *__restrict__ status) {
-    vote_center_body<CHUNK, MODE>(pc, idx, preds_tr, T, cos_tab, sin_tab, R, geom, grid, capacity, replicas_max, smem_cells, status,
-                                  blockIdx.x, gridDim.x);
+    __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
+    vote_center_body<CHUNK, MODE, NITER>(pc, idx, preds_tr, T, cos_tab, sin_tab, R, geom, grid, capacity, replicas_max, smem_cells,
+                                         status, blockIdx.x, gridDim.x, s_cos, s_sin);
 }
 
 // sums replicas 1..K-1 into replica 0
@@ -319,19 +331,26 @@ CPPF_API int cppf_vote_center_ex(const float *pc, int64_t n, const void *idx, in
     if (T == 0) return CPPF_OK;
     IdxView iv{idx, idx_stride, idx_is_i64};
     const int warps_per_block = kVoteThreads / 32;
+    const bool six = (R + 31) / 32 == 6;        // the reference's num_rots = 180: the unrolled instantiation
     if (mode == 1) {
         const size_t smem = static_cast<size_t>(smem_cells) * sizeof(uint32_t);
         const int smem_max = dev.max_smem_optin - 2 * kMaxRotsSmem * static_cast<int>(sizeof(float)) - 1024;
         if (smem_cells <= 0 || smem > static_cast<size_t>(smem_max)) return CPPF_ERR_UNSUPPORTED;
         // the opt-in is per device and must be taken once, whichever host thread gets here first
-        CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(vote_center_kernel<8, 1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(vote_center_kernel<8, 1, 1024, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      smem_max));
+        CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(vote_center_kernel<8, 1, 1024, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                       smem_max));
         int64_t warps = (T + 7) / 8;
         int64_t blocks = (warps + 31) / 32;
         const int64_t per_sm = smem > 100 * 1024 ? 1 : 2;
         if (blocks > dev.sm_count * per_sm) blocks = dev.sm_count * per_sm;
-        vote_center_kernel<8, 1, 1024><<<static_cast<int>(blocks), 1024, smem, s>>>(
-            pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, 1, smem_cells, status);
+        if (six)
+            vote_center_kernel<8, 1, 1024, 6><<<static_cast<int>(blocks), 1024, smem, s>>>(
+                pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, 1, smem_cells, status);
+        else
+            vote_center_kernel<8, 1, 1024, 0><<<static_cast<int>(blocks), 1024, smem, s>>>(
+                pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, 1, smem_cells, status);
         CPPF_LAUNCH_CHECK();
         return CPPF_OK;
     }
@@ -339,15 +358,23 @@ CPPF_API int cppf_vote_center_ex(const float *pc, int64_t n, const void *idx, in
     const int64_t warps_full = static_cast<int64_t>(dev.sm_count) * 8 * warps_per_block;
     if (T >= warps_full * 32) {
         int blocks = dev.sm_count * 8;
-        vote_center_kernel<32, 0, kVoteThreads><<<blocks, kVoteThreads, 0, s>>>(pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom,
-                                                                                grid, grid_capacity, replicas_max, 0, status);
+        if (six)
+            vote_center_kernel<32, 0, kVoteThreads, 6><<<blocks, kVoteThreads, 0, s>>>(pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom,
+                                                                                       grid, grid_capacity, replicas_max, 0, status);
+        else
+            vote_center_kernel<32, 0, kVoteThreads, 0><<<blocks, kVoteThreads, 0, s>>>(pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom,
+                                                                                       grid, grid_capacity, replicas_max, 0, status);
     } else {
         int64_t warps = (T + 7) / 8;
         int64_t blocks = (warps + warps_per_block - 1) / warps_per_block;
         int64_t cap = static_cast<int64_t>(dev.sm_count) * 8;
         if (blocks > cap) blocks = cap;
-        vote_center_kernel<8, 0, kVoteThreads><<<static_cast<int>(blocks), kVoteThreads, 0, s>>>(
-            pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, replicas_max, 0, status);
+        if (six)
+            vote_center_kernel<8, 0, kVoteThreads, 6><<<static_cast<int>(blocks), kVoteThreads, 0, s>>>(
+                pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, replicas_max, 0, status);
+        else
+            vote_center_kernel<8, 0, kVoteThreads, 0><<<static_cast<int>(blocks), kVoteThreads, 0, s>>>(
+                pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, replicas_max, 0, status);
     }
     CPPF_LAUNCH_CHECK();
     if (replicas_max > 1) {
@@ -453,8 +480,13 @@ __global__ void __launch_bounds__(kVoteThreads) frame_vote_center_kernel(const F
     int64_t nblk = (warps + kVoteThreads / 32 - 1) / (kVoteThreads / 32);
     if (nblk > static_cast<int64_t>(gridDim.x)) nblk = gridDim.x;
     if (static_cast<int64_t>(blockIdx.x) >= nblk) return;
-    vote_center_body<8, 0>(in.pc, in.idx, j.targets_tr, in.T, sh.cos_tab, sh.sin_tab, sh.R, j.geom, j.grid, j.grid_capacity,
-                           sh.replicas_max, 0, j.status, blockIdx.x, static_cast<int>(nblk));
+    __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
+    if ((sh.R + 31) / 32 == 6)
+        vote_center_body<8, 0, 6>(in.pc, in.idx, j.targets_tr, in.T, sh.cos_tab, sh.sin_tab, sh.R, j.geom, j.grid, j.grid_capacity,
+                                  sh.replicas_max, 0, j.status, blockIdx.x, static_cast<int>(nblk), s_cos, s_sin);
+    else
+        vote_center_body<8, 0, 0>(in.pc, in.idx, j.targets_tr, in.T, sh.cos_tab, sh.sin_tab, sh.R, j.geom, j.grid, j.grid_capacity,
+                                  sh.replicas_max, 0, j.status, blockIdx.x, static_cast<int>(nblk), s_cos, s_sin);
 }
 
 // replicas folded into copy 0 and the first-maximum arg-max in ONE pass (the fold kernel's sum feeds the key directly);
