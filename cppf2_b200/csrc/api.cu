@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace cppf {
@@ -26,6 +27,14 @@ const DeviceInfo &device_info() {
         info[dev].max_smem_optin = static_cast<int>(p.sharedMemPerBlockOptin);
     });
     return info[dev];
+}
+
+bool frame_pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("CPPF_FRAME_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 // True exactly once per (call site tag, device): the caller then performs its per-device one-time setup.

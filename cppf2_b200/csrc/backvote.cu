@@ -431,6 +431,7 @@ CPPF_API int cppf_backvote_filter(const float *pc, int64_t n, const void *idx, i
 namespace cppf {
 
 __global__ void __launch_bounds__(256) frame_backvote_errors_kernel(const FrameTable *__restrict__ t) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
     const FrameInst &in = t->inst[j.inst];
@@ -438,6 +439,7 @@ __global__ void __launch_bounds__(256) frame_backvote_errors_kernel(const FrameT
 }
 
 __global__ void __launch_bounds__(1024) frame_select_kernel(const FrameTable *__restrict__ t, int cached) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.x) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.x];
     const FrameInst &in = t->inst[j.inst];
@@ -447,6 +449,7 @@ __global__ void __launch_bounds__(1024) frame_select_kernel(const FrameTable *__
 }
 
 __global__ void __launch_bounds__(256) frame_backvote_mask_kernel(const FrameTable *__restrict__ t) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
     const FrameInst &in = t->inst[j.inst];
@@ -459,16 +462,13 @@ int frame_launch_backvote(const FrameTable *t, int nj, int64_t T_cap, cudaStream
     if (nj <= 0) return CPPF_OK;
     if (T_cap > kSelectSmallMax) return CPPF_ERR_UNSUPPORTED;      // the single-CTA selection; larger T: the per-job path
     const int per_job = std::max(1, std::min<int>(div_up(T_cap, 256), (device_info().sm_count * 8 + nj - 1) / nj));
-    frame_backvote_errors_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t);
-    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_backvote_errors_kernel, dim3(per_job, nj), dim3(256), 0, s, t));
     const size_t cache = select_cache_bytes(T_cap);
     if (cache > 48 * 1024)
         CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(frame_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                       static_cast<int>(kSelectCachedMax * sizeof(uint32_t))));
-    frame_select_kernel<<<nj, 1024, cache, s>>>(t, cache ? 1 : 0);
-    CPPF_LAUNCH_CHECK();
-    frame_backvote_mask_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t);
-    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_select_kernel, dim3(nj), dim3(1024), cache, s, t, cache ? 1 : 0));
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_backvote_mask_kernel, dim3(per_job, nj), dim3(256), 0, s, t));
     return CPPF_OK;
 }
 

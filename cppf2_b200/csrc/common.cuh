@@ -24,6 +24,35 @@
 
 namespace cppf {
 
+// Programmatic dependent launch along the frame's kernel sequence (cppf_frame_pose): every frame kernel begins with
+// pdl_wait() -- the previous kernel has completed and its writes are visible, i.e. plain stream order -- and then lets the
+// NEXT kernel's CTAs be scheduled (pdl_trigger) as soon as all of this kernel's CTAs have started: launch latency, CTA
+// scheduling and the next kernel's prologue overlap this kernel's tail instead of following it.  Without the launch
+// attribute both instructions are no-ops, so the same kernels serve the single-job entry points.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_wait();
+    pdl_trigger();
+}
+
+bool frame_pdl_enabled();      // CPPF_FRAME_PDL=0 switches the attribute off (api.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_frame_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = frame_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct DeviceInfo {
     int sm_count;
     int64_t l2_bytes;

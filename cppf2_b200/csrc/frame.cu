@@ -35,6 +35,11 @@ static FrameShared shared_of(const cppf_vote_params *p, int replicas_max) {
     sh.band = p->band;
     sh.lut_g = p->lut_g;
     sh.replicas_max = replicas_max > 0 ? replicas_max : 1;      // measured on B200 with the run-length aggregated vote: 1 / 2 / 4 / 8 copies -> centre stage 0.413 / 0.423 / 0.437 / 0.482 ms per frame (before the aggregation 4 copies won: 0.630 / 0.584 / 0.573 / 0.615)
+    static const int vote_lanes = [] {
+        const char *e = getenv("CPPF_VOTE_LANES");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    sh.vote_lanes = vote_lanes;
     sh.cos_thr = p->cos_thr;
     sh.lut_cells = p->lut ? reinterpret_cast<const uint2 *>(static_cast<const unsigned char *>(p->lut) + 16) : nullptr;
     sh.cos_tab = p->cos_tab;

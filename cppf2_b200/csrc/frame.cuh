@@ -110,6 +110,7 @@ struct FrameTable {
 
 struct FrameShared {                    // identical for every job of a frame; passed by value
     int R, S, num_bins, band, lut_g, replicas_max;
+    int vote_lanes;                     // centre vote: lane-per-tuple form (vote_center.cu; CPPF_VOTE_LANES=0: warp-per-tuple)
     float cos_thr;
     const uint2 *lut_cells;
     const float *cos_tab, *sin_tab, *sphere;

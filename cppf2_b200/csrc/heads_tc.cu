@@ -518,6 +518,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
     if (tmem != 0) __trap();     // one CTA per SM owning all 512 columns: the allocation starts at lane 0, column 0
+    pdl_enter();                 // frame path (programmatic dependent launch): barriers and tensor memory are set up; everything
+                                 // below reads what the previous kernel of the frame wrote
     bool single;
     const int n_ctas = cta_share(multi, one, single);               // CTAs that take part (see pair_of)
     const int64_t q0 = static_cast<int>(blockIdx.x) < n_ctas ? static_cast<int64_t>(blockIdx.x) : (1ll << 60);   // others: no pair
@@ -785,7 +787,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                             for (int it = ew; it < 32 * 4; it += kEpiWarps) {
                                 // a warp pass = 4 rows x 128 contiguous bytes: whole 128-byte lines per L2 request (a 64-byte
                                 // half-line mapping moves the same sectors with twice the requests); the shared-memory stores
-                                // then land 2-way conflicted, which is the cheaper side
+                                // then land 2-way conflicted, which is the cheaper side.  (Two passes in flight at once -- ten
+                                // loads per lane -- measured the same: the gather is not bound by the loads in flight.)
                                 const int r = (it & 31) * 4 + (lane >> 3), c8 = (it >> 5) * 8 + (lane & 7);
                                 uint4 g[5];
 #pragma unroll
@@ -1389,9 +1392,8 @@ int frame_launch_heads(const FrameTable *t, const void *const *tc_states, int ni
             if (!st) continue;
             const int64_t pairs = pairs_of(kind == 0 ? n_cap : T_cap) * ni;
             Args none{};
-            chain_tc_kernel<false><<<blocks_for_pairs(pairs), kThreads, kSmemTotal, s>>>(kind == 0 ? st->point_prog : st->tuple_prog, none,
-                                                                                       &t->heads[kind][branch]);
-            CPPF_LAUNCH_CHECK();
+            CPPF_CUDA_TRY(launch_frame_kernel(chain_tc_kernel<false>, dim3(blocks_for_pairs(pairs)), dim3(kThreads), kSmemTotal, s,
+                                              kind == 0 ? st->point_prog : st->tuple_prog, none, &t->heads[kind][branch]));
         }
     return CPPF_OK;
 }

@@ -518,6 +518,7 @@ __global__ void __launch_bounds__(256) pose_loss_kernel(const float *__restrict_
 // reuses the DINO scale) -- recomputed here rather than read from the other job's record, so that the jobs of one launch
 // stay independent.
 __global__ void __launch_bounds__(1024) frame_pose_dirs_scale_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
     if (blockIdx.x == 0) {
@@ -529,6 +530,7 @@ __global__ void __launch_bounds__(1024) frame_pose_dirs_scale_kernel(const Frame
 }
 
 __global__ void __launch_bounds__(512, 1) frame_pose_refine_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.x) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.x];
     if (j.refine_iters <= 0) return;
@@ -538,6 +540,7 @@ __global__ void __launch_bounds__(512, 1) frame_pose_refine_kernel(const FrameTa
 }
 
 __global__ void __launch_bounds__(256) frame_pose_loss_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
     const FrameInst &in = t->inst[j.inst];
@@ -548,15 +551,12 @@ __global__ void __launch_bounds__(256) frame_pose_loss_kernel(const FrameTable *
 int frame_launch_pose(const FrameTable *t, int nj, int64_t T_cap, int any_refine, const FrameShared &sh, cudaStream_t s) {
     (void)T_cap;
     if (nj <= 0) return CPPF_OK;
-    frame_pose_dirs_scale_kernel<<<dim3(4, nj), 1024, 0, s>>>(t, sh);
-    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_pose_dirs_scale_kernel, dim3(4, nj), dim3(1024), 0, s, t, sh));
     if (any_refine) {
-        frame_pose_refine_kernel<<<nj, 512, 0, s>>>(t, sh);
-        CPPF_LAUNCH_CHECK();
+        CPPF_CUDA_TRY(launch_frame_kernel(frame_pose_refine_kernel, dim3(nj), dim3(512), 0, s, t, sh));
     }
     const int per_job = std::max(4, device_info().sm_count * 2 / nj);
-    frame_pose_loss_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t, sh);
-    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_pose_loss_kernel, dim3(per_job, nj), dim3(256), 0, s, t, sh));
     return CPPF_OK;
 }
 

@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
 // Batched frame path (frame.cuh): the rotation votes of every job (angle columns 0 and 2: `up` and `right`, eval.py:277-293)
 // in one launch; blockIdx.y = job.
 __global__ void __launch_bounds__(256) frame_rotation_hist_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
     const FrameInst &in = t->inst[j.inst];
@@ -276,8 +277,7 @@ int frame_launch_rotation(const FrameTable *t, int nj, int64_t T_cap, const Fram
     // CTAs per SM
     const int64_t guess = T_cap / 8 + 1;
     const int per_job = std::max(1, std::min<int>(div_up(guess * 32, 256), std::max(8, device_info().sm_count * 4 / nj)));
-    frame_rotation_hist_kernel<<<dim3(per_job, nj), 256, smem, s>>>(t, sh);
-    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_rotation_hist_kernel, dim3(per_job, nj), dim3(256), smem, s, t, sh));
     return CPPF_OK;
 }
 

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256) sample_tuples_kernel(int64_t n, int64_t c
 // Batched frame path (frame.cuh): the tuple indices of every instance that brought none (eval.py:207), one launch.  Same
 // generator and counters as sample_tuples_kernel with the instance's seed, so cppf_sample_tuples reproduces them.
 __global__ void __launch_bounds__(256) frame_sample_tuples_kernel(const FrameTable *__restrict__ t) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_inst) return;
     const FrameInst &in = t->inst[blockIdx.y];
     if (in.idx_draw == nullptr) return;
@@ -110,8 +111,7 @@ __global__ void __launch_bounds__(256) frame_sample_tuples_kernel(const FrameTab
 int frame_launch_sample_tuples(const FrameTable *t, int ni, int64_t T_cap, cudaStream_t s) {
     if (ni <= 0 || T_cap <= 0) return CPPF_OK;
     const int per_inst = std::max(1, std::min<int>(div_up(T_cap * 5, 256), (device_info().sm_count * 8 + ni - 1) / ni));
-    frame_sample_tuples_kernel<<<dim3(per_inst, ni), 256, 0, s>>>(t);
-    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_sample_tuples_kernel, dim3(per_inst, ni), dim3(256), 0, s, t));
     return CPPF_OK;
 }
 

@@ -200,6 +200,112 @@ __device__ __forceinline__ void vote_center_body(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Lane-per-tuple form of the same vote (round 2): every lane owns ONE tuple and walks its circle rotation by rotation.
+// cos/sin are warp-uniform shared-memory broadcasts, the pair frame never crosses lanes (no shuffles, no ballot), all 32
+// lanes build frames (the warp-per-tuple form keeps 8 of 32 busy there), and the run-length aggregation is temporal:
+// consecutive rotations that fall into one cell are counted in a register and leave the SM as one reduction, runs no
+// longer cut at 32-rotation boundaries.  Same float operations per vote => the same integer grid.
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void vote_center_lanes_body(
+    const float *__restrict__ pc, const IdxView &idx, const float *__restrict__ preds_tr, int64_t T,
+    const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R,
+    const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ grid, int64_t capacity, int replicas_max,
+    int64_t smem_cells, uint32_t *__restrict__ status, int bid, int nblk, float *__restrict__ s_cos, float *__restrict__ s_sin) {
+    extern __shared__ __align__(16) uint32_t s_grid[];
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        s_cos[r] = cos_tab[r];
+        s_sin[r] = sin_tab[r];
+    }
+    const int64_t cells = geom->cells;
+    if (MODE == 1) {
+        if (cells > smem_cells) {  // the caller's bound on the grid size was wrong: flag, never corrupt
+            if (bid == 0 && threadIdx.x == 0 && status) atomicOr(status, CPPF_STATUS_GRID_OVERFLOW);
+            return;
+        }
+        for (int64_t i = threadIdx.x; i < cells; i += blockDim.x) s_grid[i] = 0u;
+    }
+    __syncthreads();
+
+    if (cells > capacity || cells > 0x7fffffffll) return;  // flagged by grid_zero_kernel
+    if (MODE == 0) grid += (bid % replica_count(cells, capacity, replicas_max)) * cells;
+    uint32_t *vote_base = MODE == 1 ? s_grid : grid;
+    if (MODE == 0) asm volatile("" : "+l"(vote_base));
+    const float res = geom->res;
+    const float inv_res = __frcp_rn(res);
+    const float lo0 = geom->lo[0], lo1 = geom->lo[1], lo2 = geom->lo[2];
+    const int g0 = static_cast<int>(geom->grid_res[0]), g1 = static_cast<int>(geom->grid_res[1]),
+              g2 = static_cast<int>(geom->grid_res[2]);
+    const int64_t first = static_cast<int64_t>(bid) * blockDim.x + threadIdx.x;
+    const int64_t stride = static_cast<int64_t>(nblk) * blockDim.x;
+    for (int64_t t = first; t - lane_id() < T; t += stride) {       // warp-uniform trip count
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f, y0 = 0.f, y1 = 0.f, y2 = 0.f;
+        bool ok = false;
+        if (t < T) {
+            const float2 tr = reinterpret_cast<const float2 *>(preds_tr)[t];  // (proj_len, odist)
+            const int64_t ia = idx.at(t, 0), ib = idx.at(t, 1);
+            float a[3] = {pc[3 * ia], pc[3 * ia + 1], pc[3 * ia + 2]};
+            float b[3] = {pc[3 * ib], pc[3 * ib + 1], pc[3 * ib + 2]};
+            float ab[3], x[3], y[3];
+            ok = (tr.y > res) && pair_frame(a, b, false, ab, x);  // :182
+            if (ok) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) x[k] = __fmul_rn(x[k], tr.y);      // :191
+                cross_torch(x, ab, y);                                          // :192
+                c0 = __fsub_rn(a[0], __fmul_rn(ab[0], tr.x));                   // :186
+                c1 = __fsub_rn(a[1], __fmul_rn(ab[1], tr.x));
+                c2 = __fsub_rn(a[2], __fmul_rn(ab[2], tr.x));
+                x0 = x[0], x1 = x[1], x2 = x[2];
+                y0 = y[0], y1 = y[1], y2 = y[2];
+            }
+        }
+        if (!__any_sync(0xffffffffu, ok)) continue;
+        if (!ok) c0 = __int_as_float(0x7fc00000);      // masked pair (:182) or past the end: every quotient NaN -> cell 0 -> no vote
+        int prev = -1;              // cell of the current run (-1: none), cnt its length so far
+        uint32_t cnt = 0u;
+#pragma unroll 4
+        for (int r = 0; r < R; ++r) {
+            const float cr = s_cos[r], sr = s_sin[r];        // one address per warp: broadcast
+            const float o0 = __fadd_rn(__fmul_rn(cr, x0), __fmul_rn(sr, y0));
+            const float o1 = __fadd_rn(__fmul_rn(cr, x1), __fmul_rn(sr, y1));
+            const float o2 = __fadd_rn(__fmul_rn(cr, x2), __fmul_rn(sr, y2));
+            const float q0 = div_by(__fsub_rn(__fadd_rn(c0, o0), lo0), res, inv_res);
+            const float q1 = div_by(__fsub_rn(__fadd_rn(c1, o1), lo1), res, inv_res);
+            const float q2 = div_by(__fsub_rn(__fadd_rn(c2, o2), lo2), res, inv_res);
+            const int i0 = __float2int_rz(__fadd_rn(q0, 0.5f));
+            const int i1 = __float2int_rz(__fadd_rn(q1, 0.5f));
+            const int i2 = __float2int_rz(__fadd_rn(q2, 0.5f));
+            // strictly inside (cell 0 excluded, :200); a masked tuple's NaN centre converts to cell 0
+            // (a predicate chain spelled out: the compiler's own choice for this expression was a chain of four SELs)
+            int lin;
+            asm("{\n\t.reg .pred p;\n\t"
+                "setp.gt.s32 p, %1, 0;\n\t"
+                "setp.lt.and.s32 p, %2, %3, p;\n\t"
+                "setp.lt.and.s32 p, %4, %5, p;\n\t"
+                "setp.lt.and.s32 p, %6, %7, p;\n\t"
+                "selp.s32 %0, %8, -1, p;\n\t}"
+                : "=r"(lin)
+                : "r"(min(i0, min(i1, i2))), "r"(i0), "r"(g0), "r"(i1), "r"(g1), "r"(i2), "r"(g2), "r"((i0 * g1 + i1) * g2 + i2));
+            const bool change = lin != prev;
+            if (change && prev >= 0) atomicAdd(vote_base + prev, cnt);      // the finished run: one reduction (result unused)
+            cnt = change ? 1u : cnt + 1u;
+            prev = lin;
+        }
+        if (prev >= 0) atomicAdd(vote_base + prev, cnt);
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        const int64_t start = (cells / nblk) * bid;
+        for (int64_t i = threadIdx.x; i < cells; i += blockDim.x) {
+            int64_t j = i + start;
+            j = j >= cells ? j - cells : j;
+            const uint32_t v = s_grid[j];
+            if (v) atomicAdd(grid + j, v);
+        }
+    }
+}
+
 template <int CHUNK, int MODE, int THREADS, int NITER>
 __global__ void __launch_bounds__(THREADS) vote_center_kernel(
     const float *__restrict__ pc, IdxView idx, const float *__restrict__ preds_tr, int64_t T,
@@ -209,6 +315,26 @@ __global__ void __launch_bounds__(THREADS) vote_center_kernel(
     __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
     vote_center_body<CHUNK, MODE, NITER>(pc, idx, preds_tr, T, cos_tab, sin_tab, R, geom, grid, capacity, replicas_max, smem_cells,
                                          status, blockIdx.x, gridDim.x, s_cos, s_sin);
+}
+
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) vote_center_lanes_kernel(
+    const float *__restrict__ pc, IdxView idx, const float *__restrict__ preds_tr, int64_t T,
+    const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R,
+    const cppf_grid_geom *__restrict__ geom, uint32_t *__restrict__ grid, int64_t capacity, int replicas_max,
+    int64_t smem_cells, uint32_t *__restrict__ status) {
+    __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
+    vote_center_lanes_body<MODE>(pc, idx, preds_tr, T, cos_tab, sin_tab, R, geom, grid, capacity, replicas_max, smem_cells, status,
+                                 blockIdx.x, gridDim.x, s_cos, s_sin);
+}
+
+// CPPF_VOTE_LANES=0 selects the warp-per-tuple form (A/B and fallback)
+static bool vote_lanes_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("CPPF_VOTE_LANES");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 // sums replicas 1..K-1 into replica 0
@@ -345,7 +471,11 @@ CPPF_API int cppf_vote_center_ex(const float *pc, int64_t n, const void *idx, in
         int64_t blocks = (warps + 31) / 32;
         const int64_t per_sm = smem > 100 * 1024 ? 1 : 2;
         if (blocks > dev.sm_count * per_sm) blocks = dev.sm_count * per_sm;
-        if (six)
+        if (vote_lanes_enabled()) {
+            CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(vote_center_lanes_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+            vote_center_lanes_kernel<1, 1024><<<static_cast<int>(std::min<int64_t>(blocks, (T + 1023) / 1024)), 1024, smem, s>>>(
+                pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, 1, smem_cells, status);
+        } else if (six)
             vote_center_kernel<8, 1, 1024, 6><<<static_cast<int>(blocks), 1024, smem, s>>>(
                 pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, 1, smem_cells, status);
         else
@@ -356,7 +486,14 @@ CPPF_API int cppf_vote_center_ex(const float *pc, int64_t n, const void *idx, in
     }
     // Tuples per warp pass: small chunks when T is small so that every SM still gets >= ~32 warps.
     const int64_t warps_full = static_cast<int64_t>(dev.sm_count) * 8 * warps_per_block;
-    if (T >= warps_full * 32) {
+    // Votes straight to L2: the lane-per-tuple form wins at a frame's sizes (12 jobs x 50 000 tuples: 0.317 against 0.336 ms)
+    // but loses at T = 2^22 on the 0.8 M-cell example grid (3.20 against 2.80 ms): a warp's 32 votes then land on 32 different
+    // circles instead of 32 neighbouring points of one, and L2 sees more distinct sectors per request.
+    if (vote_lanes_enabled() && T < (1 << 18)) {
+        const int64_t blocks = std::min<int64_t>((T + kVoteThreads - 1) / kVoteThreads, static_cast<int64_t>(dev.sm_count) * 8);
+        vote_center_lanes_kernel<0, kVoteThreads><<<static_cast<int>(blocks), kVoteThreads, 0, s>>>(
+            pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom, grid, grid_capacity, replicas_max, 0, status);
+    } else if (T >= warps_full * 32) {
         int blocks = dev.sm_count * 8;
         if (six)
             vote_center_kernel<32, 0, kVoteThreads, 6><<<blocks, kVoteThreads, 0, s>>>(pc, iv, preds_tr, T, cos_tab, sin_tab, R, geom,
@@ -439,6 +576,7 @@ namespace cppf {
 // prep: bounds of the job's cloud -> geom, and every small accumulator of the chain zeroed (centre record incl. its key /
 // ticket words, back-vote summary incl. kept and imp_max, status, sphere bins, importance counts, pose scratch)
 __global__ void __launch_bounds__(1024) frame_prep_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.x) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.x];
     const FrameInst &in = t->inst[j.inst];
@@ -457,6 +595,7 @@ __global__ void __launch_bounds__(1024) frame_prep_kernel(const FrameTable *__re
 
 // decode + targets of the job's tuples (eval.py:230-240), and the live part of its grid zeroed
 __global__ void __launch_bounds__(256) frame_decode_zero_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
     const FrameInst &in = t->inst[j.inst];
@@ -472,15 +611,16 @@ __global__ void __launch_bounds__(256) frame_decode_zero_kernel(const FrameTable
 // grids; at the frame's T <= 2^17 it is also the faster one for those: ncu 37 us against 48 us per job, and a launch whose
 // CTAs each reserve a whole SM's shared memory would serialise the jobs).
 __global__ void __launch_bounds__(kVoteThreads) frame_vote_center_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
     const FrameInst &in = t->inst[j.inst];
+    __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
     // as many CTAs as the single-job launch would use for this T (the grid is sized for the capacity)
     const int64_t warps = (in.T + 7) / 8;
     int64_t nblk = (warps + kVoteThreads / 32 - 1) / (kVoteThreads / 32);
     if (nblk > static_cast<int64_t>(gridDim.x)) nblk = gridDim.x;
     if (static_cast<int64_t>(blockIdx.x) >= nblk) return;
-    __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
     if ((sh.R + 31) / 32 == 6)
         vote_center_body<8, 0, 6>(in.pc, in.idx, j.targets_tr, in.T, sh.cos_tab, sh.sin_tab, sh.R, j.geom, j.grid, j.grid_capacity,
                                   sh.replicas_max, 0, j.status, blockIdx.x, static_cast<int>(nblk), s_cos, s_sin);
@@ -489,9 +629,24 @@ __global__ void __launch_bounds__(kVoteThreads) frame_vote_center_kernel(const F
                                   sh.replicas_max, 0, j.status, blockIdx.x, static_cast<int>(nblk), s_cos, s_sin);
 }
 
+// lane-per-tuple form (vote_center_lanes_body): one CTA per 256 tuples of the job; 32 registers, all 64 warp slots of an SM
+__global__ void __launch_bounds__(kVoteThreads) frame_vote_center_lanes_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
+    const FrameJob &j = t->job[blockIdx.y];
+    const FrameInst &in = t->inst[j.inst];
+    __shared__ float s_cos[kMaxRotsSmem], s_sin[kMaxRotsSmem];
+    int64_t nblk = (in.T + kVoteThreads - 1) / kVoteThreads;
+    if (nblk > static_cast<int64_t>(gridDim.x)) nblk = gridDim.x;
+    if (static_cast<int64_t>(blockIdx.x) >= nblk) return;
+    vote_center_lanes_body<0>(in.pc, in.idx, j.targets_tr, in.T, sh.cos_tab, sh.sin_tab, sh.R, j.geom, j.grid, j.grid_capacity,
+                              sh.replicas_max, 0, j.status, blockIdx.x, static_cast<int>(nblk), s_cos, s_sin);
+}
+
 // replicas folded into copy 0 and the first-maximum arg-max in ONE pass (the fold kernel's sum feeds the key directly);
 // the last CTA of a job converts to world space (train_dino.py:212-213) exactly like grid_argmax_kernel
 __global__ void __launch_bounds__(256) frame_fold_argmax_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
     const cppf_grid_geom *geom = j.geom;
@@ -551,19 +706,20 @@ __global__ void __launch_bounds__(256) frame_fold_argmax_kernel(const FrameTable
 int frame_launch_center(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s) {
     const DeviceInfo &dev = device_info();
     if (nj <= 0) return CPPF_OK;
-    frame_prep_kernel<<<nj, 1024, 0, s>>>(t, sh);
-    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_prep_kernel, dim3(nj), dim3(1024), 0, s, t, sh));
     const int per_job = std::max(1, std::min<int>(div_up(T_cap, 256), (dev.sm_count * 8 + nj - 1) / nj));
-    frame_decode_zero_kernel<<<dim3(per_job, nj), 256, 0, s>>>(t, sh);
-    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_decode_zero_kernel, dim3(per_job, nj), dim3(256), 0, s, t, sh));
     {
         const int64_t warps = (T_cap + 7) / 8;
         const int blocks = static_cast<int>(std::min<int64_t>((warps + 7) / 8, static_cast<int64_t>(dev.sm_count) * 8));
-        frame_vote_center_kernel<<<dim3(blocks, nj), kVoteThreads, 0, s>>>(t, sh);
-        CPPF_LAUNCH_CHECK();
+        if (sh.vote_lanes) {
+            const int lane_blocks = static_cast<int>(std::min<int64_t>((T_cap + kVoteThreads - 1) / kVoteThreads, static_cast<int64_t>(dev.sm_count) * 8));
+            CPPF_CUDA_TRY(launch_frame_kernel(frame_vote_center_lanes_kernel, dim3(lane_blocks, nj), dim3(kVoteThreads), 0, s, t, sh));
+        } else {
+            CPPF_CUDA_TRY(launch_frame_kernel(frame_vote_center_kernel, dim3(blocks, nj), dim3(kVoteThreads), 0, s, t, sh));
+        }
     }
-    frame_fold_argmax_kernel<<<dim3(std::max(1, dev.sm_count * 4 / std::max(1, nj / 2)), nj), 256, 0, s>>>(t, sh);
-    CPPF_LAUNCH_CHECK();
+    CPPF_CUDA_TRY(launch_frame_kernel(frame_fold_argmax_kernel, dim3(std::max(1, dev.sm_count * 4 / std::max(1, nj / 2)), nj), dim3(256), 0, s, t, sh));
     return CPPF_OK;
 }
 
