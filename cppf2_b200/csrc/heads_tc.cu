@@ -27,8 +27,10 @@
 #include <vector>
 
 #ifndef CPPF_TC_EXP
-#define CPPF_TC_EXP 0      // timing experiments only (tools/heads_profile.py): bit 0 no bias loads, 1 issuer sleeps when idle,
-#endif                     // 2 no Final stores, 3 no TMEM loads
+#define CPPF_TC_EXP 0      // timing experiments only (tools/heads_profile.py; results are garbage): bit 2 no Final stores, 3 no
+#endif                     // TMEM loads, 5 no MMA issue, 6 slot 1 ignores the weight ring (no wait, no release), 7 no
+                           // fence.proxy.async, 8 nobody waits for weights and the producer does not run; 9 / 10 (valid
+                           // results) the epilogue's / the issuers' critical waits spin on test_wait instead of try_wait
 
 namespace cppf {
 namespace tc {
@@ -156,6 +158,12 @@ __device__ __forceinline__ bool elect_one() {   // one lane of the (converged) w
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
         if (spin > (1u << 22)) __trap();      // >> any legitimate wait (a whole launch is < 1 ms): a deadlock surfaces within seconds
+}
+// Spinning on the non-blocking test instead of try_wait (which may suspend the warp for a HW-defined time before it looks
+// again): for the waits that sit on the MMA <-> epilogue critical path of a slot.
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_test(bar, parity); ++spin)
+        if (spin > (1u << 24)) __trap();
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -496,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, kSlots);     // a slab is shared: both slots' MMAs must retire before it is refilled
+            mbar_init(bar_empty + 8 * s, (CPPF_TC_EXP & 64) ? 1 : kSlots);     // a slab is shared: both slots' MMAs must retire before it is refilled
         }
         for (int s = 0; s < kSlots; ++s) {
             mbar_init(bar_act + 8 * s, kEpiWarps);      // every epilogue warp arrives for whichever slot it has just served
@@ -524,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
     const int n_ctas = cta_share(multi, one, single);               // CTAs that take part (see pair_of)
     const int64_t q0 = static_cast<int>(blockIdx.x) < n_ctas ? static_cast<int64_t>(blockIdx.x) : (1ll << 60);   // others: no pair
 
-    if (warp == kEpiWarps) {
+    if (warp == kEpiWarps && !(CPPF_TC_EXP & 256)) {
         // =============================== weight producer ===============================================
         // One pass over the slab stream per round; every slab serves both slots of the round.  The whole warp runs
         // the (uniform) loop; the elected lane issues the copies.
@@ -555,6 +563,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             one.prof[blockIdx.x * 64 + 4] = prof_clock<kProf>() - t_begin;
             one.prof[blockIdx.x * 64 + 5] = t_wait;
         }
+    } else if (warp == kEpiWarps) {
+        // (experiment 8: no producer)
     } else if (warp > kEpiWarps) {
         // =============================== MMA issuers (one warp per slot) ================================
         // Each slot has its own issuing warp walking the slab list in order with blocking waits, exactly like a GEMM
@@ -582,6 +592,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                 // the producer: mbarrier waits are by phase PARITY, and a warp that skipped a whole round (~30 turns) would
                 // pass or block on the wrong phases in its next round.
                 for (int i = 0; i < prog.n_slabs; ++i) {
+                    if ((CPPF_TC_EXP & 256) || ((CPPF_TC_EXP & 64) && s == 1)) break;
                     mbar_wait(bar_full + 8 * stage, turn);
                     if (leader) mbar_arrive(bar_empty + 8 * stage);
                     __syncwarp();
@@ -597,13 +608,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                 const uint32_t flags = w.w >> 24;
                 long long t0 = prof_clock<kProf>();
                 if (flags & kSlabFirst) {        // the slot's A operand is ready and its accumulator is free
-                    mbar_wait(bar_act + 8 * s, act_par);
+                    if (CPPF_TC_EXP & 1024) mbar_spin(bar_act + 8 * s, act_par);
+                    else mbar_wait(bar_act + 8 * s, act_par);
                     act_par ^= 1u;
                     tc_fence_after();            // the epilogue's tcgen05.ld/st of this slot are ordered before the MMAs below
                 }
                 long long t1 = prof_clock<kProf>();
                 // weights arrive through the async proxy (cp.async.bulk, complete_tx on this barrier): no tcgen05 fence needed
-                mbar_wait(bar_full + 8 * stage, turn);
+                const bool no_ring = (CPPF_TC_EXP & 256) || ((CPPF_TC_EXP & 64) && s == 1);
+                if (!no_ring) mbar_wait(bar_full + 8 * stage, turn);
                 long long t2 = prof_clock<kProf>();
                 if (leader && !(CPPF_TC_EXP & 32)) {
                     // every value below is warp-uniform: descriptors stay in uniform registers, a handful of adds per MMA
@@ -635,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                             }
                         }
                     }
-                    umma_commit(bar_empty + 8 * stage);                 // this slot is done with the slab once these MMAs retire
+                    if (!no_ring) umma_commit(bar_empty + 8 * stage);   // this slot is done with the slab once these MMAs retire
                     if (flags & kSlabLast) umma_commit(bar_done + 8 * s);
                 }
                 __syncwarp();
@@ -704,7 +717,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                     const bool live = grow < a.rows;
                     long long t0 = prof_clock<kProf>();
                     if (ph.wait_done) {
-                        mbar_wait(bar_done + 8 * slot, done_seq[slot] & 1u);
+                        if (CPPF_TC_EXP & 512) mbar_spin(bar_done + 8 * slot, done_seq[slot] & 1u);
+                        else mbar_wait(bar_done + 8 * slot, done_seq[slot] & 1u);
                         ++done_seq[slot];
                         tc_fence_after();
                     }
@@ -836,7 +850,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                     t0 = prof_clock<kProf>();
                     if (kProf) t_actn[ph.action] += t0 - t1;
                     if (ph.n_parts) {
-                        if (ph.action != kActHiddenT && ph.action != kActOutT) fence_async_smem();   // generic-proxy writes to X -> visible to the tensor core's async proxy
+                        if (ph.action != kActHiddenT && ph.action != kActOutT && !(CPPF_TC_EXP & 128)) fence_async_smem();   // generic-proxy writes to X -> visible to the tensor core's async proxy
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_act + 8 * slot);
