@@ -5,7 +5,7 @@ network (SAR-Net's Mask-RCNN results, eval.py:74-77, 103-127): a dict (or a list
 `pred_bboxes [n,4]`, `pred_masks [H,W,n]`, `pred_class_ids [n]`, `gt_RTs`, `gt_scales`, `gt_class_ids` and, in newer
 files, `gt_handle_visibility`.  Downstream it writes the same dict back with `pred_RTs [n,4,4]` (R * ||scale|| and t) and
 `pred_scales [n,3]` (scale / ||scale||) filled in (eval.py:143-144, 369-371, 399), which is what `compute_degree_cm_mAP`
-(utils/util.py:2736-2955, offline CPU scoring: out of scope) consumes.
+(utils/util.py:2736-2955; here `cppf2_b200.scoring.compute_degree_cm_mAP`, offline host code) consumes.
 
 This module is host code only (pickle, numpy, paths); the hot path itself runs through `PoseEstimator.estimate_frame`.
 """
