@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "frame.cuh"
 
+#include <cooperative_groups.h>
+
 namespace cppf {
 
 struct Axes {
@@ -273,6 +275,148 @@ __global__ void __launch_bounds__(1024) select_small_kernel(const float *__restr
     else select_small_body<false>(errs, T, rank_lo, gamma, summary);
 }
 
+// The same selection spread over a thread-block CLUSTER of kSelectCluster CTAs (round 2, session 3).  One CTA sweeping
+// 50 000 keys five times is bound by its own issue rate (49 keys per thread and pass, ~25 instructions each: 54 us per frame on
+// 12 of the 148 SMs, ncu).  Here every CTA of the cluster caches 1/8 of the keys in its shared memory and histograms only
+// those; after one cluster barrier per pass every CTA sums the eight 256-bin histograms through distributed shared memory and
+// narrows the prefix by itself (identical integer arithmetic in all eight, so there is nothing to broadcast).  The histograms of
+// the four passes are separate arrays: a pass needs ONE cluster barrier, none to recycle a buffer.  Integer counts, hence the
+// same order statistics and the same threshold bits as the single-CTA and the multi-launch forms.
+constexpr int kSelectCluster = 8;
+constexpr int kSelectClusterThreads = 512;
+
+static size_t select_cluster_cache_bytes(int64_t T) {
+    return static_cast<size_t>((T + kSelectCluster - 1) / kSelectCluster) * sizeof(uint32_t);
+}
+
+__device__ __forceinline__ void select_cluster_body(const float *__restrict__ errs, int64_t T, int64_t rank_lo, float gamma,
+                                                    cppf_backvote_summary *__restrict__ summary) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = static_cast<int>(cluster.block_rank());
+    __shared__ uint32_t s_hist[4][256];
+    __shared__ unsigned long long s_cum[256];
+    __shared__ unsigned long long s_warp_tot[8];
+    __shared__ uint32_t s_min;
+    __shared__ int s_digit;
+    extern __shared__ __align__(16) uint32_t s_keys[];
+    const int tid = threadIdx.x, lane = lane_id();
+    const int64_t per_cta = (T + kSelectCluster - 1) / kSelectCluster;
+    const int64_t first = static_cast<int64_t>(rank) * per_cta;
+    const int n = static_cast<int>(max(static_cast<int64_t>(0), min(T, first + per_cta) - first));
+    for (int i = tid; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0u;
+    if (tid == 0) s_min = 0xffffffffu;
+    for (int i = tid; i < n; i += blockDim.x) s_keys[i] = float_to_key(__ldg(errs + first + i));       // all loads in flight at once
+    __syncthreads();
+    // the selection state lives in registers: every thread of every CTA derives the same values from the summed histograms
+    uint32_t prefix = 0u;
+    unsigned long long k = static_cast<unsigned long long>(rank_lo), below = 0ull, equal = 0ull;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const uint32_t decided = pass == 0 ? 0u : ~((1u << (shift + 8)) - 1u);
+        // whole warps iterate together (warp_hist_add is a full-warp operation)
+        for (int i0 = tid - lane; i0 < n; i0 += blockDim.x) {
+            const int i = i0 + lane;
+            const bool in = i < n;
+            const uint32_t key = in ? s_keys[i] : 0u;
+            warp_hist_add(s_hist[pass], (key >> shift) & 0xffu, in && (key & decided) == (prefix & decided));
+        }
+        if (tid == 0) s_digit = 256;
+        cluster.sync();                                   // every CTA's histogram of this pass is complete and visible
+        unsigned long long incl = 0ull;
+        if (tid < 256) {
+#pragma unroll
+            for (int r = 0; r < kSelectCluster; ++r) incl += *cluster.map_shared_rank(&s_hist[pass][tid], r);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {            // inclusive scan of the 256 bins: warp scans, then the warp totals
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) s_warp_tot[tid >> 5] = incl;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            for (int w = 0; w < (tid >> 5); ++w) incl += s_warp_tot[w];
+            s_cum[tid] = incl;
+            if (incl > k) atomicMin(&s_digit, tid);
+        }
+        __syncthreads();
+        int d = s_digit;
+        if (d == 256) d = 255;                            // rank beyond the data; keeps the state well defined
+        const unsigned long long cum = d > 0 ? s_cum[d - 1] : 0ull;
+        prefix |= static_cast<uint32_t>(d) << shift;
+        equal = s_cum[d] - cum;
+        k -= cum;
+        below += cum;
+        __syncthreads();                                  // s_cum / s_digit / s_warp_tot are rewritten by the next pass
+    }
+    uint32_t local_min = 0xffffffffu;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const uint32_t key = s_keys[i];
+        if (key > prefix && key < local_min) local_min = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, local_min, o);
+        local_min = other < local_min ? other : local_min;
+    }
+    if (lane == 0 && local_min != 0xffffffffu) atomicMin(&s_min, local_min);
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+        uint32_t min_gt = 0xffffffffu;
+        for (int r = 0; r < kSelectCluster; ++r) {
+            const uint32_t v = *cluster.map_shared_rank(&s_min, r);
+            min_gt = v < min_gt ? v : min_gt;
+        }
+        // both order statistics are known (same rules as the last pass of select_pass_kernel)
+        const float s_lo = key_to_float(prefix);
+        float s_hi = s_lo;
+        const unsigned long long next_rank = static_cast<unsigned long long>(rank_lo) + 1ull;
+        if (next_rank >= below + equal && next_rank < static_cast<unsigned long long>(T)) s_hi = key_to_float(min_gt);
+        const float diff = __fsub_rn(s_hi, s_lo);
+        float thr = __fadd_rn(s_lo, __fmul_rn(diff, gamma));
+        if (gamma >= 0.5f) thr = __fsub_rn(s_hi, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+        summary->threshold = thr;
+        summary->s_lo = s_lo;
+        summary->s_hi = s_hi;
+    }
+    cluster.sync();                                       // nobody leaves while CTA 0 still reads its neighbours' minima
+}
+
+__global__ void __launch_bounds__(kSelectClusterThreads) select_cluster_kernel(const float *__restrict__ errs, int64_t T, int64_t rank_lo,
+                                                                              float gamma, cppf_backvote_summary *__restrict__ summary) {
+    select_cluster_body(errs, T, rank_lo, gamma, summary);
+}
+
+// cluster launch (kSelectCluster CTAs along x), with the frame path's programmatic-dependent-launch attribute when asked for
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_select_cluster(void (*kernel)(KArgs...), int jobs, size_t smem, bool pdl, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kSelectCluster, jobs);
+    cfg.blockDim = dim3(kSelectClusterThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2]{};
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kSelectCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && frame_pdl_enabled()) ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// CPPF_SELECT_CLUSTER=0 keeps the single-CTA form (A/B measurements)
+static bool select_cluster_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("CPPF_SELECT_CLUSTER");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 // dynamic shared memory of the cached form for up to T keys (0: the keys do not fit, sweep L2)
 static size_t select_cache_bytes(int64_t T) { return T <= kSelectCachedMax ? static_cast<size_t>(T) * sizeof(uint32_t) : 0; }
 
@@ -366,6 +510,14 @@ CPPF_API int cppf_backvote_select(const float *errs, int64_t T, int64_t rank_lo,
     if (!errs || !summary || !ws || T <= 0 || rank_lo < 0 || rank_lo >= T) return CPPF_ERR_INVALID_ARGUMENT;
     if (ws_bytes < cppf_backvote_workspace_bytes(T, 0)) return CPPF_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (T <= kSelectSmallMax && select_cluster_enabled()) {
+        const size_t cache = select_cluster_cache_bytes(T);
+        if (cache > 48 * 1024)
+            CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          static_cast<int>(select_cluster_cache_bytes(kSelectSmallMax))));
+        CPPF_CUDA_TRY(launch_select_cluster(select_cluster_kernel, 1, cache, false, s, errs, T, rank_lo, gamma, summary));
+        return CPPF_OK;
+    }
     if (T <= kSelectSmallMax) {
         const size_t cache = select_cache_bytes(T);
         if (cache > 48 * 1024)
@@ -448,6 +600,15 @@ __global__ void __launch_bounds__(1024) frame_select_kernel(const FrameTable *__
     else select_small_body<false>(j.errs, in.T, j.rank_lo, j.gamma, j.summary);
 }
 
+__global__ void __launch_bounds__(kSelectClusterThreads) frame_select_cluster_kernel(const FrameTable *__restrict__ t) {
+    pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
+    if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;          // the whole cluster of a job leaves together
+    const FrameJob &j = t->job[blockIdx.y];
+    const FrameInst &in = t->inst[j.inst];
+    if (in.T <= 0) return;
+    select_cluster_body(j.errs, in.T, j.rank_lo, j.gamma, j.summary);
+}
+
 __global__ void __launch_bounds__(256) frame_backvote_mask_kernel(const FrameTable *__restrict__ t) {
     pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
@@ -463,11 +624,19 @@ int frame_launch_backvote(const FrameTable *t, int nj, int64_t T_cap, cudaStream
     if (T_cap > kSelectSmallMax) return CPPF_ERR_UNSUPPORTED;      // the single-CTA selection; larger T: the per-job path
     const int per_job = std::max(1, std::min<int>(div_up(T_cap, 256), (device_info().sm_count * 8 + nj - 1) / nj));
     CPPF_CUDA_TRY(launch_frame_kernel(frame_backvote_errors_kernel, dim3(per_job, nj), dim3(256), 0, s, t));
-    const size_t cache = select_cache_bytes(T_cap);
-    if (cache > 48 * 1024)
-        CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(frame_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                      static_cast<int>(kSelectCachedMax * sizeof(uint32_t))));
-    CPPF_CUDA_TRY(launch_frame_kernel(frame_select_kernel, dim3(nj), dim3(1024), cache, s, t, cache ? 1 : 0));
+    if (select_cluster_enabled()) {
+        const size_t cache = select_cluster_cache_bytes(T_cap);
+        if (cache > 48 * 1024)
+            CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(frame_select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          static_cast<int>(select_cluster_cache_bytes(kSelectSmallMax))));
+        CPPF_CUDA_TRY(launch_select_cluster(frame_select_cluster_kernel, nj, cache, true, s, t));
+    } else {
+        const size_t cache = select_cache_bytes(T_cap);
+        if (cache > 48 * 1024)
+            CPPF_TRY_ONCE_PER_DEVICE(cudaFuncSetAttribute(frame_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          static_cast<int>(kSelectCachedMax * sizeof(uint32_t))));
+        CPPF_CUDA_TRY(launch_frame_kernel(frame_select_kernel, dim3(nj), dim3(1024), cache, s, t, cache ? 1 : 0));
+    }
     CPPF_CUDA_TRY(launch_frame_kernel(frame_backvote_mask_kernel, dim3(per_job, nj), dim3(256), 0, s, t));
     return CPPF_OK;
 }

@@ -31,6 +31,7 @@ struct ShotWorkspace {
     ShotGrid *grid;
     int *cell_of, *cell_count, *cell_start, *cell_fill;
     float4 *sorted, *normals_sorted;
+    double *lrf;         // [n][8] per sorted position: scatter matrix (6), weight sum, counts -> LRF axes (shot.cu, kLrf*)
 };
 
 size_t shot_carve(void *ws, int64_t n, ShotWorkspace *out);

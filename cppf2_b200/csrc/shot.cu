@@ -403,21 +403,96 @@ __device__ void jacobi_eigen3(const double Ain[6] /* xx xy xz yy yz zz */, doubl
     for (int i = 0; i < 9; ++i) V[i] = Vs[i];
 }
 
-// ---- LRF + SHOT352 histogram ----------------------------------------------------------------------------
+// ---- LRF (shot_lrf.hpp::getLocalRF) in three stages -------------------------------------------------------------
+// The eigen-solve is scalar work: inside the one-warp-per-key-point kernel all 32 lanes repeated it (~3 000 of the ~8 100
+// warp instructions a key-point cost, ncu + SASS count of the sweep body).  It now runs one THREAD per key-point between
+// two warp-per-key-point kernels; the scatter matrix and the axes cross in `lrf`, 8 doubles per sorted position:
+//   after shot_lrf_cov_point:   [0..5] weighted scatter matrix (xx xy xz yy yz zz, not yet divided), [6] weight sum,
+//                               [7] bits: valid | total << 32 (neighbours that are not the key-point itself | all in radius)
+//   after shot_lrf_solve_one:   [0..2] eigenvector of the largest eigenvalue (x axis before sign disambiguation),
+//                               [3..5] of the smallest (z axis), [6] 1.0 if the frame is usable else 0.0, [7] unchanged
+// Same operations in the same order as the fused form, so descriptors are unchanged bit for bit.
+constexpr int kLrfStride = 8;
+
+// stage 1 (one warp): weighted scatter matrix in double
+__device__ __forceinline__ void shot_lrf_cov_point(const ShotGrid &g, const int *__restrict__ cell_start,
+                                                   const float4 *__restrict__ sorted, double radius, double *__restrict__ lrf,
+                                                   int s, int lane) {
+    const float radius_sq = static_cast<float>(radius * radius);
+    const float4 pq = sorted[s];
+    const float p[3] = {pq.x, pq.y, pq.z};
+    double cov[6] = {0, 0, 0, 0, 0, 0}, wsum = 0.0;
+    int valid = 0, total = 0;
+    for_each_candidate(g, cell_start, sorted, p, lane, [&](int, const float4 &q) {
+        const float d2 = flann_dist2(p, q);
+        if (d2 < radius_sq) {
+            ++total;
+            if (!(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
+                const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
+                             vz = static_cast<double>(__fsub_rn(q.z, p[2]));
+                const double w = radius - sqrt(static_cast<double>(d2));
+                cov[0] += w * (vx * vx);
+                cov[1] += w * (vx * vy);
+                cov[2] += w * (vx * vz);
+                cov[3] += w * (vy * vy);
+                cov[4] += w * (vy * vz);
+                cov[5] += w * (vz * vz);
+                wsum += w;
+                ++valid;
+            }
+        }
+    });
+#pragma unroll
+    for (int i = 0; i < 6; ++i) cov[i] = warp_sum(cov[i]);
+    wsum = warp_sum(wsum);
+    valid = warp_sum(valid);
+    total = warp_sum(total);
+    // lanes 0..7 write one double each (one 64-byte row)
+    const long long counts = static_cast<long long>(static_cast<unsigned int>(valid)) | (static_cast<long long>(total) << 32);
+    double v = __longlong_as_double(counts);
+    v = lane == 6 ? wsum : v;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v = lane == i ? cov[i] : v;
+    if (lane < kLrfStride) lrf[static_cast<size_t>(s) * kLrfStride + lane] = v;
+}
+
+// stage 2 (one thread): normalise, eigen-solve, keep the two axes
+__device__ __forceinline__ void shot_lrf_solve_one(double *__restrict__ row) {
+    const long long counts = __double_as_longlong(row[7]);
+    const int valid = static_cast<int>(counts & 0xffffffffll), total = static_cast<int>(counts >> 32);
+    bool ok = valid >= 5 && total >= 5;
+    if (ok) {
+        const double wsum = row[6];
+        double cov[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cov[i] = row[i] / wsum;
+        double w[3], V[9];
+        jacobi_eigen3(cov, w, V);
+        ok = isfinite(w[0]) && isfinite(w[1]) && isfinite(w[2]);
+        row[0] = V[2];  // largest eigenvalue  -> x
+        row[1] = V[5];
+        row[2] = V[8];
+        row[3] = V[0];  // smallest eigenvalue -> z
+        row[4] = V[3];
+        row[5] = V[6];
+    }
+    row[6] = ok ? 1.0 : 0.0;
+}
+
+// ---- stage 3: sign disambiguation + SHOT352 histogram --------------------------------------------------------------
 // REAL = double reproduces PCL's double interpolation weights; REAL = float evaluates acos/atan2 and the
 // weights in float (SHOT's quadrilinear interpolation is continuous across every bin boundary, so the
 // descriptor moves by ~1e-7).
-// SHOT-352 row of the point at sorted position s (one warp): LRF (shot_lrf.hpp::getLocalRF) + histogram (shot.hpp).
+// SHOT-352 row of the point at sorted position s (one warp): LRF signs (shot_lrf.hpp::getLocalRF) + histogram (shot.hpp).
 // hist [352] and list [kShotListCap] are this warp's shared-memory scratch.
 template <typename REAL>
 __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const int *__restrict__ cell_start,
                                                       const float4 *__restrict__ sorted, const float4 *__restrict__ normals_sorted,
-                                                      float radius_f, double radius, float *__restrict__ desc,
+                                                      const double *__restrict__ lrf, double radius, float *__restrict__ desc,
                                                       float *__restrict__ rf_out, unsigned int *hist, int *list, int s, int lane) {
     const float radius_sq = static_cast<float>(radius * radius);
     float hist_scale = 1.0f;
     auto hist_add = [&](int bin_index, float v) { atomicAdd(&hist[bin_index], __float2uint_rn(v * hist_scale)); };
-    (void)radius_f;
     const REAL r12 = static_cast<REAL>(radius / 2), r14 = static_cast<REAL>(radius / 4), r34 = static_cast<REAL>((radius * 3) / 4);
     const REAL RAD_45 = static_cast<REAL>(0.78539816339744830961566084581988);
     const REAL RAD_90 = static_cast<REAL>(1.5707963267948966192313216916398);
@@ -429,9 +504,17 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
     const int orig = __float_as_int(pq.w);
     float *out = desc + static_cast<size_t>(orig) * CPPF_SHOT_DIM;
 
-    // pass A: weighted scatter matrix in double (shot_lrf.hpp::getLocalRF)
-    double cov[6] = {0, 0, 0, 0, 0, 0}, wsum = 0.0;
-    int valid = 0, total = 0;
+    const double *row = lrf + static_cast<size_t>(s) * kLrfStride;   // warp-uniform loads
+    const bool ok = row[6] != 0.0;
+    const long long counts = __double_as_longlong(row[7]);
+    const int valid = static_cast<int>(counts & 0xffffffffll), total = static_cast<int>(counts >> 32);
+    if (!ok) {  // invalid LRF or fewer than 5 neighbours: NaN row (shot.hpp::computeFeature / computePointSHOT)
+        if (rf_out && lane < 9) rf_out[static_cast<size_t>(orig) * 9 + lane] = CUDART_NAN_F;
+        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) out[j] = CUDART_NAN_F;
+        return;
+    }
+
+    // the in-radius neighbours, in sweep order (positions in the sorted array)
     int n_list = 0;                                  // warp-uniform
     {
         const int cx = shot_coord(p[0], g.lo[0], g.inv, g.dim[0]);
@@ -440,32 +523,11 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
         const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
         for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x)
             for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
-                const int row = (x * g.dim[1] + y) * g.dim[2];
-                const int b = cell_start[row + z0], e = cell_start[row + z1 + 1];  // z-neighbours are contiguous
+                const int crow = (x * g.dim[1] + y) * g.dim[2];
+                const int b = cell_start[crow + z0], e = cell_start[crow + z1 + 1];  // z-neighbours are contiguous
                 for (int j0 = b; j0 < e; j0 += 32) {     // same visiting order as for_each_candidate, whole warp converged
                     const int j = j0 + lane;
-                    bool hit = false;
-                    if (j < e) {
-                        const float4 q = sorted[j];
-                        const float d2 = flann_dist2(p, q);
-                        if (d2 < radius_sq) {
-                            hit = true;
-                            ++total;
-                            if (!(q.x == p[0] && q.y == p[1] && q.z == p[2])) {
-                                const double vx = static_cast<double>(__fsub_rn(q.x, p[0])), vy = static_cast<double>(__fsub_rn(q.y, p[1])),
-                                             vz = static_cast<double>(__fsub_rn(q.z, p[2]));
-                                const double w = radius - sqrt(static_cast<double>(d2));
-                                cov[0] += w * (vx * vx);
-                                cov[1] += w * (vx * vy);
-                                cov[2] += w * (vx * vz);
-                                cov[3] += w * (vy * vy);
-                                cov[4] += w * (vy * vz);
-                                cov[5] += w * (vz * vz);
-                                wsum += w;
-                                ++valid;
-                            }
-                        }
-                    }
+                    const bool hit = j < e && flann_dist2(p, sorted[j]) < radius_sq;
                     const unsigned m = __ballot_sync(0xffffffffu, hit);
                     if (m) {
                         const int pos = n_list + __popc(m & ((1u << lane) - 1u));
@@ -488,22 +550,11 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
             for_each_candidate(g, cell_start, sorted, p, lane, f);
         }
     };
-#pragma unroll
-    for (int i = 0; i < 6; ++i) cov[i] = warp_sum(cov[i]);
-    wsum = warp_sum(wsum);
-    valid = warp_sum(valid);
-    total = warp_sum(total);
 
-    bool ok = valid >= 5 && total >= 5;
     float fx[3], fy[3], fz[3];
-    if (ok) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) cov[i] /= wsum;
-        double w[3], V[9];
-        jacobi_eigen3(cov, w, V);
-        ok = isfinite(w[0]) && isfinite(w[1]) && isfinite(w[2]);
-        double v1[3] = {V[2], V[5], V[8]};  // largest eigenvalue  -> x
-        double v3[3] = {V[0], V[3], V[6]};  // smallest eigenvalue -> z
+    {
+        double v1[3] = {row[0], row[1], row[2]};
+        double v3[3] = {row[3], row[4], row[5]};
         // pass B: sign disambiguation votes
         int plus_t = 0, plus_n = 0;
         for_each_neighbour([&](int, const float4 &q) {
@@ -528,12 +579,8 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
         cross3f(fz, fx, fy);
     }
     if (rf_out && lane < 9) {
-        const float v = !ok ? CUDART_NAN_F : (lane < 3 ? fx[lane] : (lane < 6 ? fy[lane - 3] : fz[lane - 6]));
+        const float v = lane < 3 ? fx[lane] : (lane < 6 ? fy[lane - 3] : fz[lane - 6]);
         rf_out[static_cast<size_t>(orig) * 9 + lane] = v;
-    }
-    if (!ok) {  // invalid LRF or fewer than 5 neighbours: NaN row (shot.hpp::computeFeature / computePointSHOT)
-        for (int j = lane; j < CPPF_SHOT_DIM; j += 32) out[j] = CUDART_NAN_F;
-        return;
     }
 
     // pass C: histogram (shot.hpp::createBinDistanceShape + interpolateSingleChannel)
@@ -635,9 +682,10 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
     // normalizeHistogram: float squares accumulated in double, divide by float(norm)
     double acc = 0.0;
     float hv[CPPF_SHOT_DIM / 32];
+    const double inv_scale = 1.0 / static_cast<double>(hist_scale);      // a power of two: the product below is the exact quotient
 #pragma unroll
     for (int u = 0; u < CPPF_SHOT_DIM / 32; ++u) {
-        hv[u] = static_cast<float>(static_cast<double>(hist[lane + 32 * u]) / static_cast<double>(hist_scale));
+        hv[u] = static_cast<float>(static_cast<double>(hist[lane + 32 * u]) * inv_scale);
         acc += static_cast<double>(hv[u] * hv[u]);
     }
     acc = warp_sum(acc);
@@ -647,11 +695,29 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
     __syncwarp();
 }
 
+__global__ void __launch_bounds__(kShotWarps * 32) shot_lrf_cov_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
+                                                                      const float4 *__restrict__ sorted, double radius,
+                                                                      double *__restrict__ lrf) {
+    const ShotGrid g = *gp;
+    const int n_sorted = cell_start[g.cells];
+    const int lane = lane_id();
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_sorted; s += n_warps)
+        shot_lrf_cov_point(g, cell_start, sorted, radius, lrf, s, lane);
+}
+
+__global__ void __launch_bounds__(64) shot_lrf_solve_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
+                                                            double *__restrict__ lrf) {
+    const int n_sorted = cell_start[gp->cells];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_sorted) shot_lrf_solve_one(lrf + static_cast<size_t>(s) * kLrfStride);
+}
+
 template <typename REAL>
-__device__ __forceinline__ void shot_descriptor_body(
+__global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
     const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
-    const float4 *__restrict__ normals_sorted, float radius_f, double radius, float *__restrict__ desc,
-    float *__restrict__ rf_out, int bid, int nblk) {
+    const float4 *__restrict__ normals_sorted, const double *__restrict__ lrf, double radius, float *__restrict__ desc,
+    float *__restrict__ rf_out) {
     // The histogram accumulates in 32-bit fixed point: shared-memory float atomicAdd is a compare-and-swap loop (60 % of this
     // kernel's stall samples, ncu; so is the 64-bit integer add), the 32-bit integer add is one native ATOMS.ADD.  A neighbour
     // adds at most 5 over all bins, so with `total` neighbours a scale of 2^k, k = 32 - bits(5 total + 1) (<= 24), cannot
@@ -659,25 +725,16 @@ __device__ __forceinline__ void shot_descriptor_body(
     // the sum itself is exact, hence independent of the order the lanes arrive in and identical from run to run (PCL adds in
     // float in kd-tree order, which nothing pins either).
     __shared__ unsigned int s_hist[kShotWarps][CPPF_SHOT_DIM];
-    // in-radius neighbours found by pass A (positions in the sorted array, sweep order): passes B and C walk this list
+    // in-radius neighbours (positions in the sorted array, sweep order): the sign votes and the histogram walk this list
     // instead of sweeping the 27 cells again -- a surface sampled at radius/10 has ~270 neighbours among ~900 candidates
     __shared__ int s_list[kShotWarps][kShotListCap];
     const ShotGrid g = *gp;
     const int n_sorted = cell_start[g.cells];
     const int lane = lane_id();
     const int wib = threadIdx.x >> 5;
-    const int warp = (bid * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (nblk * blockDim.x) >> 5;
-    for (int s = warp; s < n_sorted; s += n_warps)
-        shot_descriptor_point<REAL>(g, cell_start, sorted, normals_sorted, radius_f, radius, desc, rf_out, s_hist[wib], s_list[wib], s, lane);
-}
-
-template <typename REAL>
-__global__ void __launch_bounds__(kShotWarps * 32) shot_descriptor_kernel(
-    const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
-    const float4 *__restrict__ normals_sorted, float radius_f, double radius, float *__restrict__ desc,
-    float *__restrict__ rf_out) {
-    shot_descriptor_body<REAL>(gp, cell_start, sorted, normals_sorted, radius_f, radius, desc, rf_out, blockIdx.x, gridDim.x);
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_sorted; s += n_warps)
+        shot_descriptor_point<REAL>(g, cell_start, sorted, normals_sorted, lrf, radius, desc, rf_out, s_hist[wib], s_list[wib], s, lane);
 }
 
 // normals_sorted[s] = normals_in[orig(s)]: used when the caller supplies the normals
@@ -711,6 +768,7 @@ size_t shot_carve(void *ws, int64_t n, ShotWorkspace *out) {
     w.cell_of = static_cast<int *>(take(sizeof(int) * static_cast<size_t>(n)));
     w.sorted = static_cast<float4 *>(take(sizeof(float4) * static_cast<size_t>(n)));
     w.normals_sorted = static_cast<float4 *>(take(sizeof(float4) * static_cast<size_t>(n)));
+    w.lrf = static_cast<double *>(take(sizeof(double) * kLrfStride * static_cast<size_t>(n)));
     if (out) *out = w;
     return off;
 }
@@ -735,7 +793,7 @@ static int shot_build_grid(const float *pc, int64_t n, float radius, const ShotW
 }
 
 // =====================================================================================================================
-// Batched frame path (frame.cuh): SHOT-352 + normals of every instance of a frame in seven launches; blockIdx.y = instance.
+// Batched frame path (frame.cuh): SHOT-352 + normals of every instance of a frame in nine launches; blockIdx.y = instance.
 // Same bodies as the single-cloud kernels, so descriptors are identical to cppf_shot_compute_ex(fast_math = 1).
 // =====================================================================================================================
 __device__ __forceinline__ bool frame_shot_instance(const FrameTable *t, const FrameInst *&in) {
@@ -814,7 +872,30 @@ __global__ void __launch_bounds__(kShotWarps * 32) frame_shot_normals_kernel(con
     }
 }
 
-__global__ void __launch_bounds__(kShotWarps * 32, 3) frame_shot_descriptor_kernel(const FrameTable *__restrict__ t) {
+// LRF stage 1 (warp per flat position) and stage 2 (thread per flat position)
+__global__ void __launch_bounds__(kShotWarps * 32) frame_shot_lrf_cov_kernel(const FrameTable *__restrict__ t) {
+    const int total = t->shot_base[t->n_inst];
+    const int lane = lane_id();
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total; g += (gridDim.x * blockDim.x) >> 5) {
+        int s;
+        const FrameInst &in = t->inst[frame_shot_locate(t, g, s)];
+        const ShotGrid gr = *in.sw.grid;
+        if (s >= in.sw.cell_start[gr.cells]) continue;
+        shot_lrf_cov_point(gr, in.sw.cell_start, in.sw.sorted, static_cast<double>(in.shot_r), in.sw.lrf, s, lane);
+    }
+}
+
+__global__ void __launch_bounds__(64) frame_shot_lrf_solve_kernel(const FrameTable *__restrict__ t) {
+    const int total = t->shot_base[t->n_inst];
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+        int s;
+        const FrameInst &in = t->inst[frame_shot_locate(t, g, s)];
+        if (s >= in.sw.cell_start[in.sw.grid->cells]) continue;
+        shot_lrf_solve_one(in.sw.lrf + static_cast<size_t>(s) * kLrfStride);
+    }
+}
+
+__global__ void __launch_bounds__(kShotWarps * 32, 4) frame_shot_descriptor_kernel(const FrameTable *__restrict__ t) {
     __shared__ unsigned int s_hist[kShotWarps][CPPF_SHOT_DIM];
     __shared__ int s_list[kShotWarps][kShotListCap];
     const int total = t->shot_base[t->n_inst];
@@ -824,12 +905,12 @@ __global__ void __launch_bounds__(kShotWarps * 32, 3) frame_shot_descriptor_kern
         const FrameInst &in = t->inst[frame_shot_locate(t, g, s)];
         const ShotGrid gr = *in.sw.grid;
         if (s >= in.sw.cell_start[gr.cells]) continue;
-        shot_descriptor_point<float>(gr, in.sw.cell_start, in.sw.sorted, in.sw.normals_sorted, in.shot_r, static_cast<double>(in.shot_r),
+        shot_descriptor_point<float>(gr, in.sw.cell_start, in.sw.sorted, in.sw.normals_sorted, in.sw.lrf, static_cast<double>(in.shot_r),
                                      in.shot_desc, nullptr, s_hist[wib], s_list[wib], s, lane);
     }
 }
 
-// Plain stream-ordered launches: with programmatic dependent launch (common.cuh) along these seven kernels the stage was
+// Plain stream-ordered launches: with programmatic dependent launch (common.cuh) along these kernels the stage was
 // slower on B200 (0.294 against 0.277 ms per frame), unlike the vote chain's.
 int frame_launch_shot(const FrameTable *t, int ni, int64_t n_cap, cudaStream_t s) {
     if (ni <= 0 || n_cap <= 0) return CPPF_OK;
@@ -854,7 +935,11 @@ int frame_launch_shot(const FrameTable *t, int ni, int64_t n_cap, cudaStream_t s
     const int64_t warps_cap = n_cap * ni;
     frame_shot_normals_kernel<<<dim3(grid_for(warps_cap * 32, kShotWarps * 32, 8)), kShotWarps * 32, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
-    frame_shot_descriptor_kernel<<<dim3(grid_for(warps_cap * 32, kShotWarps * 32, 3)), kShotWarps * 32, 0, s>>>(t);
+    frame_shot_lrf_cov_kernel<<<dim3(grid_for(warps_cap * 32, kShotWarps * 32, 8)), kShotWarps * 32, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_shot_lrf_solve_kernel<<<dim3(static_cast<int>(std::min<int64_t>(div_up(warps_cap, 64), sms * 32))), 64, 0, s>>>(t);
+    CPPF_LAUNCH_CHECK();
+    frame_shot_descriptor_kernel<<<dim3(grid_for(warps_cap * 32, kShotWarps * 32, 4)), kShotWarps * 32, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }
@@ -897,13 +982,18 @@ static int shot_run(const float *pc, int64_t n, float normal_r, float shot_r, fl
         CPPF_LAUNCH_CHECK();
     }
     if (!desc) return CPPF_OK;
+    shot_lrf_cov_kernel<<<grid_for(n * 32, kShotWarps * 32, 8), kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted,
+                                                                                        static_cast<double>(shot_r), w.lrf);
+    CPPF_LAUNCH_CHECK();
+    shot_lrf_solve_kernel<<<div_up(n, 64), 64, 0, s>>>(w.grid, w.cell_start, w.lrf);
+    CPPF_LAUNCH_CHECK();
     const int dblocks = grid_for(n * 32, kShotWarps * 32, 4);
     if (fast_math)
-        shot_descriptor_kernel<float><<<dblocks, kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted, w.normals_sorted,
-                                                                         shot_r, static_cast<double>(shot_r), desc, rf_out);
+        shot_descriptor_kernel<float><<<dblocks, kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted, w.normals_sorted, w.lrf,
+                                                                         static_cast<double>(shot_r), desc, rf_out);
     else
-        shot_descriptor_kernel<double><<<dblocks, kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted, w.normals_sorted,
-                                                                          shot_r, static_cast<double>(shot_r), desc, rf_out);
+        shot_descriptor_kernel<double><<<dblocks, kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted, w.normals_sorted, w.lrf,
+                                                                          static_cast<double>(shot_r), desc, rf_out);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }

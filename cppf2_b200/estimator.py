@@ -367,8 +367,8 @@ class PoseEstimator:
         self._tables[3][k] = ev
         self._frame_live = keep
         n_jobs = sum(len(p["slots"]) for p in plan)
-        # sample (1) + SHOT (7) + heads (2 per branch run) + centre (4) + back-vote (3) + rotation (1) + pose (2 or 3), + the table copy
-        self.launches = 1 + (7 if any_shot is not None else 0) + 2 * ((any_dino is not None) + (any_shot is not None)) + 4 + 3 + 1 + \
+        # sample (1) + SHOT (9) + heads (2 per branch run) + centre (4) + back-vote (3) + rotation (1) + pose (2 or 3), + the table copy
+        self.launches = 1 + (9 if any_shot is not None else 0) + 2 * ((any_dino is not None) + (any_shot is not None)) + 4 + 3 + 1 + \
             (3 if self.opt else 2) + 1 if n_jobs else 0
         return plan
 
@@ -450,7 +450,7 @@ class PoseEstimator:
         if sh is not None:
             slots["shot"] = 2 * i + 1
         chain = (18 if T <= (1 << 17) else 24) + (1 if self.opt else 0)       # PoseVoter.vote_bins' count
-        return (9 if sh is not None else 0) + (2 + chain) * len(slots), slots
+        return (11 if sh is not None else 0) + (2 + chain) * len(slots), slots
 
     def _enqueue_instance(self, i: int, inst: Instance, pose_buf: torch.Tensor, draws, st):
         voter = self.voters[i % self.n_streams]
@@ -479,7 +479,7 @@ class PoseEstimator:
         self._mark("shot", True)
         desc352, normals = shot.compute_device(pc, vc.res * 10, vc.res * 10)      # eval.py:210
         self._mark("shot", False)
-        launches += 9
+        launches += 11
         slots = {}
         scale_from_dino = None
         for b, branch in enumerate(("dino", "shot")):                              # eval.py:219
