@@ -128,22 +128,40 @@ __global__ void __launch_bounds__(256) shot_scatter_kernel(const float *__restri
 // point of a cell by its original index (one warp per cell, counting sort by comparison: segments hold
 // ~100 points when the cloud is voxel-sampled at radius/10 as the reference does) so that the sorted copy,
 // and with it every floating-point accumulation order downstream, is deterministic.
+constexpr int kOrderStage = 256;                 // keys of one cell staged in shared memory per warp (more: read from L2)
+
 __device__ __forceinline__ void shot_cell_order_body(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
                                                      const float4 *__restrict__ scattered, float4 *__restrict__ sorted,
                                                      int bid, int nblk) {
+    // the original indices of the cell's points, staged once: the rank loop then reads shared-memory broadcasts instead of
+    // issuing a dependent 16-byte L2 load per comparison
+    __shared__ int s_key[8][kOrderStage];
+    int *keys = s_key[(threadIdx.x >> 5) & 7];
     const int cells = gp->cells;
     const int lane = lane_id();
     const int warp = (bid * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (nblk * blockDim.x) >> 5;
     for (int c = warp; c < cells; c += n_warps) {
         const int b = cell_start[c], e = cell_start[c + 1];
+        const int k = e - b;
+        if (k <= 0) continue;
+        const bool staged = k <= kOrderStage;
+        if (staged)
+            for (int u = lane; u < k; u += 32) keys[u] = __float_as_int(scattered[b + u].w);
+        __syncwarp();
         for (int t = b + lane; t < e; t += 32) {
             const float4 mine = scattered[t];
             const int key = __float_as_int(mine.w);
             int rank = 0;
-            for (int u = b; u < e; ++u) rank += (__float_as_int(scattered[u].w) < key) ? 1 : 0;
+            if (staged) {
+#pragma unroll 4
+                for (int u = 0; u < k; ++u) rank += (keys[u] < key) ? 1 : 0;
+            } else {
+                for (int u = b; u < e; ++u) rank += (__float_as_int(scattered[u].w) < key) ? 1 : 0;
+            }
             sorted[b + rank] = mine;
         }
+        __syncwarp();                                 // the staging buffer is rewritten for the warp's next cell
     }
 }
 
@@ -414,16 +432,46 @@ __device__ void jacobi_eigen3(const double Ain[6] /* xx xy xz yy yz zz */, doubl
 // Same operations in the same order as the fused form, so descriptors are unchanged bit for bit.
 constexpr int kLrfStride = 8;
 
-// stage 1 (one warp): weighted scatter matrix in double
+// The in-radius neighbours of p in sweep order (positions in the sorted array) -> list[0 .. min(count, kShotListCap)); returns
+// the count (warp-uniform).  Whole warp converged; same visiting order as for_each_candidate.
+__device__ __forceinline__ int shot_neighbour_list(const ShotGrid &g, const int *__restrict__ cell_start,
+                                                   const float4 *__restrict__ sorted, const float p[3], float radius_sq, int *list,
+                                                   int lane) {
+    int n_list = 0;
+    const int cx = shot_coord(p[0], g.lo[0], g.inv, g.dim[0]);
+    const int cy = shot_coord(p[1], g.lo[1], g.inv, g.dim[1]);
+    const int cz = shot_coord(p[2], g.lo[2], g.inv, g.dim[2]);
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+    for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+            const int crow = (x * g.dim[1] + y) * g.dim[2];
+            const int b = cell_start[crow + z0], e = cell_start[crow + z1 + 1];  // z-neighbours are contiguous
+            for (int j0 = b; j0 < e; j0 += 32) {
+                const int j = j0 + lane;
+                const bool hit = j < e && flann_dist2(p, sorted[j]) < radius_sq;
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    const int pos = n_list + __popc(m & ((1u << lane) - 1u));
+                    if (hit && pos < kShotListCap) list[pos] = j;
+                    n_list += __popc(m);
+                }
+            }
+        }
+    __syncwarp();
+    return n_list;
+}
+
+// stage 1 (one warp): weighted scatter matrix in double.  The ~270 neighbours are first compacted out of the ~900 candidates
+// (list: this warp's shared-memory scratch), so the double-precision part runs on full warps (9 passes instead of 28 sparse ones).
 __device__ __forceinline__ void shot_lrf_cov_point(const ShotGrid &g, const int *__restrict__ cell_start,
                                                    const float4 *__restrict__ sorted, double radius, double *__restrict__ lrf,
-                                                   int s, int lane) {
+                                                   int *list, int s, int lane) {
     const float radius_sq = static_cast<float>(radius * radius);
     const float4 pq = sorted[s];
     const float p[3] = {pq.x, pq.y, pq.z};
     double cov[6] = {0, 0, 0, 0, 0, 0}, wsum = 0.0;
     int valid = 0, total = 0;
-    for_each_candidate(g, cell_start, sorted, p, lane, [&](int, const float4 &q) {
+    auto accumulate = [&](int, const float4 &q) {
         const float d2 = flann_dist2(p, q);
         if (d2 < radius_sq) {
             ++total;
@@ -441,7 +489,17 @@ __device__ __forceinline__ void shot_lrf_cov_point(const ShotGrid &g, const int 
                 ++valid;
             }
         }
-    });
+    };
+    const int n_list = shot_neighbour_list(g, cell_start, sorted, p, radius_sq, list, lane);
+    if (n_list <= kShotListCap) {
+        for (int k = lane; k < n_list; k += 32) {
+            const int j = list[k];
+            accumulate(j, sorted[j]);
+        }
+    } else {
+        for_each_candidate(g, cell_start, sorted, p, lane, accumulate);
+    }
+    __syncwarp();                                    // the list is rewritten for the warp's next key-point
 #pragma unroll
     for (int i = 0; i < 6; ++i) cov[i] = warp_sum(cov[i]);
     wsum = warp_sum(wsum);
@@ -493,11 +551,18 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
     const float radius_sq = static_cast<float>(radius * radius);
     float hist_scale = 1.0f;
     auto hist_add = [&](int bin_index, float v) { atomicAdd(&hist[bin_index], __float2uint_rn(v * hist_scale)); };
+    // REAL = float: quotients by the constants radius/2, 90 and 45 degrees become products with their reciprocals (<= 1 ulp of
+    // the weight, the documented ~1e-7 of this mode), and the double square root of a float is the float square root bit for bit
+    constexpr bool kFast = sizeof(REAL) == 4;
     const REAL r12 = static_cast<REAL>(radius / 2), r14 = static_cast<REAL>(radius / 4), r34 = static_cast<REAL>((radius * 3) / 4);
+    const REAL inv_r12 = REAL(1) / r12;
+    auto over = [&](REAL x, REAL c, REAL inv_c) { return kFast ? x * inv_c : x / c; };
     const REAL RAD_45 = static_cast<REAL>(0.78539816339744830961566084581988);
     const REAL RAD_90 = static_cast<REAL>(1.5707963267948966192313216916398);
     const REAL RAD_135 = static_cast<REAL>(2.3561944901923449288469825374596);
     const REAL RAD_7_8 = static_cast<REAL>(2.7488935718910690836548129603691);
+    const REAL INV_RAD_90 = static_cast<REAL>(1.0 / 1.5707963267948966192313216916398);
+    const REAL INV_RAD_45 = static_cast<REAL>(1.0 / 0.78539816339744830961566084581988);
 
     const float4 pq = sorted[s];
     const float p[3] = {pq.x, pq.y, pq.z};
@@ -515,29 +580,7 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
     }
 
     // the in-radius neighbours, in sweep order (positions in the sorted array)
-    int n_list = 0;                                  // warp-uniform
-    {
-        const int cx = shot_coord(p[0], g.lo[0], g.inv, g.dim[0]);
-        const int cy = shot_coord(p[1], g.lo[1], g.inv, g.dim[1]);
-        const int cz = shot_coord(p[2], g.lo[2], g.inv, g.dim[2]);
-        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
-        for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x)
-            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
-                const int crow = (x * g.dim[1] + y) * g.dim[2];
-                const int b = cell_start[crow + z0], e = cell_start[crow + z1 + 1];  // z-neighbours are contiguous
-                for (int j0 = b; j0 < e; j0 += 32) {     // same visiting order as for_each_candidate, whole warp converged
-                    const int j = j0 + lane;
-                    const bool hit = j < e && flann_dist2(p, sorted[j]) < radius_sq;
-                    const unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (m) {
-                        const int pos = n_list + __popc(m & ((1u << lane) - 1u));
-                        if (hit && pos < kShotListCap) list[pos] = j;
-                        n_list += __popc(m);
-                    }
-                }
-            }
-    }
-    __syncwarp();
+    const int n_list = shot_neighbour_list(g, cell_start, sorted, p, radius_sq, list, lane);     // warp-uniform
     const bool listed = n_list <= kShotListCap;
     // passes B and C: the cached neighbours when they fit, else the cells again
     auto for_each_neighbour = [&](auto &&f) {
@@ -600,7 +643,7 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
         cosine = cosine > REAL(1) ? REAL(1) : (cosine < REAL(-1) ? REAL(-1) : cosine);
         REAL bin = ((REAL(1) + cosine) * REAL(10)) / REAL(2);
         const float dl[3] = {__fsub_rn(q.x, p[0]), __fsub_rn(q.y, p[1]), __fsub_rn(q.z, p[2])};
-        const REAL distance = static_cast<REAL>(sqrt(static_cast<double>(d2)));
+        const REAL distance = kFast ? static_cast<REAL>(__fsqrt_rn(d2)) : static_cast<REAL>(sqrt(static_cast<double>(d2)));
         if (fabs(static_cast<double>(distance)) < 1e-15) return;
         REAL xr = static_cast<REAL>(dl[0] * fx[0] + dl[1] * fx[1] + dl[2] * fx[2]);
         REAL yr = static_cast<REAL>(dl[0] * fy[0] + dl[1] * fy[1] + dl[2] * fy[2]);
@@ -627,7 +670,7 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
         else
             hist_add(vol + ((step - 1 + 10) % 10), -static_cast<float>(bin));
         if (distance > r12) {
-            const REAL rd = (distance - r34) / r12;
+            const REAL rd = over(distance - r34, r12, inv_r12);
             if (distance > r34)
                 wgt += REAL(1) - rd;
             else {
@@ -635,7 +678,7 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
                 hist_add((di - 2) * 11 + step, -static_cast<float>(rd));
             }
         } else {
-            const REAL rd = (distance - r14) / r12;
+            const REAL rd = over(distance - r14, r12, inv_r12);
             if (distance < r14)
                 wgt += REAL(1) + rd;
             else {
@@ -647,7 +690,7 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
         ic = ic < REAL(-1) ? REAL(-1) : (ic > REAL(1) ? REAL(1) : ic);
         const REAL incl = acos(ic);
         if (incl > RAD_90 || (fabs(static_cast<double>(incl - RAD_90)) < 1e-30 && zr <= 0)) {
-            const REAL id = (incl - RAD_135) / RAD_90;
+            const REAL id = over(incl - RAD_135, RAD_90, INV_RAD_90);
             if (incl > RAD_135)
                 wgt += REAL(1) - id;
             else {
@@ -655,7 +698,7 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
                 hist_add((di + 1) * 11 + step, -static_cast<float>(id));
             }
         } else {
-            const REAL id = (incl - RAD_45) / RAD_90;
+            const REAL id = over(incl - RAD_45, RAD_90, INV_RAD_90);
             if (incl < RAD_45)
                 wgt += REAL(1) + id;
             else {
@@ -666,7 +709,7 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
         if (yr != 0 || xr != 0) {
             const REAL az = atan2(yr, xr);
             const int sel = di >> 2;
-            REAL ad = (az - (-RAD_7_8 + RAD_45 * static_cast<REAL>(sel))) / RAD_45;
+            REAL ad = over(az - (-RAD_7_8 + RAD_45 * static_cast<REAL>(sel)), RAD_45, INV_RAD_45);
             ad = ad < REAL(-0.5) ? REAL(-0.5) : (ad > REAL(0.5) ? REAL(0.5) : ad);
             if (ad > 0) {
                 wgt += REAL(1) - ad;
@@ -695,15 +738,16 @@ __device__ __forceinline__ void shot_descriptor_point(const ShotGrid &g, const i
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kShotWarps * 32) shot_lrf_cov_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
+__global__ void __launch_bounds__(kShotWarps * 32, 4) shot_lrf_cov_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
                                                                       const float4 *__restrict__ sorted, double radius,
                                                                       double *__restrict__ lrf) {
+    __shared__ int s_list[kShotWarps][kShotListCap];
     const ShotGrid g = *gp;
     const int n_sorted = cell_start[g.cells];
     const int lane = lane_id();
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_sorted; s += n_warps)
-        shot_lrf_cov_point(g, cell_start, sorted, radius, lrf, s, lane);
+        shot_lrf_cov_point(g, cell_start, sorted, radius, lrf, s_list[threadIdx.x >> 5], s, lane);
 }
 
 __global__ void __launch_bounds__(64) shot_lrf_solve_kernel(const ShotGrid *__restrict__ gp, const int *__restrict__ cell_start,
@@ -873,7 +917,8 @@ __global__ void __launch_bounds__(kShotWarps * 32) frame_shot_normals_kernel(con
 }
 
 // LRF stage 1 (warp per flat position) and stage 2 (thread per flat position)
-__global__ void __launch_bounds__(kShotWarps * 32) frame_shot_lrf_cov_kernel(const FrameTable *__restrict__ t) {
+__global__ void __launch_bounds__(kShotWarps * 32, 4) frame_shot_lrf_cov_kernel(const FrameTable *__restrict__ t) {
+    __shared__ int s_list[kShotWarps][kShotListCap];
     const int total = t->shot_base[t->n_inst];
     const int lane = lane_id();
     for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total; g += (gridDim.x * blockDim.x) >> 5) {
@@ -881,7 +926,7 @@ __global__ void __launch_bounds__(kShotWarps * 32) frame_shot_lrf_cov_kernel(con
         const FrameInst &in = t->inst[frame_shot_locate(t, g, s)];
         const ShotGrid gr = *in.sw.grid;
         if (s >= in.sw.cell_start[gr.cells]) continue;
-        shot_lrf_cov_point(gr, in.sw.cell_start, in.sw.sorted, static_cast<double>(in.shot_r), in.sw.lrf, s, lane);
+        shot_lrf_cov_point(gr, in.sw.cell_start, in.sw.sorted, static_cast<double>(in.shot_r), in.sw.lrf, s_list[threadIdx.x >> 5], s, lane);
     }
 }
 
@@ -935,7 +980,7 @@ int frame_launch_shot(const FrameTable *t, int ni, int64_t n_cap, cudaStream_t s
     const int64_t warps_cap = n_cap * ni;
     frame_shot_normals_kernel<<<dim3(grid_for(warps_cap * 32, kShotWarps * 32, 8)), kShotWarps * 32, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
-    frame_shot_lrf_cov_kernel<<<dim3(grid_for(warps_cap * 32, kShotWarps * 32, 8)), kShotWarps * 32, 0, s>>>(t);
+    frame_shot_lrf_cov_kernel<<<dim3(grid_for(warps_cap * 32, kShotWarps * 32, 4)), kShotWarps * 32, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
     frame_shot_lrf_solve_kernel<<<dim3(static_cast<int>(std::min<int64_t>(div_up(warps_cap, 64), sms * 32))), 64, 0, s>>>(t);
     CPPF_LAUNCH_CHECK();
@@ -982,7 +1027,7 @@ static int shot_run(const float *pc, int64_t n, float normal_r, float shot_r, fl
         CPPF_LAUNCH_CHECK();
     }
     if (!desc) return CPPF_OK;
-    shot_lrf_cov_kernel<<<grid_for(n * 32, kShotWarps * 32, 8), kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted,
+    shot_lrf_cov_kernel<<<grid_for(n * 32, kShotWarps * 32, 4), kShotWarps * 32, 0, s>>>(w.grid, w.cell_start, w.sorted,
                                                                                         static_cast<double>(shot_r), w.lrf);
     CPPF_LAUNCH_CHECK();
     shot_lrf_solve_kernel<<<div_up(n, 64), 64, 0, s>>>(w.grid, w.cell_start, w.lrf);
