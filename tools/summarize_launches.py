@@ -4,7 +4,7 @@ import sys
 from collections import defaultdict
 
 
-def main(path):
+def main(path, per_frame=None):
     rows = []
     with open(path, newline="") as f:
         lines = [ln for ln in f if not ln.startswith("==")]
@@ -23,7 +23,17 @@ def main(path):
     for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| `{k}` | {n} | {v:.1f} | {v / tot:.1%} |")
     print(f"| **all** | {len(rows)} | {tot:.1f} | 100% |")
+    if per_frame:
+        # the window is rarely a whole number of frames: per-frame view = mean duration of a launch x its launches per frame
+        frame = {k: v / n * per_frame.get(k.split("::")[-1].split("<")[0], 1) for k, (n, v) in agg.items() if "FillFunctor" not in k}
+        ftot = sum(frame.values())
+        print(f"\n| kernel | launches / frame | us / frame | share of the frame |\n|---|---:|---:|---:|")
+        for k, v in sorted(frame.items(), key=lambda kv: -kv[1]):
+            print(f"| `{k}` | {per_frame.get(k.split('::')[-1].split('<')[0], 1)} | {v:.1f} | {v / ftot:.1%} |")
+        print(f"| **frame** | | {ftot:.1f} | 100% |")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    # optional second argument: kernel=launches-per-frame pairs, e.g. chain_tc_kernel=4
+    pf = dict((a.split("=")[0], int(a.split("=")[1])) for a in sys.argv[2:])
+    main(sys.argv[1], pf or None)
