@@ -112,6 +112,7 @@ struct FrameTable {
 struct FrameShared {                    // identical for every job of a frame; passed by value
     int R, S, num_bins, band, lut_g, replicas_max;
     int vote_lanes;                     // centre vote: lane-per-tuple form (vote_center.cu; CPPF_VOTE_LANES=0: warp-per-tuple)
+    int rot_fast;                       // rotation vote: cheap lattice test with an exact slow path (rotation.cu; CPPF_ROT_FAST=0: exact only)
     float cos_thr;
     const uint2 *lut_cells;
     const float *cos_tab, *sin_tab, *sphere;
@@ -127,6 +128,7 @@ int frame_launch_heads(const FrameTable *t, const void *const *tc_states, int ni
 
 int frame_launch_center(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s);        // vote_center.cu
 int frame_launch_backvote(const FrameTable *t, int nj, int64_t T_cap, cudaStream_t s);                            // backvote.cu
+bool rotation_fast_enabled();                                                                                     // rotation.cu
 int frame_launch_rotation(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s);     // rotation.cu
 int frame_launch_pose(const FrameTable *t, int nj, int64_t T_cap, int any_refine, const FrameShared &sh, cudaStream_t s);  // pose.cu
 

@@ -15,6 +15,19 @@
 
 namespace cppf {
 
+// CPPF_ROT_FAST=0: every candidate is normalised and tested with the reference's arithmetic (A/B and fallback; lut_vote_fast)
+bool rotation_fast_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("CPPF_ROT_FAST");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+#ifndef CPPF_ROT_MINB
+#define CPPF_ROT_MINB 4      // resident CTAs per SM the frame kernel's registers are capped for (5: 48 registers with spills, measured in session 3)
+#endif
+
 struct RotFrame {
     float ab[3], x[3], y[3], tn, sg;
 };
@@ -28,13 +41,17 @@ __device__ __forceinline__ bool rotation_frame(const float a[3], const float b[3
     return true;
 }
 
-__device__ __forceinline__ void rotation_candidate(const RotFrame &f, float cr, float sr, float up[3]) {
-    float v[3];
+// the candidate direction before normalisation (train_dino.py:231-233)
+__device__ __forceinline__ void rotation_direction(const RotFrame &f, float cr, float sr, float v[3]) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float off = __fadd_rn(__fmul_rn(cr, f.x[k]), __fmul_rn(sr, f.y[k]));
         v[k] = __fadd_rn(__fmul_rn(f.tn, off), __fmul_rn(f.sg, f.ab[k]));
     }
+}
+
+// up = v / max(|v|, 1e-7) as torch computes it (train_dino.py:234-235)
+__device__ __forceinline__ void rotation_normalise(const float v[3], float up[3]) {
     float nv = norm3_torch(v[0], v[1], v[2]);
     nv = nv < 1e-7f ? 1e-7f : nv;
     // three correctly rounded quotients by one divisor: one reciprocal + FMA corrections (div_by) instead of three IEEE
@@ -43,6 +60,12 @@ __device__ __forceinline__ void rotation_candidate(const RotFrame &f, float cr, 
     up[0] = div_by(v[0], nv, inv);
     up[1] = div_by(v[1], nv, inv);
     up[2] = div_by(v[2], nv, inv);
+}
+
+__device__ __forceinline__ void rotation_candidate(const RotFrame &f, float cr, float sr, float up[3]) {
+    float v[3];
+    rotation_direction(f, cr, sr, v);
+    rotation_normalise(v, up);
 }
 
 // Tests direction p against the lattice band and adds w to every bin it hits.
@@ -94,6 +117,45 @@ __device__ __forceinline__ void lut_vote(const float p[3], const float *__restri
         if (i == 0xffffu) break;     // entries are packed front to back
         const float d = __fmaf_rn(p[2], s_sphere[3 * i + 2], __fmaf_rn(p[1], s_sphere[3 * i + 1], __fmul_rn(p[0], s_sphere[3 * i])));
         if (d > cos_thr) add(static_cast<int>(i));
+    }
+}
+
+// The same hit set without normalising the common candidate (session 3).  The reference's test is dot(v / |v|, s) > cos_thr in
+// float32 with correctly rounded quotients -- ~30 of a candidate's ~160 instructions -- but its OUTCOME is decided by the
+// unnormalised dot product for every (candidate, lattice point) pair that is not within rounding of the threshold:
+// d' = dot(v, s) against cos_thr * |v|.  The two evaluations differ by < 1e-6 relative (|v| from MUFU.RSQ: 3e-7; the rounded
+// quotients and the FMA chains: 4e-7), so outside a band of +-4e-6 around the threshold the cheap test is the reference's
+// answer, and inside it (and for |v| near the 1e-7 clamp, infinities and NaNs) the exact sequence decides.  The cube-map cell is
+// taken from v directly (its formula is scale invariant; the table's 1e-3 rad margin covers the rounding).
+template <class Add>
+__device__ __forceinline__ void lut_vote_fast(const float v[3], const float *__restrict__ s_sphere, float cos_thr,
+                                              const uint2 *__restrict__ lut_cells, int G, Add &&add) {
+    const float n2 = __fmaf_rn(v[2], v[2], __fmaf_rn(v[1], v[1], __fmul_rn(v[0], v[0])));
+    if (!(n2 > 1.1e-14f && n2 < 1e30f)) {           // rare: the exact path as it is
+        float p[3];
+        rotation_normalise(v, p);
+        lut_vote(p, s_sphere, cos_thr, lut_cells, G, add);
+        return;
+    }
+    const float t = cos_thr * (n2 * rsqrtf(n2));
+    const float t_lo = t * 0.999996f, t_hi = t * 1.000004f;
+    const uint2 e = __ldg(lut_cells + cube_cell(v, G));
+    const uint32_t word[2] = {e.x, e.y};
+#pragma unroll
+    for (int k = 0; k < kLutCap; ++k) {
+        const uint32_t i = (word[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+        if (i == 0xffffu) break;     // entries are packed front to back
+        const float dv = __fmaf_rn(v[2], s_sphere[3 * i + 2], __fmaf_rn(v[1], s_sphere[3 * i + 1], __fmul_rn(v[0], s_sphere[3 * i])));
+        if (dv > t_lo) {
+            bool hit = dv > t_hi;
+            if (!hit) {              // within rounding of the threshold: the reference's arithmetic decides
+                float p[3];
+                rotation_normalise(v, p);
+                const float d = __fmaf_rn(p[2], s_sphere[3 * i + 2], __fmaf_rn(p[1], s_sphere[3 * i + 1], __fmul_rn(p[0], s_sphere[3 * i])));
+                hit = d > cos_thr;
+            }
+            if (hit) add(static_cast<int>(i));
+        }
     }
 }
 
@@ -173,7 +235,7 @@ __device__ __forceinline__ void rotation_hist_body(
     const int32_t *__restrict__ imp, const cppf_backvote_summary *__restrict__ summary, double margin,
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R, const float *__restrict__ sphere, int S,
     float cos_thr, int band, const uint2 *__restrict__ lut_cells, int lut_g, double *__restrict__ counts, int part, int n_parts,
-    int bid, int nblk) {
+    int bid, int nblk, bool fast_test) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *s_bins = reinterpret_cast<unsigned long long *>(smem_raw);     // [n_theta][S], 32.32 fixed point
     float *s_sphere = reinterpret_cast<float *>(s_bins + cols.n * S);        // [S][3]
@@ -221,11 +283,19 @@ __device__ __forceinline__ void rotation_hist_body(
             f.sg = f.tn > 0.0f ? 1.0f : -1.0f;  // torch.where(tan > 0, 1., -1.)
             unsigned long long *bins = s_bins + c * S;
             auto add = [&](int i) { fixed_add(&bins[i], wv); };
-            for (int r = lane; r < R; r += 32) {
-                float p[3];
-                rotation_candidate(f, s_cos[r], s_sin[r], p);
-                if (lut_cells) lut_vote(p, s_sphere, cos_thr, lut_cells, lut_g, add);
-                else band_vote(p, s_sphere, S, cos_thr, band, half_sm1, add);
+            if (lut_cells && fast_test) {
+                for (int r = lane; r < R; r += 32) {
+                    float v[3];
+                    rotation_direction(f, s_cos[r], s_sin[r], v);
+                    lut_vote_fast(v, s_sphere, cos_thr, lut_cells, lut_g, add);
+                }
+            } else {
+                for (int r = lane; r < R; r += 32) {
+                    float p[3];
+                    rotation_candidate(f, s_cos[r], s_sin[r], p);
+                    if (lut_cells) lut_vote(p, s_sphere, cos_thr, lut_cells, lut_g, add);
+                    else band_vote(p, s_sphere, S, cos_thr, band, half_sm1, add);
+                }
             }
         }
     }
@@ -239,14 +309,15 @@ __global__ void __launch_bounds__(256) rotation_hist_kernel(
     const int32_t *__restrict__ kept_list, const int64_t *__restrict__ kept_count, int64_t M,
     const int32_t *__restrict__ imp, const cppf_backvote_summary *__restrict__ summary, double margin,
     const float *__restrict__ cos_tab, const float *__restrict__ sin_tab, int R, const float *__restrict__ sphere, int S,
-    float cos_thr, int band, const uint2 *__restrict__ lut_cells, int lut_g, double *__restrict__ counts, int part, int n_parts) {
+    float cos_thr, int band, const uint2 *__restrict__ lut_cells, int lut_g, double *__restrict__ counts, int part, int n_parts,
+    int fast_test) {
     rotation_hist_body(pc, idx, theta, theta_stride, cols, kept_list, kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere,
-                       S, cos_thr, band, lut_cells, lut_g, counts, part, n_parts, blockIdx.x, gridDim.x);
+                       S, cos_thr, band, lut_cells, lut_g, counts, part, n_parts, blockIdx.x, gridDim.x, fast_test != 0);
 }
 
 // Batched frame path (frame.cuh): the rotation votes of every job (angle columns 0 and 2: `up` and `right`, eval.py:277-293)
 // in one launch; blockIdx.y = job.
-__global__ void __launch_bounds__(256) frame_rotation_hist_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+__global__ void __launch_bounds__(256, CPPF_ROT_MINB) frame_rotation_hist_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
     pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];
@@ -263,7 +334,7 @@ __global__ void __launch_bounds__(256) frame_rotation_hist_kernel(const FrameTab
     if (static_cast<int>(blockIdx.x) >= nblk) return;
     rotation_hist_body(in.pc, in.idx, j.targets_rot, 3, cols, j.kept_list, &j.summary->kept, in.T, j.imp, j.summary, j.imp_margin,
                        sh.cos_tab, sh.sin_tab, sh.R, sh.sphere, sh.S, sh.cos_thr, sh.band, sh.lut_cells, sh.lut_g, j.counts, 0, 1,
-                       blockIdx.x, nblk);
+                       blockIdx.x, nblk, sh.rot_fast != 0);
 }
 
 int frame_launch_rotation(const FrameTable *t, int nj, int64_t T_cap, const FrameShared &sh, cudaStream_t s) {
@@ -406,7 +477,7 @@ CPPF_API int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_i
     const int per_sm = (lut && guess < 32768) ? 2 : 4;
     rotation_hist_kernel<<<grid_for(guess * 32, 256, per_sm), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         pc, iv, theta, theta_stride, cols, kept_list, kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere, S,
-        cos_thr, band, cells, lut_g, counts, part, n_parts);
+        cos_thr, band, cells, lut_g, counts, part, n_parts, rotation_fast_enabled() ? 1 : 0);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }
