@@ -195,6 +195,7 @@ __device__ __forceinline__ void for_each_candidate(const ShotGrid &g, const int 
         for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
             const int row = (x * g.dim[1] + y) * g.dim[2];
             const int b = cell_start[row + z0], e = cell_start[row + z1 + 1];  // z-neighbours are contiguous
+#pragma unroll 2
             for (int j = b + lane; j < e; j += 32) f(j, sorted[j]);
         }
 }
@@ -446,14 +447,22 @@ __device__ __forceinline__ int shot_neighbour_list(const ShotGrid &g, const int 
         for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
             const int crow = (x * g.dim[1] + y) * g.dim[2];
             const int b = cell_start[crow + z0], e = cell_start[crow + z1 + 1];  // z-neighbours are contiguous
-            for (int j0 = b; j0 < e; j0 += 32) {
-                const int j = j0 + lane;
-                const bool hit = j < e && flann_dist2(p, sorted[j]) < radius_sq;
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    const int pos = n_list + __popc(m & ((1u << lane) - 1u));
-                    if (hit && pos < kShotListCap) list[pos] = j;
-                    n_list += __popc(m);
+            for (int j0 = b; j0 < e; j0 += 64) {         // two candidates per lane and pass: both loads in flight together
+                const int ja = j0 + lane, jb = ja + 32;
+                float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+                if (ja < e) qa = sorted[ja];
+                if (jb < e) qb = sorted[jb];
+                const bool hit_a = ja < e && flann_dist2(p, qa) < radius_sq;
+                const bool hit_b = jb < e && flann_dist2(p, qb) < radius_sq;
+                const unsigned ma = __ballot_sync(0xffffffffu, hit_a), mb = __ballot_sync(0xffffffffu, hit_b);
+                const unsigned below = (1u << lane) - 1u;
+                if (ma | mb) {                           // appended in sweep order: the first 32 candidates, then the next 32
+                    const int pos_a = n_list + __popc(ma & below);
+                    if (hit_a && pos_a < kShotListCap) list[pos_a] = ja;
+                    n_list += __popc(ma);
+                    const int pos_b = n_list + __popc(mb & below);
+                    if (hit_b && pos_b < kShotListCap) list[pos_b] = jb;
+                    n_list += __popc(mb);
                 }
             }
         }
