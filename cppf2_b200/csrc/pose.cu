@@ -104,52 +104,90 @@ __global__ void __launch_bounds__(256) pose_directions_kernel(const double *__re
 }
 
 // ---- lower median of the kept scale predictions, one CTA per axis ------------------------------------
+constexpr int kScaleRegKeys = 8;      // keys a thread keeps in registers across the four passes (kept <= 8 * 1024: one frame's ~5 000)
+
 __device__ __forceinline__ void scale_median_body(const float *__restrict__ pred_scales, const int32_t *__restrict__ kept_list,
                                                   const cppf_backvote_summary *__restrict__ summary,
                                                   const float *__restrict__ scale_override, cppf_pose *__restrict__ pose,
                                                   int axis) {
     __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_prefix;
-    __shared__ unsigned long long s_k;
+    __shared__ unsigned long long s_cum[256];
+    __shared__ unsigned long long s_warp_tot[8];
+    __shared__ int s_digit;
     const int64_t M = summary->kept;
+    const int tid = threadIdx.x, lane = lane_id();
     if (scale_override || M <= 0) {
-        if (threadIdx.x == 0) pose->scale[axis] = scale_override ? scale_override[axis] : 0.0f;
-    } else {
-        if (threadIdx.x == 0) {
-            s_prefix = 0u;
-            s_k = static_cast<unsigned long long>((M - 1) / 2);  // torch.median: lower middle element
-        }
-        for (int pass = 0; pass < 4; ++pass) {
-            if (threadIdx.x < 256) s_hist[threadIdx.x] = 0u;
-            __syncthreads();
-            const int shift = 24 - 8 * pass;
-            const uint32_t decided = pass == 0 ? 0u : ~((1u << (shift + 8)) - 1u);
-            const uint32_t prefix = s_prefix;
-            // whole warps iterate together; scale predictions share their leading digits, so lanes with equal digits elect one
-            // leader that adds the group's size instead of serialising on one shared-memory address
-            for (int64_t base = threadIdx.x - lane_id(); base < M; base += blockDim.x) {
-                const int64_t i = base + lane_id();
-                const bool live = i < M;
-                const uint32_t key = live ? float_to_key(pred_scales[3 * static_cast<int64_t>(kept_list[i]) + axis]) : 0u;
-                const bool on = live && (key & decided) == (prefix & decided);
-                warp_hist_add(s_hist, (key >> shift) & 0xffu, on);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned long long k = s_k, cum = 0;
-                int d = 0;
-                for (; d < 256; ++d) {
-                    if (cum + s_hist[d] > k) break;
-                    cum += s_hist[d];
-                }
-                if (d == 256) d = 255;
-                s_prefix = prefix | (static_cast<uint32_t>(d) << shift);
-                s_k = k - cum;
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) pose->scale[axis] = key_to_float(s_prefix);
+        if (tid == 0) pose->scale[axis] = scale_override ? scale_override[axis] : 0.0f;
+        return;
     }
+    // The keys are gathered once (two dependent L2 reads each) and stay in registers when the kept set is a frame's size;
+    // thread tid owns the tuples u * blockDim.x + tid, so every warp iterates the same u (full-width ballots).
+    const bool in_regs = M <= static_cast<int64_t>(kScaleRegKeys) * blockDim.x;
+    uint32_t reg_key[kScaleRegKeys];
+    auto load_key = [&](int64_t i) { return float_to_key(pred_scales[3 * static_cast<int64_t>(kept_list[i]) + axis]); };
+    if (in_regs) {
+#pragma unroll
+        for (int u = 0; u < kScaleRegKeys; ++u) {
+            const int64_t i = static_cast<int64_t>(u) * blockDim.x + tid;
+            reg_key[u] = i < M ? load_key(i) : 0u;
+        }
+    }
+    // the selection state lives in registers: every thread derives the same values from the histogram
+    uint32_t prefix = 0u;
+    unsigned long long k = static_cast<unsigned long long>((M - 1) / 2);  // torch.median: lower middle element
+    for (int pass = 0; pass < 4; ++pass) {
+        if (tid < 256) s_hist[tid] = 0u;
+        if (tid == 0) s_digit = 256;
+        __syncthreads();
+        const int shift = 24 - 8 * pass;
+        const uint32_t decided = pass == 0 ? 0u : ~((1u << (shift + 8)) - 1u);
+        // scale predictions share their leading digits, so lanes with equal digits elect one leader that adds the group's size
+        // instead of serialising on one shared-memory address (warp_hist_add)
+        if (in_regs) {
+#pragma unroll
+            for (int u = 0; u < kScaleRegKeys; ++u) {
+                const int64_t i = static_cast<int64_t>(u) * blockDim.x + tid;
+                if (static_cast<int64_t>(u) * blockDim.x < M) {          // warp-uniform (and CTA-uniform)
+                    const uint32_t key = reg_key[u];
+                    warp_hist_add(s_hist, (key >> shift) & 0xffu, i < M && (key & decided) == (prefix & decided));
+                }
+            }
+        } else {
+            for (int64_t base = tid - lane; base < M; base += blockDim.x) {
+                const int64_t i = base + lane;
+                const bool live = i < M;
+                const uint32_t key = live ? load_key(i) : 0u;
+                warp_hist_add(s_hist, (key >> shift) & 0xffu, live && (key & decided) == (prefix & decided));
+            }
+        }
+        __syncthreads();
+        // the first digit whose cumulative count exceeds the remaining rank: inclusive scan of the 256 bins by warp shuffles
+        // (a one-thread walk over the bins is 256 dependent shared-memory reads: ~4 us of a pass)
+        unsigned long long incl = 0ull;
+        if (tid < 256) {
+            incl = s_hist[tid];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) s_warp_tot[tid >> 5] = incl;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            for (int w = 0; w < (tid >> 5); ++w) incl += s_warp_tot[w];
+            s_cum[tid] = incl;
+            if (incl > k) atomicMin(&s_digit, tid);
+        }
+        __syncthreads();
+        int d = s_digit;
+        if (d == 256) d = 255;
+        const unsigned long long cum = d > 0 ? s_cum[d - 1] : 0ull;
+        prefix |= static_cast<uint32_t>(d) << shift;
+        k -= cum;
+        __syncthreads();                                  // s_cum / s_digit / s_hist are rewritten by the next pass
+    }
+    if (tid == 0) pose->scale[axis] = key_to_float(prefix);
 }
 
 __global__ void __launch_bounds__(1024) scale_median_kernel(const float *__restrict__ pred_scales,
