@@ -8,8 +8,11 @@
 // order-preserving uint32 image of the float32 errors.  Each pass is one grid-wide histogram
 // (shared-memory privatised, one global atomic per non-empty bin per CTA); the last CTA to finish a
 // pass (ticket counter) scans the 256 bins and narrows the prefix, so the whole selection is four
-// stream-ordered launches with no host involvement.  It is split into errors / select / mask entry
-// points so that a tuple-sharded run can all-gather the errors (4*T bytes) between them.
+// stream-ordered launches with no host involvement.  Up to 2^17 errors (a frame's jobs) the selection
+// is ONE launch instead: a cluster of 8 CTAs per job, each with its slice of the keys in shared memory and
+// the per-pass histograms summed through distributed shared memory (select_cluster_body).  The filter is
+// split into errors / select / mask entry points so that a tuple-sharded run can all-gather the errors
+// (4*T bytes) between them.
 #include "common.cuh"
 #include "frame.cuh"
 

@@ -10,10 +10,12 @@
 // runs in L1.  Membership uses FLANN's float arithmetic exactly (((dx*dx)+dy*dy)+dz*dz < float(r*r)),
 // so the neighbour SETS are identical to the CPU restatement; only accumulation order differs.
 //
-// Per key-point (one warp):  normals: 9 float sums + count, warp-shuffle reduction, pcl::eigen33 closed
-// form in float, flip towards the origin.  LRF: weighted scatter matrix in double, cyclic Jacobi, sign
-// votes.  Histogram: every neighbour's quadrilinear contributions go to a per-warp 352-float histogram in
-// shared memory (float atomics), then L2-normalised and written as one coalesced 1408-byte row.
+// Per key-point:  normals (one warp): 9 float sums + count, warp-shuffle reduction, pcl::eigen33 closed
+// form in float, flip towards the origin.  LRF in three stages: weighted scatter matrix in double over the
+// compacted neighbour list (one warp), cyclic Jacobi (one THREAD: the solve is scalar work), sign votes (one
+// warp, in the descriptor kernel).  Histogram: every neighbour's quadrilinear contributions go to a per-warp
+// 352-bin histogram in shared memory (32-bit fixed point, native integer atomics: exact sums), then
+// L2-normalised and written as one coalesced 1408-byte row.
 #include "common.cuh"
 #include "frame.cuh"
 
