@@ -40,7 +40,7 @@ static FrameShared shared_of(const cppf_vote_params *p, int replicas_max) {
         return (e && e[0] == '0') ? 0 : 1;
     }();
     sh.vote_lanes = vote_lanes;
-    sh.rot_fast = rotation_fast_enabled() ? 1 : 0;
+    sh.rot_fast = (rotation_fast_enabled() && p->cos_thr > 0.0f) ? 1 : 0;      // the cheap test's band assumes a positive threshold
     sh.cos_thr = p->cos_thr;
     sh.lut_cells = p->lut ? reinterpret_cast<const uint2 *>(static_cast<const unsigned char *>(p->lut) + 16) : nullptr;
     sh.cos_tab = p->cos_tab;

@@ -125,7 +125,8 @@ __device__ __forceinline__ void lut_vote(const float p[3], const float *__restri
 // unnormalised dot product for every (candidate, lattice point) pair that is not within rounding of the threshold:
 // d' = dot(v, s) against cos_thr * |v|.  The two evaluations differ by < 1e-6 relative (|v| from MUFU.RSQ: 3e-7; the rounded
 // quotients and the FMA chains: 4e-7), so outside a band of +-4e-6 around the threshold the cheap test is the reference's
-// answer, and inside it (and for |v| near the 1e-7 clamp, infinities and NaNs) the exact sequence decides.  The cube-map cell is
+// answer, and inside it (and for |v| near the 1e-7 clamp, infinities and NaNs) the exact sequence decides (the launchers use this
+// form only for cos_thr > 0: the band's two bounds are ordered for a positive threshold).  The cube-map cell is
 // taken from v directly (its formula is scale invariant; the table's 1e-3 rad margin covers the rounding).
 template <class Add>
 __device__ __forceinline__ void lut_vote_fast(const float v[3], const float *__restrict__ s_sphere, float cos_thr,
@@ -477,7 +478,7 @@ CPPF_API int cppf_rotation_hist_part(const float *pc, const void *idx, int idx_i
     const int per_sm = (lut && guess < 32768) ? 2 : 4;
     rotation_hist_kernel<<<grid_for(guess * 32, 256, per_sm), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         pc, iv, theta, theta_stride, cols, kept_list, kept_count, M, imp, summary, margin, cos_tab, sin_tab, R, sphere, S,
-        cos_thr, band, cells, lut_g, counts, part, n_parts, rotation_fast_enabled() ? 1 : 0);
+        cos_thr, band, cells, lut_g, counts, part, n_parts, (rotation_fast_enabled() && cos_thr > 0.0f) ? 1 : 0);
     CPPF_LAUNCH_CHECK();
     return CPPF_OK;
 }
