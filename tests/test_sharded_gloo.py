@@ -1,4 +1,4 @@
-"""World-size-2 `gloo` test of the tuple-sharded vote orchestration (cppf2_b200/sharded.py) on CPU.
+"""World-size-2 and -3 `gloo` tests of the tuple-sharded vote orchestration (cppf2_b200/sharded.py) on CPU.
 
 The collectives and the sharding arithmetic are the product's; the stage kernels need a GPU, so this test
 plugs an oracle-backed implementation of the stage interface into `ShardedVote` (test infrastructure only)
@@ -188,14 +188,14 @@ def test_shard_bounds():
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_vote_equals_single_process(oracle):
+@pytest.mark.parametrize("world", [2, 3])          # 3: blocks that are not a power-of-two share of the tuples
+def test_multi_rank_vote_equals_single_process(oracle, world):
     pc, idx, bins, scales = _inputs()
     ref = oracle.instance_body(pc, idx, bins, scales, [0, 1, 0], [1, 0, 0], [0, 0, 1], 0.002)
-    world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), (pc, idx, bins, scales), ret), nprocs=world, join=True)
-    assert set(ret.keys()) == {0, 1}
+    assert set(ret.keys()) == set(range(world))
     # each rank masked only its own block; together the blocks are the single-process kept set
     assert np.array_equal(np.concatenate([ret[r]["pairs_mask_local"] for r in range(world)]), ref["pairs_mask"])
     for r in range(world):
