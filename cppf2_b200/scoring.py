@@ -96,6 +96,11 @@ def oriented_box_iou(R1, t1, s1, R2, t2, s2) -> float:
     R1, R2 = np.asarray(R1, np.float64), np.asarray(R2, np.float64)
     t1, t2 = np.asarray(t1, np.float64).reshape(3), np.asarray(t2, np.float64).reshape(3)
     s1, s2 = np.asarray(s1, np.float64).reshape(3), np.asarray(s2, np.float64).reshape(3)
+    # bounding spheres apart: no solid overlap (most prediction / ground-truth pairs of a frame end here)
+    r1 = 0.5 * math.sqrt(float(((np.linalg.norm(R1, axis=0) * s1) ** 2).sum()))
+    r2 = 0.5 * math.sqrt(float(((np.linalg.norm(R2, axis=0) * s2) ** 2).sum()))
+    if float(np.linalg.norm(t1 - t2)) > r1 + r2:
+        return 0.0
     pts: List[np.ndarray] = []
     for (Ra, ta, sa), (Rb, tb, sb) in (((R1, t1, s1), (R2, t2, s2)), ((R2, t2, s2), (R1, t1, s1))):
         n, d = _half_spaces(Ra, ta, sa)
