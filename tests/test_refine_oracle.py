@@ -27,6 +27,17 @@ def test_matrix_is_the_rotation_of_the_normalised_quaternion():
     assert np.allclose(Q @ axis, axis, atol=1e-12)               # rotation about the vector part
 
 
+def test_matrix_matches_scipy_scalar_last_quaternions():
+    """lietorch stores an SO3 element as (x, y, z, w) (`delta_rot = [0, 0, 0, 1]` is the identity, eval.py:323); scipy's
+    Rotation uses the same scalar-last layout, so it is an independent reading of `SO3.InitFromVec(q).matrix()` for unit q."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(4)
+    assert np.array_equal(_rot([0.0, 0.0, 0.0, 1.0]), np.eye(3))
+    for _ in range(20):
+        q = rng.standard_normal(4)
+        np.testing.assert_allclose(_rot(q), Rotation.from_quat(q / np.linalg.norm(q)).as_matrix(), atol=1e-12)
+
+
 def test_gradient_is_the_left_perturbation_derivative():
     rng = np.random.default_rng(0)
     q = np.array([0.1, -0.25, 0.4, 1.0])
